@@ -1,0 +1,186 @@
+/*
+ * unetdc_b200.h -- C ABI of libunetdc_b200.so: the B200 (sm_100a) implementation of the
+ * inference + quantification hot path behind the reference's quantify_droplets_batch.py.
+ *
+ * The reference (malani86/unet-DC-segmentation) is pure Python and has no FFI; the boundary
+ * it offers is the Python call surface quantify_droplets_batch.py itself uses.
+ * Each entry point below replaces the device work of one of those calls; the Python mirror in
+ * unet_dc_segmentation_b200/ binds them with ctypes:
+ *
+ *   dc_model_* / dc_forward      UNetDC.__call__            models/model_2.py:56-80, called at
+ *                                                           quantify_droplets_batch.py:52, and the
+ *                                                           `> thresh` of quantify_droplets_batch.py:56
+ *   dc_conv_tc / dc_stem         the nn.Conv2d / ConvTranspose2d / BatchNorm2d / ReLU /
+ *                                max_pool2d / cat / sigmoid calls inside that forward
+ *                                (models/model_2.py:20-32,40-54,58-80), one layer at a time
+ *   dc_rolling_ball              rolling_ball_correction_rgb  utils/data_loader.py:11-24
+ *   dc_label_stats               quantify                     quantify_droplets_batch.py:81-95
+ *
+ * Conventions: every function returns 0 (DC_OK) or a negative DC_E* code and never throws;
+ * dc_last_error() gives the message of the calling thread's last failure.  All data pointers
+ * are DEVICE pointers owned by the caller (the Python side passes torch tensors' data_ptr()),
+ * `stream` is a cudaStream_t passed as void*; no entry point synchronises the device or
+ * allocates device memory (workspaces are caller-provided, sized by the *_workspace_bytes
+ * queries).  There is no CPU fallback: on a device that is not compute capability 10.x the
+ * calls fail with DC_EDEVICE.
+ */
+#ifndef UNETDC_B200_H
+#define UNETDC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DC_OK 0
+#define DC_EINVAL (-1)    /* bad argument / unsupported shape */
+#define DC_ECUDA (-2)     /* CUDA runtime or driver error */
+#define DC_EDEVICE (-3)   /* not an sm_100 device */
+#define DC_ECAPACITY (-4) /* droplet table capacity exceeded (counts are still exact) */
+#define DC_EWORKSPACE (-5)
+
+const char* dc_last_error(void);
+int dc_version(void);
+/* 0 when `device` is usable (compute capability 10.x); fills *sm_count when non-NULL. */
+int dc_device_check(int device, int* sm_count);
+
+/* ------------------------------------------------------------------ tensor-core conv layer
+ * One 3x3 dilated convolution (padding = dilation) or one 2x2 / stride-2 transposed
+ * convolution as an implicit GEMM on tcgen05: A = NHWC bf16 activations fetched by TMA
+ * (out-of-bounds zero fill = the padding), B = packed bf16 weights, fp32 accumulators in
+ * TMEM, epilogue fused per `epilogue`.
+ *
+ * Weights (prepared by the host wrapper, BatchNorm already folded in fp32):
+ *   DC_KIND_CONV3X3 : w[co][(ky*3 + kx)*Cin + ci]            bf16, row length 9*Cin
+ *   DC_KIND_UPCONV2 : w[(a*2 + b)*Cout + co][ci]             bf16, row length Cin
+ *                     (a, b = output row / column parity, models/model_2.py:20)
+ * bias: fp32 [Cout].
+ */
+enum { DC_KIND_CONV3X3 = 0, DC_KIND_UPCONV2 = 1 };
+enum {
+    DC_EPI_STORE = 0,      /* bias (+ReLU) -> bf16 NHWC                                   */
+    DC_EPI_STORE_POOL = 1, /* ... and the 2x2/stride-2 max of it -> pool_out               */
+    DC_EPI_HEAD = 2,       /* bias+ReLU, then 1x1 conv (Cout -> 1) + sigmoid [+ threshold] */
+    DC_EPI_UPSCATTER = 3   /* transposed conv: bias, parity scatter into [B,2H,2W,*]        */
+};
+
+typedef struct dc_conv_args {
+    int kind;     /* DC_KIND_*  */
+    int epilogue; /* DC_EPI_*   */
+    int relu;     /* apply max(x, 0) after bias (ignored for UPSCATTER)                    */
+    int B, H, W;  /* input (= output for conv3x3) spatial shape of this layer              */
+    int Cin, Cout;
+    int dilation;
+    const void* in;    /* bf16 [B,H,W,in_stride] ; channels [0,Cin) are read               */
+    int in_stride;     /* elements between consecutive pixels (>= Cin, multiple of 8)      */
+    const void* weight;
+    const float* bias;
+    void* out;         /* bf16; pixel stride out_stride, channel offset out_offset          */
+    int out_stride;
+    int out_offset;
+    void* pool_out;    /* DC_EPI_STORE_POOL: bf16 [B,H/2,W/2,pool_stride]                  */
+    int pool_stride;
+    const float* head_w; /* DC_EPI_HEAD: fp32 [Cout]                                        */
+    float head_b;
+    float thresh;
+    float* prob_out;     /* DC_EPI_HEAD: fp32 [B,H,W] or NULL                               */
+    uint8_t* mask_out;   /* DC_EPI_HEAD: u8   [B,H,W] {0,1} or NULL                         */
+} dc_conv_args_t;
+
+int dc_conv_tc(const dc_conv_args_t* args, void* stream);
+
+/* First layer (Cin = 3, models/model_2.py:10 first conv): direct fp32 convolution.
+ * in_kind 0: fp32 NCHW [B,3,H,W] (the nn.Module contract)
+ * in_kind 1: u8 planar [B,H,W]   grayscale, replicated to 3 channels, scaled by 1/255
+ * in_kind 2: u8 HWC    [B,H,W,3] scaled by 1/255               (quantify_droplets_batch.py:41-45)
+ * weight fp32 [64][3][3][3] (BN folded), bias fp32 [64]; out bf16 NHWC. */
+typedef struct dc_stem_args {
+    int in_kind;
+    int B, H, W;
+    int Cout; /* must be 64 */
+    int dilation;
+    const void* in;
+    const float* weight;
+    const float* bias;
+    void* out;
+    int out_stride;
+    int out_offset;
+} dc_stem_args_t;
+
+int dc_stem(const dc_stem_args_t* args, void* stream);
+
+/* ------------------------------------------------------------------ whole network */
+typedef struct dc_model dc_model_t;
+
+/* Layer order of the 23 weight blobs handed to dc_model_create (names = state_dict prefixes):
+ *  0 enc1.0 (stem, fp32)  1 enc1.3  2 enc2.0  3 enc2.3  4 enc3.0  5 enc3.3  6 enc4.0  7 enc4.3
+ *  8 bottleneck.0  9 bottleneck.3  10 upconv4  11 dec4.0  12 dec4.3  13 upconv3  14 dec3.0
+ * 15 dec3.3  16 upconv2  17 dec2.0  18 dec2.3  19 upconv1  20 dec1.0  21 dec1.3
+ * 22 out_conv (fp32 weight [64], bias[1]) */
+#define DC_NUM_LAYERS 23
+typedef struct dc_model_desc {
+    const void* weight[DC_NUM_LAYERS];
+    const float* bias[DC_NUM_LAYERS];
+    int dilations[5]; /* enc1..enc4, bottleneck: (1,2,4,8,16) for UNetDC, all 1 for plain UNet */
+    int base_channels; /* 64 */
+} dc_model_desc_t;
+
+int dc_model_create(dc_model_t** out, int device, const dc_model_desc_t* desc);
+int dc_model_destroy(dc_model_t* m);
+int dc_forward_workspace_bytes(const dc_model_t* m, int B, int H, int W, size_t* bytes);
+/* in_kind as dc_stem_args.  prob_out fp32 [B,H,W] and/or mask_out u8 [B,H,W] may be NULL.
+ * mask = prob > thresh (fp32 compare, quantify_droplets_batch.py:56). H, W multiples of 16. */
+int dc_forward(dc_model_t* m, int in_kind, const void* in, int B, int H, int W, float thresh, float* prob_out,
+               uint8_t* mask_out, void* workspace, size_t workspace_bytes, void* stream);
+/* number of kernels one dc_forward launches (for bench accounting) */
+int dc_forward_num_launches(const dc_model_t* m);
+
+/* ------------------------------------------------------------------ rolling-ball correction
+ * Per plane: opening with the radius x radius ellipse of cv2.getStructuringElement, saturating
+ * subtract, min-max stretch to 0..255 (utils/data_loader.py:11-24).
+ * in/out: u8, `planes` = B*C planes addressed as in[(b*H*W + y*W + x)*C + c] (HWC interleaved;
+ * C = 1 is planar grayscale). */
+typedef struct dc_rolling_ball_args {
+    const uint8_t* in;
+    uint8_t* out;
+    int B, H, W, C;
+    int radius;
+    void* workspace;
+    size_t workspace_bytes;
+} dc_rolling_ball_args_t;
+
+int dc_rolling_ball_workspace_bytes(int B, int H, int W, int C, size_t* bytes);
+int dc_rolling_ball(const dc_rolling_ball_args_t* args, void* stream);
+
+/* ------------------------------------------------------------------ labelling + droplet table
+ * quantify() of quantify_droplets_batch.py:81-95 for a batch of masks: 4-connected labelling,
+ * min_area filter, consecutive relabelling in raster order of first pixel, per-droplet
+ * area / centroid / equivalent diameter (+ micron columns when px_per_um > 0).
+ * Table row r of image b lives at index b*capacity + r (label = r + 1). */
+typedef struct dc_label_args {
+    const uint8_t* mask; /* u8 [B,H,W], non-zero = foreground */
+    int B, H, W;
+    int64_t min_area;
+    double px_per_um;    /* <= 0: micron columns not written */
+    int32_t* labels_out; /* int32 [B,H,W] or NULL */
+    int capacity;        /* table rows per image */
+    int32_t* counts;     /* int32 [B]: droplets kept per image (exact even on overflow) */
+    int64_t* area;       /* [B*capacity] */
+    double* centroid0;   /* row  */
+    double* centroid1;   /* col  */
+    double* eq_diam;
+    double* area_um2;    /* may be NULL when px_per_um <= 0 */
+    double* diam_um;
+    void* workspace;
+    size_t workspace_bytes;
+} dc_label_args_t;
+
+int dc_label_workspace_bytes(int B, int H, int W, size_t* bytes);
+int dc_label_stats(const dc_label_args_t* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNETDC_B200_H */

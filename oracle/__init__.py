@@ -1,0 +1,197 @@
+"""CPU oracle for the droplet-quantification hot path -- TEST INFRASTRUCTURE ONLY.
+
+Restates, on the CPU, what the reference (malani86/unet-DC-segmentation) computes on the path
+behind ``quantify_droplets_batch.py``.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import this package; the
+product package ``unet_dc_segmentation_b200`` never does (it fails loudly without its CUDA
+library instead of falling back to anything here).
+
+Parity pin: the reference ships no tests for this path, so the pin is
+``tests/golden/*.npz`` -- outputs of the reference's OWN functions, generated in the build
+container by ``tests/golden/make_golden.py`` (imports /root/reference unmodified under
+sys.modules shims), plus the known-answer rows of the reference's ``outputs/all_droplets.csv``.
+
+Integer/byte stages live in ``oracle.c`` (gcc); the network is a plain PyTorch fp32
+restatement (``unetdc_forward``), the one floating-point kernel on the path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = None
+
+
+def build(force: bool = False) -> Path:
+    """Compile oracle.c -> liboracle.so with gcc (a few hundred ms)."""
+    so = _HERE / "liboracle.so"
+    src = _HERE / "oracle.c"
+    if force or not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(_HERE), "-B", "liboracle.so"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return so
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        lib = ctypes.CDLL(str(build()))
+        i32p = ctypes.POINTER(ctypes.c_int32)
+        i64p = ctypes.POINTER(ctypes.c_int64)
+        f64p = ctypes.POINTER(ctypes.c_double)
+        u8p = ctypes.POINTER(ctypes.c_uint8)
+        lib.orc_ellipse_rows.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+        lib.orc_rolling_ball_u8.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        lib.orc_label4.argtypes = [i32p, i32p, ctypes.c_int, ctypes.c_int]
+        lib.orc_quantify.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_double,
+                                     i32p, ctypes.c_int, i64p, f64p, f64p, f64p, f64p, f64p]
+        _LIB = lib
+    return _LIB
+
+
+def _ptr(a, ct):
+    return a.ctypes.data_as(ctypes.POINTER(ct))
+
+
+# ----------------------------------------------------------------------------- rolling ball
+
+def ellipse_rows(k: int):
+    """[j1, j2) column span of each row of cv2.getStructuringElement(MORPH_ELLIPSE, (k, k))."""
+    j1 = np.zeros(k, np.intc)
+    j2 = np.zeros(k, np.intc)
+    _lib().orc_ellipse_rows(k, _ptr(j1, ctypes.c_int), _ptr(j2, ctypes.c_int))
+    return j1, j2
+
+
+def rolling_ball_correction_rgb(image: np.ndarray, radius: int = 50) -> np.ndarray:
+    """Follows reference utils/data_loader.py:11-24.  image: u8 [H, W, C]."""
+    image = np.ascontiguousarray(image, dtype=np.uint8)
+    if image.ndim == 2:
+        image = image[:, :, None]
+    H, W, C = image.shape
+    out = np.empty_like(image)
+    rc = _lib().orc_rolling_ball_u8(_ptr(image, ctypes.c_uint8), _ptr(out, ctypes.c_uint8), H, W, C, int(radius))
+    if rc != 0:
+        raise RuntimeError(f"orc_rolling_ball_u8 failed: {rc}")
+    return out
+
+
+# ----------------------------------------------------------------------------- labelling / table
+
+def label4(img: np.ndarray) -> tuple[np.ndarray, int]:
+    """skimage.measure.label(img, connectivity=1) semantics (reference qdb:82,86)."""
+    img = np.ascontiguousarray(img, dtype=np.int32)
+    H, W = img.shape
+    out = np.empty((H, W), np.int32)
+    n = _lib().orc_label4(_ptr(img, ctypes.c_int32), _ptr(out, ctypes.c_int32), H, W)
+    if n < 0:
+        raise RuntimeError(f"orc_label4 failed: {n}")
+    return out, n
+
+
+COLUMNS = ["label", "area", "equivalent_diameter", "centroid-0", "centroid-1"]
+MICRON_COLUMNS = ["area_sqmicron", "eq_diam_micron"]
+
+
+def quantify_arrays(bin_mask: np.ndarray, min_area: int = 1, px_per_um: float | None = None):
+    """Reference quantify() (qdb:81-95) as plain arrays: (labels int32 [H,W], dict of columns)."""
+    mask = np.ascontiguousarray(bin_mask, dtype=np.uint8)
+    H, W = mask.shape
+    cap = max(1, (H * W + 1) // 2)
+    labels = np.empty((H, W), np.int32)
+    area = np.empty(cap, np.int64)
+    c0, c1, dia, aum, dum = (np.empty(cap, np.float64) for _ in range(5))
+    n = _lib().orc_quantify(_ptr(mask, ctypes.c_uint8), H, W, int(min_area),
+                            float(px_per_um) if px_per_um else 0.0,
+                            _ptr(labels, ctypes.c_int32), cap, _ptr(area, ctypes.c_int64),
+                            _ptr(c0, ctypes.c_double), _ptr(c1, ctypes.c_double), _ptr(dia, ctypes.c_double),
+                            _ptr(aum, ctypes.c_double), _ptr(dum, ctypes.c_double))
+    if n < 0:
+        raise RuntimeError(f"orc_quantify failed: {n}")
+    cols = {"label": np.arange(1, n + 1, dtype=np.int64), "area": area[:n].copy(),
+            "equivalent_diameter": dia[:n].copy(), "centroid-0": c0[:n].copy(), "centroid-1": c1[:n].copy()}
+    if px_per_um:
+        cols["area_sqmicron"] = aum[:n].copy()
+        cols["eq_diam_micron"] = dum[:n].copy()
+    return labels, cols
+
+
+def quantify(bin_mask: np.ndarray, min_area: int = 1, px_per_um: float | None = None):
+    """Reference quantify() (qdb:81-95) -> pandas.DataFrame (empty, column-less, when no droplets)."""
+    import pandas as pd
+    _, cols = quantify_arrays(bin_mask, min_area, px_per_um)
+    if len(cols["label"]) == 0:
+        return pd.DataFrame()
+    return pd.DataFrame(cols)
+
+
+# ----------------------------------------------------------------------------- network (fp32)
+
+_BLOCKS = [("enc1", 1), ("enc2", 2), ("enc3", 4), ("enc4", 8), ("bottleneck", 16)]
+
+
+def unetdc_forward(state_dict, x, dilations=(1, 2, 4, 8, 16)):
+    """Plain PyTorch fp32 restatement of reference models/model_2.py:56-80 in eval mode.
+
+    state_dict uses the reference's 136 keys; x: f32 [B,3,H,W]; returns f32 [B,1,H,W] probs.
+    ``dilations`` = (1,1,1,1,1) gives reference models/model.py:35-50 (plain UNet)."""
+    import torch
+    import torch.nn.functional as F
+
+    sd = {k: v.detach().to(torch.float32).cpu() for k, v in state_dict.items()}
+
+    def cbr(t, p, idx, d):                                  # model_2.py:40-54 (one conv+BN+ReLU)
+        t = F.conv2d(t, sd[f"{p}.{idx}.weight"], sd[f"{p}.{idx}.bias"], padding=d, dilation=d)
+        t = F.batch_norm(t, sd[f"{p}.{idx + 1}.running_mean"], sd[f"{p}.{idx + 1}.running_var"],
+                         sd[f"{p}.{idx + 1}.weight"], sd[f"{p}.{idx + 1}.bias"], False, 0.0, 1e-5)
+        return F.relu(t)
+
+    def block(t, p, d):
+        return cbr(cbr(t, p, 0, d), p, 3, d)
+
+    with torch.no_grad():
+        x = x.detach().to(torch.float32).cpu()
+        skips = []
+        t = x
+        for i, (name, _) in enumerate(_BLOCKS[:4]):          # model_2.py:58-61
+            t = block(t, name, dilations[i])
+            skips.append(t)
+            t = F.max_pool2d(t, 2)
+        t = block(t, "bottleneck", dilations[4])            # model_2.py:64
+        for lvl in (4, 3, 2, 1):                            # model_2.py:67-77
+            t = F.conv_transpose2d(t, sd[f"upconv{lvl}.weight"], sd[f"upconv{lvl}.bias"], stride=2)
+            t = torch.cat([t, skips[lvl - 1]], dim=1)
+            t = block(t, f"dec{lvl}", 1)
+        t = F.conv2d(t, sd["out_conv.weight"], sd["out_conv.bias"])   # model_2.py:79
+        return torch.sigmoid(t)                                        # model_2.py:80
+
+
+def run_path(state_dict, images_u8, radius=50, prob_thresh=0.3, min_area=1, px_per_um=None,
+             use_cv2=False):
+    """Whole reference path at native size (IMG_SIZE == image size, identity resizes):
+    preprocess (qdb:40-46) -> forward (qdb:52) -> threshold (qdb:56) -> quantify (qdb:61).
+
+    images_u8: list of u8 [H,W,3].  Returns (probs f32 [B,H,W], masks u8 [B,H,W], tables)."""
+    import torch
+    if use_cv2:
+        import cv2
+        def rb(im, r):
+            k = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (r, r))
+            chans = []
+            for ch in cv2.split(im):
+                bg = cv2.morphologyEx(ch, cv2.MORPH_OPEN, k)
+                chans.append(cv2.normalize(cv2.subtract(ch, bg), None, 0, 255, cv2.NORM_MINMAX))
+            return cv2.merge(chans)
+    else:
+        rb = rolling_ball_correction_rgb
+    pre = [rb(im, radius).astype(np.float32) / 255.0 for im in images_u8]
+    batch = torch.from_numpy(np.stack(pre)).permute(0, 3, 1, 2).contiguous()
+    probs = unetdc_forward(state_dict, batch)[:, 0].numpy()
+    masks = (probs > prob_thresh).astype(np.uint8)
+    tables = [quantify(m, min_area, px_per_um) for m in masks]
+    return probs, masks, tables

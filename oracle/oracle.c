@@ -1,0 +1,211 @@
+/*
+ * oracle.c -- CPU restatement (TEST INFRASTRUCTURE, not product) of the integer / byte
+ * stages of the droplet-quantification hot path of malani86/unet-DC-segmentation.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library.  The product path (unet_dc_segmentation_b200) never calls it.
+ *
+ * Parity pin: the reference has no tests for this path.  The restatement is
+ * pinned against outputs of the reference's own functions run in the build container
+ * (tests/golden/make_golden.py imports /root/reference unmodified under sys.modules shims
+ * and commits the vectors), and against OpenCV / scipy where those are importable.
+ *
+ * What each function follows:
+ *   orc_ellipse_rows      cv2.getStructuringElement(MORPH_ELLIPSE, (radius, radius))
+ *                         as called at reference utils/data_loader.py:17
+ *   orc_rolling_ball_u8   reference utils/data_loader.py:11-24 (per channel: MORPH_OPEN,
+ *                         cv2.subtract, cv2.normalize NORM_MINMAX 0..255)
+ *   orc_label4            skimage.measure.label(mask, connectivity=1) as called at
+ *                         reference quantify_droplets_batch.py:82 and :86
+ *   orc_quantify          reference quantify_droplets_batch.py:81-95 (label, min_area
+ *                         filter, relabel, regionprops_table, micron columns)
+ *
+ * Third-party arithmetic restated here (not vendored in /root/reference; requirements.txt
+ * pins nothing): opencv-python (probe: 4.13.0 in this image) and scikit-image (absent in
+ * this image; published semantics: 4-connectivity, labels 1..n in raster order of each
+ * component's first pixel, area = pixel count, centroid = mean of integer coordinates,
+ * equivalent_diameter = sqrt(4*area/pi)).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ structuring element */
+
+/* Row i of the k x k ellipse covers columns [j1[i], j2[i]) (empty when j1 == j2).
+ * OpenCV: r = k/2, c = k/2, dx = cvRound(c * sqrt((r*r - dy*dy) / (r*r))). */
+int orc_ellipse_rows(int k, int *j1, int *j2)
+{
+    if (k < 1) return -1;
+    int r = k / 2, c = k / 2;
+    double inv_r2 = r ? 1.0 / ((double)r * r) : 0.0;
+    for (int i = 0; i < k; ++i) {
+        int dy = i - r;
+        j1[i] = j2[i] = 0;
+        if (abs(dy) <= r) {
+            int dx = (int)nearbyint(c * sqrt(((double)r * r - (double)dy * dy) * inv_r2));
+            int a = c - dx, b = c + dx + 1;
+            j1[i] = a < 0 ? 0 : a;
+            j2[i] = b > k ? k : b;
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ morphology */
+
+/* One flat-SE pass.  is_max = 0: erode (min), 1: dilate (max).  Both use the SAME offsets
+ * (OpenCV does not reflect the element for dilation), anchor = (k/2, k/2); taps falling
+ * outside the image are ignored (cv2 morphologyDefaultBorderValue). */
+static void morph_pass(const uint8_t *src, uint8_t *dst, int H, int W, int k,
+                       const int *j1, const int *j2, int is_max)
+{
+    int an = k / 2;
+    for (int y = 0; y < H; ++y) {
+        for (int x = 0; x < W; ++x) {
+            int acc = is_max ? 0 : 255;
+            for (int i = 0; i < k; ++i) {
+                int yy = y + i - an;
+                if (yy < 0 || yy >= H || j1[i] >= j2[i]) continue;
+                int xa = x + j1[i] - an, xb = x + j2[i] - an; /* [xa, xb) */
+                if (xa < 0) xa = 0;
+                if (xb > W) xb = W;
+                const uint8_t *row = src + (size_t)yy * W;
+                if (is_max) { for (int xx = xa; xx < xb; ++xx) if (row[xx] > acc) acc = row[xx]; }
+                else        { for (int xx = xa; xx < xb; ++xx) if (row[xx] < acc) acc = row[xx]; }
+            }
+            dst[(size_t)y * W + x] = (uint8_t)acc;
+        }
+    }
+}
+
+/* cv2.normalize(src, None, 0, 255, NORM_MINMAX) on a u8 plane.  OpenCV computes, in double,
+ * scale = 255 * (1/(max-min)) (0 when max == min) and shift = 0 - min*scale, then convertTo
+ * evaluates fma(src, float(scale), float(shift)) in fp32 and rounds half-to-even with
+ * saturation.  Checked exhaustively (all 32,640 (min,max) pairs x all values) against
+ * cv2 4.13.0: the fused form matches everywhere, the unfused form differs on 6,498 values. */
+static void minmax_stretch(uint8_t *p, size_t n)
+{
+    int mn = 255, mx = 0;
+    for (size_t i = 0; i < n; ++i) { if (p[i] < mn) mn = p[i]; if (p[i] > mx) mx = p[i]; }
+    double scale = (mx - mn) > 0 ? 255.0 * (1.0 / (double)(mx - mn)) : 0.0;
+    double shift = 0.0 - (double)mn * scale;
+    float a = (float)scale, b = (float)shift;
+    uint8_t lut[256];
+    for (int v = 0; v < 256; ++v) {
+        float f = fmaf((float)v, a, b);
+        long q = lrintf(f);
+        lut[v] = (uint8_t)(q < 0 ? 0 : q > 255 ? 255 : q);
+    }
+    for (size_t i = 0; i < n; ++i) p[i] = lut[p[i]];
+}
+
+/* image: u8 [H, W, C] interleaved (HWC); out: same shape.  Returns 0 on success. */
+int orc_rolling_ball_u8(const uint8_t *image, uint8_t *out, int H, int W, int C, int radius)
+{
+    if (H <= 0 || W <= 0 || C <= 0 || radius < 1) return -1;
+    size_t n = (size_t)H * W;
+    int *j1 = (int *)malloc(sizeof(int) * radius), *j2 = (int *)malloc(sizeof(int) * radius);
+    uint8_t *ch = (uint8_t *)malloc(n), *er = (uint8_t *)malloc(n), *bg = (uint8_t *)malloc(n);
+    if (!j1 || !j2 || !ch || !er || !bg) { free(j1); free(j2); free(ch); free(er); free(bg); return -2; }
+    orc_ellipse_rows(radius, j1, j2);
+    for (int c = 0; c < C; ++c) {
+        for (size_t i = 0; i < n; ++i) ch[i] = image[i * C + c];
+        morph_pass(ch, er, H, W, radius, j1, j2, 0);
+        morph_pass(er, bg, H, W, radius, j1, j2, 1);
+        for (size_t i = 0; i < n; ++i) { int d = (int)ch[i] - (int)bg[i]; ch[i] = (uint8_t)(d < 0 ? 0 : d); }
+        minmax_stretch(ch, n);
+        for (size_t i = 0; i < n; ++i) out[i * C + c] = ch[i];
+    }
+    free(j1); free(j2); free(ch); free(er); free(bg);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ labelling */
+
+static int32_t uf_find(int32_t *p, int32_t x)
+{
+    while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; }
+    return x;
+}
+
+/* 4-connected labelling of equal-valued non-zero pixels (so it serves both the first call on
+ * a 0/1 mask and the second call on a label image, where it is a pure compaction).
+ * labels: int32 [H, W]; returns the number of components (labels are 1..n in raster order of
+ * first pixel), or <0 on error. */
+int orc_label4(const int32_t *img, int32_t *labels, int H, int W)
+{
+    size_t n = (size_t)H * W;
+    int32_t *parent = (int32_t *)malloc(sizeof(int32_t) * (n ? n : 1));
+    if (!parent) return -2;
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            size_t i = (size_t)y * W + x;
+            parent[i] = (int32_t)i;
+            if (!img[i]) continue;
+            if (x > 0 && img[i - 1] == img[i]) parent[i] = uf_find(parent, (int32_t)(i - 1));
+            if (y > 0 && img[i - W] == img[i]) {
+                int32_t a = uf_find(parent, (int32_t)i), b = uf_find(parent, (int32_t)(i - W));
+                if (a < b) parent[b] = a; else if (b < a) parent[a] = b;
+            }
+        }
+    /* roots are minimal raster indices, so numbering roots in raster order is skimage's order */
+    int32_t next = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (!img[i]) { labels[i] = 0; continue; }
+        int32_t r = uf_find(parent, (int32_t)i);
+        if ((size_t)r == i) labels[i] = ++next;     /* first pixel of its component */
+        else labels[i] = labels[r];                 /* r < i, already numbered */
+    }
+    free(parent);
+    return next;
+}
+
+/* Reference quantify(): returns the number of droplets kept (<= capacity is required, else
+ * -3) and fills per-droplet rows.  labels_out (optional) receives the final label image.
+ *   area[i], sum_row[i], sum_col[i] : exact integers
+ *   centroid0/1 = sum/area (f64), eq_diam = sqrt(4*area/pi) (f64)
+ *   area_um2 = area / px^2, diam_um = eq_diam / px when px_per_um > 0 (else untouched). */
+int orc_quantify(const uint8_t *mask, int H, int W, int64_t min_area, double px_per_um,
+                 int32_t *labels_out, int capacity,
+                 int64_t *area, double *centroid0, double *centroid1, double *eq_diam,
+                 double *area_um2, double *diam_um)
+{
+    size_t n = (size_t)H * W;
+    int32_t *img = (int32_t *)malloc(sizeof(int32_t) * (n ? n : 1));
+    int32_t *lbl = (int32_t *)malloc(sizeof(int32_t) * (n ? n : 1));
+    if (!img || !lbl) { free(img); free(lbl); return -2; }
+    for (size_t i = 0; i < n; ++i) img[i] = mask[i] ? 1 : 0;
+    int n1 = orc_label4(img, lbl, H, W);                       /* qdb:82 */
+    if (n1 < 0) { free(img); free(lbl); return n1; }
+    int64_t *cnt = (int64_t *)calloc((size_t)n1 + 1, sizeof(int64_t));
+    for (size_t i = 0; i < n; ++i) cnt[lbl[i]]++;
+    for (size_t i = 0; i < n; ++i)                             /* qdb:83-85 */
+        if (lbl[i] && cnt[lbl[i]] < min_area) lbl[i] = 0;
+    free(cnt);
+    int n2 = orc_label4(lbl, img, H, W);                       /* qdb:86 (compaction) */
+    if (n2 < 0 || n2 > capacity) { free(img); free(lbl); return n2 < 0 ? n2 : -3; }
+    int64_t *sr = (int64_t *)calloc((size_t)n2 + 1, sizeof(int64_t));
+    int64_t *sc = (int64_t *)calloc((size_t)n2 + 1, sizeof(int64_t));
+    int64_t *ar = (int64_t *)calloc((size_t)n2 + 1, sizeof(int64_t));
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            int32_t l = img[(size_t)y * W + x];
+            if (l) { ar[l]++; sr[l] += y; sc[l] += x; }
+        }
+    const double pi = 3.14159265358979323846;
+    for (int l = 1; l <= n2; ++l) {                            /* qdb:89-94 */
+        area[l - 1] = ar[l];
+        centroid0[l - 1] = (double)sr[l] / (double)ar[l];
+        centroid1[l - 1] = (double)sc[l] / (double)ar[l];
+        eq_diam[l - 1] = sqrt(4.0 * (double)ar[l] / pi);
+        if (px_per_um > 0) {
+            area_um2[l - 1] = (double)ar[l] / (px_per_um * px_per_um);
+            diam_um[l - 1] = eq_diam[l - 1] / px_per_um;
+        }
+    }
+    if (labels_out) memcpy(labels_out, img, sizeof(int32_t) * n);
+    free(sr); free(sc); free(ar); free(img); free(lbl);
+    return n2;
+}

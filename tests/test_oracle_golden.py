@@ -1,0 +1,104 @@
+"""CPU: the oracle (oracle/oracle.c + oracle/__init__.py) against the golden vectors produced by the
+reference's own functions (tests/golden/make_golden.py) -- this is what pins the oracle."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import assert_table_equal, golden_cases, golden_table, load_golden, unpack_mask
+
+RB = load_golden("rolling_ball.npz")
+QT = load_golden("quantify.npz")
+
+
+@pytest.mark.parametrize("case", golden_cases(RB))
+def test_rolling_ball_matches_reference(case):
+    img, radius, want = RB[f"{case}/in"], int(RB[f"{case}/radius"]), RB[f"{case}/out"]
+    got = oracle.rolling_ball_correction_rgb(img, radius)
+    np.testing.assert_array_equal(got, want)
+
+
+def test_ellipse_rows_match_survey_probe():
+    # row widths of cv2.getStructuringElement(MORPH_ELLIPSE, (50, 50)), 1995 taps
+    j1, j2 = oracle.ellipse_rows(50)
+    widths = (j2 - j1).tolist()
+    assert sum(widths) == 1995
+    assert widths[:8] == [1, 15, 21, 25, 29, 31, 33, 35] and widths[-3:] == [25, 21, 15]
+    assert widths[21:30] == [50] * 9
+
+
+@pytest.mark.parametrize("case", golden_cases(QT))
+def test_quantify_matches_reference(case):
+    mask = unpack_mask(QT, case)
+    px = float(QT[f"{case}/px"])
+    labels, cols = oracle.quantify_arrays(mask, int(QT[f"{case}/min_area"]), px if px else None)
+    assert_table_equal(cols, golden_table(QT, f"{case}/t/"), case)
+    assert labels.max() == len(cols["label"])
+
+
+def test_quantify_empty_frame_contract():
+    df = oracle.quantify(np.zeros((8, 8), np.uint8), 1, 3.45)
+    assert df.empty and len(df.columns) == 0            # qdb:87-88
+
+
+def test_label4_is_raster_ordered_and_compacting():
+    img = np.array([[0, 7, 0, 3],
+                    [5, 7, 0, 3],
+                    [5, 0, 9, 9]], np.int32)
+    lab, n = oracle.label4(img)
+    assert n == 4
+    assert lab.tolist() == [[0, 1, 0, 2], [3, 1, 0, 2], [3, 0, 4, 4]]
+
+
+@pytest.mark.parametrize("tag", ["unetdc", "unet"])
+def test_forward_restatement_matches_reference_module(tag):
+    import torch
+    from unet_dc_segmentation_b200.synth import calibrated_state_dict
+    g = load_golden("forward.npz")
+    dil = tuple(int(v) for v in g[f"{tag}/dilations"])
+    torch.manual_seed(0)
+    sd = calibrated_state_dict(seed=0, calib_size=64, n_calib=2, dilations=dil)
+    x = torch.from_numpy(np.repeat(g[f"{tag}/images"][:, None], 3, 1).astype(np.float32) / 255.0)
+    y = oracle.unetdc_forward(sd, x, dil).numpy()
+    # fp32 on both sides; only thread-count / instruction-set differences in the CPU conv kernels remain
+    np.testing.assert_allclose(y, g[f"{tag}/probs"], atol=2e-4, rtol=0)
+
+
+def test_whole_path_matches_reference():
+    import torch
+    from unet_dc_segmentation_b200.synth import calibrated_state_dict
+    g = load_golden("end_to_end.npz")
+    sd = calibrated_state_dict(seed=0, calib_size=64, n_calib=2)
+    imgs = [np.repeat(im[:, :, None], 3, 2) for im in g["images"]]
+    probs, masks, tables = oracle.run_path(sd, imgs, radius=50, prob_thresh=0.3, min_area=1, px_per_um=3.45)
+    pre = np.stack([oracle.rolling_ball_correction_rgb(im, 50) for im in imgs]).transpose(0, 3, 1, 2)
+    np.testing.assert_array_equal(pre, g["pre"])
+    np.testing.assert_allclose(probs, g["probs"][:, 0], atol=2e-4, rtol=0)
+    for i in range(2):
+        want_mask = np.unpackbits(g[f"mask{i}"])[: 96 * 96].reshape(96, 96)
+        near = np.abs(g["probs"][i, 0] - 0.3) < 1e-3
+        assert np.all((masks[i] == want_mask) | near)
+        # tables are bit-exact given the same mask: feed the oracle the reference's mask
+        _, cols = oracle.quantify_arrays(want_mask, 1, 3.45)
+        assert_table_equal(cols, golden_table(g, f"t{i}/"), f"image {i}")
+
+
+def test_reference_sample_outputs_known_answers():
+    """The reference's shipped outputs/all_droplets.csv pins the column contract and the formulas
+    (SURVEY.md 4): eq.diam = sqrt(4*area/pi), area_sqmicron = area/3.45^2, eq_diam_micron = diam/3.45."""
+    g = load_golden("reference_outputs.npz")
+    assert list(g["columns"]) == ["filename"] + oracle.COLUMNS + oracle.MICRON_COLUMNS
+    area = g["area"].astype(np.int64)
+    px = 3.45
+    # evaluate with the oracle's own arithmetic: a 1 x area strip has exactly that area
+    for a in np.unique(area)[:40]:
+        _, cols = oracle.quantify_arrays(np.ones((1, int(a)), np.uint8), 1, px)
+        sel = area == a
+        assert cols["area"][0] == a
+        # the CSV text carries 16 significant digits, so a parsed value may be a few ulp off the f64 it printed
+        for col in ("equivalent_diameter", "area_sqmicron", "eq_diam_micron"):
+            np.testing.assert_allclose(g[col][sel], cols[col][0], rtol=2e-15, atol=0, err_msg=f"{col} area={a}")
+    # labels are 1..n per image, and the summary is count / sum(area)
+    for fn, cnt, tot in zip(g["summary_filename"], g["summary_count"], g["summary_area"]):
+        sel = g["filename"] == fn
+        assert sel.sum() == cnt and area[sel].sum() == tot
+        assert g["label"][sel].tolist() == list(range(1, int(cnt) + 1))

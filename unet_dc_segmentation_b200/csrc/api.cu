@@ -1,0 +1,281 @@
+// api.cu -- the extern "C" surface of libunetdc_b200.so (include/unetdc_b200.h): argument checks,
+// error plumbing, and the layer schedule of one UNetDC forward (reference models/model_2.py:56-80).
+#include "common.cuh"
+
+#include <new>
+#include <stdarg.h>
+#include <string.h>
+
+namespace dc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return DC_ECUDA;
+}
+
+// Device gate: every entry point that launches work refuses anything that is not sm_100.
+static int check_current_device(int* sms_out) {
+    static thread_local int cached_dev = -1, cached_sms = 0, cached_rc = DC_OK;
+    int dev = -1;
+    DC_CUDA(cudaGetDevice(&dev));
+    if (dev != cached_dev) {
+        cudaDeviceProp prop;
+        DC_CUDA(cudaGetDeviceProperties(&prop, dev));
+        cached_dev = dev;
+        cached_sms = prop.multiProcessorCount;
+        cached_rc = (prop.major == 10) ? DC_OK : DC_EDEVICE;
+        if (cached_rc != DC_OK)
+            set_error("device %d (%s) is compute capability %d.%d; this library is sm_100a only and has no fallback",
+                      dev, prop.name, prop.major, prop.minor);
+    } else if (cached_rc != DC_OK) {
+        set_error("current device is not compute capability 10.x; this library is sm_100a only and has no fallback");
+    }
+    if (sms_out) *sms_out = cached_sms;
+    return cached_rc;
+}
+
+int num_sms() {
+    int sms = 0;
+    check_current_device(&sms);
+    return sms > 0 ? sms : 148;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace dc
+
+using namespace dc;
+
+struct dc_model {
+    int device;
+    dc_model_desc_t desc;
+    float head_b;
+};
+
+namespace {
+
+// Activation buffers of one forward, carved out of the caller's workspace (all bf16 NHWC).
+struct ForwardBuffers {
+    char* a[5];      // first-conv output of enc1..enc4 / bottleneck; reused as dec{l}.0 output for l < 4
+    char* cat[4];    // [B,Hl,Wl,2*Cl]: channels [0,Cl) <- upconv, [Cl,2Cl) <- encoder skip (torch.cat order)
+    char* pool[4];   // 2x2 max-pooled encoder output
+    char* bott;      // bottleneck.3 output
+    char* db[4];     // dec{l}.3 output for l = 1..3 (index l); dec1.3 goes straight to the head
+    size_t total;
+};
+
+ForwardBuffers carve(char* base, int B, int H, int W) {
+    ForwardBuffers f;
+    memset(&f, 0, sizeof(f));
+    size_t off = 0;
+    auto take = [&](size_t elems) {
+        char* p = base ? base + off : nullptr;
+        off += align256(elems * 2);
+        return p;
+    };
+    for (int l = 0; l < 5; ++l) {
+        const size_t px = (size_t)B * (H >> l) * (W >> l);
+        const size_t C = (size_t)64 << l;
+        f.a[l] = take(px * C);
+        if (l < 4) {
+            f.cat[l] = take(px * 2 * C);
+            f.pool[l] = take(px / 4 * C);
+            if (l > 0) f.db[l] = take(px * C);
+        } else {
+            f.bott = take(px * C);
+        }
+    }
+    f.total = off;
+    return f;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dc_last_error(void) { return g_err; }
+
+int dc_version(void) { return 100; }
+
+int dc_device_check(int device, int* sm_count) {
+    cudaDeviceProp prop;
+    DC_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    DC_REQUIRE(prop.major == 10, DC_EDEVICE, "device %d (%s) is compute capability %d.%d, need 10.x", device, prop.name,
+               prop.major, prop.minor);
+    return DC_OK;
+}
+
+int dc_conv_tc(const dc_conv_args_t* args, void* stream) {
+    int rc = check_current_device(nullptr);
+    if (rc != DC_OK) return rc;
+    return launch_conv_tc(args, (cudaStream_t)stream);
+}
+
+int dc_stem(const dc_stem_args_t* args, void* stream) {
+    int rc = check_current_device(nullptr);
+    if (rc != DC_OK) return rc;
+    return launch_stem(args, (cudaStream_t)stream);
+}
+
+int dc_rolling_ball_workspace_bytes(int B, int H, int W, int C, size_t* bytes) {
+    DC_REQUIRE(bytes && B > 0 && H > 0 && W > 0 && C > 0, DC_EINVAL, "dc_rolling_ball_workspace_bytes: bad argument");
+    *bytes = rolling_ball_workspace_bytes(B * C, H, W);
+    return DC_OK;
+}
+
+int dc_rolling_ball(const dc_rolling_ball_args_t* args, void* stream) {
+    int rc = check_current_device(nullptr);
+    if (rc != DC_OK) return rc;
+    return launch_rolling_ball(args, (cudaStream_t)stream);
+}
+
+int dc_label_workspace_bytes(int B, int H, int W, size_t* bytes) {
+    DC_REQUIRE(bytes && B > 0 && H > 0 && W > 0, DC_EINVAL, "dc_label_workspace_bytes: bad argument");
+    *bytes = label_workspace_bytes(B, H, W);
+    return DC_OK;
+}
+
+int dc_label_stats(const dc_label_args_t* args, void* stream) {
+    int rc = check_current_device(nullptr);
+    if (rc != DC_OK) return rc;
+    return launch_label_stats(args, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------ whole network
+
+int dc_model_create(dc_model_t** out, int device, const dc_model_desc_t* desc) {
+    DC_REQUIRE(out && desc, DC_EINVAL, "dc_model_create: null argument");
+    *out = nullptr;
+    int rc = dc_device_check(device, nullptr);
+    if (rc != DC_OK) return rc;
+    DC_REQUIRE(desc->base_channels == 64, DC_EINVAL, "dc_model_create: base_channels must be 64 (got %d)",
+               desc->base_channels);
+    for (int i = 0; i < DC_NUM_LAYERS; ++i)
+        DC_REQUIRE(desc->weight[i] && desc->bias[i], DC_EINVAL, "dc_model_create: layer %d has a null blob", i);
+    for (int i = 0; i < 5; ++i)
+        DC_REQUIRE(desc->dilations[i] >= 1 && desc->dilations[i] <= 64, DC_EINVAL, "dc_model_create: dilation[%d] = %d", i,
+                   desc->dilations[i]);
+    dc_model* m = new (std::nothrow) dc_model;
+    DC_REQUIRE(m, DC_EINVAL, "dc_model_create: out of host memory");
+    m->device = device;
+    m->desc = *desc;
+    cudaError_t e = cudaMemcpy(&m->head_b, desc->bias[22], sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+        delete m;
+        return cuda_fail(e, "cudaMemcpy(out_conv.bias)");
+    }
+    *out = m;
+    return DC_OK;
+}
+
+int dc_model_destroy(dc_model_t* m) {
+    delete m;
+    return DC_OK;
+}
+
+int dc_forward_workspace_bytes(const dc_model_t* m, int B, int H, int W, size_t* bytes) {
+    DC_REQUIRE(m && bytes, DC_EINVAL, "dc_forward_workspace_bytes: null argument");
+    DC_REQUIRE(B > 0 && H > 0 && W > 0 && H % 16 == 0 && W % 16 == 0, DC_EINVAL,
+               "dc_forward: H and W must be positive multiples of 16 (got %d x %d x %d)", B, H, W);
+    *bytes = carve(nullptr, B, H, W).total;
+    return DC_OK;
+}
+
+int dc_forward_num_launches(const dc_model_t* m) {
+    (void)m;
+    return 22;   // stem + 17 conv3x3 + 4 upconv
+}
+
+int dc_forward(dc_model_t* m, int in_kind, const void* in, int B, int H, int W, float thresh, float* prob_out,
+               uint8_t* mask_out, void* workspace, size_t workspace_bytes, void* stream_) {
+    DC_REQUIRE(m && in && workspace, DC_EINVAL, "dc_forward: null argument");
+    DC_REQUIRE(prob_out || mask_out, DC_EINVAL, "dc_forward: prob_out and mask_out are both NULL");
+    DC_REQUIRE(B > 0 && H > 0 && W > 0 && H % 16 == 0 && W % 16 == 0, DC_EINVAL,
+               "dc_forward: H and W must be positive multiples of 16 (got %d x %d x %d)", B, H, W);
+    int rc = check_current_device(nullptr);
+    if (rc != DC_OK) return rc;
+    int dev = -1;
+    DC_CUDA(cudaGetDevice(&dev));
+    DC_REQUIRE(dev == m->device, DC_EINVAL, "dc_forward: model lives on device %d, current device is %d", m->device, dev);
+    ForwardBuffers f = carve((char*)workspace, B, H, W);
+    DC_REQUIRE(workspace_bytes >= f.total, DC_EWORKSPACE, "dc_forward: workspace too small (%zu < %zu)", workspace_bytes,
+               f.total);
+    DC_REQUIRE(((uintptr_t)workspace & 255) == 0, DC_EINVAL, "dc_forward: workspace must be 256-byte aligned");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const dc_model_desc_t& d = m->desc;
+
+    auto conv = [&](int layer, int kind, int epi, int relu, int h, int w, int cin, int cout, int dil, const void* src,
+                    int src_stride, void* dst, int dst_stride, int dst_off, void* pool) -> int {
+        dc_conv_args_t a;
+        memset(&a, 0, sizeof(a));
+        a.kind = kind; a.epilogue = epi; a.relu = relu;
+        a.B = B; a.H = h; a.W = w; a.Cin = cin; a.Cout = cout; a.dilation = dil;
+        a.in = src; a.in_stride = src_stride;
+        a.weight = d.weight[layer]; a.bias = d.bias[layer];
+        a.out = dst; a.out_stride = dst_stride; a.out_offset = dst_off;
+        a.pool_out = pool; a.pool_stride = cout;
+        if (epi == DC_EPI_HEAD) {
+            a.head_w = (const float*)d.weight[22];
+            a.head_b = m->head_b;
+            a.thresh = thresh;
+            a.prob_out = prob_out;
+            a.mask_out = mask_out;
+        }
+        return launch_conv_tc(&a, stream);
+    };
+#define DC_TRY(x) do { int _rc = (x); if (_rc != DC_OK) return _rc; } while (0)
+
+    // encoder (model_2.py:58-61) -- layer ids per include/unetdc_b200.h
+    {
+        dc_stem_args_t s;
+        memset(&s, 0, sizeof(s));
+        s.in_kind = in_kind; s.B = B; s.H = H; s.W = W; s.Cout = 64; s.dilation = d.dilations[0];
+        s.in = in; s.weight = (const float*)d.weight[0]; s.bias = d.bias[0];
+        s.out = f.a[0]; s.out_stride = 64; s.out_offset = 0;
+        DC_TRY(launch_stem(&s, stream));
+    }
+    DC_TRY(conv(1, DC_KIND_CONV3X3, DC_EPI_STORE_POOL, 1, H, W, 64, 64, d.dilations[0], f.a[0], 64, f.cat[0], 128, 64,
+                f.pool[0]));
+    for (int l = 1; l < 4; ++l) {
+        const int h = H >> l, w = W >> l, c = 64 << l;
+        DC_TRY(conv(2 * l, DC_KIND_CONV3X3, DC_EPI_STORE, 1, h, w, c / 2, c, d.dilations[l], f.pool[l - 1], c / 2, f.a[l], c,
+                    0, nullptr));
+        DC_TRY(conv(2 * l + 1, DC_KIND_CONV3X3, DC_EPI_STORE_POOL, 1, h, w, c, c, d.dilations[l], f.a[l], c, f.cat[l], 2 * c,
+                    c, f.pool[l]));
+    }
+    // bottleneck (model_2.py:64)
+    DC_TRY(conv(8, DC_KIND_CONV3X3, DC_EPI_STORE, 1, H >> 4, W >> 4, 512, 1024, d.dilations[4], f.pool[3], 512, f.a[4], 1024,
+                0, nullptr));
+    DC_TRY(conv(9, DC_KIND_CONV3X3, DC_EPI_STORE, 1, H >> 4, W >> 4, 1024, 1024, d.dilations[4], f.a[4], 1024, f.bott, 1024,
+                0, nullptr));
+    // decoder (model_2.py:67-77): upconv -> [up | skip] -> double conv, dilation 1
+    const void* src = f.bott;
+    for (int l = 3; l >= 0; --l) {
+        const int h = H >> l, w = W >> l, c = 64 << l;
+        const int base = 10 + 3 * (3 - l);
+        DC_TRY(conv(base, DC_KIND_UPCONV2, DC_EPI_UPSCATTER, 0, h / 2, w / 2, 2 * c, c, 1, src, 2 * c, f.cat[l], 2 * c, 0,
+                    nullptr));
+        DC_TRY(conv(base + 1, DC_KIND_CONV3X3, DC_EPI_STORE, 1, h, w, 2 * c, c, 1, f.cat[l], 2 * c, f.a[l], c, 0, nullptr));
+        if (l > 0) {
+            DC_TRY(conv(base + 2, DC_KIND_CONV3X3, DC_EPI_STORE, 1, h, w, c, c, 1, f.a[l], c, f.db[l], c, 0, nullptr));
+            src = f.db[l];
+        } else {
+            // dec1.3 + out_conv + sigmoid + threshold (model_2.py:79-80, qdb:56)
+            DC_TRY(conv(base + 2, DC_KIND_CONV3X3, DC_EPI_HEAD, 1, h, w, c, c, 1, f.a[l], c, nullptr, 0, 0, nullptr));
+        }
+    }
+#undef DC_TRY
+    return DC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,424 @@
+// conv_tc.cu -- the tensor-core layers of UNetDC as one persistent, warp-specialised
+// implicit-GEMM kernel for sm_100a (tcgen05.mma, accumulators in TMEM, operands fed by TMA).
+//
+// Replaces, layer by layer (reference models/model_2.py):
+//   nn.Conv2d(k=3, padding=d, dilation=d) + BatchNorm2d(eval) + ReLU        :40-54
+//   F.max_pool2d(x, 2)                       (fused: DC_EPI_STORE_POOL)      :59-61,64
+//   nn.ConvTranspose2d(k=2, stride=2)        (DC_KIND_UPCONV2/UPSCATTER)     :20,23,26,29
+//   torch.cat([up, enc], 1)                  (never copied: both producers write straight into
+//                                             channel slices of one NHWC buffer)  :68,71,74,77
+//   out_conv 1x1 + sigmoid, and the `> prob_thresh` of quantify_droplets_batch.py:56
+//                                            (fused: DC_EPI_HEAD)            :32,79-80
+//
+// GEMM view.  M = 128 output pixels (an 8 x 16 patch of one image), N = BN output channels,
+// K = taps x Cin walked in chunks of 64 channels (64 bf16 = 128 B = one swizzle row).
+//   A chunk = TMA box (64 ch, 16 w, 8 h, 1 img) of the NHWC activation tensor at the signed offset
+//             ((ky-1)*d, (kx-1)*d): TMA's out-of-bounds zero fill IS the conv padding.  Lands in
+//             shared memory as 128 rows x 128 B, 128B-swizzled = the canonical K-major UMMA layout.
+//   B chunk = TMA box (64 k, BN rows) of the packed weights [rows][K], same layout.
+//   D       = 128 lanes x BN fp32 columns in TMEM, double buffered (2*BN columns) so the epilogue
+//             of tile i overlaps the MMAs of tile i+1.
+// Taps whose shifted patch is wholly outside the image (large dilation on small maps) are skipped.
+//
+// Warp roles (256 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0 lane 0 : TMA producer           warp 1 lane 0 : tcgen05.mma issuer
+//   warp 2        : TMEM alloc / dealloc   warps 4..7    : epilogue (TMEM -> regs -> global)
+#include "common.cuh"
+
+#include <cuda.h>
+
+namespace dc {
+
+namespace {
+
+constexpr int TILE_H = 8, TILE_W = 16, TILE_M = TILE_H * TILE_W;
+constexpr int KCHUNK = 64;
+constexpr int A_STAGE_BYTES = TILE_M * KCHUNK * 2;   // 16 KB
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+
+struct alignas(64) ConvParams {
+    CUtensorMap tmA;
+    CUtensorMap tmB;
+    int B, H, W, Cin, Cout;
+    int dil, ntaps, kchunks;
+    int tiles_w, tiles_h, n_tiles, total_tiles;
+    int epilogue, relu;
+    const float* bias;
+    __nv_bfloat16* out;
+    int out_stride, out_offset;
+    __nv_bfloat16* pool_out;
+    int pool_stride;
+    const float* head_w;
+    float head_b, thresh;
+    float* prob_out;
+    uint8_t* mask_out;
+};
+
+struct TileCoord {
+    int img, h0, w0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, int BN) {
+    TileCoord t;
+    int nt = tile % p.n_tiles;
+    int m = tile / p.n_tiles;
+    int per_img = p.tiles_h * p.tiles_w;
+    t.img = m / per_img;
+    int r = m - t.img * per_img;
+    int th = r / p.tiles_w;
+    t.h0 = th * TILE_H;
+    t.w0 = (r - th * p.tiles_w) * TILE_W;
+    t.n0 = nt * BN;
+    return t;
+}
+
+// Offset of tap `tap`; false when the shifted 8x16 patch has no pixel inside the image.
+__device__ __forceinline__ bool tap_offset(const ConvParams& p, const TileCoord& t, int tap, int& dy, int& dx) {
+    if (p.ntaps == 1) { dy = 0; dx = 0; return true; }
+    int ky = tap / 3, kx = tap - ky * 3;
+    dy = (ky - 1) * p.dil;
+    dx = (kx - 1) * p.dil;
+    return (t.h0 + dy + TILE_H > 0) && (t.h0 + dy < p.H) && (t.w0 + dx + TILE_W > 0) && (t.w0 + dx < p.W);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+
+template <int BN, int NSTAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+    constexpr int B_STAGE_BYTES = BN * KCHUNK * 2;
+    constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    constexpr int TMEM_COLS = 2 * BN;   // 128 / 256 / 512: a power of two >= 32
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B wants 1024 B
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NSTAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + NSTAGES;
+    uint64_t* tfull_bar = empty_bar + NSTAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < NSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord t = decode_tile(p, tile, BN);
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    int dy, dx;
+                    if (!tap_offset(p, t, tap, dy, dx)) continue;
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        uint8_t* sa = smem + stage * STAGE_BYTES;
+                        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                        tma_load_4d(sa, &p.tmA, &full_bar[stage], kc * KCHUNK, t.w0 + dx, t.h0 + dy, t.img);
+                        tma_load_2d(sa + A_STAGE_BYTES, &p.tmB, &full_bar[stage], tap * p.Cin + kc * KCHUNK, t.n0);
+                        if (++stage == NSTAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const TileCoord t = decode_tile(p, tile, BN);
+                const int as = it & 1;
+                const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(&tempty_bar[as], aphase ^ 1u);      // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                uint32_t accumulate = 0;
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    int dy, dx;
+                    if (!tap_offset(p, t, tap, dy, dx)) continue;
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                        const uint64_t adesc = umma_desc_sw128(sa);
+                        const uint64_t bdesc = umma_desc_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < KCHUNK / 16; ++k) {
+                            // +32 B per K=16 step inside the 128 B swizzle row (address field is >>4)
+                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate);
+                            accumulate = 1;
+                        }
+                        umma_commit(&empty_bar[stage]);        // frees the stage once these MMAs retire
+                        if (++stage == NSTAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+                umma_commit(&tfull_bar[as]);                    // accumulator complete -> epilogue
+            }
+        }
+        __syncwarp();
+    } else if (warp >= EPI_WARP0) {
+        // ------------------------------------------------------------------ epilogue
+        const int e = warp - EPI_WARP0;                          // == warp % 4: TMEM lanes [32e, 32e+32)
+        const int L = e * 32 + lane;
+        const int lh = L / TILE_W, lw = L % TILE_W;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const TileCoord t = decode_tile(p, tile, BN);
+            const int as = it & 1;
+            const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+            const int h = t.h0 + lh, w = t.w0 + lw;
+            const bool valid = (h < p.H) && (w < p.W);
+
+            __nv_bfloat16* optr = nullptr;
+            __nv_bfloat16* pptr = nullptr;
+            int bias_base = t.n0;
+            if (p.epilogue == DC_EPI_UPSCATTER) {
+                const int q = t.n0 / p.Cout;
+                bias_base = t.n0 - q * p.Cout;
+                const size_t opix = ((size_t)t.img * (2 * p.H) + (2 * h + (q >> 1))) * (size_t)(2 * p.W) + (2 * w + (q & 1));
+                optr = p.out + opix * p.out_stride + p.out_offset + bias_base;
+            } else if (p.epilogue != DC_EPI_HEAD) {
+                const size_t opix = ((size_t)t.img * p.H + h) * (size_t)p.W + w;
+                optr = p.out + opix * p.out_stride + p.out_offset + t.n0;
+                if (p.epilogue == DC_EPI_STORE_POOL) {
+                    const size_t ppix = ((size_t)t.img * (p.H >> 1) + (h >> 1)) * (size_t)(p.W >> 1) + (w >> 1);
+                    pptr = p.pool_out + ppix * p.pool_stride + t.n0;
+                }
+            }
+            const bool pool_writer = valid && !(lane & 1) && !(lane & 16);
+            float head_acc = p.head_b;
+
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)c0, v);
+                tmem_ld_wait();
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + bias_base + c0);
+                float x[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = __ldg(b4 + j);
+                    x[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+                    x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+                    x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+                    x[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+                }
+                if (p.epilogue == DC_EPI_HEAD) {
+                    const float4* w4 = reinterpret_cast<const float4*>(p.head_w + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 hw = __ldg(w4 + j);
+                        head_acc = fmaf(x[4 * j + 0], hw.x, head_acc);
+                        head_acc = fmaf(x[4 * j + 1], hw.y, head_acc);
+                        head_acc = fmaf(x[4 * j + 2], hw.z, head_acc);
+                        head_acc = fmaf(x[4 * j + 3], hw.w, head_acc);
+                    }
+                } else {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
+                    if (valid) {
+                        uint4* o4 = reinterpret_cast<uint4*>(optr + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) o4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    }
+                    if (p.epilogue == DC_EPI_STORE_POOL) {
+                        // 2x2 window = lanes {l, l^1 (w+1), l^16 (h+1), l^17}: all inside this warp
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            uint32_t m = max_bf16x2(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
+                            pk[j] = max_bf16x2(m, __shfl_xor_sync(0xffffffffu, m, 16));
+                        }
+                        if (pool_writer) {
+                            uint4* o4 = reinterpret_cast<uint4*>(pptr + c0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) o4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        }
+                    }
+                }
+            }
+            // accumulator fully read: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+
+            if (p.epilogue == DC_EPI_HEAD && valid) {
+                const float prob = 1.0f / (1.0f + expf(-head_acc));              // torch.sigmoid, fp32
+                const size_t opix = ((size_t)t.img * p.H + h) * (size_t)p.W + w;
+                if (p.prob_out) p.prob_out[opix] = prob;
+                if (p.mask_out) p.mask_out[opix] = prob > p.thresh ? 1 : 0;      // qdb:56
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------- host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box) {
+    EncodeTiledFn fn = encode_fn();
+    DC_REQUIRE(fn, DC_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DC_REQUIRE(r == CUDA_SUCCESS, DC_ECUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return DC_OK;
+}
+
+template <int BN, int NSTAGES>
+int launch_variant(const ConvParams& p, cudaStream_t stream) {
+    constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * KCHUNK * 2;
+    constexpr size_t SMEM = (size_t)NSTAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+    static_assert(SMEM <= 227 * 1024, "stage ring exceeds shared memory");
+    static bool attr_done = false;
+    if (!attr_done) {
+        DC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        attr_done = true;
+    }
+    int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    conv_tc_kernel<BN, NSTAGES><<<grid, NUM_THREADS, SMEM, stream>>>(p);
+    DC_CUDA(cudaGetLastError());
+    return DC_OK;
+}
+
+}  // namespace
+
+int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
+    DC_REQUIRE(a && a->in && a->weight && a->bias, DC_EINVAL, "dc_conv_tc: null pointer argument");
+    DC_REQUIRE(a->kind == DC_KIND_CONV3X3 || a->kind == DC_KIND_UPCONV2, DC_EINVAL, "dc_conv_tc: kind %d", a->kind);
+    DC_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0, DC_EINVAL, "dc_conv_tc: bad shape %d x %d x %d", a->B, a->H, a->W);
+    DC_REQUIRE(a->Cin > 0 && a->Cin % KCHUNK == 0, DC_EINVAL, "dc_conv_tc: Cin %d must be a multiple of 64", a->Cin);
+    DC_REQUIRE(a->Cout > 0 && a->Cout % 64 == 0, DC_EINVAL, "dc_conv_tc: Cout %d must be a multiple of 64", a->Cout);
+    DC_REQUIRE(a->in_stride >= a->Cin && a->in_stride % 8 == 0, DC_EINVAL, "dc_conv_tc: in_stride %d", a->in_stride);
+    DC_REQUIRE(((uintptr_t)a->in & 15) == 0 && ((uintptr_t)a->weight & 15) == 0, DC_EINVAL,
+               "dc_conv_tc: in / weight must be 16-byte aligned");
+    const bool up = a->kind == DC_KIND_UPCONV2;
+    DC_REQUIRE(up == (a->epilogue == DC_EPI_UPSCATTER), DC_EINVAL, "dc_conv_tc: kind %d with epilogue %d", a->kind,
+               a->epilogue);
+    DC_REQUIRE(a->epilogue >= DC_EPI_STORE && a->epilogue <= DC_EPI_UPSCATTER, DC_EINVAL, "dc_conv_tc: epilogue %d",
+               a->epilogue);
+    DC_REQUIRE(up || a->dilation >= 1, DC_EINVAL, "dc_conv_tc: dilation %d", a->dilation);
+    if (a->epilogue == DC_EPI_HEAD) {
+        DC_REQUIRE(a->Cout == 64 && a->head_w && (a->prob_out || a->mask_out), DC_EINVAL,
+                   "dc_conv_tc: HEAD epilogue needs Cout == 64, head_w and prob_out or mask_out");
+    } else {
+        DC_REQUIRE(a->out && ((uintptr_t)a->out & 15) == 0, DC_EINVAL, "dc_conv_tc: out must be 16-byte aligned");
+        DC_REQUIRE(a->out_stride % 8 == 0 && a->out_offset % 8 == 0 && a->out_offset >= 0 &&
+                       a->out_stride >= a->out_offset + a->Cout,
+                   DC_EINVAL, "dc_conv_tc: out_stride %d / out_offset %d", a->out_stride, a->out_offset);
+    }
+    if (a->epilogue == DC_EPI_STORE_POOL) {
+        DC_REQUIRE(a->pool_out && ((uintptr_t)a->pool_out & 15) == 0 && a->pool_stride % 8 == 0 &&
+                       a->pool_stride >= a->Cout,
+                   DC_EINVAL, "dc_conv_tc: pool_out / pool_stride");
+        DC_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0, DC_EINVAL, "dc_conv_tc: pooled layer needs even H, W");
+    }
+    const int BN = a->Cout % 256 == 0 ? 256 : (a->Cout % 128 == 0 ? 128 : 64);
+
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B};
+        cuuint64_t str[3] = {(cuuint64_t)a->in_stride * 2, (cuuint64_t)a->W * a->in_stride * 2,
+                             (cuuint64_t)a->H * a->W * a->in_stride * 2};
+        cuuint32_t box[4] = {KCHUNK, TILE_W, TILE_H, 1};
+        int rc = encode_map(&p.tmA, a->in, 4, dims, str, box);
+        if (rc != DC_OK) return rc;
+    }
+    {
+        const int ktot = up ? a->Cin : 9 * a->Cin;
+        const int rows = up ? 4 * a->Cout : a->Cout;
+        cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)rows};
+        cuuint64_t str[1] = {(cuuint64_t)ktot * 2};
+        cuuint32_t box[2] = {KCHUNK, (cuuint32_t)BN};
+        int rc = encode_map(&p.tmB, a->weight, 2, dims, str, box);
+        if (rc != DC_OK) return rc;
+    }
+    p.B = a->B; p.H = a->H; p.W = a->W; p.Cin = a->Cin; p.Cout = a->Cout;
+    p.dil = up ? 1 : a->dilation;
+    p.ntaps = up ? 1 : 9;
+    p.kchunks = a->Cin / KCHUNK;
+    p.tiles_w = ceil_div(a->W, TILE_W);
+    p.tiles_h = ceil_div(a->H, TILE_H);
+    p.n_tiles = (up ? 4 * a->Cout : a->Cout) / BN;
+    const long long total = (long long)a->B * p.tiles_w * p.tiles_h * p.n_tiles;
+    DC_REQUIRE(total < (1ll << 31), DC_EINVAL, "dc_conv_tc: too many tiles");
+    p.total_tiles = (int)total;
+    p.epilogue = a->epilogue;
+    p.relu = up ? 0 : (a->relu != 0);
+    p.bias = a->bias;
+    p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+    p.out_stride = a->out_stride; p.out_offset = a->out_offset;
+    p.pool_out = reinterpret_cast<__nv_bfloat16*>(a->pool_out);
+    p.pool_stride = a->pool_stride;
+    p.head_w = a->head_w; p.head_b = a->head_b; p.thresh = a->thresh;
+    p.prob_out = a->prob_out; p.mask_out = a->mask_out;
+
+    switch (BN) {
+        case 256: return launch_variant<256, 4>(p, stream);
+        case 128: return launch_variant<128, 6>(p, stream);
+        default:  return launch_variant<64, 8>(p, stream);
+    }
+}
+
+}  // namespace dc

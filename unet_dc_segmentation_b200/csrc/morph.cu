@@ -1,0 +1,247 @@
+// morph.cu -- "rolling ball" background correction on the GPU.
+//
+// Replaces rolling_ball_correction_rgb (reference utils/data_loader.py:11-24), per plane:
+//   kernel  = cv2.getStructuringElement(MORPH_ELLIPSE, (radius, radius))        :17
+//   bg      = cv2.morphologyEx(channel, MORPH_OPEN, kernel)   erode, then dilate  :19
+//   corr    = cv2.subtract(channel, bg)                       saturating u8       :20
+//   out     = cv2.normalize(corr, None, 0, 255, NORM_MINMAX)                      :21
+//
+// The element is a radius x radius flat ellipse (NOT separable, not symmetric for even sizes):
+// row i covers columns [j1[i], j2[i]).  erode(y,x) = min_i min_{j in row i} src[y+i-an, x+j-an],
+// dilate uses max over the SAME offsets, taps outside the image are ignored (OpenCV semantics).
+//
+// Kernel plan: a block stages its tile + halo in shared memory, builds a power-of-two
+// range-min (or max) table along x (levels 2^0..2^L), then every thread owns 4 adjacent pixels
+// and combines, for each of the `radius` element rows, two overlapping 2^l windows with byte-SIMD
+// __vminu4 / __vmaxu4.  All arithmetic is u8, so the result is bit-exact.
+#include "common.cuh"
+#include <math.h>
+
+namespace dc {
+
+namespace {
+
+constexpr int TW = 64;           // tile width  (16 threads x 4 pixels)
+constexpr int TH = 32;           // tile height
+constexpr int MAX_RADIUS = 100;
+constexpr int MAX_LEVELS = 7;    // windows up to 64 wide
+
+struct SERows {
+    int k;                        // element size (= radius), anchor = k/2
+    int nlevels;                  // levels 0..nlevels-1 are built
+    unsigned char j1[MAX_RADIUS]; // first column of row i
+    unsigned char j2m[MAX_RADIUS];// j2 - 2^level: start of the second window
+    unsigned char lvl[MAX_RADIUS];// level used by row i; 255 = empty row
+};
+
+template <bool IS_MAX>
+__device__ __forceinline__ unsigned vop(unsigned a, unsigned b) {
+    return IS_MAX ? __vmaxu4(a, b) : __vminu4(a, b);
+}
+
+// 4 bytes starting at byte offset `off` of a word-aligned shared array
+__device__ __forceinline__ unsigned ld4_unaligned(const unsigned* base, int off) {
+    int w = off >> 2;
+    unsigned lo = base[w], hi = base[w + 1];
+    return __funnelshift_r(lo, hi, (off & 3) * 8);
+}
+
+// One morphology pass over planes addressed as in[((p/C)*H*W + y*W + x)*C + p%C] (in_c = C) and
+// written planar.  SUBTRACT: out = saturate(orig - result), plus a per-plane min/max reduction.
+template <bool IS_MAX, bool SUBTRACT>
+__global__ void __launch_bounds__(512) morph_pass_kernel(const uint8_t* __restrict__ in, int in_c,
+                                                         uint8_t* __restrict__ out, const uint8_t* __restrict__ orig,
+                                                         int orig_c, int H, int W, int* __restrict__ minmax,
+                                                         const __grid_constant__ SERows se) {
+    extern __shared__ unsigned smem[];
+    const int k = se.k, an = k / 2;
+    const int RW = TW + k;                       // region width in bytes (tile + halo), halo = k-1 (+1 pad)
+    const int pitch = ((RW + 3) >> 2) + 1;       // words per region row (+1 so unaligned fetches stay in-row)
+    const int RH = TH + k - 1;
+    const int level_words = pitch * RH;
+    const unsigned ident = IS_MAX ? 0u : 0xffffffffu;
+
+    const int plane = blockIdx.z;
+    const int b = plane / in_c, c = plane % in_c;
+    const int x0 = blockIdx.x * TW - an, y0 = blockIdx.y * TH - an;   // region origin in the image
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int nthreads = blockDim.x * blockDim.y;
+
+    // ---- stage level 0 (tile + halo), identity outside the image ----
+    uint8_t* s8 = reinterpret_cast<uint8_t*>(smem);
+    const uint8_t* src = in + (size_t)b * H * W * in_c + c;
+    for (int i = tid; i < RH * pitch * 4; i += nthreads) {
+        int ry = i / (pitch * 4), rx = i - ry * (pitch * 4);
+        int gy = y0 + ry, gx = x0 + rx;
+        uint8_t v = IS_MAX ? 0 : 255;
+        if (rx < RW && gy >= 0 && gy < H && gx >= 0 && gx < W) v = src[((size_t)gy * W + gx) * in_c];
+        s8[i] = v;
+    }
+    __syncthreads();
+    // ---- levels 1..: T_l[x] = op(T_{l-1}[x], T_{l-1}[x + 2^(l-1)]) ----
+    for (int l = 1; l < se.nlevels; ++l) {
+        const unsigned* prev = smem + (l - 1) * level_words;
+        unsigned* cur = smem + l * level_words;
+        const int step = 1 << (l - 1);           // bytes
+        for (int i = tid; i < level_words; i += nthreads) {
+            int rx = i % pitch;
+            unsigned a = prev[i], bb;
+            if (step < 4) {
+                unsigned nxt = (rx + 1 < pitch) ? prev[i + 1] : ident;
+                bb = __funnelshift_r(a, nxt, step * 8);
+            } else {
+                int ws = step >> 2;
+                bb = (rx + ws < pitch) ? prev[i + ws] : ident;
+            }
+            cur[i] = vop<IS_MAX>(a, bb);
+        }
+        __syncthreads();
+    }
+    // ---- combine the element rows ----
+    const int lx4 = threadIdx.x * 4, ly = threadIdx.y;
+    unsigned acc = ident;
+    for (int i = 0; i < k; ++i) {
+        const int l = se.lvl[i];
+        if (l == 255) continue;
+        const unsigned* row = smem + l * level_words + (ly + i) * pitch;
+        unsigned a = ld4_unaligned(row, lx4 + se.j1[i]);
+        unsigned bb = ld4_unaligned(row, lx4 + se.j2m[i]);
+        acc = vop<IS_MAX>(acc, vop<IS_MAX>(a, bb));
+    }
+    // ---- write (and, for the second pass, subtract + reduce) ----
+    const int gx = blockIdx.x * TW + lx4, gy = blockIdx.y * TH + ly;
+    int mn = 255, mx = 0;
+    if (gy < H && gx < W) {
+        uint8_t* dst = out + ((size_t)plane * H + gy) * W + gx;
+        unsigned res = acc;
+        if (SUBTRACT) {
+            const int ob = plane / orig_c, oc = plane % orig_c;
+            const uint8_t* o = orig + ((size_t)ob * H * W + (size_t)gy * W + gx) * orig_c + oc;
+            unsigned ov = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (gx + j < W) ov |= (unsigned)o[(size_t)j * orig_c] << (8 * j);
+            res = __vsubus4(ov, acc);            // cv2.subtract saturates at 0
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (gx + j < W) {
+                int v = (res >> (8 * j)) & 0xff;
+                dst[j] = (uint8_t)v;
+                mn = min(mn, v); mx = max(mx, v);
+            }
+        }
+    }
+    if (SUBTRACT) {
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if ((tid & 31) == 0) {
+            atomicMin(&minmax[2 * plane], mn);
+            atomicMax(&minmax[2 * plane + 1], mx);
+        }
+    }
+}
+
+__global__ void init_minmax_kernel(int* minmax, int planes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < planes) { minmax[2 * i] = 255; minmax[2 * i + 1] = 0; }
+}
+
+// cv2.normalize(NORM_MINMAX, 0..255) on u8: scale = 255 * (1/(max-min)) and shift = -min*scale in
+// double, then fp32 fma(v, scale, shift) rounded half-to-even (matches cv2 4.13 on every input).
+__global__ void __launch_bounds__(256) stretch_kernel(const uint8_t* __restrict__ corr, uint8_t* __restrict__ out,
+                                                      int out_c, int H, int W, const int* __restrict__ minmax) {
+    __shared__ uint8_t lut[256];
+    const int plane = blockIdx.y;
+    const int b = plane / out_c, c = plane % out_c;
+    {
+        int mn = minmax[2 * plane], mx = minmax[2 * plane + 1];
+        double scale = (mx - mn) > 0 ? __dmul_rn(255.0, __ddiv_rn(1.0, (double)(mx - mn))) : 0.0;
+        double shift = __dsub_rn(0.0, __dmul_rn((double)mn, scale));
+        float a = (float)scale, sh = (float)shift;
+        int q = __float2int_rn(__fmaf_rn((float)threadIdx.x, a, sh));
+        lut[threadIdx.x] = (uint8_t)min(255, max(0, q));
+    }
+    __syncthreads();
+    const size_t HW = (size_t)H * W;
+    const uint8_t* src = corr + (size_t)plane * HW;
+    uint8_t* dst = out + (size_t)b * HW * out_c + c;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (size_t)gridDim.x * blockDim.x)
+        dst[i * out_c] = lut[src[i]];
+}
+
+int build_rows(int radius, SERows* se) {
+    const int k = radius;
+    se->k = k;
+    int r = k / 2, c = k / 2;
+    double inv_r2 = r ? 1.0 / ((double)r * r) : 0.0;
+    int maxw = 1;
+    for (int i = 0; i < k; ++i) {
+        int dy = i - r, j1 = 0, j2 = 0;
+        if (abs(dy) <= r) {
+            int dx = (int)nearbyint(c * sqrt(((double)r * r - (double)dy * dy) * inv_r2));   // cvRound
+            j1 = c - dx < 0 ? 0 : c - dx;
+            j2 = c + dx + 1 > k ? k : c + dx + 1;
+        }
+        int w = j2 - j1;
+        if (w <= 0) { se->lvl[i] = 255; se->j1[i] = 0; se->j2m[i] = 0; continue; }
+        int l = 0;
+        while ((2 << l) <= w) ++l;               // 2^l <= w < 2^(l+1)
+        se->lvl[i] = (unsigned char)l;
+        se->j1[i] = (unsigned char)j1;
+        se->j2m[i] = (unsigned char)(j2 - (1 << l));
+        if (w > maxw) maxw = w;
+    }
+    int nl = 1;
+    while ((1 << nl) <= maxw) ++nl;
+    se->nlevels = nl;
+    return nl <= MAX_LEVELS ? 0 : -1;
+}
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+size_t rolling_ball_workspace_bytes(int planes, int H, int W) {
+    return 2 * align256((size_t)planes * H * W) + align256(sizeof(int) * 2 * (size_t)planes);
+}
+
+int launch_rolling_ball(const dc_rolling_ball_args_t* a, cudaStream_t stream) {
+    DC_REQUIRE(a && a->in && a->out, DC_EINVAL, "dc_rolling_ball: null pointer argument");
+    DC_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0 && a->C > 0, DC_EINVAL, "dc_rolling_ball: bad shape");
+    DC_REQUIRE(a->radius >= 1 && a->radius <= MAX_RADIUS, DC_EINVAL, "dc_rolling_ball: radius %d outside [1,%d]",
+               a->radius, MAX_RADIUS);
+    const int planes = a->B * a->C, H = a->H, W = a->W;
+    DC_REQUIRE(planes <= 65535, DC_EINVAL, "dc_rolling_ball: more than 65535 planes in one call");
+    DC_REQUIRE(a->workspace && a->workspace_bytes >= rolling_ball_workspace_bytes(planes, H, W), DC_EWORKSPACE,
+               "dc_rolling_ball: workspace too small");
+    SERows se;
+    DC_REQUIRE(build_rows(a->radius, &se) == 0, DC_EINVAL, "dc_rolling_ball: element too wide");
+
+    char* p = (char*)a->workspace;
+    uint8_t* er = (uint8_t*)p;   p += align256((size_t)planes * H * W);
+    uint8_t* corr = (uint8_t*)p; p += align256((size_t)planes * H * W);
+    int* minmax = (int*)p;
+
+    const int RW = TW + se.k, pitch = ((RW + 3) >> 2) + 1, RH = TH + se.k - 1;
+    const size_t smem = (size_t)se.nlevels * pitch * RH * 4;
+    DC_REQUIRE(smem <= 227 * 1024, DC_EINVAL, "dc_rolling_ball: radius %d needs %zu B of shared memory", a->radius, smem);
+    static bool attr_done = false;
+    if (!attr_done) {
+        DC_CUDA(cudaFuncSetAttribute(morph_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DC_CUDA(cudaFuncSetAttribute(morph_pass_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    dim3 block(TW / 4, TH);
+    dim3 grid(ceil_div(W, TW), ceil_div(H, TH), planes);
+    init_minmax_kernel<<<ceil_div(planes, 256), 256, 0, stream>>>(minmax, planes);
+    morph_pass_kernel<false, false><<<grid, block, smem, stream>>>(a->in, a->C, er, nullptr, 0, H, W, nullptr, se);
+    morph_pass_kernel<true, true><<<grid, block, smem, stream>>>(er, 1, corr, a->in, a->C, H, W, minmax, se);
+    int sblocks = ceil_div(H * W, 256 * 8);
+    if (sblocks > 4096) sblocks = 4096;
+    stretch_kernel<<<dim3(sblocks, planes), 256, 0, stream>>>(corr, a->out, a->C, H, W, minmax);
+    DC_CUDA(cudaGetLastError());
+    return DC_OK;
+}
+
+}  // namespace dc

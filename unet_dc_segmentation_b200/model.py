@@ -1,0 +1,214 @@
+"""``UNetDC`` -- drop-in for the reference ``models/model_2.py`` nn.Module, computed by libunetdc_b200.
+
+Same constructor, same 136 ``state_dict`` keys and shapes, same call contract
+(``f32 [B,3,H,W] in [0,1] -> f32 [B,1,H,W]`` probabilities, reference models/model_2.py:56-80), so
+``load_model`` of reference quantify_droplets_batch.py:34-37 works unchanged with this class.  The
+parameters live in ordinary ``nn.Conv2d`` / ``nn.BatchNorm2d`` / ``nn.ConvTranspose2d`` holders (that is
+what fixes the state_dict), but ``forward`` never calls them: on the first call in eval mode the weights
+are BatchNorm-folded in fp32, repacked K-major to bf16 and handed to ``dc_model_create``; every call then
+runs ``dc_forward`` (22 kernel launches, see csrc/api.cu).  There is no PyTorch or CPU fallback.
+
+``UNet`` is the reference's plain ``models/model.py`` network: identical state_dict, dilation 1 everywhere.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_ENCODER = (("enc1", 64), ("enc2", 128), ("enc3", 256), ("enc4", 512), ("bottleneck", 1024))
+# blob order of dc_model_desc_t (include/unetdc_b200.h)
+_LAYER_ORDER = (
+    ("enc1", 0), ("enc1", 3), ("enc2", 0), ("enc2", 3), ("enc3", 0), ("enc3", 3), ("enc4", 0), ("enc4", 3),
+    ("bottleneck", 0), ("bottleneck", 3),
+    ("upconv4", None), ("dec4", 0), ("dec4", 3), ("upconv3", None), ("dec3", 0), ("dec3", 3),
+    ("upconv2", None), ("dec2", 0), ("dec2", 3), ("upconv1", None), ("dec1", 0), ("dec1", 3),
+)
+
+
+def _conv_pair(cin: int, cout: int, d: int) -> nn.Sequential:
+    # indices 0/1 and 3/4 are what the reference's state_dict names (models/model_2.py:40-54)
+    return nn.Sequential(
+        nn.Conv2d(cin, cout, 3, padding=d, dilation=d), nn.BatchNorm2d(cout), nn.ReLU(inplace=True),
+        nn.Conv2d(cout, cout, 3, padding=d, dilation=d), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
+
+
+def fold_conv_bn(conv_w, conv_b, bn_w, bn_b, bn_mean, bn_var, eps: float = 1e-5):
+    """Eval-mode BatchNorm folded into the preceding conv, in fp32 (model_2.py:41-46)."""
+    scale = bn_w.float() / torch.sqrt(bn_var.float() + eps)
+    w = conv_w.float() * scale.view(-1, 1, 1, 1)
+    b = (conv_b.float() - bn_mean.float()) * scale + bn_b.float()
+    return w, b
+
+
+def pack_conv3x3(w):
+    """[Cout,Cin,3,3] -> bf16 [Cout, (ky*3+kx)*Cin + ci] (DC_KIND_CONV3X3 layout)."""
+    co, ci = w.shape[:2]
+    return w.permute(0, 2, 3, 1).reshape(co, 9 * ci).to(torch.bfloat16).contiguous()
+
+
+def pack_upconv(w):
+    """ConvTranspose2d weight [Cin,Cout,2,2] -> bf16 [(a*2+b)*Cout + co, ci] (DC_KIND_UPCONV2 layout)."""
+    ci, co = w.shape[:2]
+    return w.float().permute(2, 3, 1, 0).reshape(4 * co, ci).to(torch.bfloat16).contiguous()
+
+
+class _Packed:
+    """Device blobs + the dc_model handle built from one state of the parameters."""
+
+    def __init__(self, module: "UNetDC", device: torch.device):
+        lib = _lib.load()
+        sd = {k: v.detach().to(device) for k, v in module.state_dict().items()}
+        self.blobs = []          # keeps the device tensors alive for the lifetime of the handle
+        desc = _lib.ModelDesc()
+        for i, (name, idx) in enumerate(_LAYER_ORDER):
+            if idx is None:
+                w = pack_upconv(sd[f"{name}.weight"])
+                b = sd[f"{name}.bias"].float().contiguous()
+            else:
+                wf, b = fold_conv_bn(sd[f"{name}.{idx}.weight"], sd[f"{name}.{idx}.bias"],
+                                     sd[f"{name}.{idx + 1}.weight"], sd[f"{name}.{idx + 1}.bias"],
+                                     sd[f"{name}.{idx + 1}.running_mean"], sd[f"{name}.{idx + 1}.running_var"],
+                                     module._bn_eps(name, idx + 1))
+                w = wf.reshape(wf.shape[0], -1).contiguous() if i == 0 else pack_conv3x3(wf)
+                b = b.contiguous()
+            self.blobs += [w, b]
+            desc.weight[i] = w.data_ptr()
+            desc.bias[i] = b.data_ptr()
+        hw = sd["out_conv.weight"].float().reshape(-1).contiguous()
+        hb = sd["out_conv.bias"].float().reshape(-1).contiguous()
+        self.blobs += [hw, hb]
+        desc.weight[22] = hw.data_ptr()
+        desc.bias[22] = hb.data_ptr()
+        for i, d in enumerate(module.dilations):
+            desc.dilations[i] = int(d)
+        desc.base_channels = 64
+        self.device = device
+        self.handle = C.c_void_p()
+        with torch.cuda.device(device):
+            torch.cuda.synchronize(device)
+            _lib.check(lib.dc_model_create(C.byref(self.handle), device.index, C.byref(desc)))
+        self.workspace = None
+
+    def workspace_for(self, B: int, H: int, W: int) -> torch.Tensor:
+        need = C.c_size_t()
+        _lib.check(_lib.load().dc_forward_workspace_bytes(self.handle, B, H, W, C.byref(need)))
+        if self.workspace is None or self.workspace.numel() < need.value:
+            self.workspace = None
+            self.workspace = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+        return self.workspace
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.load().dc_model_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class UNetDC(nn.Module):
+    """Dilated U-Net of reference models/model_2.py:5-80 (dilations 1/2/4/8/16 in the encoder)."""
+
+    dilations = (1, 2, 4, 8, 16)
+
+    def __init__(self, in_channels: int = 3, out_channels: int = 1):
+        super().__init__()
+        if in_channels != 3 or out_channels != 1:
+            raise ValueError("the sm_100a kernels implement UNetDC(in_channels=3, out_channels=1), the only "
+                             "configuration the reference's inference path builds (quantify_droplets_batch.py:35)")
+        cin = in_channels
+        for (name, width), d in zip(_ENCODER, self.dilations):
+            setattr(self, name, _conv_pair(cin, width, d))
+            cin = width
+        for lvl, width in ((4, 512), (3, 256), (2, 128), (1, 64)):
+            setattr(self, f"upconv{lvl}", nn.ConvTranspose2d(2 * width, width, kernel_size=2, stride=2))
+            setattr(self, f"dec{lvl}", _conv_pair(2 * width, width, 1))
+        self.out_conv = nn.Conv2d(64, out_channels, kernel_size=1)
+        self._packed: _Packed | None = None
+
+    # ------------------------------------------------------------------ packing
+    def _bn_eps(self, name: str, idx: int) -> float:
+        return float(getattr(self, name)[idx].eps)
+
+    def invalidate(self) -> None:
+        """Drop the packed device weights (call after changing parameters in place)."""
+        self._packed = None
+
+    def load_state_dict(self, *args, **kwargs):
+        self._packed = None
+        return super().load_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._packed = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def packed(self) -> _Packed:
+        dev = self.out_conv.weight.device
+        _lib.require_cuda(self.out_conv.weight, "UNetDC parameters (call .to('cuda') first)")
+        if self._packed is None or self._packed.device != dev:
+            self._packed = _Packed(self, dev)
+        return self._packed
+
+    # ------------------------------------------------------------------ inference
+    def _run(self, in_kind: int, x: torch.Tensor, B: int, H: int, W: int, thresh: float,
+             want_prob: bool, want_mask: bool):
+        if self.training:
+            raise RuntimeError("UNetDC (sm_100a) implements eval-mode inference only; call .eval() "
+                               "(reference quantify_droplets_batch.py:37)")
+        if H % 16 or W % 16:
+            raise ValueError(f"H and W must be multiples of 16 (four 2x2 pools), got {H}x{W}")
+        pk = self.packed()
+        dev = pk.device
+        with torch.cuda.device(dev):
+            ws = pk.workspace_for(B, H, W)
+            prob = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev) if want_prob else None
+            mask = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if want_mask else None
+            _lib.check(_lib.load().dc_forward(
+                pk.handle, in_kind, x.data_ptr(), B, H, W, float(thresh),
+                prob.data_ptr() if want_prob else None, mask.data_ptr() if want_mask else None,
+                ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)))
+        return prob, mask
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """f32 [B,3,H,W] -> f32 [B,1,H,W] probabilities (sigmoid applied, model_2.py:80)."""
+        _lib.require_cuda(x, "UNetDC input")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected [B,3,H,W], got {tuple(x.shape)}")
+        x = x.to(torch.float32).contiguous()
+        B, _, H, W = x.shape
+        prob, _ = self._run(0, x, B, H, W, 0.5, True, False)
+        return prob
+
+    @torch.no_grad()
+    def predict_u8(self, images: torch.Tensor, prob_thresh: float, return_prob: bool = False):
+        """Fused path of quantify_droplets_batch.py:45,51-52,56 for device-resident u8 images.
+
+        images: u8 [B,H,W] (grayscale, replicated to RGB as ``Image.convert("RGB")`` does, qdb:41)
+                or u8 [B,H,W,3]; the /255 is done in the first kernel.
+        Returns (mask u8 [B,H,W] {0,1}, probs f32 [B,1,H,W] or None)."""
+        _lib.require_cuda(images, "images")
+        if images.dtype != torch.uint8:
+            raise TypeError("predict_u8 takes uint8 images")
+        images = images.contiguous()
+        if images.dim() == 3:
+            kind = 1
+        elif images.dim() == 4 and images.shape[-1] == 3:
+            kind = 2
+        else:
+            raise ValueError(f"expected u8 [B,H,W] or [B,H,W,3], got {tuple(images.shape)}")
+        B, H, W = images.shape[:3]
+        prob, mask = self._run(kind, images, B, H, W, prob_thresh, return_prob, True)
+        return mask, prob
+
+    def num_launches(self) -> int:
+        return int(_lib.load().dc_forward_num_launches(self.packed().handle))
+
+
+class UNet(UNetDC):
+    """Plain U-Net of reference models/model.py:7-50: the same state_dict with dilation 1 everywhere."""
+
+    dilations = (1, 1, 1, 1, 1)
