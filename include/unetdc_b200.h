@@ -136,6 +136,11 @@ int dc_forward(dc_model_t* m, int in_kind, const void* in, int B, int H, int W, 
                uint8_t* mask_out, void* workspace, size_t workspace_bytes, void* stream);
 /* number of kernels one dc_forward launches (for bench accounting) */
 int dc_forward_num_launches(const dc_model_t* m);
+/* Measurement aid: the same forward with a CUDA event between consecutive launches; synchronises the
+ * stream and fills launch_ms[dc_forward_num_launches()] (launch order = the layer order above, with
+ * out_conv fused into the last one).  Not used on the product path. */
+int dc_forward_profile(dc_model_t* m, int in_kind, const void* in, int B, int H, int W, float thresh, float* prob_out,
+                       uint8_t* mask_out, void* workspace, size_t workspace_bytes, void* stream, float* launch_ms);
 
 /* ------------------------------------------------------------------ rolling-ball correction
  * Per plane: opening with the radius x radius ellipse of cv2.getStructuringElement, saturating

@@ -1,0 +1,167 @@
+"""GPU: the tensor-core layers (csrc/conv_tc.cu) and the stem (csrc/stem.cu), one layer at a time, against
+a plain PyTorch fp32 CPU evaluation of the same op on the same bf16-rounded operands.
+
+Tolerance (floating point, stated here): operands are bf16 on both sides, the kernel accumulates in fp32
+(TMEM) like the fp32 CPU reference, and the only extra error is the final bf16 rounding of the output
+(rel 2^-9) plus accumulation-order noise: |got - want| <= 1e-2 * max(1, |want|)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(got, want, what=""):
+    import torch
+    got = got.float().cpu()
+    err = (got - want).abs()
+    tol = 1e-2 * want.abs().clamp(min=1.0)
+    bad = err > tol
+    assert not bool(bad.any()), (f"{what}: {int(bad.sum())}/{bad.numel()} elements off, max err {float(err.max()):.4g}, "
+                                 f"first bad index {tuple(int(v) for v in bad.nonzero()[0])}")
+
+
+def _rand_layer(cin, cout, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (3.0 * cin ** 0.5)).bfloat16().float()
+    b = torch.randn(cout, generator=g) * 0.1
+    return w, b
+
+
+def _rand_act(B, H, W, C, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, H, W, C, generator=g).bfloat16()
+
+
+CONV_CASES = [
+    # B, H, W, Cin, Cout, dilation
+    (1, 8, 16, 64, 64, 1),        # exactly one tile
+    (2, 16, 32, 64, 64, 1),
+    (1, 24, 40, 64, 128, 2),      # partial tiles in both directions
+    (2, 16, 16, 128, 128, 2),
+    (1, 32, 48, 128, 256, 4),
+    (1, 16, 16, 256, 512, 8),     # two N tiles
+    (2, 8, 8, 512, 1024, 16),     # dilation > map: only the centre tap is in bounds
+    (1, 16, 32, 1024, 512, 1),    # long K
+    (3, 40, 24, 192, 64, 3),      # Cin not a power of two, odd dilation
+]
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,d", CONV_CASES)
+def test_conv3x3_store(cuda_device, B, H, W, cin, cout, d):
+    import torch
+    import torch.nn.functional as F
+    from unet_dc_segmentation_b200 import layers
+    from unet_dc_segmentation_b200.model import pack_conv3x3
+    w, b = _rand_layer(cin, cout, 1000 + cin + cout + d)
+    x = _rand_act(B, H, W, cin, 7 + H * W)
+    want = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w, b, padding=d, dilation=d)).permute(0, 2, 3, 1)
+    got = layers.conv3x3(x.cuda(), pack_conv3x3(w).cuda(), b.cuda(), dilation=d, relu=True)
+    torch.cuda.synchronize()
+    _close(got, want, f"conv {cin}->{cout} d{d} {B}x{H}x{W}")
+
+
+def test_conv3x3_no_relu_and_channel_slices(cuda_device):
+    """Reads channels [0,64) of a 128-wide buffer and writes channels [64,128) of another (the concat layout)."""
+    import torch
+    import torch.nn.functional as F
+    from unet_dc_segmentation_b200 import layers
+    from unet_dc_segmentation_b200.model import pack_conv3x3
+    w, b = _rand_layer(64, 64, 5)
+    xin = _rand_act(2, 16, 32, 128, 9)
+    out = torch.full((2, 16, 32, 128), 7.0, dtype=torch.bfloat16).cuda()
+    want = F.conv2d(xin[..., :64].float().permute(0, 3, 1, 2), w, b, padding=1).permute(0, 2, 3, 1)
+    layers.conv3x3(xin.cuda(), pack_conv3x3(w).cuda(), b.cuda(), relu=False, cin=64, out=out, out_offset=64)
+    torch.cuda.synchronize()
+    _close(out[..., 64:], want, "sliced conv")
+    assert bool((out[..., :64].float() == 7.0).all()), "wrote outside its channel slice"
+
+
+@pytest.mark.parametrize("B,H,W,c,d", [(1, 16, 32, 64, 1), (2, 24, 48, 128, 2), (1, 16, 16, 256, 4)])
+def test_conv3x3_store_pool(cuda_device, B, H, W, c, d):
+    import torch
+    import torch.nn.functional as F
+    from unet_dc_segmentation_b200 import layers
+    from unet_dc_segmentation_b200.model import pack_conv3x3
+    w, b = _rand_layer(c, c, 77 + c)
+    x = _rand_act(B, H, W, c, 3 + c)
+    full = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w, b, padding=d, dilation=d))
+    got, pooled = layers.conv3x3(x.cuda(), pack_conv3x3(w).cuda(), b.cuda(), dilation=d, pool=True)
+    torch.cuda.synchronize()
+    _close(got, full.permute(0, 2, 3, 1), "pool: full-res output")
+    # the pooled tensor must be EXACTLY the 2x2 max of the bf16 full-res tensor the kernel wrote
+    want_pool = F.max_pool2d(got.float().cpu().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    assert torch.equal(pooled.float().cpu(), want_pool)
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout", [(1, 8, 16, 128, 64), (2, 12, 20, 256, 128), (1, 8, 8, 1024, 512)])
+def test_upconv2x2(cuda_device, B, H, W, cin, cout):
+    import torch
+    import torch.nn.functional as F
+    from unet_dc_segmentation_b200 import layers
+    from unet_dc_segmentation_b200.model import pack_upconv
+    g = torch.Generator().manual_seed(cin + cout)
+    w = (torch.randn(cin, cout, 2, 2, generator=g) / cin ** 0.5).bfloat16().float()
+    b = torch.randn(cout, generator=g) * 0.1
+    x = _rand_act(B, H, W, cin, 11 + cin)
+    want = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), w, b, stride=2).permute(0, 2, 3, 1)
+    cat = torch.zeros((B, 2 * H, 2 * W, 2 * cout), dtype=torch.bfloat16).cuda()
+    layers.upconv2x2(x.cuda(), pack_upconv(w).cuda(), b.cuda(), out=cat, out_offset=0)
+    torch.cuda.synchronize()
+    _close(cat[..., :cout], want, f"upconv {cin}->{cout}")
+    assert bool((cat[..., cout:] == 0).all())
+
+
+def test_head_epilogue(cuda_device):
+    import torch
+    import torch.nn.functional as F
+    from unet_dc_segmentation_b200 import layers
+    from unet_dc_segmentation_b200.model import pack_conv3x3
+    w, b = _rand_layer(64, 64, 31)
+    g = torch.Generator().manual_seed(2)
+    hw = torch.randn(64, generator=g) * 0.3
+    hb = -0.2
+    x = _rand_act(2, 24, 32, 64, 13)
+    feat = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w, b, padding=1))
+    want = torch.sigmoid((feat * hw.view(1, -1, 1, 1)).sum(1) + hb)
+    prob, mask = layers.conv3x3_head(x.cuda(), pack_conv3x3(w).cuda(), b.cuda(), hw.cuda(), hb, 0.3)
+    torch.cuda.synchronize()
+    err = (prob.cpu() - want).abs().max()
+    assert float(err) < 2e-3, f"head prob max err {float(err)}"             # no bf16 rounding of the features here
+    assert torch.equal(mask.cpu(), (prob.cpu() > 0.3).to(torch.uint8))     # mask is exactly `prob > thresh`
+
+
+@pytest.mark.parametrize("kind", ["f32_nchw", "u8_gray", "u8_hwc"])
+@pytest.mark.parametrize("d", [1, 2])
+def test_stem(cuda_device, kind, d):
+    import torch
+    import torch.nn.functional as F
+    from unet_dc_segmentation_b200 import layers
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(64, 3, 3, 3, generator=g) * 0.2
+    b = torch.randn(64, generator=g) * 0.1
+    B, H, W = 2, 20, 36
+    if kind == "f32_nchw":
+        x = torch.rand(B, 3, H, W, generator=g)
+        ref_in, dev_in = x, x.cuda()
+    elif kind == "u8_gray":
+        u = torch.randint(0, 256, (B, H, W), generator=g, dtype=torch.uint8)
+        ref_in, dev_in = (u.float() / 255.0)[:, None].expand(B, 3, H, W), u.cuda()
+    else:
+        u = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
+        ref_in, dev_in = (u.float() / 255.0).permute(0, 3, 1, 2), u.cuda()
+    want = F.relu(F.conv2d(ref_in, w, b, padding=d, dilation=d)).permute(0, 2, 3, 1)
+    got = layers.stem(dev_in, w.reshape(64, 27).contiguous().cuda(), b.cuda(), dilation=d)
+    torch.cuda.synchronize()
+    _close(got, want, f"stem {kind} d{d}")
+
+
+def test_bad_arguments_raise(cuda_device):
+    import torch
+    from unet_dc_segmentation_b200 import _lib, layers
+    x = torch.zeros((1, 8, 16, 48), dtype=torch.bfloat16).cuda()
+    w = torch.zeros((64, 9 * 48), dtype=torch.bfloat16).cuda()
+    with pytest.raises(_lib.DcError) as ei:
+        layers.conv3x3(x, w, torch.zeros(64).cuda())
+    assert ei.value.code == _lib.DC_EINVAL and "multiple of 64" in str(ei.value)

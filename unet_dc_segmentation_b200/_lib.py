@@ -18,7 +18,7 @@ DC_NUM_LAYERS = 23
 
 EXPORTS = [
     "dc_last_error", "dc_version", "dc_device_check", "dc_conv_tc", "dc_stem", "dc_model_create",
-    "dc_model_destroy", "dc_forward_workspace_bytes", "dc_forward", "dc_forward_num_launches",
+    "dc_model_destroy", "dc_forward_workspace_bytes", "dc_forward", "dc_forward_num_launches", "dc_forward_profile",
     "dc_rolling_ball_workspace_bytes", "dc_rolling_ball", "dc_label_workspace_bytes", "dc_label_stats",
 ]
 
@@ -109,6 +109,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.dc_forward.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                c_void_p, c_size_t, c_void_p]
     lib.dc_forward_num_launches.argtypes = [c_void_p]
+    lib.dc_forward_profile.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                                       c_void_p, c_size_t, c_void_p, POINTER(c_float)]
     lib.dc_rolling_ball_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, POINTER(c_size_t)]
     lib.dc_rolling_ball.argtypes = [POINTER(RollingBallArgs), c_void_p]
     lib.dc_label_workspace_bytes.argtypes = [c_int, c_int, c_int, POINTER(c_size_t)]

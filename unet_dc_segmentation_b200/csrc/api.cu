@@ -196,8 +196,11 @@ int dc_forward_num_launches(const dc_model_t* m) {
     return 22;   // stem + 17 conv3x3 + 4 upconv
 }
 
-int dc_forward(dc_model_t* m, int in_kind, const void* in, int B, int H, int W, float thresh, float* prob_out,
-               uint8_t* mask_out, void* workspace, size_t workspace_bytes, void* stream_) {
+}  // extern "C"
+
+// One forward; when `ev` is non-NULL it receives DC_FORWARD_LAUNCHES + 1 events recorded around the launches.
+static int forward_impl(dc_model_t* m, int in_kind, const void* in, int B, int H, int W, float thresh, float* prob_out,
+                        uint8_t* mask_out, void* workspace, size_t workspace_bytes, void* stream_, cudaEvent_t* ev) {
     DC_REQUIRE(m && in && workspace, DC_EINVAL, "dc_forward: null argument");
     DC_REQUIRE(prob_out || mask_out, DC_EINVAL, "dc_forward: prob_out and mask_out are both NULL");
     DC_REQUIRE(B > 0 && H > 0 && W > 0 && H % 16 == 0 && W % 16 == 0, DC_EINVAL,
@@ -233,7 +236,15 @@ int dc_forward(dc_model_t* m, int in_kind, const void* in, int B, int H, int W, 
         }
         return launch_conv_tc(&a, stream);
     };
-#define DC_TRY(x) do { int _rc = (x); if (_rc != DC_OK) return _rc; } while (0)
+    int launch_no = 0;
+#define DC_TRY(x)                                                        \
+    do {                                                                 \
+        if (ev && launch_no == 0) DC_CUDA(cudaEventRecord(ev[0], stream)); \
+        int _rc = (x);                                                   \
+        if (_rc != DC_OK) return _rc;                                    \
+        ++launch_no;                                                     \
+        if (ev) DC_CUDA(cudaEventRecord(ev[launch_no], stream));         \
+    } while (0)
 
     // encoder (model_2.py:58-61) -- layer ids per include/unetdc_b200.h
     {
@@ -276,6 +287,32 @@ int dc_forward(dc_model_t* m, int in_kind, const void* in, int B, int H, int W, 
     }
 #undef DC_TRY
     return DC_OK;
+}
+
+extern "C" {
+
+int dc_forward(dc_model_t* m, int in_kind, const void* in, int B, int H, int W, float thresh, float* prob_out,
+               uint8_t* mask_out, void* workspace, size_t workspace_bytes, void* stream) {
+    return forward_impl(m, in_kind, in, B, H, W, thresh, prob_out, mask_out, workspace, workspace_bytes, stream, nullptr);
+}
+
+int dc_forward_profile(dc_model_t* m, int in_kind, const void* in, int B, int H, int W, float thresh, float* prob_out,
+                       uint8_t* mask_out, void* workspace, size_t workspace_bytes, void* stream, float* launch_ms) {
+    DC_REQUIRE(launch_ms, DC_EINVAL, "dc_forward_profile: launch_ms is NULL");
+    const int n = dc_forward_num_launches(m);
+    cudaEvent_t ev[64];
+    for (int i = 0; i <= n; ++i) DC_CUDA(cudaEventCreate(&ev[i]));
+    int rc = forward_impl(m, in_kind, in, B, H, W, thresh, prob_out, mask_out, workspace, workspace_bytes, stream, ev);
+    if (rc == DC_OK) {
+        cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+    }
+    for (int i = 0; i < n && rc == DC_OK; ++i) {
+        cudaError_t e = cudaEventElapsedTime(&launch_ms[i], ev[i], ev[i + 1]);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventElapsedTime");
+    }
+    for (int i = 0; i <= n; ++i) cudaEventDestroy(ev[i]);
+    return rc;
 }
 
 }  // extern "C"
