@@ -45,6 +45,10 @@ CONV_CASES = [
     (2, 8, 8, 512, 1024, 16),     # dilation > map: only the centre tap is in bounds
     (1, 16, 32, 1024, 512, 1),    # long K
     (3, 40, 24, 192, 64, 3),      # Cin not a power of two, odd dilation
+    (2, 48, 24, 128, 64, 1),      # dec1.0 shape: halo kernel, two chunks, weights resident
+    (1, 40, 40, 64, 128, 2),      # enc2.0 shape: halo kernel, BN = 128, dilation 2
+    (1, 32, 16, 64, 64, 4),       # halo kernel, dilation 4
+    (2, 16, 8, 64, 64, 1),        # exactly one 16 x 8 halo tile per image
 ]
 
 
@@ -60,6 +64,13 @@ def test_conv3x3_store(cuda_device, B, H, W, cin, cout, d):
     got = layers.conv3x3(x.cuda(), pack_conv3x3(w).cuda(), b.cuda(), dilation=d, relu=True)
     torch.cuda.synchronize()
     _close(got, want, f"conv {cin}->{cout} d{d} {B}x{H}x{W}")
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,d", [(2, 16, 32, 64, 64, 1), (1, 24, 40, 64, 128, 2)])
+def test_conv3x3_generic_path_forced(cuda_device, monkeypatch, B, H, W, cin, cout, d):
+    """Thin layers normally take conv_halo_kernel; DC_CONV_PATH=generic keeps the per-tap kernel covered."""
+    monkeypatch.setenv("DC_CONV_PATH", "generic")
+    test_conv3x3_store(cuda_device, B, H, W, cin, cout, d)
 
 
 def test_conv3x3_no_relu_and_channel_slices(cuda_device):

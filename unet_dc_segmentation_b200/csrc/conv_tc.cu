@@ -20,12 +20,24 @@
 //             of tile i overlaps the MMAs of tile i+1.
 // Taps whose shifted patch is wholly outside the image (large dilation on small maps) are skipped.
 //
+// Two kernels share the roles and the epilogue:
+//   conv_tc_kernel    (generic)  one TMA box per (tap, 64-channel chunk): A is re-fetched per tap from L2.
+//                                Right for Cout >= 256 where each A chunk feeds 256 output channels.
+//   conv_halo_kernel  (Cout = 64 / 128, small dilation)  the packed weights of the whole layer stay
+//                                resident in shared memory and ONE haloed activation region
+//                                (16+2d) x (8+2d) pixels x 64 ch is loaded per tile and chunk; the nine taps
+//                                are nine UMMA descriptors into that region (start = base + (ky*d*RW + kx*d)
+//                                rows, stride between 8-pixel groups = RW rows).  L2->SM traffic drops ~9x,
+//                                which is what bounds the thin layers (profiles/r01_*).
+//
 // Warp roles (256 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0 lane 0 : TMA producer           warp 1 lane 0 : tcgen05.mma issuer
 //   warp 2        : TMEM alloc / dealloc   warps 4..7    : epilogue (TMEM -> regs -> global)
 #include "common.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace dc {
 
@@ -53,12 +65,15 @@ struct alignas(64) ConvParams {
     float head_b, thresh;
     float* prob_out;
     uint8_t* mask_out;
+    // conv_halo_kernel only
+    int region_w, region_h, region_stride, nstages;
 };
 
 struct TileCoord {
     int img, h0, w0, n0;
 };
 
+template <int TH = TILE_H, int TW = TILE_W>
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, int BN) {
     TileCoord t;
     int nt = tile % p.n_tiles;
@@ -67,19 +82,20 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, 
     t.img = m / per_img;
     int r = m - t.img * per_img;
     int th = r / p.tiles_w;
-    t.h0 = th * TILE_H;
-    t.w0 = (r - th * p.tiles_w) * TILE_W;
+    t.h0 = th * TH;
+    t.w0 = (r - th * p.tiles_w) * TW;
     t.n0 = nt * BN;
     return t;
 }
 
 // Offset of tap `tap`; false when the shifted 8x16 patch has no pixel inside the image.
+template <int TH = TILE_H, int TW = TILE_W>
 __device__ __forceinline__ bool tap_offset(const ConvParams& p, const TileCoord& t, int tap, int& dy, int& dx) {
     if (p.ntaps == 1) { dy = 0; dx = 0; return true; }
     int ky = tap / 3, kx = tap - ky * 3;
     dy = (ky - 1) * p.dil;
     dx = (kx - 1) * p.dil;
-    return (t.h0 + dy + TILE_H > 0) && (t.h0 + dy < p.H) && (t.w0 + dx + TILE_W > 0) && (t.w0 + dx < p.W);
+    return (t.h0 + dy + TH > 0) && (t.h0 + dy < p.H) && (t.w0 + dx + TW > 0) && (t.w0 + dx < p.W);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -89,6 +105,113 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
     __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
     return *reinterpret_cast<uint32_t*>(&r);
+}
+
+// Epilogue warps (4 x 32 threads = the 128 TMEM lanes): thread L owns pixel (L / TW, L % TW) of the tile.
+// TMEM -> registers -> (+bias, ReLU) -> bf16 NHWC stores, with the fused 2x2 max-pool, the transposed-conv
+// parity scatter or the out_conv + sigmoid + threshold head as `p.epilogue` says.
+template <int BN, int TH, int TW>
+__device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, const int lane, const uint32_t tmem_base,
+                                             uint64_t* tfull_bar, uint64_t* tempty_bar) {
+    {
+        const int L = e * 32 + lane;                               // e == warp % 4: TMEM lanes [32e, 32e+32)
+        const int lh = L / TW, lw = L % TW;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const TileCoord t = decode_tile<TH, TW>(p, tile, BN);
+            const int as = it & 1;
+            const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+            const int h = t.h0 + lh, w = t.w0 + lw;
+            const bool valid = (h < p.H) && (w < p.W);
+
+            __nv_bfloat16* optr = nullptr;
+            __nv_bfloat16* pptr = nullptr;
+            int bias_base = t.n0;
+            if (p.epilogue == DC_EPI_UPSCATTER) {
+                const int q = t.n0 / p.Cout;
+                bias_base = t.n0 - q * p.Cout;
+                const size_t opix = ((size_t)t.img * (2 * p.H) + (2 * h + (q >> 1))) * (size_t)(2 * p.W) + (2 * w + (q & 1));
+                optr = p.out + opix * p.out_stride + p.out_offset + bias_base;
+            } else if (p.epilogue != DC_EPI_HEAD) {
+                const size_t opix = ((size_t)t.img * p.H + h) * (size_t)p.W + w;
+                optr = p.out + opix * p.out_stride + p.out_offset + t.n0;
+                if (p.epilogue == DC_EPI_STORE_POOL) {
+                    const size_t ppix = ((size_t)t.img * (p.H >> 1) + (h >> 1)) * (size_t)(p.W >> 1) + (w >> 1);
+                    pptr = p.pool_out + ppix * p.pool_stride + t.n0;
+                }
+            }
+            const bool pool_writer = valid && !(lane & 1) && !(lane & TW);
+            float head_acc = p.head_b;
+
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)c0, v);
+                tmem_ld_wait();
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + bias_base + c0);
+                float x[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = __ldg(b4 + j);
+                    x[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+                    x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+                    x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+                    x[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+                }
+                if (p.epilogue == DC_EPI_HEAD) {
+                    const float4* w4 = reinterpret_cast<const float4*>(p.head_w + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 hw = __ldg(w4 + j);
+                        head_acc = fmaf(x[4 * j + 0], hw.x, head_acc);
+                        head_acc = fmaf(x[4 * j + 1], hw.y, head_acc);
+                        head_acc = fmaf(x[4 * j + 2], hw.z, head_acc);
+                        head_acc = fmaf(x[4 * j + 3], hw.w, head_acc);
+                    }
+                } else {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
+                    if (valid) {
+                        uint4* o4 = reinterpret_cast<uint4*>(optr + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) o4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    }
+                    if (p.epilogue == DC_EPI_STORE_POOL) {
+                        // 2x2 window = lanes {l, l^1 (w+1), l^TW (h+1), l^(TW+1)}: all inside this warp
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            uint32_t m = max_bf16x2(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
+                            pk[j] = max_bf16x2(m, __shfl_xor_sync(0xffffffffu, m, TW));
+                        }
+                        if (pool_writer) {
+                            uint4* o4 = reinterpret_cast<uint4*>(pptr + c0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) o4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        }
+                    }
+                }
+            }
+            // accumulator fully read: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+
+            if (p.epilogue == DC_EPI_HEAD && valid) {
+                const float prob = 1.0f / (1.0f + expf(-head_acc));              // torch.sigmoid, fp32
+                const size_t opix = ((size_t)t.img * p.H + h) * (size_t)p.W + w;
+                if (p.prob_out) p.prob_out[opix] = prob;
+                if (p.mask_out) p.mask_out[opix] = prob > p.thresh ? 1 : 0;      // qdb:56
+            }
+        }
+    }
 }
 
 template <int BN, int NSTAGES>
@@ -187,104 +310,137 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         __syncwarp();
     } else if (warp >= EPI_WARP0) {
         // ------------------------------------------------------------------ epilogue
-        const int e = warp - EPI_WARP0;                          // == warp % 4: TMEM lanes [32e, 32e+32)
-        const int L = e * 32 + lane;
-        const int lh = L / TILE_W, lw = L % TILE_W;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const TileCoord t = decode_tile(p, tile, BN);
-            const int as = it & 1;
-            const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-            const int h = t.h0 + lh, w = t.w0 + lw;
-            const bool valid = (h < p.H) && (w < p.W);
+        run_epilogue<BN, TILE_H, TILE_W>(p, warp - EPI_WARP0, lane, tmem_base, tfull_bar, tempty_bar);
+    }
 
-            __nv_bfloat16* optr = nullptr;
-            __nv_bfloat16* pptr = nullptr;
-            int bias_base = t.n0;
-            if (p.epilogue == DC_EPI_UPSCATTER) {
-                const int q = t.n0 / p.Cout;
-                bias_base = t.n0 - q * p.Cout;
-                const size_t opix = ((size_t)t.img * (2 * p.H) + (2 * h + (q >> 1))) * (size_t)(2 * p.W) + (2 * w + (q & 1));
-                optr = p.out + opix * p.out_stride + p.out_offset + bias_base;
-            } else if (p.epilogue != DC_EPI_HEAD) {
-                const size_t opix = ((size_t)t.img * p.H + h) * (size_t)p.W + w;
-                optr = p.out + opix * p.out_stride + p.out_offset + t.n0;
-                if (p.epilogue == DC_EPI_STORE_POOL) {
-                    const size_t ppix = ((size_t)t.img * (p.H >> 1) + (h >> 1)) * (size_t)(p.W >> 1) + (w >> 1);
-                    pptr = p.pool_out + ppix * p.pool_stride + t.n0;
-                }
-            }
-            const bool pool_writer = valid && !(lane & 1) && !(lane & 16);
-            float head_acc = p.head_b;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
 
-            mbar_wait(&tfull_bar[as], aphase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(as * BN);
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + (uint32_t)c0, v);
-                tmem_ld_wait();
-                const float4* b4 = reinterpret_cast<const float4*>(p.bias + bias_base + c0);
-                float x[32];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 b = __ldg(b4 + j);
-                    x[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
-                    x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-                    x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
-                    x[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
-                }
-                if (p.relu) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
-                }
-                if (p.epilogue == DC_EPI_HEAD) {
-                    const float4* w4 = reinterpret_cast<const float4*>(p.head_w + c0);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 hw = __ldg(w4 + j);
-                        head_acc = fmaf(x[4 * j + 0], hw.x, head_acc);
-                        head_acc = fmaf(x[4 * j + 1], hw.y, head_acc);
-                        head_acc = fmaf(x[4 * j + 2], hw.z, head_acc);
-                        head_acc = fmaf(x[4 * j + 3], hw.w, head_acc);
-                    }
-                } else {
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
-                    if (valid) {
-                        uint4* o4 = reinterpret_cast<uint4*>(optr + c0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) o4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                    }
-                    if (p.epilogue == DC_EPI_STORE_POOL) {
-                        // 2x2 window = lanes {l, l^1 (w+1), l^16 (h+1), l^17}: all inside this warp
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            uint32_t m = max_bf16x2(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
-                            pk[j] = max_bf16x2(m, __shfl_xor_sync(0xffffffffu, m, 16));
-                        }
-                        if (pool_writer) {
-                            uint4* o4 = reinterpret_cast<uint4*>(pptr + c0);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) o4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                        }
-                    }
-                }
-            }
-            // accumulator fully read: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+// ---------------------------------------------------------------------------- halo variant
+constexpr int HT_H = 16, HT_W = 8;      // 16 x 8 output patch: each 8-pixel row is one UMMA 8-row group
+constexpr int HALO_MAX_STAGES = 8;
 
-            if (p.epilogue == DC_EPI_HEAD && valid) {
-                const float prob = 1.0f / (1.0f + expf(-head_acc));              // torch.sigmoid, fp32
-                const size_t opix = ((size_t)t.img * p.H + h) * (size_t)p.W + w;
-                if (p.prob_out) p.prob_out[opix] = prob;
-                if (p.mask_out) p.mask_out[opix] = prob > p.thresh ? 1 : 0;      // qdb:56
+// K-major SWIZZLE_128B descriptor whose 8-row groups are `sbo_bytes` apart and whose start may sit on any
+// 128 B row of a 1024 B-aligned region.  Measured on B200 (tests/test_gpu_conv.py halo cases): the MMA unit
+// derives the swizzle phase from the absolute shared-memory address bits [7,10), exactly as TMA does when it
+// writes the region, so base_offset stays 0 and a window may start on any row.
+__device__ __forceinline__ uint64_t umma_desc_sw128_strided(uint32_t smem_addr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvParams p) {
+    constexpr int W_TILE_BYTES = BN * KCHUNK * 2;     // one (tap, chunk) slice of the weights
+    constexpr int TMEM_COLS = 2 * BN;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int n_wtiles = 9 * p.kchunks;
+    uint8_t* w_res = smem;                                             // resident weights
+    uint8_t* a_ring = smem + n_wtiles * W_TILE_BYTES;                  // haloed activation regions
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(a_ring + p.nstages * p.region_stride);
+    uint64_t* empty_bar = full_bar + HALO_MAX_STAGES;
+    uint64_t* tfull_bar = empty_bar + HALO_MAX_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint64_t* w_bar = tempty_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NST = p.nstages;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        mbar_init(w_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t region_bytes = (uint32_t)(p.region_w * p.region_h * KCHUNK * 2);
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            mbar_expect_tx(w_bar, (uint32_t)(n_wtiles * W_TILE_BYTES));
+            for (int j = 0; j < n_wtiles; ++j) tma_load_2d(w_res + j * W_TILE_BYTES, &p.tmB, w_bar, j * KCHUNK, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord t = decode_tile<HT_H, HT_W>(p, tile, BN);
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    mbar_expect_tx(&full_bar[stage], region_bytes);
+                    tma_load_4d(a_ring + stage * p.region_stride, &p.tmA, &full_bar[stage], kc * KCHUNK, t.w0 - p.dil,
+                                t.h0 - p.dil, t.img);
+                    if (++stage == NST) { stage = 0; phase ^= 1u; }
+                }
             }
         }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
+            const uint32_t sbo = (uint32_t)p.region_w * 128u;
+            const uint32_t w_addr = smem_u32(w_res);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            mbar_wait(w_bar, 0);
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const TileCoord t = decode_tile<HT_H, HT_W>(p, tile, BN);
+                const int as = it & 1;
+                const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(&tempty_bar[as], aphase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                uint32_t accumulate = 0;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t region = smem_u32(a_ring + stage * p.region_stride);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        int dy, dx;
+                        if (!tap_offset<HT_H, HT_W>(p, t, tap, dy, dx)) continue;   // window wholly in the padding
+                        const uint32_t a_addr = region + (uint32_t)((dy + p.dil) * p.region_w + (dx + p.dil)) * 128u;
+                        const uint64_t adesc = umma_desc_sw128_strided(a_addr, sbo);
+                        const uint64_t bdesc = umma_desc_sw128(w_addr + (uint32_t)((tap * p.kchunks + kc) * W_TILE_BYTES));
+#pragma unroll
+                        for (int k = 0; k < KCHUNK / 16; ++k) {
+                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate);
+                            accumulate = 1;
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == NST) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&tfull_bar[as]);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= EPI_WARP0) {
+        run_epilogue<BN, HT_H, HT_W>(p, warp - EPI_WARP0, lane, tmem_base, tfull_bar, tempty_bar);
     }
 
     tc_fence_before();
@@ -377,11 +533,32 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
 
     ConvParams p;
     memset(&p, 0, sizeof(p));
+
+    // Thin layers (Cout = 64 / 128): resident weights + one haloed region per tile, when it fits shared memory.
+    bool halo = false;
+    size_t halo_smem = 0;
+    if (!up && a->Cout == BN && BN <= 128 && a->dilation <= 4) {
+        const int rw = HT_W + 2 * a->dilation, rh = HT_H + 2 * a->dilation;
+        const size_t region_stride = ((size_t)rw * rh * KCHUNK * 2 + 1023) & ~(size_t)1023;
+        const size_t w_bytes = (size_t)9 * (a->Cin / KCHUNK) * BN * KCHUNK * 2;
+        const size_t budget = 227 * 1024 - 1024 /* alignment slack */ - 512 /* barriers */;
+        const long long nst = w_bytes < budget ? (long long)((budget - w_bytes) / region_stride) : 0;
+        if (nst >= 2) {
+            halo = true;
+            p.region_w = rw; p.region_h = rh; p.region_stride = (int)region_stride;
+            p.nstages = nst > HALO_MAX_STAGES ? HALO_MAX_STAGES : (int)nst;
+            halo_smem = w_bytes + (size_t)p.nstages * region_stride + 1024 + 512;
+        }
+    }
+    if (const char* force = getenv("DC_CONV_PATH")) {        // measurement aid: A/B the two kernels
+        if (!strcmp(force, "generic")) halo = false;
+    }
     {
         cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B};
         cuuint64_t str[3] = {(cuuint64_t)a->in_stride * 2, (cuuint64_t)a->W * a->in_stride * 2,
                              (cuuint64_t)a->H * a->W * a->in_stride * 2};
         cuuint32_t box[4] = {KCHUNK, TILE_W, TILE_H, 1};
+        if (halo) { box[1] = (cuuint32_t)p.region_w; box[2] = (cuuint32_t)p.region_h; }
         int rc = encode_map(&p.tmA, a->in, 4, dims, str, box);
         if (rc != DC_OK) return rc;
     }
@@ -398,8 +575,8 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
     p.dil = up ? 1 : a->dilation;
     p.ntaps = up ? 1 : 9;
     p.kchunks = a->Cin / KCHUNK;
-    p.tiles_w = ceil_div(a->W, TILE_W);
-    p.tiles_h = ceil_div(a->H, TILE_H);
+    p.tiles_w = ceil_div(a->W, halo ? HT_W : TILE_W);
+    p.tiles_h = ceil_div(a->H, halo ? HT_H : TILE_H);
     p.n_tiles = (up ? 4 * a->Cout : a->Cout) / BN;
     const long long total = (long long)a->B * p.tiles_w * p.tiles_h * p.n_tiles;
     DC_REQUIRE(total < (1ll << 31), DC_EINVAL, "dc_conv_tc: too many tiles");
@@ -414,6 +591,19 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
     p.head_w = a->head_w; p.head_b = a->head_b; p.thresh = a->thresh;
     p.prob_out = a->prob_out; p.mask_out = a->mask_out;
 
+    if (halo) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            DC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            DC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_done = true;
+        }
+        const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+        if (BN == 64) conv_halo_kernel<64><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
+        else          conv_halo_kernel<128><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
+        DC_CUDA(cudaGetLastError());
+        return DC_OK;
+    }
     switch (BN) {
         case 256: return launch_variant<256, 4>(p, stream);
         case 128: return launch_variant<128, 6>(p, stream);
