@@ -83,6 +83,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// One lane of a converged warp.  Role loops run warp-uniform and only the issuing instructions sit under this
+// predicate: ptxas then keeps descriptors / coordinates in uniform registers and emits UTCHMMA / UTMALDG
+// back to back (a role body under `if (lane == 0)` gets an ELECT + branch waterfall around every one).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // TMA tiled loads (global -> shared, completion on an mbarrier)
 __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1) {
     asm volatile(

@@ -110,7 +110,8 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
 // Epilogue warps (4 x 32 threads = the 128 TMEM lanes): thread L owns pixel (L / TW, L % TW) of the tile.
 // TMEM -> registers -> (+bias, ReLU) -> bf16 NHWC stores, with the fused 2x2 max-pool, the transposed-conv
 // parity scatter or the out_conv + sigmoid + threshold head as `p.epilogue` says.
-template <int BN, int TH, int TW>
+// NHALF > 1: the tile is NHALF side-by-side TW-wide patches, each with its own BN-column accumulator.
+template <int BN, int TH, int TW, int NHALF = 1>
 __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, const int lane, const uint32_t tmem_base,
                                              uint64_t* tfull_bar, uint64_t* tempty_bar) {
     {
@@ -118,10 +119,14 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
         const int lh = L / TW, lw = L % TW;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const TileCoord t = decode_tile<TH, TW>(p, tile, BN);
+            const TileCoord t = decode_tile<TH, TW * NHALF>(p, tile, BN);
             const int as = it & 1;
             const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-            const int h = t.h0 + lh, w = t.w0 + lw;
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+#pragma unroll 1
+          for (int half = 0; half < NHALF; ++half) {
+            const int h = t.h0 + lh, w = t.w0 + half * TW + lw;
             const bool valid = (h < p.H) && (w < p.W);
 
             __nv_bfloat16* optr = nullptr;
@@ -143,9 +148,7 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
             const bool pool_writer = valid && !(lane & 1) && !(lane & TW);
             float head_acc = p.head_b;
 
-            mbar_wait(&tfull_bar[as], aphase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(as * BN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)((as * NHALF + half) * BN);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
@@ -199,10 +202,12 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                     }
                 }
             }
-            // accumulator fully read: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (half == NHALF - 1) {
+                // accumulators fully read: hand them back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            }
 
             if (p.epilogue == DC_EPI_HEAD && valid) {
                 const float prob = 1.0f / (1.0f + expf(-head_acc));              // torch.sigmoid, fp32
@@ -210,6 +215,7 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                 if (p.prob_out) p.prob_out[opix] = prob;
                 if (p.mask_out) p.mask_out[opix] = prob > p.thresh ? 1 : 0;      // qdb:56
             }
+          }
         }
     }
 }
@@ -249,65 +255,67 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const TileCoord t = decode_tile(p, tile, BN);
-                for (int tap = 0; tap < p.ntaps; ++tap) {
-                    int dy, dx;
-                    if (!tap_offset(p, t, tap, dy, dx)) continue;
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        // ------------------------------------------------------------------ TMA producer (warp-uniform loop)
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const TileCoord t = decode_tile(p, tile, BN);
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+                int dy, dx;
+                if (!tap_offset(p, t, tap, dy, dx)) continue;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    if (elect_one()) {
                         uint8_t* sa = smem + stage * STAGE_BYTES;
                         mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                         tma_load_4d(sa, &p.tmA, &full_bar[stage], kc * KCHUNK, t.w0 + dx, t.h0 + dy, t.img);
                         tma_load_2d(sa + A_STAGE_BYTES, &p.tmB, &full_bar[stage], tap * p.Cin + kc * KCHUNK, t.n0);
-                        if (++stage == NSTAGES) { stage = 0; phase ^= 1u; }
                     }
+                    __syncwarp();
+                    if (++stage == NSTAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-                const TileCoord t = decode_tile(p, tile, BN);
-                const int as = it & 1;
-                const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-                mbar_wait(&tempty_bar[as], aphase ^ 1u);      // epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-                uint32_t accumulate = 0;
-                for (int tap = 0; tap < p.ntaps; ++tap) {
-                    int dy, dx;
-                    if (!tap_offset(p, t, tap, dy, dx)) continue;
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
-                        mbar_wait(&full_bar[stage], phase);
-                        tc_fence_after();
-                        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                        const uint64_t adesc = umma_desc_sw128(sa);
-                        const uint64_t bdesc = umma_desc_sw128(sa + A_STAGE_BYTES);
+        // ------------------------------------------------------------------ MMA issuer (warp-uniform loop)
+        const uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const TileCoord t = decode_tile(p, tile, BN);
+            const int as = it & 1;
+            const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(&tempty_bar[as], aphase ^ 1u);      // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+            uint32_t accumulate = 0;
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+                int dy, dx;
+                if (!tap_offset(p, t, tap, dy, dx)) continue;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint64_t adesc = umma_desc_sw128(sa);
+                    const uint64_t bdesc = umma_desc_sw128(sa + A_STAGE_BYTES);
+                    if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < KCHUNK / 16; ++k) {
                             // +32 B per K=16 step inside the 128 B swizzle row (address field is >>4)
-                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate);
-                            accumulate = 1;
+                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                      (k == 0) ? accumulate : 1u);
                         }
                         umma_commit(&empty_bar[stage]);        // frees the stage once these MMAs retire
-                        if (++stage == NSTAGES) { stage = 0; phase ^= 1u; }
                     }
+                    __syncwarp();
+                    accumulate = 1;
+                    if (++stage == NSTAGES) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(&tfull_bar[as]);                    // accumulator complete -> epilogue
             }
+            if (elect_one()) umma_commit(&tfull_bar[as]);       // accumulator complete -> epilogue
+            __syncwarp();
         }
-        __syncwarp();
     } else if (warp >= EPI_WARP0) {
         // ------------------------------------------------------------------ epilogue
         run_epilogue<BN, TILE_H, TILE_W>(p, warp - EPI_WARP0, lane, tmem_base, tfull_bar, tempty_bar);
@@ -323,6 +331,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
 // ---------------------------------------------------------------------------- halo variant
 constexpr int HT_H = 16, HT_W = 8;      // 16 x 8 output patch: each 8-pixel row is one UMMA 8-row group
+// NHALF = 2: two patches side by side (16 x 16 pixels) share one haloed region and accumulate into separate
+// TMEM tiles -- two independent MMA chains hide the latency of back-to-back accumulating MMAs at N = 64 / 128.
+// NHALF = 1 is kept for layers whose resident weights leave no room for two 16-wide regions.
 constexpr int HALO_MAX_STAGES = 8;
 
 // K-major SWIZZLE_128B descriptor whose 8-row groups are `sbo_bytes` apart and whose start may sit on any
@@ -339,10 +350,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_strided(uint32_t smem_addr, 
     return d;
 }
 
-template <int BN>
+template <int BN, int HT_NHALF>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvParams p) {
+    constexpr int HT_TW = HT_W * HT_NHALF;
     constexpr int W_TILE_BYTES = BN * KCHUNK * 2;     // one (tap, chunk) slice of the weights
-    constexpr int TMEM_COLS = 2 * BN;
+    constexpr int TMEM_COLS = 2 * HT_NHALF * BN;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -380,67 +392,86 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
     const uint32_t region_bytes = (uint32_t)(p.region_w * p.region_h * KCHUNK * 2);
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        // ------------------------------------------------------------------ TMA producer (warp-uniform loop)
+        if (elect_one()) {
             mbar_expect_tx(w_bar, (uint32_t)(n_wtiles * W_TILE_BYTES));
             for (int j = 0; j < n_wtiles; ++j) tma_load_2d(w_res + j * W_TILE_BYTES, &p.tmB, w_bar, j * KCHUNK, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const TileCoord t = decode_tile<HT_H, HT_W>(p, tile, BN);
-                for (int kc = 0; kc < p.kchunks; ++kc) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+        }
+        __syncwarp();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const TileCoord t = decode_tile<HT_H, HT_TW>(p, tile, BN);
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                if (elect_one()) {
                     mbar_expect_tx(&full_bar[stage], region_bytes);
                     tma_load_4d(a_ring + stage * p.region_stride, &p.tmA, &full_bar[stage], kc * KCHUNK, t.w0 - p.dil,
                                 t.h0 - p.dil, t.img);
-                    if (++stage == NST) { stage = 0; phase ^= 1u; }
                 }
+                __syncwarp();
+                if (++stage == NST) { stage = 0; phase ^= 1u; }
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
-            const uint32_t sbo = (uint32_t)p.region_w * 128u;
-            const uint32_t w_addr = smem_u32(w_res);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            mbar_wait(w_bar, 0);
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-                const TileCoord t = decode_tile<HT_H, HT_W>(p, tile, BN);
-                const int as = it & 1;
-                const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-                mbar_wait(&tempty_bar[as], aphase ^ 1u);
+        // ------------------------------------------------------------------ MMA issuer (warp-uniform loop)
+        const uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
+        const uint32_t sbo = (uint32_t)p.region_w * 128u;
+        const uint32_t w_addr = smem_u32(w_res);
+        const uint32_t tap_dy_bytes = (uint32_t)(p.dil * p.region_w) * 128u;     // one tap row down
+        const uint32_t tap_dx_bytes = (uint32_t)p.dil * 128u;                    // one tap column right
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        mbar_wait(w_bar, 0);
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const TileCoord t = decode_tile<HT_H, HT_TW>(p, tile, BN);
+            const int as = it & 1;
+            const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+            // taps whose window lies wholly in the zero padding contribute nothing: skip their MMAs
+            uint32_t tap_mask = 0;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                int dy, dx;
+                if (tap_offset<HT_H, HT_TW>(p, t, tap, dy, dx)) tap_mask |= 1u << tap;
+            }
+            mbar_wait(&tempty_bar[as], aphase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * HT_NHALF * BN);
+            uint32_t accumulate = 0;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-                uint32_t accumulate = 0;
-                for (int kc = 0; kc < p.kchunks; ++kc) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t region = smem_u32(a_ring + stage * p.region_stride);
+                const uint32_t region = smem_u32(a_ring + stage * p.region_stride);
+                const uint32_t w_chunk = w_addr + (uint32_t)(kc * W_TILE_BYTES);
+                const uint32_t w_tap_stride = (uint32_t)(p.kchunks * W_TILE_BYTES);
+                if (elect_one()) {
+#pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
-                        int dy, dx;
-                        if (!tap_offset<HT_H, HT_W>(p, t, tap, dy, dx)) continue;   // window wholly in the padding
-                        const uint32_t a_addr = region + (uint32_t)((dy + p.dil) * p.region_w + (dx + p.dil)) * 128u;
+                        if (!((tap_mask >> tap) & 1u)) continue;
+                        const uint32_t a_addr = region + (uint32_t)(tap / 3) * tap_dy_bytes + (uint32_t)(tap % 3) * tap_dx_bytes;
                         const uint64_t adesc = umma_desc_sw128_strided(a_addr, sbo);
-                        const uint64_t bdesc = umma_desc_sw128(w_addr + (uint32_t)((tap * p.kchunks + kc) * W_TILE_BYTES));
+                        const uint64_t bdesc = umma_desc_sw128(w_chunk + (uint32_t)tap * w_tap_stride);
 #pragma unroll
                         for (int k = 0; k < KCHUNK / 16; ++k) {
-                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate);
+#pragma unroll
+                            for (int half = 0; half < HT_NHALF; ++half)   // right patch = 8 region rows (1024 B) further
+                                umma_bf16(d_tmem + (uint32_t)(half * BN), adesc + (uint64_t)(2 * k + 64 * half),
+                                          bdesc + (uint64_t)(2 * k), idesc, accumulate);
                             accumulate = 1;
                         }
                     }
                     umma_commit(&empty_bar[stage]);
-                    if (++stage == NST) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(&tfull_bar[as]);
+                __syncwarp();
+                accumulate = 1;
+                if (++stage == NST) { stage = 0; phase ^= 1u; }
             }
+            if (elect_one()) umma_commit(&tfull_bar[as]);
+            __syncwarp();
         }
-        __syncwarp();
     } else if (warp >= EPI_WARP0) {
-        run_epilogue<BN, HT_H, HT_W>(p, warp - EPI_WARP0, lane, tmem_base, tfull_bar, tempty_bar);
+        run_epilogue<BN, HT_H, HT_W, HT_NHALF>(p, warp - EPI_WARP0, lane, tmem_base, tfull_bar, tempty_bar);
     }
 
     tc_fence_before();
@@ -536,18 +567,24 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
 
     // Thin layers (Cout = 64 / 128): resident weights + one haloed region per tile, when it fits shared memory.
     bool halo = false;
+    int halo_nhalf = 1;
     size_t halo_smem = 0;
     if (!up && a->Cout == BN && BN <= 128 && a->dilation <= 4) {
-        const int rw = HT_W + 2 * a->dilation, rh = HT_H + 2 * a->dilation;
-        const size_t region_stride = ((size_t)rw * rh * KCHUNK * 2 + 1023) & ~(size_t)1023;
+        // TMA and the MMA unit both take the swizzle phase from absolute address bits, so a region only needs
+        // TMA's 128 B alignment, not a 1024 B one: regions are packed back to back
         const size_t w_bytes = (size_t)9 * (a->Cin / KCHUNK) * BN * KCHUNK * 2;
         const size_t budget = 227 * 1024 - 1024 /* alignment slack */ - 512 /* barriers */;
-        const long long nst = w_bytes < budget ? (long long)((budget - w_bytes) / region_stride) : 0;
-        if (nst >= 2) {
-            halo = true;
-            p.region_w = rw; p.region_h = rh; p.region_stride = (int)region_stride;
-            p.nstages = nst > HALO_MAX_STAGES ? HALO_MAX_STAGES : (int)nst;
-            halo_smem = w_bytes + (size_t)p.nstages * region_stride + 1024 + 512;
+        for (int nhalf = 2; nhalf >= 1 && !halo; --nhalf) {
+            const int rw = HT_W * nhalf + 2 * a->dilation, rh = HT_H + 2 * a->dilation;
+            const size_t region_stride = (size_t)rw * rh * KCHUNK * 2;
+            const long long nst = w_bytes < budget ? (long long)((budget - w_bytes) / region_stride) : 0;
+            if (nst >= 2) {
+                halo = true;
+                halo_nhalf = nhalf;
+                p.region_w = rw; p.region_h = rh; p.region_stride = (int)region_stride;
+                p.nstages = nst > HALO_MAX_STAGES ? HALO_MAX_STAGES : (int)nst;
+                halo_smem = w_bytes + (size_t)p.nstages * region_stride + 1024 + 512;
+            }
         }
     }
     if (const char* force = getenv("DC_CONV_PATH")) {        // measurement aid: A/B the two kernels
@@ -575,7 +612,7 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
     p.dil = up ? 1 : a->dilation;
     p.ntaps = up ? 1 : 9;
     p.kchunks = a->Cin / KCHUNK;
-    p.tiles_w = ceil_div(a->W, halo ? HT_W : TILE_W);
+    p.tiles_w = ceil_div(a->W, halo ? HT_W * halo_nhalf : TILE_W);
     p.tiles_h = ceil_div(a->H, halo ? HT_H : TILE_H);
     p.n_tiles = (up ? 4 * a->Cout : a->Cout) / BN;
     const long long total = (long long)a->B * p.tiles_w * p.tiles_h * p.n_tiles;
@@ -594,13 +631,17 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
     if (halo) {
         static bool attr_done = false;
         if (!attr_done) {
-            DC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            DC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            DC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            DC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            DC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            DC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             attr_done = true;
         }
         const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-        if (BN == 64) conv_halo_kernel<64><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
-        else          conv_halo_kernel<128><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
+        if (BN == 64 && halo_nhalf == 2)       conv_halo_kernel<64, 2><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
+        else if (BN == 64)                     conv_halo_kernel<64, 1><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
+        else if (halo_nhalf == 2)              conv_halo_kernel<128, 2><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
+        else                                   conv_halo_kernel<128, 1><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
         DC_CUDA(cudaGetLastError());
         return DC_OK;
     }
