@@ -55,7 +55,12 @@ def test_forward_vs_oracle_sizes(cuda_device, B, H, W):
     assert np.abs(prob_g.cpu().numpy() - want).max() <= PROB_TOL
     rgb = torch.from_numpy(np.repeat(imgs[..., None], 3, -1)).to(cuda_device)
     mask_c, prob_c = m.predict_u8(rgb, 0.3, return_prob=True)
-    assert torch.equal(prob_c, prob_g) and torch.equal(mask_c, mask_g)
+    # grayscale frames fold the three (identical) input channels into one K=9 tap set before the bf16
+    # rounding of the weights; the RGB entry rounds 27 weights separately.  Two different bf16 roundings of
+    # the same fp32 layer: both must sit inside the stated tolerance of the fp32 reference.
+    assert np.abs(prob_c.cpu().numpy() - want).max() <= PROB_TOL
+    near = (prob_g[:, 0] - 0.3).abs() <= PROB_TOL
+    assert bool(((mask_c == mask_g) | near).all())
     assert torch.equal(mask_g.cpu(), (prob_g[:, 0].cpu() > 0.3).to(torch.uint8))
 
 

@@ -46,7 +46,7 @@ namespace {
 constexpr int TILE_H = 8, TILE_W = 16, TILE_M = TILE_H * TILE_W;
 constexpr int KCHUNK = 64;
 constexpr int A_STAGE_BYTES = TILE_M * KCHUNK * 2;   // 16 KB
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;      // 4 role warps + 2 epilogue groups x 4 warps
 constexpr int EPI_WARP0 = 4;
 
 struct alignas(64) ConvParams {
@@ -107,37 +107,50 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
     return *reinterpret_cast<uint32_t*>(&r);
 }
 
-// Epilogue warps (4 x 32 threads = the 128 TMEM lanes): thread L owns pixel (L / TW, L % TW) of the tile.
-// TMEM -> registers -> (+bias, ReLU) -> bf16 NHWC stores, with the fused 2x2 max-pool, the transposed-conv
-// parity scatter or the out_conv + sigmoid + threshold head as `p.epilogue` says.
+// tcgen05.wait::ld that also names the registers an earlier tcgen05.ld fills: the compiler must not touch
+// them before this point (the loads are asynchronous; a plain wait carries no data dependency).
+__device__ __forceinline__ void tmem_ld_wait_on(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+
+// Epilogue: EPI_GROUPS groups of 4 warps; group g owns accumulator stage g and every EPI_GROUPS-th tile of the
+// CTA, so two tiles drain concurrently while the MMA warp fills the next.  Within a group the 4 x 32 threads are
+// the 128 TMEM lanes: thread L owns pixel (L / TW, L % TW) of the tile.  TMEM -> registers (next 32-column chunk
+// in flight while this one is processed) -> +bias (staged in smem), ReLU -> bf16 NHWC stores, with the fused
+// 2x2 max-pool, the transposed-conv parity scatter or the out_conv + sigmoid + threshold head as `p.epilogue` says.
 // NHALF > 1: the tile is NHALF side-by-side TW-wide patches, each with its own BN-column accumulator.
+constexpr int EPI_GROUPS = 2;
+
 template <int BN, int TH, int TW, int NHALF = 1>
-__device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, const int lane, const uint32_t tmem_base,
-                                             uint64_t* tfull_bar, uint64_t* tempty_bar) {
-    {
-        const int L = e * 32 + lane;                               // e == warp % 4: TMEM lanes [32e, 32e+32)
-        const int lh = L / TW, lw = L % TW;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const TileCoord t = decode_tile<TH, TW * NHALF>(p, tile, BN);
-            const int as = it & 1;
-            const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-            mbar_wait(&tfull_bar[as], aphase);
-            tc_fence_after();
+__device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, const int lane, const int group,
+                                             const uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                             const float* bias_s) {
+    const int L = e * 32 + lane;                               // e == warp % 4: TMEM lanes [32e, 32e+32)
+    const int lh = L / TW, lw = L % TW;
+    const float* head_s = bias_s + p.Cout;                     // out_conv weights follow the bias (HEAD only)
+    for (int it = group;; it += EPI_GROUPS) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        if (tile >= p.total_tiles) break;
+        const TileCoord t = decode_tile<TH, TW * NHALF>(p, tile, BN);
+        const int as = it & 1;                                 // == group
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
 #pragma unroll 1
-          for (int half = 0; half < NHALF; ++half) {
+        for (int half = 0; half < NHALF; ++half) {
             const int h = t.h0 + lh, w = t.w0 + half * TW + lw;
             const bool valid = (h < p.H) && (w < p.W);
 
             __nv_bfloat16* optr = nullptr;
             __nv_bfloat16* pptr = nullptr;
             int bias_base = t.n0;
-            if (p.epilogue == DC_EPI_UPSCATTER) {
-                const int q = t.n0 / p.Cout;
-                bias_base = t.n0 - q * p.Cout;
-                const size_t opix = ((size_t)t.img * (2 * p.H) + (2 * h + (q >> 1))) * (size_t)(2 * p.W) + (2 * w + (q & 1));
-                optr = p.out + opix * p.out_stride + p.out_offset + bias_base;
-            } else if (p.epilogue != DC_EPI_HEAD) {
+            if (p.epilogue == DC_EPI_STORE || p.epilogue == DC_EPI_STORE_POOL) {
                 const size_t opix = ((size_t)t.img * p.H + h) * (size_t)p.W + w;
                 optr = p.out + opix * p.out_stride + p.out_offset + t.n0;
                 if (p.epilogue == DC_EPI_STORE_POOL) {
@@ -149,16 +162,28 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
             float head_acc = p.head_b;
 
             const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)((as * NHALF + half) * BN);
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + (uint32_t)c0, v);
-                tmem_ld_wait();
-                const float4* b4 = reinterpret_cast<const float4*>(p.bias + bias_base + c0);
+            uint32_t vbuf[2][32];
+            tmem_ld32(taddr, vbuf[0]);
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+                const int c0 = c * 32;
+                uint32_t* v = vbuf[c & 1];
+                tmem_ld_wait_on(v);
+                if (c + 1 < BN / 32) tmem_ld32(taddr + (uint32_t)(c0 + 32), vbuf[(c + 1) & 1]);
+                if (p.epilogue == DC_EPI_UPSCATTER) {
+                    // GEMM column n = (a*2 + b)*Cout + co  ->  output pixel (2h + a, 2w + b), channel co
+                    const int n = t.n0 + c0;
+                    const int q = n / p.Cout;
+                    const int co = n - q * p.Cout;
+                    const size_t opix = ((size_t)t.img * (2 * p.H) + (2 * h + (q >> 1))) * (size_t)(2 * p.W) + (2 * w + (q & 1));
+                    optr = p.out + opix * p.out_stride + p.out_offset + co - c0;
+                    bias_base = co - c0;
+                }
+                const float4* b4 = reinterpret_cast<const float4*>(bias_s + bias_base + c0);
                 float x[32];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 b = __ldg(b4 + j);
+                    const float4 b = b4[j];
                     x[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
                     x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
                     x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
@@ -169,10 +194,10 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                     for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
                 }
                 if (p.epilogue == DC_EPI_HEAD) {
-                    const float4* w4 = reinterpret_cast<const float4*>(p.head_w + c0);
+                    const float4* w4 = reinterpret_cast<const float4*>(head_s + c0);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4 hw = __ldg(w4 + j);
+                        const float4 hw = w4[j];
                         head_acc = fmaf(x[4 * j + 0], hw.x, head_acc);
                         head_acc = fmaf(x[4 * j + 1], hw.y, head_acc);
                         head_acc = fmaf(x[4 * j + 2], hw.z, head_acc);
@@ -208,16 +233,21 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[as]);
             }
-
             if (p.epilogue == DC_EPI_HEAD && valid) {
                 const float prob = 1.0f / (1.0f + expf(-head_acc));              // torch.sigmoid, fp32
                 const size_t opix = ((size_t)t.img * p.H + h) * (size_t)p.W + w;
                 if (p.prob_out) p.prob_out[opix] = prob;
                 if (p.mask_out) p.mask_out[opix] = prob > p.thresh ? 1 : 0;      // qdb:56
             }
-          }
         }
     }
+}
+
+// bias (+ out_conv weights for the HEAD epilogue) -> shared memory, by every thread, before the role split
+__device__ __forceinline__ void stage_bias(const ConvParams& p, float* bias_s) {
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) bias_s[i] = p.bias[i];
+    if (p.epilogue == DC_EPI_HEAD)
+        for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) bias_s[p.Cout + i] = p.head_w[i];
 }
 
 template <int BN, int NSTAGES>
@@ -233,9 +263,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     uint64_t* tfull_bar = empty_bar + NSTAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* bias_s = reinterpret_cast<float*>(smem + NSTAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    stage_bias(p, bias_s);
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
@@ -318,7 +350,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
     } else if (warp >= EPI_WARP0) {
         // ------------------------------------------------------------------ epilogue
-        run_epilogue<BN, TILE_H, TILE_W>(p, warp - EPI_WARP0, lane, tmem_base, tfull_bar, tempty_bar);
+        run_epilogue<BN, TILE_H, TILE_W>(p, warp & 3, lane, (warp - EPI_WARP0) >> 2, tmem_base, tfull_bar, tempty_bar, bias_s);
     }
 
     tc_fence_before();
@@ -367,10 +399,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
     uint64_t* tempty_bar = tfull_bar + 2;
     uint64_t* w_bar = tempty_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+    float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NST = p.nstages;
 
+    stage_bias(p, bias_s);
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
@@ -471,12 +505,182 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
             __syncwarp();
         }
     } else if (warp >= EPI_WARP0) {
-        run_epilogue<BN, HT_H, HT_W, HT_NHALF>(p, warp - EPI_WARP0, lane, tmem_base, tfull_bar, tempty_bar);
+        run_epilogue<BN, HT_H, HT_W, HT_NHALF>(p, warp & 3, lane, (warp - EPI_WARP0) >> 2, tmem_base, tfull_bar, tempty_bar, bias_s);
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------- stem on tensor cores
+// First layer, Conv2d(3, 64, 3, padding=d, dilation=d) + BN + ReLU (reference models/model_2.py:10, :41-46),
+// fused with the input conversion of quantify_droplets_batch.py:45-46 (u8 -> /255 -> NCHW float).
+// K = 27 is far too thin for TMA boxes, so four producer warps build the im2col tile themselves, straight
+// into the 128B-swizzled K-major layout the MMA reads:
+//   u8 inputs are exact in bf16 (0..255) and the 1/255 is folded into the bf16 weights;
+//   grayscale input (the reference replicates it to 3 identical channels, qdb:41) folds the three channel
+//   weights into one, K = 9 -> one K=16 MMA per 128-pixel tile; RGB / float input: K = 27 -> two MMAs.
+// Roles (416 threads): warps 0-7 two epilogue groups, warps 8-11 im2col producers, warp 12 MMA + TMEM.
+constexpr int STEM_THREADS = 416;
+constexpr int STEM_PROD0 = 256;          // first producer thread
+constexpr int STEM_STAGES = 4;
+
+struct alignas(64) StemParams {
+    ConvParams c;            // epilogue fields (bias, out, strides, tiles); tensor maps unused
+    const void* in;
+    const float* weight;     // fp32 [64][27] = (co, ci*9 + ky*3 + kx), BatchNorm folded
+    int in_kind;
+};
+
+// Raw tap value (u8 as an integer, or the float's bits): converted only when the tile is packed, so the
+// prefetched loads of the next tile stay in flight instead of stalling on an early int->float conversion.
+template <int IN_KIND>
+__device__ __forceinline__ uint32_t stem_px_raw(const void* in, int img, int c, int y, int x, int H, int W) {
+    if (y < 0 || y >= H || x < 0 || x >= W) return 0u;                        // zero padding (0 and 0.0f)
+    if (IN_KIND == 0) return __float_as_uint(reinterpret_cast<const float*>(in)[(((size_t)img * 3 + c) * H + y) * W + x]);
+    if (IN_KIND == 1) return reinterpret_cast<const uint8_t*>(in)[((size_t)img * H + y) * W + x];
+    return reinterpret_cast<const uint8_t*>(in)[(((size_t)img * H + y) * W + x) * 3 + c];
+}
+template <int IN_KIND>
+__device__ __forceinline__ float stem_val(uint32_t raw) {
+    return IN_KIND == 0 ? __uint_as_float(raw) : (float)raw;
+}
+
+template <int IN_KIND>
+__global__ void __launch_bounds__(STEM_THREADS, 1) stem_tc_kernel(const __grid_constant__ StemParams sp) {
+    constexpr int BN = 64;
+    constexpr int NK = IN_KIND == 1 ? 1 : 2;          // K = 16 * NK
+    constexpr int KREAL = IN_KIND == 1 ? 9 : 27;
+    constexpr int TMEM_COLS = 2 * BN;
+    const ConvParams& p = sp.c;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* b_tile = smem;                                        // 64 rows x 128 B
+    uint8_t* a_ring = smem + BN * 128;                             // STEM_STAGES x (128 rows x 128 B)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(a_ring + STEM_STAGES * A_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STEM_STAGES;
+    uint64_t* tfull_bar = empty_bar + STEM_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    stage_bias(p, bias_s);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STEM_STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 12) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    if (warp >= 8 && warp < 12) {
+        // weights -> bf16 B tile (row = co, 16-byte chunk c of row r sits at chunk c ^ (r & 7))
+        const float scale = IN_KIND == 0 ? 1.0f : 1.0f / 255.0f;
+        for (int i = threadIdx.x - STEM_PROD0; i < BN * NK * 2; i += 128) {
+            const int co = i / (NK * 2), chunk = i % (NK * 2);
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int kk = chunk * 8 + j * 2 + u;
+                    float w = 0.f;
+                    if (kk < KREAL) {
+                        const float* wr = sp.weight + co * 27;
+                        w = IN_KIND == 1 ? (wr[kk] + wr[9 + kk] + wr[18 + kk]) : wr[kk];
+                    }
+                    v[u] = w * scale;
+                }
+                pk[j] = pack_bf16(v[0], v[1]);
+            }
+            *reinterpret_cast<uint4*>(b_tile + co * 128 + ((chunk ^ (co & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        run_epilogue<BN, TILE_H, TILE_W>(p, warp & 3, lane, warp >> 2, tmem_base, tfull_bar, tempty_bar, bias_s);
+    } else if (warp < 12) {
+        // ------------------------------------------------------------------ im2col producers: one tile row each
+        // The taps of tile i+1 are requested before tile i is converted and stored, so the global-load latency
+        // overlaps a whole tile of work instead of stalling every tile.
+        const int r = threadIdx.x - STEM_PROD0;
+        const int lh = r / TILE_W, lw = r % TILE_W;
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t cur[KREAL], nxt[KREAL];
+        auto fetch = [&](int tile, uint32_t* dst) {
+            const TileCoord t = decode_tile(p, tile, BN);
+            const int y = t.h0 + lh, x = t.w0 + lw;
+#pragma unroll
+            for (int kk = 0; kk < KREAL; ++kk) {
+                const int c = kk / 9, tap = kk % 9;
+                dst[kk] = stem_px_raw<IN_KIND>(sp.in, t.img, c, y + (tap / 3 - 1) * p.dil, x + (tap % 3 - 1) * p.dil, p.H, p.W);
+            }
+        };
+        if ((int)blockIdx.x < p.total_tiles) fetch(blockIdx.x, cur);
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int next = tile + gridDim.x;
+            if (next < p.total_tiles) fetch(next, nxt);
+            uint32_t pk[NK * 8];
+#pragma unroll
+            for (int j = 0; j < NK * 8; ++j)
+                pk[j] = pack_bf16(2 * j < KREAL ? stem_val<IN_KIND>(cur[2 * j]) : 0.f,
+                                  2 * j + 1 < KREAL ? stem_val<IN_KIND>(cur[2 * j + 1]) : 0.f);
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* row = a_ring + stage * A_STAGE_BYTES + r * 128;
+#pragma unroll
+            for (int chunk = 0; chunk < NK * 2; ++chunk)
+                *reinterpret_cast<uint4*>(row + ((chunk ^ (r & 7)) << 4)) =
+                    make_uint4(pk[4 * chunk], pk[4 * chunk + 1], pk[4 * chunk + 2], pk[4 * chunk + 3]);
+            fence_proxy_async();                    // generic-proxy stores -> visible to the tensor core (async proxy)
+            mbar_arrive(&full_bar[stage]);
+            if (++stage == STEM_STAGES) { stage = 0; phase ^= 1u; }
+#pragma unroll
+            for (int kk = 0; kk < KREAL; ++kk) cur[kk] = nxt[kk];
+        }
+    } else {
+        // ------------------------------------------------------------------ MMA issuer (warp-uniform loop)
+        const uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(b_tile));
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(&tempty_bar[as], aphase ^ 1u);
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_sw128(smem_u32(a_ring + stage * A_STAGE_BYTES));
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < NK; ++k)
+                    umma_bf16(tmem_base + (uint32_t)(as * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                              k ? 1u : 0u);
+                umma_commit(&empty_bar[stage]);
+                umma_commit(&tfull_bar[as]);
+            }
+            __syncwarp();
+            if (++stage == STEM_STAGES) { stage = 0; phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
@@ -515,7 +719,8 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dim
 template <int BN, int NSTAGES>
 int launch_variant(const ConvParams& p, cudaStream_t stream) {
     constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * KCHUNK * 2;
-    constexpr size_t SMEM = (size_t)NSTAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+    constexpr size_t SMEM = (size_t)NSTAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ +
+                            4096 + 256 /* bias (<= 1024 ch) + out_conv weights */;
     static_assert(SMEM <= 227 * 1024, "stage ring exceeds shared memory");
     static bool attr_done = false;
     if (!attr_done) {
@@ -535,7 +740,8 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
     DC_REQUIRE(a->kind == DC_KIND_CONV3X3 || a->kind == DC_KIND_UPCONV2, DC_EINVAL, "dc_conv_tc: kind %d", a->kind);
     DC_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0, DC_EINVAL, "dc_conv_tc: bad shape %d x %d x %d", a->B, a->H, a->W);
     DC_REQUIRE(a->Cin > 0 && a->Cin % KCHUNK == 0, DC_EINVAL, "dc_conv_tc: Cin %d must be a multiple of 64", a->Cin);
-    DC_REQUIRE(a->Cout > 0 && a->Cout % 64 == 0, DC_EINVAL, "dc_conv_tc: Cout %d must be a multiple of 64", a->Cout);
+    DC_REQUIRE(a->Cout > 0 && a->Cout % 64 == 0 && a->Cout <= 1024, DC_EINVAL,
+               "dc_conv_tc: Cout %d must be a multiple of 64 and at most 1024", a->Cout);
     DC_REQUIRE(a->in_stride >= a->Cin && a->in_stride % 8 == 0, DC_EINVAL, "dc_conv_tc: in_stride %d", a->in_stride);
     DC_REQUIRE(((uintptr_t)a->in & 15) == 0 && ((uintptr_t)a->weight & 15) == 0, DC_EINVAL,
                "dc_conv_tc: in / weight must be 16-byte aligned");
@@ -560,7 +766,8 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
                    DC_EINVAL, "dc_conv_tc: pool_out / pool_stride");
         DC_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0, DC_EINVAL, "dc_conv_tc: pooled layer needs even H, W");
     }
-    const int BN = a->Cout % 256 == 0 ? 256 : (a->Cout % 128 == 0 ? 128 : 64);
+    const int gemm_n = up ? 4 * a->Cout : a->Cout;      // upconv: the four output parities are one wide GEMM N
+    const int BN = gemm_n % 256 == 0 ? 256 : (gemm_n % 128 == 0 ? 128 : 64);
 
     ConvParams p;
     memset(&p, 0, sizeof(p));
@@ -573,7 +780,7 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
         // TMA and the MMA unit both take the swizzle phase from absolute address bits, so a region only needs
         // TMA's 128 B alignment, not a 1024 B one: regions are packed back to back
         const size_t w_bytes = (size_t)9 * (a->Cin / KCHUNK) * BN * KCHUNK * 2;
-        const size_t budget = 227 * 1024 - 1024 /* alignment slack */ - 512 /* barriers */;
+        const size_t budget = 227 * 1024 - 1024 /* alignment slack */ - 256 /* barriers */ - 768 /* bias + out_conv */;
         for (int nhalf = 2; nhalf >= 1 && !halo; --nhalf) {
             const int rw = HT_W * nhalf + 2 * a->dilation, rh = HT_H + 2 * a->dilation;
             const size_t region_stride = (size_t)rw * rh * KCHUNK * 2;
@@ -583,7 +790,7 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
                 halo_nhalf = nhalf;
                 p.region_w = rw; p.region_h = rh; p.region_stride = (int)region_stride;
                 p.nstages = nst > HALO_MAX_STAGES ? HALO_MAX_STAGES : (int)nst;
-                halo_smem = w_bytes + (size_t)p.nstages * region_stride + 1024 + 512;
+                halo_smem = w_bytes + (size_t)p.nstages * region_stride + 1024 + 256 + 768;
             }
         }
     }
@@ -650,6 +857,48 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
         case 128: return launch_variant<128, 6>(p, stream);
         default:  return launch_variant<64, 8>(p, stream);
     }
+}
+
+int launch_stem(const dc_stem_args_t* a, cudaStream_t stream) {
+    DC_REQUIRE(a && a->in && a->weight && a->bias && a->out, DC_EINVAL, "dc_stem: null pointer argument");
+    DC_REQUIRE(a->Cout == 64, DC_EINVAL, "dc_stem: Cout must be 64 (got %d)", a->Cout);
+    DC_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0 && a->dilation >= 1, DC_EINVAL, "dc_stem: bad shape");
+    DC_REQUIRE(a->out_stride % 8 == 0 && a->out_offset % 8 == 0 && a->out_stride >= a->out_offset + 64, DC_EINVAL,
+               "dc_stem: output stride/offset must be multiples of 8 channels");
+    DC_REQUIRE(((uintptr_t)a->out & 15) == 0, DC_EINVAL, "dc_stem: out must be 16-byte aligned");
+    DC_REQUIRE(a->in_kind >= 0 && a->in_kind <= 2, DC_EINVAL, "dc_stem: in_kind %d", a->in_kind);
+    StemParams sp;
+    memset(&sp, 0, sizeof(sp));
+    ConvParams& p = sp.c;
+    p.B = a->B; p.H = a->H; p.W = a->W; p.Cin = 3; p.Cout = 64;
+    p.dil = a->dilation; p.ntaps = 9; p.kchunks = 1;
+    p.tiles_w = ceil_div(a->W, TILE_W);
+    p.tiles_h = ceil_div(a->H, TILE_H);
+    p.n_tiles = 1;
+    const long long total = (long long)a->B * p.tiles_w * p.tiles_h;
+    DC_REQUIRE(total < (1ll << 31), DC_EINVAL, "dc_stem: too many tiles");
+    p.total_tiles = (int)total;
+    p.epilogue = DC_EPI_STORE; p.relu = 1;
+    p.bias = a->bias;
+    p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+    p.out_stride = a->out_stride; p.out_offset = a->out_offset;
+    sp.in = a->in; sp.weight = a->weight; sp.in_kind = a->in_kind;
+    constexpr size_t SMEM = 64 * 128 + (size_t)STEM_STAGES * A_STAGE_BYTES + 1024 + 256 + 512;
+    static bool attr_done = false;
+    if (!attr_done) {
+        DC_CUDA(cudaFuncSetAttribute(stem_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        DC_CUDA(cudaFuncSetAttribute(stem_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        DC_CUDA(cudaFuncSetAttribute(stem_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        attr_done = true;
+    }
+    const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    switch (a->in_kind) {
+        case 0: stem_tc_kernel<0><<<grid, STEM_THREADS, SMEM, stream>>>(sp); break;
+        case 1: stem_tc_kernel<1><<<grid, STEM_THREADS, SMEM, stream>>>(sp); break;
+        default: stem_tc_kernel<2><<<grid, STEM_THREADS, SMEM, stream>>>(sp); break;
+    }
+    DC_CUDA(cudaGetLastError());
+    return DC_OK;
 }
 
 }  // namespace dc
