@@ -135,38 +135,59 @@ def quantify(bin_mask: np.ndarray, min_area: int = 1, px_per_um: float | None = 
 _BLOCKS = [("enc1", 1), ("enc2", 2), ("enc3", 4), ("enc4", 8), ("bottleneck", 16)]
 
 
-def unetdc_forward(state_dict, x, dilations=(1, 2, 4, 8, 16)):
+def unetdc_forward(state_dict, x, dilations=(1, 2, 4, 8, 16), emulate_bf16=False, gray_input=False):
     """Plain PyTorch fp32 restatement of reference models/model_2.py:56-80 in eval mode.
 
     state_dict uses the reference's 136 keys; x: f32 [B,3,H,W]; returns f32 [B,1,H,W] probs.
-    ``dilations`` = (1,1,1,1,1) gives reference models/model.py:35-50 (plain UNet)."""
+    ``dilations`` = (1,1,1,1,1) gives reference models/model.py:35-50 (plain UNet).
+
+    ``emulate_bf16``: the same network with values rounded to bf16 at exactly the points where the CUDA
+    path stores bf16 (BatchNorm folded into the conv in fp32, folded weights -> bf16, every stored
+    activation -> bf16, fp32 accumulation, the last feature map and the 1x1 head kept in fp32).  It separates
+    "the kernels compute what they claim" (GPU vs this, tight) from "bf16 storage vs the fp32 reference"
+    (this vs fp32, inherent to the precision choice).  ``gray_input``: x holds u8 grey levels / 255 replicated
+    to 3 channels; the CUDA stem then feeds the exact integers and folds 1/255 and the 3 channels into the weights."""
     import torch
     import torch.nn.functional as F
 
     sd = {k: v.detach().to(torch.float32).cpu() for k, v in state_dict.items()}
+    r = (lambda t: t.to(torch.bfloat16).to(torch.float32)) if emulate_bf16 else (lambda t: t)
 
-    def cbr(t, p, idx, d):                                  # model_2.py:40-54 (one conv+BN+ReLU)
-        t = F.conv2d(t, sd[f"{p}.{idx}.weight"], sd[f"{p}.{idx}.bias"], padding=d, dilation=d)
-        t = F.batch_norm(t, sd[f"{p}.{idx + 1}.running_mean"], sd[f"{p}.{idx + 1}.running_var"],
-                         sd[f"{p}.{idx + 1}.weight"], sd[f"{p}.{idx + 1}.bias"], False, 0.0, 1e-5)
-        return F.relu(t)
+    def cbr(t, p, idx, d, first=False):                     # model_2.py:40-54 (one conv+BN+ReLU)
+        w, b = sd[f"{p}.{idx}.weight"], sd[f"{p}.{idx}.bias"]
+        g, beta = sd[f"{p}.{idx + 1}.weight"], sd[f"{p}.{idx + 1}.bias"]
+        mu, var = sd[f"{p}.{idx + 1}.running_mean"], sd[f"{p}.{idx + 1}.running_var"]
+        if not emulate_bf16:
+            t = F.conv2d(t, w, b, padding=d, dilation=d)
+            t = F.batch_norm(t, mu, var, g, beta, False, 0.0, 1e-5)
+            return F.relu(t)
+        scale = g / torch.sqrt(var + 1e-5)                  # fold in fp32, then round the weights
+        wf = w * scale.view(-1, 1, 1, 1)
+        bf = (b - mu) * scale + beta
+        if first and gray_input:
+            wq = r(wf.sum(1, keepdim=True) * (1.0 / 255.0))   # 3 identical channels -> one; 1/255 into the weights
+            t = torch.round(t[:, :1] * 255.0)                 # the exact u8 grey levels
+            return F.relu(F.conv2d(t, wq, bf, padding=d, dilation=d))
+        return F.relu(F.conv2d(r(t), r(wf), bf, padding=d, dilation=d))
 
-    def block(t, p, d):
-        return cbr(cbr(t, p, 0, d), p, 3, d)
+    def block(t, p, d, first=False, round_out=True):
+        t = r(cbr(t, p, 0, d, first))
+        t = cbr(t, p, 3, d)
+        return r(t) if round_out else t
 
     with torch.no_grad():
         x = x.detach().to(torch.float32).cpu()
         skips = []
         t = x
         for i, (name, _) in enumerate(_BLOCKS[:4]):          # model_2.py:58-61
-            t = block(t, name, dilations[i])
+            t = block(t, name, dilations[i], first=(i == 0))
             skips.append(t)
             t = F.max_pool2d(t, 2)
         t = block(t, "bottleneck", dilations[4])            # model_2.py:64
         for lvl in (4, 3, 2, 1):                            # model_2.py:67-77
-            t = F.conv_transpose2d(t, sd[f"upconv{lvl}.weight"], sd[f"upconv{lvl}.bias"], stride=2)
+            t = r(F.conv_transpose2d(t, r(sd[f"upconv{lvl}.weight"]), sd[f"upconv{lvl}.bias"], stride=2))
             t = torch.cat([t, skips[lvl - 1]], dim=1)
-            t = block(t, f"dec{lvl}", 1)
+            t = block(t, f"dec{lvl}", 1, round_out=(lvl > 1))
         t = F.conv2d(t, sd["out_conv.weight"], sd["out_conv.bias"])   # model_2.py:79
         return torch.sigmoid(t)                                        # model_2.py:80
 

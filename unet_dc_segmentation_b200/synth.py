@@ -20,11 +20,13 @@ import math
 import numpy as np
 
 
-def synthetic_image(size: int, index: int = 0, n_droplets: int | None = None) -> np.ndarray:
-    """u8 [size, size] grayscale frame: background 20 + N(0,3), planted Gaussian blobs."""
+def synthetic_image(size: int, index: int = 0, n_droplets: int | None = None, with_truth: bool = False):
+    """u8 [size, size] grayscale frame: background 20 + N(0,3), planted Gaussian blobs.
+    with_truth: also return the u8 {0,1} map of pixels where the planted blobs add >= 25 grey levels."""
     rs = np.random.RandomState(index)
     h = w = int(size)
     img = 20.0 + 3.0 * rs.standard_normal((h, w)).astype(np.float32)
+    blobs = np.zeros((h, w), np.float32)
     if n_droplets is None:
         n_droplets = max(1, int(round(60 * (h * w) / (256.0 * 256.0))))
     amp = rs.uniform(60, 200, n_droplets)
@@ -37,8 +39,11 @@ def synthetic_image(size: int, index: int = 0, n_droplets: int | None = None) ->
         x0, x1 = max(0, int(x) - r), min(w, int(x) + r + 1)
         yy = np.arange(y0, y1, dtype=np.float32)[:, None] - np.float32(y)
         xx = np.arange(x0, x1, dtype=np.float32)[None, :] - np.float32(x)
-        img[y0:y1, x0:x1] += np.float32(a) * np.exp(-(yy * yy + xx * xx) / np.float32(2 * s * s))
-    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+        blobs[y0:y1, x0:x1] += np.float32(a) * np.exp(-(yy * yy + xx * xx) / np.float32(2 * s * s))
+    out = np.clip(np.rint(img + blobs), 0, 255).astype(np.uint8)
+    if with_truth:
+        return out, (blobs >= 25.0).astype(np.uint8)
+    return out
 
 
 def synthetic_rgb(size: int, index: int = 0) -> np.ndarray:
@@ -76,24 +81,31 @@ def default_init_state_dict(seed: int = 0):
     return {k: v.clone() for k, v in UNetDC(3, 1).state_dict().items()}
 
 
-def calibrated_state_dict(seed: int = 0, calib_size: int = 128, n_calib: int = 3,
-                          foreground: float = 0.15, prob_thresh: float = 0.3,
-                          dilations=(1, 2, 4, 8, 16)):
-    """Default init + BatchNorm statistics calibration + out_conv bias placement.
+def calibrated_state_dict(seed: int = 0, calib_size: int = 512, n_calib: int = 1,
+                          prob_thresh: float = 0.3, dilations=(1, 2, 4, 8, 16), fit_head: bool = True):
+    """Default init + BatchNorm statistics calibration + a least-squares ``out_conv``.
 
     One training-mode pass (momentum 1.0) over ``n_calib`` synthetic frames sets every BN's
-    running_mean / running_var to that batch's statistics; ``out_conv.bias`` is then shifted
-    so that about ``foreground`` of the calibration pixels exceed ``prob_thresh``.
+    running_mean / running_var to that batch's statistics (without it the net outputs ~0.476 everywhere).
+    ``out_conv`` (the final 1x1 conv: 64 weights + 1 bias) is then fitted by ridge regression on the
+    random 64-channel features so that the logit is about +4 on the planted droplets and -6 elsewhere:
+    the 31 M convolution weights stay random-init, but the mask has droplet-like components
+    (IoU ~0.74 with the planted droplets, ~3 k components per 1024^2 frame at prob_thresh 0.3) instead of
+    ~100 k single-pixel speckles, which is what the labelling stage is sized for.  Calibrate at >= 512 px for
+    frames of 1024 px and up (at small sizes the dilated layers see mostly padding and the statistics differ).
     """
     import torch
     import torch.nn.functional as F
 
     sd = default_init_state_dict(seed)
-    frames = []
+    frames, truth = [], []
     for i in range(n_calib):
-        g = synthetic_image(calib_size, 1000 + i).astype(np.float32)
-        g = (g - g.min()) / max(1.0, float(g.max() - g.min()))       # crude background stretch
+        g, tr = synthetic_image(calib_size, 1000 + i, with_truth=True)
+        g = g.astype(np.float32)
+        g = np.clip(g - (np.median(g) - 9.0), 0.0, None)              # stand-in for the rolling-ball correction
+        g = (g - g.min()) / max(1.0, float(g.max() - g.min()))
         frames.append(np.repeat(g[None], 3, axis=0))
+        truth.append(tr)
     t = torch.from_numpy(np.stack(frames))
 
     def cbr(t, p, idx, d):
@@ -119,8 +131,17 @@ def calibrated_state_dict(seed: int = 0, calib_size: int = 128, n_calib: int = 3
             t = F.conv_transpose2d(t, sd[f"upconv{lvl}.weight"], sd[f"upconv{lvl}.bias"], stride=2)
             t = torch.cat([t, skips[lvl - 1]], dim=1)
             t = cbr(cbr(t, f"dec{lvl}", 0, 1), f"dec{lvl}", 3, 1)
-        logits = F.conv2d(t, sd["out_conv.weight"], sd["out_conv.bias"])
-        q = torch.quantile(logits.flatten(), 1.0 - foreground)
-        target = math.log(prob_thresh / (1.0 - prob_thresh))
-        sd["out_conv.bias"] = sd["out_conv.bias"] + (target - q)
+        if fit_head:
+            X = t.permute(0, 2, 3, 1).reshape(-1, 64).double()
+            X = torch.cat([X, torch.ones(X.shape[0], 1, dtype=torch.float64)], 1)
+            y = torch.from_numpy(np.stack(truth).reshape(-1).astype(np.float64)) * 10.0 - 6.0
+            wgt = 1.0 + 2.0 * (y > 0).double()                          # droplets are ~10 % of the pixels
+            A = (X * wgt[:, None]).T @ X + 1e-3 * X.shape[0] * torch.eye(65, dtype=torch.float64)
+            sol = torch.linalg.solve(A, (X * wgt[:, None]).T @ y)
+            sd["out_conv.weight"] = sol[:64].float().reshape(1, 64, 1, 1).clone()
+            sd["out_conv.bias"] = sol[64:].float().clone()
+        else:
+            logits = F.conv2d(t, sd["out_conv.weight"], sd["out_conv.bias"])
+            q = torch.quantile(logits.flatten(), 0.85)
+            sd["out_conv.bias"] = sd["out_conv.bias"] + (math.log(prob_thresh / (1.0 - prob_thresh)) - q)
     return sd
