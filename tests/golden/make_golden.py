@@ -180,6 +180,13 @@ def main():
     sys.path.insert(0, str(REPO))
     from unet_dc_segmentation_b200.synth import calibrated_state_dict, synthetic_image
 
+    # ---- state_dict contract of the reference module (keys, shapes, dtypes)
+    import json
+    ref_sd = RefUNetDC(3, 1).state_dict()
+    assert list(ref_sd.keys()) == list(RefUNet(3, 1).state_dict().keys())
+    (HERE / "state_dict_keys.json").write_text(json.dumps(
+        [[k, list(v.shape), str(v.dtype)] for k, v in ref_sd.items()], indent=0))
+
     # ---- rolling ball (reference function, real cv2)
     rb = {}
     for name, img, radius in rolling_ball_cases():

@@ -1,0 +1,117 @@
+"""CPU: host-side logic of the product -- weight folding / packing, the module's state_dict contract,
+the FLOP model behind roofline.achieved, the synthetic inputs."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def test_state_dict_contract_matches_reference():
+    """Same 136 keys, shapes and dtypes as reference models/model_2.py UNetDC (keys captured by make_golden.py)."""
+    from unet_dc_segmentation_b200 import UNet, UNetDC
+    want = json.loads((GOLDEN / "state_dict_keys.json").read_text())
+    for cls in (UNetDC, UNet):
+        sd = cls(3, 1).state_dict()
+        got = [[k, list(v.shape), str(v.dtype)] for k, v in sd.items()]
+        assert got == want
+    assert len(want) == 136
+    assert sum(int(np.prod(s)) for k, s, _ in want if "running" not in k and "num_batches" not in k) == 31_043_521
+
+
+def test_load_state_dict_roundtrip_and_constructor_contract():
+    from unet_dc_segmentation_b200 import UNetDC
+    from unet_dc_segmentation_b200.synth import calibrated_state_dict
+    sd = calibrated_state_dict(seed=1, calib_size=32, n_calib=1)
+    m = UNetDC(in_channels=3, out_channels=1)
+    missing = m.load_state_dict(sd)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    with pytest.raises(ValueError):
+        UNetDC(1, 1)
+
+
+def test_bn_fold_equals_conv_then_bn():
+    from unet_dc_segmentation_b200.model import fold_conv_bn
+    g = torch.Generator().manual_seed(0)
+    w, b = torch.randn(8, 4, 3, 3, generator=g), torch.randn(8, generator=g)
+    gamma, beta = torch.rand(8, generator=g) + 0.5, torch.randn(8, generator=g)
+    mean, var = torch.randn(8, generator=g), torch.rand(8, generator=g) + 0.1
+    x = torch.randn(2, 4, 9, 9, generator=g)
+    want = F.batch_norm(F.conv2d(x, w, b, padding=2, dilation=2), mean, var, gamma, beta, False, 0.0, 1e-5)
+    wf, bf = fold_conv_bn(w, b, gamma, beta, mean, var)
+    np.testing.assert_allclose(F.conv2d(x, wf, bf, padding=2, dilation=2).numpy(), want.numpy(), atol=2e-5)
+
+
+def test_pack_layouts():
+    from unet_dc_segmentation_b200.model import pack_conv3x3, pack_upconv
+    w = torch.arange(2 * 3 * 9, dtype=torch.float32).reshape(2, 3, 3, 3)
+    p = pack_conv3x3(w).float()
+    assert p.shape == (2, 27)
+    for co in range(2):
+        for ci in range(3):
+            for ky in range(3):
+                for kx in range(3):
+                    assert p[co, (ky * 3 + kx) * 3 + ci] == w[co, ci, ky, kx]
+    wt = torch.arange(4 * 5 * 4, dtype=torch.float32).reshape(4, 5, 2, 2)        # [Cin, Cout, 2, 2]
+    q = pack_upconv(wt).float()
+    assert q.shape == (20, 4)
+    for ci in range(4):
+        for co in range(5):
+            for a in range(2):
+                for b in range(2):
+                    assert q[(a * 2 + b) * 5 + co, ci] == wt[ci, co, a, b]
+    # the packed matrix reproduces conv_transpose2d(k=2, s=2): out[.., 2i+a, 2j+b] = W_q @ x[.., i, j]
+    x = torch.randn(1, 4, 3, 3)
+    y = F.conv_transpose2d(x, wt, None, stride=2)
+    yq = torch.einsum("nk,bkij->bnij", q, x).reshape(1, 2, 2, 5, 3, 3)
+    for a in range(2):
+        for b in range(2):
+            np.testing.assert_allclose(y[0, :, a::2, b::2].numpy(), yq[0, a, b].numpy(), rtol=1e-5, atol=1e-4)
+
+
+def test_flop_model_matches_baseline_md():
+    from unet_dc_segmentation_b200 import workload as wl
+    for size, tflop, frac in ((256, 0.0963, 0.8905), (512, 0.3853, 0.9363), (1024, 1.5414, 0.9659),
+                              (2048, 6.1654, 0.9824), (4096, 24.662, 0.9911)):
+        nominal = wl.forward_flops(size, size, in_bounds=False)
+        assert nominal == 2 * 734_976 * size * size
+        assert abs(nominal / 1e12 - tflop) / tflop < 5e-4          # BASELINE.md prints 4 significant digits
+        assert abs(wl.forward_flops(size, size) / nominal - frac) < 1e-4
+    names, fl = wl.launch_flops(1024, 1024)
+    assert len(names) == 22 and names[0] == "enc1.0" and names[-1] == "dec1.3"
+    assert abs(sum(fl) - wl.forward_flops(1024, 1024)) < 1.0
+    # plain UNet (models/model.py) = dilation 1 everywhere: same nominal FLOPs, more in-bounds taps
+    assert wl.forward_flops(256, 256, (1, 1, 1, 1, 1)) > wl.forward_flops(256, 256)
+
+
+def test_synthetic_inputs_are_seeded():
+    from unet_dc_segmentation_b200.synth import synthetic_image, synthetic_mask, synthetic_rgb
+    a, b = synthetic_image(64, 5), synthetic_image(64, 5)
+    assert a.dtype == np.uint8 and a.shape == (64, 64) and np.array_equal(a, b)
+    assert not np.array_equal(a, synthetic_image(64, 6))
+    img, truth = synthetic_image(64, 5, with_truth=True)
+    assert np.array_equal(img, a) and set(np.unique(truth)) <= {0, 1} and 0 < truth.mean() < 0.5
+    rgb = synthetic_rgb(32, 1)
+    assert rgb.shape == (32, 32, 3) and np.array_equal(rgb[..., 0], rgb[..., 2])
+    m = synthetic_mask(128, 50, seed=2)
+    assert set(np.unique(m)) == {0, 1}
+
+
+def test_shard_helpers():
+    from unet_dc_segmentation_b200 import shard
+    assert shard.shard_indices(10, 1, 4) == [1, 5, 9]
+    assert sum((shard.shard_indices(4096, r, 8) for r in range(8)), []).__len__() == 4096
+    assert shard.batches([0, 2, 4, 6, 8], 2) == [[0, 2], [4, 6], [8]]
+    per_rank = [[(i, f"t{i}") for i in shard.shard_indices(7, r, 3)] for r in range(3)]
+    assert shard.merge_in_frame_order(per_rank, 7) == [f"t{i}" for i in range(7)]
+    with pytest.raises(ValueError):
+        shard.merge_in_frame_order(per_rank[:2], 7)
+    with pytest.raises(ValueError):
+        shard.merge_in_frame_order(per_rank + [[(0, "dup")]], 7)
+    assert shard.gather_results([(0, "a"), (1, "b")], 2) == ["a", "b"]       # no process group: identity
