@@ -1,0 +1,74 @@
+"""GPU: the drop-in CLI (unet_dc_segmentation_b200/cli.py <- reference quantify_droplets_batch.py:100-201):
+same flags, same output files and columns; every per-image table equals the oracle's quantify() of the mask
+PNG the CLI itself wrote (bit-exact through the CSV round trip)."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def workdir(tmp_path_factory):
+    import torch
+    from PIL import Image
+    from unet_dc_segmentation_b200.synth import calibrated_state_dict, synthetic_image
+    d = tmp_path_factory.mktemp("cli")
+    (d / "in").mkdir()
+    for i in range(3):
+        Image.fromarray(synthetic_image(96, 400 + i, n_droplets=10)).save(d / "in" / f"frame{i}.png")
+    Image.fromarray(synthetic_image(128, 410, n_droplets=14)[:80, :112]).save(d / "in" / "wide.tif")
+    (d / "in" / "notes.txt").write_text("not an image")
+    torch.save(calibrated_state_dict(seed=0, calib_size=64, n_calib=2), d / "ckpt.pth")
+    return d
+
+
+def test_cli_native_size_outputs(cuda_device, workdir):
+    import cv2
+    import pandas as pd
+    from unet_dc_segmentation_b200 import cli
+    out = workdir / "out_native"
+    rc = cli.main(["--img_dir", str(workdir / "in"), "--ckpt_path", str(workdir / "ckpt.pth"), "--out_dir", str(out),
+                   "--batch", "2", "--px_per_micron", "3.45", "--save_overlays", "--skip_histogram", "--img_size", "96"])
+    assert rc == 0
+    names = ["frame0", "frame1", "frame2", "wide"]
+    ref_cols = list(load_golden("reference_outputs.npz")["columns"])          # the reference's own all_droplets.csv header
+    frames = []
+    for n in names:
+        mask = cv2.imread(str(out / "predicted_masks" / f"{n}_pred.png"), cv2.IMREAD_GRAYSCALE)
+        assert mask is not None and set(np.unique(mask)) <= {0, 255}
+        assert mask.shape == ((80, 112) if n == "wide" else (96, 96))
+        assert (out / "overlays" / f"{n}_overlay.png").exists()
+        df = pd.read_csv(out / f"{n}_droplets.csv", float_precision="round_trip")   # the default parser is 1 ulp sloppy
+        want = oracle.quantify(mask // 255, 1, 3.45)
+        if want.empty:
+            assert len(df) == 0
+            continue
+        assert list(df.columns) == ref_cols
+        for c in want.columns:
+            np.testing.assert_array_equal(df[c].to_numpy(), want[c].to_numpy(), err_msg=f"{n}.{c}")
+        frames.append(df)
+    summary = pd.read_csv(out / "summary_per_image.csv")
+    assert list(summary.columns) == ["filename", "droplet_count", "total_area_px"]
+    assert list(summary["filename"]) == ["frame0.png", "frame1.png", "frame2.png", "wide.tif"]       # sorted, qdb:143
+    combined = pd.read_csv(out / "all_droplets.csv", float_precision="round_trip")
+    assert len(combined) == int(summary["droplet_count"].sum()) and combined["area"].sum() == summary["total_area_px"].sum()
+    assert (out / "all_droplets.xlsx").exists() or (out / "all_droplets_noexcel.csv").exists()       # qdb:171-181
+    stats = pd.read_csv(out / "droplet_size_stats.csv", index_col=0).iloc[:, 0]
+    d = combined["eq_diam_micron"]
+    np.testing.assert_allclose([stats["mean"], stats["median"], stats["std"]], [d.mean(), d.median(), d.std(ddof=1)])
+
+
+def test_cli_default_img_size_resizes_like_the_reference(cuda_device, workdir):
+    """IMG_SIZE = 512 (qdb:30): frames are up-sized for the network and the mask comes back at the original size."""
+    import cv2
+    from unet_dc_segmentation_b200 import cli
+    out = workdir / "out_512"
+    assert cli.main(["--img_dir", str(workdir / "in"), "--ckpt_path", str(workdir / "ckpt.pth"), "--out_dir", str(out),
+                     "--batch", "8", "--skip_excel", "--skip_histogram"]) == 0
+    mask = cv2.imread(str(out / "predicted_masks" / "wide_pred.png"), cv2.IMREAD_GRAYSCALE)
+    assert mask.shape == (80, 112)
+    assert not (out / "all_droplets.xlsx").exists() and not (out / "all_droplets_noexcel.csv").exists()
+    assert not (out / "overlays").exists()

@@ -1,0 +1,204 @@
+"""Drop-in front end for reference quantify_droplets_batch.py: same functions, same flags, same output files,
+with the device work done by libunetdc_b200 (rolling ball, UNetDC, threshold, labelling, droplet table).
+
+    python -m unet_dc_segmentation_b200.cli --img_dir IN --ckpt_path model.pth --out_dir OUT [flags as the reference]
+
+Function-for-function (reference file:line):
+    load_model   qdb:34-37     preprocess  qdb:40-46     run_batch  qdb:48-79     quantify  qdb:81-95
+    main         qdb:100-201   (argparse flags qdb:101-128; report files qdb:163-199, read back by gui_qt.py:470-589)
+
+What stays on the host, exactly as in the reference: PIL decode, the two cv2.resize calls (which are bilinear --
+the reference passes the interpolation flag in the `dst` slot, SURVEY.md 0.2 -- and the identity when the frame
+is already IMG_SIZE), PNG / CSV / XLSX writing, overlays.  `--img_size` (default 512 = the reference's IMG_SIZE
+constant) and `--gpus` are the only additions; with `--gpus N` (under torchrun) frames are sharded i -> rank
+i mod N and the tables are gathered on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from .model import UNetDC
+from .morphology import rolling_ball_correction_rgb
+from .quantify import quantify
+
+IMG_SIZE = 512                     # qdb:30
+SUFFIXES = {".png", ".jpg", ".jpeg", ".tif", ".tiff"}     # qdb:143-144
+
+
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("unet_dc_segmentation_b200 needs an sm_100 GPU; there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def load_model(ckpt) -> UNetDC:
+    """qdb:34-37: build UNetDC(3, 1), load the checkpoint's state_dict, eval mode on the GPU."""
+    dev = _device()
+    m = UNetDC(in_channels=3, out_channels=1)
+    m.load_state_dict(torch.load(ckpt, map_location=dev))
+    return m.to(dev).eval()
+
+
+def preprocess(path, background_radius: int, img_size: int | None = None):
+    """qdb:40-46: decode to RGB, rolling-ball correct, resize to the network size, /255, HWC -> CHW."""
+    import cv2
+    from PIL import Image
+    size = IMG_SIZE if img_size is None else int(img_size)
+    im = np.array(Image.open(path).convert("RGB"))
+    oh, ow = im.shape[:2]
+    im = rolling_ball_correction_rgb(im, background_radius)
+    if (oh, ow) != (size, size):
+        im = cv2.resize(im, (size, size), interpolation=cv2.INTER_LINEAR)      # what qdb:44 effectively does
+    im = im.astype(np.float32) / 255.0
+    return torch.from_numpy(im).permute(2, 0, 1), (oh, ow)
+
+
+@torch.no_grad()
+def run_batch(tensors, meta, model, mask_dir, overlay_dir, thresh, min_area, px_per_um, per_image_rows, all_props):
+    """qdb:48-79: forward one batch, then per image: mask, PNG, droplet table, CSV, summary row, overlay."""
+    import cv2
+    dev = next(model.parameters()).device
+    batch = torch.stack(tensors).to(dev)
+    probs = model(batch)
+    masks = (probs[:, 0] > thresh).to(torch.uint8).cpu().numpy()
+    for i in range(len(tensors)):
+        fpath, (oh, ow) = meta[i]
+        name = Path(fpath).stem
+        mask = masks[i]
+        if mask.shape != (oh, ow):
+            mask = cv2.resize(mask, (ow, oh), interpolation=cv2.INTER_LINEAR)   # what qdb:57 effectively does
+        cv2.imwrite(str(Path(mask_dir) / f"{name}_pred.png"), mask * 255)
+        df = quantify(mask, min_area, px_per_um)
+        df.insert(0, "filename", Path(fpath).name)
+        df.to_csv(Path(mask_dir).parent / f"{name}_droplets.csv", index=False)
+        all_props.append(df)
+        per_image_rows.append({"filename": Path(fpath).name, "droplet_count": len(df),
+                               "total_area_px": df["area"].sum() if not df.empty else 0})
+        if overlay_dir is not None:
+            img = cv2.imread(str(fpath))
+            if img is not None:
+                cnts, _ = cv2.findContours(mask, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+                cv2.drawContours(img, cnts, -1, (0, 255, 0), 2)
+                cv2.imwrite(str(Path(overlay_dir) / f"{name}_overlay.png"), img)
+
+
+def write_reports(out_dir: Path, per_image_rows, all_props, skip_excel: bool, skip_histogram: bool) -> None:
+    """qdb:163-199: summary_per_image.csv, all_droplets.csv (+xlsx or the noexcel copy), stats, histogram."""
+    import pandas as pd
+    summary_df = pd.DataFrame(per_image_rows)
+    summary_df.to_csv(out_dir / "summary_per_image.csv", index=False)
+    if not all_props:
+        return
+    combined = pd.concat(all_props, ignore_index=True)
+    combined.to_csv(out_dir / "all_droplets.csv", index=False)
+    if not skip_excel:
+        try:
+            import xlsxwriter  # noqa: F401
+            with pd.ExcelWriter(out_dir / "all_droplets.xlsx", engine="xlsxwriter") as xw:
+                combined.to_excel(xw, index=False, sheet_name="droplets")
+                summary_df.to_excel(xw, index=False, sheet_name="per_image")
+        except (ImportError, AttributeError):
+            combined.to_csv(out_dir / "all_droplets_noexcel.csv", index=False)
+            print("Skipped Excel file; install 'xlsxwriter' if you need .xlsx output.")
+    size_col = "eq_diam_micron" if "eq_diam_micron" in combined.columns else "equivalent_diameter"
+    if size_col in combined.columns:
+        stats = combined[size_col].describe()[["mean", "50%", "std"]].rename({"50%": "median"})
+        stats.to_csv(out_dir / "droplet_size_stats.csv")
+        if not skip_histogram:
+            try:
+                import matplotlib
+                matplotlib.use("Agg")
+                import matplotlib.pyplot as plt
+            except ImportError:
+                print("Skipped histogram; matplotlib is not installed.")
+                return
+            plt.figure(figsize=(6, 4))
+            plt.hist(combined[size_col], bins=40)
+            plt.xlabel("Diameter (µm)" if "micron" in size_col else "Diameter (pixels)")
+            plt.ylabel("Count")
+            plt.title("Droplet size distribution")
+            plt.tight_layout()
+            plt.savefig(out_dir / "size_histogram.png", dpi=300)
+            plt.close()
+
+
+def build_parser() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser("Segment lipid droplets and build a report")
+    p.add_argument("--img_dir", required=True)
+    p.add_argument("--ckpt_path", default="best_UNetDC_focal_model.pth")
+    p.add_argument("--out_dir", default="quant_results")
+    p.add_argument("--batch", type=int, default=8)
+    p.add_argument("--prob_thresh", type=float, default=0.3)
+    p.add_argument("--min_area", type=int, default=1, help="ignore objects smaller than this (pixels²)")
+    p.add_argument("--px_per_micron", type=float, help="pixels per micron for physical-unit columns")
+    p.add_argument("--save_overlays", action="store_true")
+    p.add_argument("--background_radius", type=int, default=50, help="radius for rolling ball background correction")
+    p.add_argument("--skip_excel", action="store_true", help="skip generation of the Excel workbook")
+    p.add_argument("--skip_histogram", action="store_true", help="skip histogram plot generation")
+    p.add_argument("--img_size", type=int, default=IMG_SIZE,
+                   help="network input size (reference constant IMG_SIZE = 512); use the frame size for native-resolution inference")
+    return p
+
+
+def main(argv=None) -> int:
+    import os
+    args = build_parser().parse_args(argv)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl")
+
+    in_dir, out_dir = Path(args.img_dir), Path(args.out_dir)
+    mask_dir = out_dir / "predicted_masks"
+    overlay_dir = out_dir / "overlays" if args.save_overlays else None
+    out_dir.mkdir(parents=True, exist_ok=True)
+    mask_dir.mkdir(exist_ok=True)
+    if overlay_dir:
+        overlay_dir.mkdir(exist_ok=True)
+
+    model = load_model(args.ckpt_path)
+    images = sorted(p for p in in_dir.iterdir() if p.suffix.lower() in SUFFIXES)
+    from . import shard
+    mine = shard.shard_indices(len(images), rank, world)
+
+    tensors, meta, idx = [], [], []
+    per_image_rows, all_props = [], []
+
+    def flush():
+        run_batch(tensors, meta, model, mask_dir, overlay_dir, args.prob_thresh, args.min_area, args.px_per_micron,
+                  per_image_rows, all_props)
+        tensors.clear()
+        meta.clear()
+
+    for i in mine:
+        t, osize = preprocess(images[i], args.background_radius, args.img_size)
+        tensors.append(t)
+        meta.append((str(images[i]), osize))
+        idx.append(i)
+        if len(tensors) == args.batch:
+            flush()
+    if tensors:
+        flush()
+
+    local = [(i, (row, df)) for i, row, df in zip(idx, per_image_rows, all_props)]
+    merged = shard.gather_results(local, len(images), dst=0)
+    if rank == 0:
+        write_reports(out_dir, [m[0] for m in merged], [m[1] for m in merged], args.skip_excel, args.skip_histogram)
+        print("\n All done. Outputs are in ", out_dir)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
