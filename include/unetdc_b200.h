@@ -91,9 +91,12 @@ typedef struct dc_conv_args {
 
 int dc_conv_tc(const dc_conv_args_t* args, void* stream);
 
-/* First layer (Cin = 3, models/model_2.py:10 first conv): direct fp32 convolution.
- * in_kind 0: fp32 NCHW [B,3,H,W] (the nn.Module contract)
- * in_kind 1: u8 planar [B,H,W]   grayscale, replicated to 3 channels, scaled by 1/255
+/* First layer (Cin = 3, models/model_2.py:10 first conv) + BatchNorm + ReLU on tcgen05: the im2col tile is
+ * built in shared memory by producer warps (K = 27 -> 32, or 9 -> 16 for grayscale where the three identical
+ * channels are folded into one), operands in bf16, fp32 accumulation.
+ * in_kind 0: fp32 NCHW [B,3,H,W] (the nn.Module contract; rounded to bf16)
+ * in_kind 1: u8 planar [B,H,W]   grayscale, replicated to 3 channels, scaled by 1/255 (exact: u8 fits bf16,
+ *            the 1/255 is folded into the weights)
  * in_kind 2: u8 HWC    [B,H,W,3] scaled by 1/255               (quantify_droplets_batch.py:41-45)
  * weight fp32 [64][3][3][3] (BN folded), bias fp32 [64]; out bf16 NHWC. */
 typedef struct dc_stem_args {
