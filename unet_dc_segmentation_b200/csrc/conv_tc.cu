@@ -66,7 +66,7 @@ struct alignas(64) ConvParams {
     float* prob_out;
     uint8_t* mask_out;
     // conv_halo_kernel only
-    int region_w, region_h, region_stride, nstages;
+    int region_w, region_h, region_stride, nstages, nbstages;
 };
 
 struct TileCoord {
@@ -367,6 +367,7 @@ constexpr int HT_H = 16, HT_W = 8;      // 16 x 8 output patch: each 8-pixel row
 // TMEM tiles -- two independent MMA chains hide the latency of back-to-back accumulating MMAs at N = 64 / 128.
 // NHALF = 1 is kept for layers whose resident weights leave no room for two 16-wide regions.
 constexpr int HALO_MAX_STAGES = 8;
+constexpr int HALO_BAR_BYTES = 512;     // 4 x 8 stage barriers + TMEM / weight barriers + TMEM slot
 
 // K-major SWIZZLE_128B descriptor whose 8-row groups are `sbo_bytes` apart and whose start may sit on any
 // 128 B row of a 1024 B-aligned region.  Measured on B200 (tests/test_gpu_conv.py halo cases): the MMA unit
@@ -382,7 +383,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_strided(uint32_t smem_addr, 
     return d;
 }
 
-template <int BN, int HT_NHALF>
+// WRES = true : the weights of the whole layer are loaded once and stay in shared memory (9*Cin*BN*2 bytes).
+// WRES = false: they do not fit (Cin*BN large), so (tap, chunk) slices stream through a ring of p.nbstages
+//               BN x 64 tiles; each slice still feeds HT_NHALF * 4 MMAs and the activations are still loaded
+//               once per chunk instead of once per tap, which is what keeps these layers off the L2 roofline.
+template <int BN, int HT_NHALF, bool WRES>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvParams p) {
     constexpr int HT_TW = HT_W * HT_NHALF;
     constexpr int W_TILE_BYTES = BN * KCHUNK * 2;     // one (tap, chunk) slice of the weights
@@ -390,19 +395,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int n_wtiles = 9 * p.kchunks;
-    uint8_t* w_res = smem;                                             // resident weights
+    const int n_wtiles = WRES ? 9 * p.kchunks : p.nbstages;
+    uint8_t* w_res = smem;                                             // resident weights, or the weight ring
     uint8_t* a_ring = smem + n_wtiles * W_TILE_BYTES;                  // haloed activation regions
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(a_ring + p.nstages * p.region_stride);
     uint64_t* empty_bar = full_bar + HALO_MAX_STAGES;
-    uint64_t* tfull_bar = empty_bar + HALO_MAX_STAGES;
+    uint64_t* bfull_bar = empty_bar + HALO_MAX_STAGES;
+    uint64_t* bempty_bar = bfull_bar + HALO_MAX_STAGES;
+    uint64_t* tfull_bar = bempty_bar + HALO_MAX_STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint64_t* w_bar = tempty_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
-    float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+    float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + HALO_BAR_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NST = p.nstages;
+    const int NBS = p.nbstages;
 
     stage_bias(p, bias_s);
     if (warp == 0 && lane == 0) {
@@ -410,7 +418,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
         tma_prefetch_desc(&p.tmB);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < HALO_MAX_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1);
+            mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1);
+        }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
         mbar_init(w_bar, 1);
         fence_barrier_init();
@@ -425,17 +436,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t region_bytes = (uint32_t)(p.region_w * p.region_h * KCHUNK * 2);
 
+    // taps whose window lies wholly in the zero padding contribute nothing: both roles skip them
+    auto tile_tap_mask = [&](const TileCoord& t) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            int dy, dx;
+            if (tap_offset<HT_H, HT_TW>(p, t, tap, dy, dx)) m |= 1u << tap;
+        }
+        return m;
+    };
+
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (warp-uniform loop)
-        if (elect_one()) {
-            mbar_expect_tx(w_bar, (uint32_t)(n_wtiles * W_TILE_BYTES));
-            for (int j = 0; j < n_wtiles; ++j) tma_load_2d(w_res + j * W_TILE_BYTES, &p.tmB, w_bar, j * KCHUNK, 0);
+        if (WRES) {
+            if (elect_one()) {
+                mbar_expect_tx(w_bar, (uint32_t)(n_wtiles * W_TILE_BYTES));
+                for (int j = 0; j < n_wtiles; ++j) tma_load_2d(w_res + j * W_TILE_BYTES, &p.tmB, w_bar, j * KCHUNK, 0);
+            }
+            __syncwarp();
         }
-        __syncwarp();
-        int stage = 0;
-        uint32_t phase = 0;
+        int stage = 0, bstage = 0;
+        uint32_t phase = 0, bphase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const TileCoord t = decode_tile<HT_H, HT_TW>(p, tile, BN);
+            const uint32_t tap_mask = WRES ? 0u : tile_tap_mask(t);
             for (int kc = 0; kc < p.kchunks; ++kc) {
                 mbar_wait(&empty_bar[stage], phase ^ 1u);
                 if (elect_one()) {
@@ -445,6 +470,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
                 }
                 __syncwarp();
                 if (++stage == NST) { stage = 0; phase ^= 1u; }
+                if (!WRES) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (!((tap_mask >> tap) & 1u)) continue;
+                        mbar_wait(&bempty_bar[bstage], bphase ^ 1u);
+                        if (elect_one()) {
+                            mbar_expect_tx(&bfull_bar[bstage], W_TILE_BYTES);
+                            tma_load_2d(w_res + bstage * W_TILE_BYTES, &p.tmB, &bfull_bar[bstage],
+                                        (tap * p.kchunks + kc) * KCHUNK, 0);
+                        }
+                        __syncwarp();
+                        if (++bstage == NBS) { bstage = 0; bphase ^= 1u; }
+                    }
+                }
             }
         }
     } else if (warp == 1) {
@@ -454,21 +492,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
         const uint32_t w_addr = smem_u32(w_res);
         const uint32_t tap_dy_bytes = (uint32_t)(p.dil * p.region_w) * 128u;     // one tap row down
         const uint32_t tap_dx_bytes = (uint32_t)p.dil * 128u;                    // one tap column right
-        int stage = 0;
-        uint32_t phase = 0;
+        int stage = 0, bstage = 0;
+        uint32_t phase = 0, bphase = 0;
         int it = 0;
-        mbar_wait(w_bar, 0);
+        if (WRES) mbar_wait(w_bar, 0);
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const TileCoord t = decode_tile<HT_H, HT_TW>(p, tile, BN);
             const int as = it & 1;
             const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-            // taps whose window lies wholly in the zero padding contribute nothing: skip their MMAs
-            uint32_t tap_mask = 0;
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-                int dy, dx;
-                if (tap_offset<HT_H, HT_TW>(p, t, tap, dy, dx)) tap_mask |= 1u << tap;
-            }
+            const uint32_t tap_mask = tile_tap_mask(t);
             mbar_wait(&tempty_bar[as], aphase ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(as * HT_NHALF * BN);
@@ -477,28 +509,55 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t region = smem_u32(a_ring + stage * p.region_stride);
-                const uint32_t w_chunk = w_addr + (uint32_t)(kc * W_TILE_BYTES);
-                const uint32_t w_tap_stride = (uint32_t)(p.kchunks * W_TILE_BYTES);
-                if (elect_one()) {
+                if (WRES) {
+                    const uint32_t w_chunk = w_addr + (uint32_t)(kc * W_TILE_BYTES);
+                    const uint32_t w_tap_stride = (uint32_t)(p.kchunks * W_TILE_BYTES);
+                    if (elect_one()) {
 #pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            if (!((tap_mask >> tap) & 1u)) continue;
+                            const uint32_t a_addr = region + (uint32_t)(tap / 3) * tap_dy_bytes + (uint32_t)(tap % 3) * tap_dx_bytes;
+                            const uint64_t adesc = umma_desc_sw128_strided(a_addr, sbo);
+                            const uint64_t bdesc = umma_desc_sw128(w_chunk + (uint32_t)tap * w_tap_stride);
+#pragma unroll
+                            for (int k = 0; k < KCHUNK / 16; ++k) {
+#pragma unroll
+                                for (int half = 0; half < HT_NHALF; ++half)   // right patch = 8 region rows (1024 B) further
+                                    umma_bf16(d_tmem + (uint32_t)(half * BN), adesc + (uint64_t)(2 * k + 64 * half),
+                                              bdesc + (uint64_t)(2 * k), idesc, accumulate);
+                                accumulate = 1;
+                            }
+                        }
+                        umma_commit(&empty_bar[stage]);
+                    }
+                    __syncwarp();
+                    accumulate = 1;
+                } else {
+#pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
                         if (!((tap_mask >> tap) & 1u)) continue;
+                        mbar_wait(&bfull_bar[bstage], bphase);
+                        tc_fence_after();
                         const uint32_t a_addr = region + (uint32_t)(tap / 3) * tap_dy_bytes + (uint32_t)(tap % 3) * tap_dx_bytes;
                         const uint64_t adesc = umma_desc_sw128_strided(a_addr, sbo);
-                        const uint64_t bdesc = umma_desc_sw128(w_chunk + (uint32_t)tap * w_tap_stride);
+                        const uint64_t bdesc = umma_desc_sw128(w_addr + (uint32_t)(bstage * W_TILE_BYTES));
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < KCHUNK / 16; ++k) {
+                            for (int k = 0; k < KCHUNK / 16; ++k) {
 #pragma unroll
-                            for (int half = 0; half < HT_NHALF; ++half)   // right patch = 8 region rows (1024 B) further
-                                umma_bf16(d_tmem + (uint32_t)(half * BN), adesc + (uint64_t)(2 * k + 64 * half),
-                                          bdesc + (uint64_t)(2 * k), idesc, accumulate);
-                            accumulate = 1;
+                                for (int half = 0; half < HT_NHALF; ++half)
+                                    umma_bf16(d_tmem + (uint32_t)(half * BN), adesc + (uint64_t)(2 * k + 64 * half),
+                                              bdesc + (uint64_t)(2 * k), idesc, (k == 0) ? accumulate : 1u);
+                            }
+                            umma_commit(&bempty_bar[bstage]);
                         }
+                        __syncwarp();
+                        accumulate = 1;
+                        if (++bstage == NBS) { bstage = 0; bphase ^= 1u; }
                     }
-                    umma_commit(&empty_bar[stage]);
+                    if (elect_one()) umma_commit(&empty_bar[stage]);
+                    __syncwarp();
                 }
-                __syncwarp();
-                accumulate = 1;
                 if (++stage == NST) { stage = 0; phase ^= 1u; }
             }
             if (elect_one()) umma_commit(&tfull_bar[as]);
@@ -772,25 +831,40 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
     ConvParams p;
     memset(&p, 0, sizeof(p));
 
-    // Thin layers (Cout = 64 / 128): resident weights + one haloed region per tile, when it fits shared memory.
-    bool halo = false;
+    // Thin layers (Cout = 64 / 128): one haloed region per tile and chunk; weights resident in shared memory when
+    // the whole layer fits, else streamed through a ring of (tap, chunk) slices.
+    bool halo = false, halo_wres = true;
     int halo_nhalf = 1;
     size_t halo_smem = 0;
     if (!up && a->Cout == BN && BN <= 128 && a->dilation <= 4) {
         // TMA and the MMA unit both take the swizzle phase from absolute address bits, so a region only needs
         // TMA's 128 B alignment, not a 1024 B one: regions are packed back to back
-        const size_t w_bytes = (size_t)9 * (a->Cin / KCHUNK) * BN * KCHUNK * 2;
-        const size_t budget = 227 * 1024 - 1024 /* alignment slack */ - 256 /* barriers */ - 768 /* bias + out_conv */;
-        for (int nhalf = 2; nhalf >= 1 && !halo; --nhalf) {
-            const int rw = HT_W * nhalf + 2 * a->dilation, rh = HT_H + 2 * a->dilation;
-            const size_t region_stride = (size_t)rw * rh * KCHUNK * 2;
-            const long long nst = w_bytes < budget ? (long long)((budget - w_bytes) / region_stride) : 0;
-            if (nst >= 2) {
-                halo = true;
-                halo_nhalf = nhalf;
-                p.region_w = rw; p.region_h = rh; p.region_stride = (int)region_stride;
-                p.nstages = nst > HALO_MAX_STAGES ? HALO_MAX_STAGES : (int)nst;
-                halo_smem = w_bytes + (size_t)p.nstages * region_stride + 1024 + 256 + 768;
+        const size_t w_tile = (size_t)BN * KCHUNK * 2;
+        const size_t w_bytes = (size_t)9 * (a->Cin / KCHUNK) * w_tile;
+        const size_t budget = 227 * 1024 - 1024 /* alignment slack */ - HALO_BAR_BYTES - 768 /* bias + out_conv */;
+        for (int pass = 0; pass < 2 && !halo; ++pass) {          // pass 0: resident weights, pass 1: streamed
+            for (int nhalf = 2; nhalf >= 1 && !halo; --nhalf) {
+                const int rw = HT_W * nhalf + 2 * a->dilation, rh = HT_H + 2 * a->dilation;
+                const size_t region_stride = (size_t)rw * rh * KCHUNK * 2;
+                size_t wsm = w_bytes;
+                int nb = 0;
+                if (pass == 1) {
+                    if (budget < 2 * region_stride + 4 * w_tile) continue;
+                    const size_t room = budget - 2 * region_stride;
+                    nb = (int)(room / w_tile);
+                    if (nb > HALO_MAX_STAGES) nb = HALO_MAX_STAGES;
+                    wsm = (size_t)nb * w_tile;
+                }
+                const long long nst = wsm < budget ? (long long)((budget - wsm) / region_stride) : 0;
+                if (nst >= 2) {
+                    halo = true;
+                    halo_wres = pass == 0;
+                    halo_nhalf = nhalf;
+                    p.region_w = rw; p.region_h = rh; p.region_stride = (int)region_stride;
+                    p.nstages = nst > HALO_MAX_STAGES ? HALO_MAX_STAGES : (int)nst;
+                    p.nbstages = nb;
+                    halo_smem = wsm + (size_t)p.nstages * region_stride + 1024 + HALO_BAR_BYTES + 768;
+                }
             }
         }
     }
@@ -836,19 +910,20 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
     p.prob_out = a->prob_out; p.mask_out = a->mask_out;
 
     if (halo) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            DC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            DC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            DC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            DC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr_done = true;
-        }
         const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-        if (BN == 64 && halo_nhalf == 2)       conv_halo_kernel<64, 2><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
-        else if (BN == 64)                     conv_halo_kernel<64, 1><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
-        else if (halo_nhalf == 2)              conv_halo_kernel<128, 2><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
-        else                                   conv_halo_kernel<128, 1><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
+#define DC_HALO_CASE(bn, nh, wr)                                                                                     \
+        if (BN == bn && halo_nhalf == nh && halo_wres == wr) {                                                       \
+            static bool attr_done = false;                                                                           \
+            if (!attr_done) {                                                                                        \
+                DC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<bn, nh, wr>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             227 * 1024));                                                           \
+                attr_done = true;                                                                                    \
+            }                                                                                                        \
+            conv_halo_kernel<bn, nh, wr><<<grid, NUM_THREADS, halo_smem, stream>>>(p);                               \
+        }
+        DC_HALO_CASE(64, 1, true) DC_HALO_CASE(64, 2, true) DC_HALO_CASE(128, 1, true) DC_HALO_CASE(128, 2, true)
+        DC_HALO_CASE(64, 1, false) DC_HALO_CASE(64, 2, false) DC_HALO_CASE(128, 1, false) DC_HALO_CASE(128, 2, false)
+#undef DC_HALO_CASE
         DC_CUDA(cudaGetLastError());
         return DC_OK;
     }
