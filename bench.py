@@ -32,6 +32,7 @@ import numpy as np
 REPO = Path(__file__).resolve().parent
 sys.path.insert(0, str(REPO))
 
+_OUT = sys.stdout
 METRIC = "images/sec end-to-end (mask + droplet table)"
 UNIT = "images/s"
 PROB_THRESH = 0.3
@@ -159,7 +160,8 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
     return 0
 
 
@@ -317,10 +319,20 @@ def run_b200(args):
                                 "sample": f"{nfr} of the batch's {S}x{S} frames, once: cv2 rolling ball + torch fp32 "
                                           f"UNetDC ({torch.get_num_threads()} threads) + threshold + oracle quantify; {dt:.1f} s"}
     if rank == 0:
-        print(json.dumps(line))
+        _OUT.write(json.dumps(line) + "\n")
+        _OUT.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def _claim_stdout():
+    """Libraries (NCCL's version banner, for one) write to fd 1; the driver wants exactly ONE JSON line there.
+    Point fd 1 at stderr for the duration of the run and return a writer for the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
 
 
 def main():
@@ -337,6 +349,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    global _OUT
+    _OUT = _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)
