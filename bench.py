@@ -245,19 +245,29 @@ def run_b200(args):
     counts = last.counts.cpu().numpy()
     value = world * B * K / (ms_total / 1e3)
 
-    # ---- end-to-end arm: pinned host frames in, masks + table rows out, copies inside the timed region
-    for w in range(max(1, Wm)):
-        pipe.run_host(host_batches[w % NVAR], dev)
+    # ---- end-to-end arm: pinned host frames in, host masks + table rows out, every copy inside the timed region.
+    # DropletPipeline.run_host_pipelined is the public streaming entry: H2D of batch k+1 and D2H of batch k-1
+    # overlap the compute of batch k (three streams, pinned buffers).
+    def host_batches_iter(n):
+        for k in range(n):
+            yield host_batches[k % NVAR]
+
+    for _ in pipe.run_host_pipelined(host_batches_iter(max(2, Wm)), dev):
+        pass
     barrier(); torch.cuda.synchronize()
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s2.record()
+    t_e2e0 = time.perf_counter()
     d2h = 0
-    for k in range(K):
-        m_h, tabs = pipe.run_host(host_batches[k % NVAR], dev)
+    n_out = 0
+    for m_h, tabs in pipe.run_host_pipelined(host_batches_iter(K), dev):
         d2h = m_h.nbytes + sum(sum(v.nbytes for c, v in t.items() if c != "label") for t in tabs) + 4 * B
+        n_out += len(tabs)
+    torch.cuda.synchronize()
     e2.record()
     torch.cuda.synchronize(); barrier()
-    ms_e2e = max_over_ranks(s2.elapsed_time(e2))
+    assert n_out == B * K
+    ms_e2e = max_over_ranks(max(s2.elapsed_time(e2), 1e3 * (time.perf_counter() - t_e2e0)))
     e2e_value = world * B * K / (ms_e2e / 1e3)
 
     # ---- per-launch profile of the forward (one extra, untimed pass) for the roofline table
@@ -304,7 +314,7 @@ def run_b200(args):
                    "label_stats": {"ms": stage_ms[2], "GBps_algorithmic": ccl_gbs, "frac_hbm": ccl_gbs / pk["hbm_gbs"]}},
         "layers": layers,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * S * S, "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": ms_e2e / K},
+                "ms_per_step": ms_e2e / K, "api": "DropletPipeline.run_host_pipelined (pinned host frames -> host masks + tables)"},
         "gpu_launches": launches_per_step * K,
         "clocks": clocks,
     }

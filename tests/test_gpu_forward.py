@@ -131,6 +131,22 @@ def test_whole_path_vs_reference_golden(cuda_device):
     for i in range(2):
         for c in tables[i]:
             np.testing.assert_array_equal(tables_h[i][c], tables[i][c])
+    # streaming host entry (three streams, two slots): five batches, alternating two inputs, results in order
+    flipped = torch.from_numpy(np.ascontiguousarray(g["images"][:, ::-1, :])).pin_memory()
+    want_f_masks, want_f_tables = pipe.run_host(flipped)
+    want_f_masks = want_f_masks.copy()
+    seq = [torch.from_numpy(g["images"]).pin_memory(), flipped]
+    n = 0
+    for k, (mk, tb) in enumerate(pipe.run_host_pipelined(seq[k % 2] for k in range(5))):
+        wm, wt = (masks, tables) if k % 2 == 0 else (want_f_masks, want_f_tables)
+        np.testing.assert_array_equal(mk, wm, err_msg=f"batch {k}")
+        for i in range(2):
+            assert set(tb[i]) == set(wt[i])
+            for c in wt[i]:
+                np.testing.assert_array_equal(tb[i][c], wt[i][c], err_msg=f"batch {k} image {i} column {c}")
+        n += 1
+    assert n == 5
+    assert list(pipe.run_host_pipelined(iter(()))) == []
 
 
 def test_config1_eight_256_images(cuda_device):

@@ -154,7 +154,7 @@ class UNetDC(nn.Module):
 
     # ------------------------------------------------------------------ inference
     def _run(self, in_kind: int, x: torch.Tensor, B: int, H: int, W: int, thresh: float,
-             want_prob: bool, want_mask: bool):
+             want_prob: bool, want_mask: bool, mask_out: torch.Tensor | None = None):
         if self.training:
             raise RuntimeError("UNetDC (sm_100a) implements eval-mode inference only; call .eval() "
                                "(reference quantify_droplets_batch.py:37)")
@@ -165,7 +165,14 @@ class UNetDC(nn.Module):
         with torch.cuda.device(dev):
             ws = pk.workspace_for(B, H, W)
             prob = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev) if want_prob else None
-            mask = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if want_mask else None
+            mask = None
+            if want_mask:
+                if mask_out is not None:
+                    if mask_out.shape != (B, H, W) or mask_out.dtype != torch.uint8 or not mask_out.is_contiguous():
+                        raise ValueError("mask_out must be a contiguous uint8 [B,H,W] tensor")
+                    mask = _lib.require_cuda(mask_out, "mask_out")
+                else:
+                    mask = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
             _lib.check(_lib.load().dc_forward(
                 pk.handle, in_kind, x.data_ptr(), B, H, W, float(thresh),
                 prob.data_ptr() if want_prob else None, mask.data_ptr() if want_mask else None,
@@ -184,7 +191,8 @@ class UNetDC(nn.Module):
         return prob
 
     @torch.no_grad()
-    def predict_u8(self, images: torch.Tensor, prob_thresh: float, return_prob: bool = False):
+    def predict_u8(self, images: torch.Tensor, prob_thresh: float, return_prob: bool = False,
+                   mask_out: torch.Tensor | None = None):
         """Fused path of quantify_droplets_batch.py:45,51-52,56 for device-resident u8 images.
 
         images: u8 [B,H,W] (grayscale, replicated to RGB as ``Image.convert("RGB")`` does, qdb:41)
@@ -201,7 +209,7 @@ class UNetDC(nn.Module):
         else:
             raise ValueError(f"expected u8 [B,H,W] or [B,H,W,3], got {tuple(images.shape)}")
         B, H, W = images.shape[:3]
-        prob, mask = self._run(kind, images, B, H, W, prob_thresh, return_prob, True)
+        prob, mask = self._run(kind, images, B, H, W, prob_thresh, return_prob, True, mask_out)
         return mask, prob
 
     def num_launches(self) -> int:

@@ -22,7 +22,7 @@ import torch
 from . import _lib
 from .model import UNetDC
 from .morphology import rolling_ball_device, rolling_ball_workspace_bytes
-from .quantify import DEFAULT_CAPACITY, DropletTables, label_stats_device, label_workspace_bytes
+from .quantify import DEFAULT_CAPACITY, DropletTables, alloc_tables, label_stats_device, label_workspace_bytes
 
 
 @dataclass
@@ -47,8 +47,9 @@ class DropletPipeline:
         self._staging = None
 
     # ------------------------------------------------------------------ device-resident entry
-    def run_device(self, images: torch.Tensor, return_prob: bool = False, want_labels: bool = False) -> BatchResult:
-        """images: CUDA u8 [B,H,W] grayscale or [B,H,W,3]."""
+    def run_device(self, images: torch.Tensor, return_prob: bool = False, want_labels: bool = False,
+                   mask_out: torch.Tensor | None = None, tables_out: DropletTables | None = None) -> BatchResult:
+        """images: CUDA u8 [B,H,W] grayscale or [B,H,W,3].  mask_out / tables_out: preallocated outputs."""
         _lib.require_cuda(images, "images")
         x = images
         if self.background_radius:
@@ -59,12 +60,12 @@ class DropletPipeline:
                 need = rolling_ball_workspace_bytes(x.shape[0], x.shape[1], x.shape[2], 1 if x.dim() == 3 else x.shape[3])
                 self._rb_ws = torch.empty(need, dtype=torch.uint8, device=x.device)
             x = rolling_ball_device(x, self.background_radius, out=self._rb_out, workspace=self._rb_ws)
-        masks, probs = self.model.predict_u8(x, self.prob_thresh, return_prob=return_prob)
+        masks, probs = self.model.predict_u8(x, self.prob_thresh, return_prob=return_prob, mask_out=mask_out)
         need = label_workspace_bytes(*masks.shape)
         if self._ccl_ws is None or self._ccl_ws.device != masks.device or self._ccl_ws.numel() < need:
             self._ccl_ws = torch.empty(need, dtype=torch.uint8, device=masks.device)
         tables = label_stats_device(masks, self.min_area, self.px_per_micron, self.capacity,
-                                    want_labels=want_labels, workspace=self._ccl_ws)
+                                    want_labels=want_labels, workspace=self._ccl_ws, out=tables_out)
         return BatchResult(masks, tables, probs)
 
     # ------------------------------------------------------------------ host entry (what a user calls)
@@ -88,3 +89,109 @@ class DropletPipeline:
             self.capacity = nmax
             tables = label_stats_device(res.masks, self.min_area, self.px_per_micron, nmax)
         return masks.numpy(), tables.to_host()
+
+    # ------------------------------------------------------------------ pipelined host entry
+    def run_host_pipelined(self, batches, device: torch.device | str = "cuda"):
+        """Generator over host batches (each u8 [B,H,W] or [B,H,W,3], ideally pinned; all the same shape):
+        yields (masks u8 numpy [B,H,W], list of per-image column dicts) per batch, in order.
+
+        Three streams and two buffer slots: the H2D copy of batch k+1 and the D2H copy of batch k-1 run while
+        batch k computes, so the steady-state rate is the device rate, not device + PCIe.  Outputs land in
+        pinned host buffers owned by the pipeline (copy them if you keep more than two batches alive)."""
+        dev = torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        it = iter(batches)
+        s_in, s_run, s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        slots = [None, None]
+        micron = bool(self.px_per_micron)
+
+        def make_slot(shape):
+            B = shape[0]
+            d = {"dev_in": torch.empty(shape, dtype=torch.uint8, device=dev),
+                 "masks": torch.empty(tuple(shape[:3]), dtype=torch.uint8, device=dev),
+                 "tables": alloc_tables(B, self.capacity, micron, dev),
+                 "h_masks": torch.empty(tuple(shape[:3]), dtype=torch.uint8).pin_memory(),
+                 "h_counts": torch.empty(B, dtype=torch.int32).pin_memory(),
+                 "h_cols": torch.empty((7 if micron else 5, B, self.capacity), dtype=torch.float64).pin_memory(),
+                 "ev_in": torch.cuda.Event(), "ev_run": torch.cuda.Event(), "ev_counts": torch.cuda.Event(),
+                 "ev_free": torch.cuda.Event()}
+            d["ev_free"].record(s_run)
+            return d
+
+        def stage(k, host):
+            host = torch.from_numpy(np.ascontiguousarray(host)) if isinstance(host, np.ndarray) else host
+            sl = slots[k % 2]
+            if sl is None or sl["dev_in"].shape != host.shape:
+                sl = slots[k % 2] = make_slot(tuple(host.shape))
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(sl["ev_free"])            # the slot's previous batch has been computed and read back
+                sl["dev_in"].copy_(host, non_blocking=True)
+                sl["ev_in"].record(s_in)
+
+        def compute(k):
+            sl = slots[k % 2]
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(sl["ev_in"])
+                self.run_device(sl["dev_in"], mask_out=sl["masks"], tables_out=sl["tables"])
+                sl["ev_run"].record(s_run)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(sl["ev_run"])
+                sl["h_counts"].copy_(sl["tables"].counts, non_blocking=True)
+                sl["ev_counts"].record(s_out)
+                sl["h_masks"].copy_(sl["masks"], non_blocking=True)
+
+        def finish(k):
+            sl = slots[k % 2]
+            t = sl["tables"]
+            sl["ev_counts"].synchronize()
+            counts = sl["h_counts"].numpy().copy()
+            nmax = int(counts.max()) if counts.size else 0
+            if nmax > t.capacity:        # rare: rerun the table with room for everything (counts are exact)
+                with torch.cuda.stream(s_run):
+                    t = label_stats_device(sl["masks"], self.min_area, self.px_per_micron, nmax)
+                    self.capacity = max(self.capacity, nmax)
+                s_run.synchronize()
+            cols_dev = [t.area.view(torch.float64), t.eq_diam, t.centroid0, t.centroid1]
+            names = ["area", "equivalent_diameter", "centroid-0", "centroid-1"]
+            if micron:
+                cols_dev += [t.area_um2, t.diam_um]
+                names += ["area_sqmicron", "eq_diam_micron"]
+            if nmax > sl["h_cols"].shape[2]:
+                sl["h_cols"] = torch.empty((7 if micron else 5, counts.size, nmax), dtype=torch.float64).pin_memory()
+            with torch.cuda.stream(s_out):
+                for j, c in enumerate(cols_dev):
+                    sl["h_cols"][j, :, :nmax].copy_(c[:, :nmax], non_blocking=True)
+                sl["ev_free"].record(s_out)
+            s_out.synchronize()
+            masks = sl["h_masks"].numpy()
+            out = []
+            for b, n in enumerate(counts):
+                n = int(n)
+                d = {"label": np.arange(1, n + 1, dtype=np.int64)}
+                for j, name in enumerate(names):
+                    col = sl["h_cols"][j, b, :n].numpy()
+                    d[name] = col.view(np.int64).copy() if name == "area" else col.copy()
+                out.append(d)
+            return masks, out
+
+        k = 0
+        pending = []                      # batch indices staged / computed but not yet yielded
+        first = next(it, None)
+        if first is None:
+            return
+        stage(0, first)
+        nxt = next(it, None)
+        while True:
+            compute(k)
+            pending.append(k)
+            if nxt is not None:
+                if len(pending) == 2:     # slot (k+1) % 2 still holds batch k-1: read it back first
+                    yield finish(pending.pop(0))
+                stage(k + 1, nxt)
+                nxt = next(it, None)
+                k += 1
+                continue
+            break
+        for j in pending:
+            yield finish(j)

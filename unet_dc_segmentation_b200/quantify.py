@@ -62,28 +62,38 @@ def label_workspace_bytes(B: int, H: int, W: int) -> int:
     return int(need.value)
 
 
+def alloc_tables(B: int, capacity: int, micron: bool, device) -> DropletTables:
+    """Device buffers for one dc_label_stats call (reusable across calls via label_stats_device(out=...))."""
+    counts = torch.empty(B, dtype=torch.int32, device=device)
+    area = torch.empty((B, capacity), dtype=torch.int64, device=device)
+    c0, c1, dia = (torch.empty((B, capacity), dtype=torch.float64, device=device) for _ in range(3))
+    aum = torch.empty((B, capacity), dtype=torch.float64, device=device) if micron else None
+    dum = torch.empty((B, capacity), dtype=torch.float64, device=device) if micron else None
+    return DropletTables(counts, area, c0, c1, dia, aum, dum, None, capacity)
+
+
 def label_stats_device(masks: torch.Tensor, min_area: int = 1, px_per_um: float | None = None,
                        capacity: int = DEFAULT_CAPACITY, want_labels: bool = False,
-                       workspace: torch.Tensor | None = None) -> DropletTables:
-    """masks: CUDA u8 [B,H,W] (non-zero = foreground).  No host synchronisation."""
+                       workspace: torch.Tensor | None = None, out: DropletTables | None = None) -> DropletTables:
+    """masks: CUDA u8 [B,H,W] (non-zero = foreground).  No host synchronisation.
+    out: buffers from alloc_tables() to fill instead of allocating (their capacity wins)."""
     _lib.require_cuda(masks, "masks")
     if masks.dtype != torch.uint8 or masks.dim() != 3:
         raise TypeError("masks must be uint8 [B,H,W]")
     masks = masks.contiguous()
     B, H, W = masks.shape
-    capacity = int(max(1, min(capacity, (H * W + 1) // 2)))
+    capacity = int(max(1, min(capacity, (H * W + 1) // 2))) if out is None else out.capacity
     lib = _lib.load()
     dev = masks.device
     need = label_workspace_bytes(B, H, W)
     with torch.cuda.device(dev):
         if workspace is None or workspace.numel() < need:
             workspace = torch.empty(need, dtype=torch.uint8, device=dev)
-        counts = torch.empty(B, dtype=torch.int32, device=dev)
-        area = torch.empty((B, capacity), dtype=torch.int64, device=dev)
-        c0, c1, dia = (torch.empty((B, capacity), dtype=torch.float64, device=dev) for _ in range(3))
         micron = bool(px_per_um)
-        aum = torch.empty((B, capacity), dtype=torch.float64, device=dev) if micron else None
-        dum = torch.empty((B, capacity), dtype=torch.float64, device=dev) if micron else None
+        t = out if out is not None else alloc_tables(B, capacity, micron, dev)
+        if t.counts.shape[0] != B or (micron and t.area_um2 is None):
+            raise ValueError("out tables do not match this call (batch size / micron columns)")
+        counts, area, c0, c1, dia, aum, dum = t.counts, t.area, t.centroid0, t.centroid1, t.eq_diam, t.area_um2, t.diam_um
         labels = torch.empty((B, H, W), dtype=torch.int32, device=dev) if want_labels else None
         args = _lib.LabelArgs(
             masks.data_ptr(), B, H, W, int(min_area), float(px_per_um) if micron else 0.0,
@@ -92,7 +102,7 @@ def label_stats_device(masks: torch.Tensor, min_area: int = 1, px_per_um: float 
             aum.data_ptr() if micron else None, dum.data_ptr() if micron else None,
             workspace.data_ptr(), workspace.numel())
         _lib.check(lib.dc_label_stats(C.byref(args), _lib.stream_ptr(dev)))
-    return DropletTables(counts, area, c0, c1, dia, aum, dum, labels, capacity)
+    return DropletTables(counts, area, c0, c1, dia, aum if micron else None, dum if micron else None, labels, capacity)
 
 
 def quantify_arrays(masks: torch.Tensor, min_area: int = 1, px_per_um: float | None = None,
