@@ -126,17 +126,36 @@ __device__ __forceinline__ void tmem_ld_wait_on(uint32_t* v) {
 // 2x2 max-pool, the transposed-conv parity scatter or the out_conv + sigmoid + threshold head as `p.epilogue` says.
 // NHALF > 1: the tile is NHALF side-by-side TW-wide patches, each with its own BN-column accumulator.
 constexpr int EPI_GROUPS = 2;
+constexpr int EPI_STAGE_BYTES = 32 * 64;                    // per warp: 32 pixels x 32 channels bf16
+constexpr int EPI_STAGE_TOTAL = EPI_GROUPS * 4 * EPI_STAGE_BYTES;
 
-template <int BN, int TH, int TW, int NHALF = 1>
+// Staging slot of 16-byte chunk q (0..3) of pixel row r in a warp's 32 x 64 B buffer (bank-conflict-free for
+// both the per-pixel writes and the 4-lanes-per-pixel reads).
+__device__ __forceinline__ uint32_t stg_off(int r, int q) { return (uint32_t)(r * 64 + ((q ^ ((r >> 1) & 3)) << 4)); }
+
+template <int BN, int TH, int TW, int NHALF = 1, bool PAIR = false>
 __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, const int lane, const int group,
                                              const uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
-                                             const float* bias_s) {
+                                             const float* bias_s, uint8_t* stg_all) {
     const int L = e * 32 + lane;                               // e == warp % 4: TMEM lanes [32e, 32e+32)
     const int lh = L / TW, lw = L % TW;
     const float* head_s = bias_s + p.Cout;                     // out_conv weights follow the bias (HEAD only)
+    uint8_t* stg = stg_all + (group * 4 + e) * EPI_STAGE_BYTES;
+    const int sq = lane & 3;                                   // the 16-byte chunk this lane stores after the transpose
+    // Stores go out transposed: a thread computes 32 channels of ONE pixel (64 B), but writing that directly makes
+    // every store instruction touch 32 different lines.  Each 32-pixel x 32-channel chunk is staged in a
+    // warp-private smem buffer and stored as 8 pixels x 64 contiguous bytes per instruction (4 lanes per pixel).
     for (int it = group;; it += EPI_GROUPS) {
-        const int tile = blockIdx.x + it * gridDim.x;
-        if (tile >= p.total_tiles) break;
+        int tile;
+        if (PAIR) {                     // CTA pair: pair = cluster + it * clusters, this CTA's tile = 2 * pair + rank
+            const int pair = (int)(blockIdx.x >> 1) + it * (int)(gridDim.x >> 1);
+            if (2 * pair >= p.total_tiles) break;
+            tile = 2 * pair + (int)(blockIdx.x & 1);
+            if (tile >= p.total_tiles) tile = p.total_tiles - 1;
+        } else {
+            tile = blockIdx.x + it * gridDim.x;
+            if (tile >= p.total_tiles) break;
+        }
         const TileCoord t = decode_tile<TH, TW * NHALF>(p, tile, BN);
         const int as = it & 1;                                 // == group
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
@@ -146,19 +165,37 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
         for (int half = 0; half < NHALF; ++half) {
             const int h = t.h0 + lh, w = t.w0 + half * TW + lw;
             const bool valid = (h < p.H) && (w < p.W);
-
-            __nv_bfloat16* optr = nullptr;
-            __nv_bfloat16* pptr = nullptr;
-            int bias_base = t.n0;
-            if (p.epilogue == DC_EPI_STORE || p.epilogue == DC_EPI_STORE_POOL) {
-                const size_t opix = ((size_t)t.img * p.H + h) * (size_t)p.W + w;
-                optr = p.out + opix * p.out_stride + p.out_offset + t.n0;
-                if (p.epilogue == DC_EPI_STORE_POOL) {
-                    const size_t ppix = ((size_t)t.img * (p.H >> 1) + (h >> 1)) * (size_t)(p.W >> 1) + (w >> 1);
-                    pptr = p.pool_out + ppix * p.pool_stride + t.n0;
+            // pixels this lane stores for (4 rounds x 8 pixels): pr = 8 j + lane / 4 of the warp's 32
+            int sh[4], sw[4];
+            bool sval[4];
+            __nv_bfloat16* sptr[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int pL = e * 32 + 8 * j + (lane >> 2);
+                sh[j] = t.h0 + pL / TW;
+                sw[j] = t.w0 + half * TW + pL % TW;
+                sval[j] = (sh[j] < p.H) && (sw[j] < p.W);
+                sptr[j] = nullptr;
+                if (p.epilogue == DC_EPI_STORE || p.epilogue == DC_EPI_STORE_POOL) {
+                    const size_t opix = ((size_t)t.img * p.H + sh[j]) * (size_t)p.W + sw[j];
+                    sptr[j] = p.out + opix * p.out_stride + p.out_offset + t.n0 + sq * 8;
                 }
             }
-            const bool pool_writer = valid && !(lane & 1) && !(lane & TW);
+            // pooled pixel this lane stores: pp = lane / 4 of the warp's 8 (2x2 windows of its 32 pixels)
+            __nv_bfloat16* pptr = nullptr;
+            bool pval = false;
+            if (p.epilogue == DC_EPI_STORE_POOL) {
+                const int pp = lane >> 2;
+                const int ph_l = (TW == 16) ? 0 : 2 * (pp >> 2);
+                const int pw_l = (TW == 16) ? 2 * pp : 2 * (pp & 3);
+                const int ph = t.h0 + e * (32 / TW) + ph_l, pw = t.w0 + half * TW + pw_l;
+                pval = (ph < p.H) && (pw < p.W);
+                const size_t ppix = ((size_t)t.img * (p.H >> 1) + (ph >> 1)) * (size_t)(p.W >> 1) + (pw >> 1);
+                pptr = p.pool_out + ppix * p.pool_stride + t.n0 + sq * 8;
+            }
+            const bool pool_writer = !(lane & 1) && !(lane & TW);
+            const int pool_row = (TW == 16) ? (lane >> 1) : (((lane >> 4) << 2) | ((lane & 7) >> 1));
+            int bias_base = t.n0;
             float head_acc = p.head_b;
 
             const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)((as * NHALF + half) * BN);
@@ -175,9 +212,13 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                     const int n = t.n0 + c0;
                     const int q = n / p.Cout;
                     const int co = n - q * p.Cout;
-                    const size_t opix = ((size_t)t.img * (2 * p.H) + (2 * h + (q >> 1))) * (size_t)(2 * p.W) + (2 * w + (q & 1));
-                    optr = p.out + opix * p.out_stride + p.out_offset + co - c0;
                     bias_base = co - c0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const size_t opix = ((size_t)t.img * (2 * p.H) + (2 * sh[j] + (q >> 1))) * (size_t)(2 * p.W) +
+                                            (2 * sw[j] + (q & 1));
+                        sptr[j] = p.out + opix * p.out_stride + p.out_offset + co - c0 + sq * 8;
+                    }
                 }
                 const float4* b4 = reinterpret_cast<const float4*>(bias_s + bias_base + c0);
                 float x[32];
@@ -207,11 +248,17 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                     uint32_t pk[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
-                    if (valid) {
-                        uint4* o4 = reinterpret_cast<uint4*>(optr + c0);
+                    // transpose through smem: row = pixel (lane), then 4 lanes per pixel read 16 B each
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) o4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<uint4*>(stg + stg_off(lane, q)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 val = *reinterpret_cast<const uint4*>(stg + stg_off(8 * j + (lane >> 2), sq));
+                        if (sval[j]) *reinterpret_cast<uint4*>(sptr[j] + c0) = val;
                     }
+                    __syncwarp();
                     if (p.epilogue == DC_EPI_STORE_POOL) {
                         // 2x2 window = lanes {l, l^1 (w+1), l^TW (h+1), l^(TW+1)}: all inside this warp
 #pragma unroll
@@ -220,10 +267,15 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                             pk[j] = max_bf16x2(m, __shfl_xor_sync(0xffffffffu, m, TW));
                         }
                         if (pool_writer) {
-                            uint4* o4 = reinterpret_cast<uint4*>(pptr + c0);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) o4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                            for (int q = 0; q < 4; ++q)
+                                *reinterpret_cast<uint4*>(stg + stg_off(pool_row, q)) =
+                                    make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                         }
+                        __syncwarp();
+                        const uint4 val = *reinterpret_cast<const uint4*>(stg + stg_off(lane >> 2, sq));
+                        if (pval) *reinterpret_cast<uint4*>(pptr + c0) = val;
+                        __syncwarp();
                     }
                 }
             }
@@ -231,7 +283,10 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                 // accumulators fully read: hand them back to the MMA warp
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[as]);
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_leader(&tempty_bar[as]);      // the leader's MMA warp waits for both CTAs
+                    else mbar_arrive(&tempty_bar[as]);
+                }
             }
             if (p.epilogue == DC_EPI_HEAD && valid) {
                 const float prob = 1.0f / (1.0f + expf(-head_acc));              // torch.sigmoid, fp32
@@ -264,6 +319,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     float* bias_s = reinterpret_cast<float*>(smem + NSTAGES * STAGE_BYTES + 256);
+    uint8_t* stg_s = smem + NSTAGES * STAGE_BYTES + 256 + 4096 + 256;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -350,7 +406,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
     } else if (warp >= EPI_WARP0) {
         // ------------------------------------------------------------------ epilogue
-        run_epilogue<BN, TILE_H, TILE_W>(p, warp & 3, lane, (warp - EPI_WARP0) >> 2, tmem_base, tfull_bar, tempty_bar, bias_s);
+        run_epilogue<BN, TILE_H, TILE_W>(p, warp & 3, lane, (warp - EPI_WARP0) >> 2, tmem_base, tfull_bar, tempty_bar, bias_s, stg_s);
     }
 
     tc_fence_before();
@@ -407,6 +463,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
     uint64_t* w_bar = tempty_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
     float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + HALO_BAR_BYTES);
+    uint8_t* stg_s = reinterpret_cast<uint8_t*>(full_bar) + HALO_BAR_BYTES + 768;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NST = p.nstages;
@@ -564,7 +621,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
             __syncwarp();
         }
     } else if (warp >= EPI_WARP0) {
-        run_epilogue<BN, HT_H, HT_W, HT_NHALF>(p, warp & 3, lane, (warp - EPI_WARP0) >> 2, tmem_base, tfull_bar, tempty_bar, bias_s);
+        run_epilogue<BN, HT_H, HT_W, HT_NHALF>(p, warp & 3, lane, (warp - EPI_WARP0) >> 2, tmem_base, tfull_bar, tempty_bar, bias_s, stg_s);
     }
 
     tc_fence_before();
@@ -572,6 +629,160 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------- halo variant on CTA pairs
+// cta_group::2: the two SMs of a pair run ONE M = 256 MMA stream.  Each CTA owns its own 16 x 16 pixel tile
+// (rows [0,128) / [128,256) of the MMA come from the leader's / the peer's haloed region at the same smem offset)
+// and HALF of the weight rows (N/2), so the weights of a layer need half the shared memory per SM -- dec1.0's
+// 144 KB become 72 KB and leave room for two-half regions -- and the B-operand smem reads per SM halve
+// (A 4 KB + B N/2 x 32 B per MMA), which is what bounds the N = 64 layers.
+// Leader = even CTA: it alone issues the MMAs; both CTAs run a TMA producer (bytes credited to the leader's
+// barriers), both run epilogues on their own TMEM half, commits are multicast to both CTAs' barriers.
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv_halo2_kernel(const __grid_constant__ ConvParams p) {
+    constexpr int NH = 2;
+    constexpr int HT_TW = HT_W * NH;
+    constexpr int W_TILE_BYTES = (BN / 2) * KCHUNK * 2;     // this CTA's half of one (tap, chunk) weight slice
+    constexpr int TMEM_COLS = 2 * NH * BN;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int n_wtiles = 9 * p.kchunks;
+    uint8_t* w_res = smem;
+    uint8_t* a_ring = smem + n_wtiles * W_TILE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(a_ring + p.nstages * p.region_stride);
+    uint64_t* empty_bar = full_bar + HALO_MAX_STAGES;
+    uint64_t* tfull_bar = empty_bar + HALO_MAX_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint64_t* w_bar = tempty_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+    float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + HALO_BAR_BYTES);
+    uint8_t* stg_s = reinterpret_cast<uint8_t*>(full_bar) + HALO_BAR_BYTES + 768;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NST = p.nstages;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int n_pairs = (p.total_tiles + 1) >> 1;
+
+    stage_bias(p, bias_s);
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < HALO_MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }   // 4 warps x 2 CTAs
+        mbar_init(w_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                 // the peer's barriers exist before anything is signalled across the pair
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t region_bytes = (uint32_t)(p.region_w * p.region_h * KCHUNK * 2);
+
+    // the pair's tiles: 2*pair + rank; an odd tile count makes the last peer redo the last tile (identical stores)
+    auto pair_tile = [&](int pair) {
+        int tile = 2 * pair + (int)rank;
+        return tile < p.total_tiles ? tile : p.total_tiles - 1;
+    };
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (one per CTA)
+        if (elect_one()) {
+            if (leader) mbar_expect_tx(w_bar, (uint32_t)(2 * n_wtiles * W_TILE_BYTES));
+            for (int j = 0; j < n_wtiles; ++j)
+                tma_load_2d_2sm(w_res + j * W_TILE_BYTES, &p.tmB, w_bar, j * KCHUNK, (int)rank * (BN / 2));
+        }
+        __syncwarp();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int pair = cluster_id; pair < n_pairs; pair += n_clusters) {
+            const TileCoord t = decode_tile<HT_H, HT_TW>(p, pair_tile(pair), BN);
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                if (elect_one()) {
+                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * region_bytes);
+                    tma_load_4d_2sm(a_ring + stage * p.region_stride, &p.tmA, &full_bar[stage], kc * KCHUNK, t.w0 - p.dil,
+                                    t.h0 - p.dil, t.img);
+                }
+                __syncwarp();
+                if (++stage == NST) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (leader) {
+            const uint32_t idesc = umma_idesc_bf16(2 * TILE_M, BN);
+            const uint32_t sbo = (uint32_t)p.region_w * 128u;
+            const uint32_t w_addr = smem_u32(w_res);
+            const uint32_t tap_dy_bytes = (uint32_t)(p.dil * p.region_w) * 128u;
+            const uint32_t tap_dx_bytes = (uint32_t)p.dil * 128u;
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            mbar_wait(w_bar, 0);
+            for (int pair = cluster_id; pair < n_pairs; pair += n_clusters, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(&tempty_bar[as], aphase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * NH * BN);
+                uint32_t accumulate = 0;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t region = smem_u32(a_ring + stage * p.region_stride);
+                    const uint32_t w_chunk = w_addr + (uint32_t)(kc * W_TILE_BYTES);
+                    const uint32_t w_tap_stride = (uint32_t)(p.kchunks * W_TILE_BYTES);
+                    if (elect_one()) {
+                        // (no tap skipping here: the two tiles of a pair may sit at different image borders;
+                        //  windows in the padding read TMA's zero fill)
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint32_t a_addr = region + (uint32_t)(tap / 3) * tap_dy_bytes + (uint32_t)(tap % 3) * tap_dx_bytes;
+                            const uint64_t adesc = umma_desc_sw128_strided(a_addr, sbo);
+                            const uint64_t bdesc = umma_desc_sw128(w_chunk + (uint32_t)tap * w_tap_stride);
+#pragma unroll
+                            for (int k = 0; k < KCHUNK / 16; ++k) {
+#pragma unroll
+                                for (int half = 0; half < NH; ++half)
+                                    umma_bf16_2sm(d_tmem + (uint32_t)(half * BN), adesc + (uint64_t)(2 * k + 64 * half),
+                                                  bdesc + (uint64_t)(2 * k), idesc, accumulate);
+                                accumulate = 1;
+                            }
+                        }
+                        umma_commit_2sm(&empty_bar[stage]);
+                    }
+                    __syncwarp();
+                    accumulate = 1;
+                    if (++stage == NST) { stage = 0; phase ^= 1u; }
+                }
+                if (elect_one()) umma_commit_2sm(&tfull_bar[as]);
+                __syncwarp();
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        run_epilogue<BN, HT_H, HT_W, NH, true>(p, warp & 3, lane, (warp - EPI_WARP0) >> 2, tmem_base, tfull_bar, tempty_bar,
+                                               bias_s, stg_s);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                 // neither CTA leaves (or frees TMEM) while the other may still signal it
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, TMEM_COLS);
     }
 }
 
@@ -627,6 +838,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_tc_kernel(const __grid_c
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+    uint8_t* stg_s = reinterpret_cast<uint8_t*>(full_bar) + 256 + 512;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     stage_bias(p, bias_s);
@@ -670,7 +882,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_tc_kernel(const __grid_c
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 8) {
-        run_epilogue<BN, TILE_H, TILE_W>(p, warp & 3, lane, warp >> 2, tmem_base, tfull_bar, tempty_bar, bias_s);
+        run_epilogue<BN, TILE_H, TILE_W>(p, warp & 3, lane, warp >> 2, tmem_base, tfull_bar, tempty_bar, bias_s, stg_s);
     } else if (warp < 12) {
         // ------------------------------------------------------------------ im2col producers: one tile row each
         // The taps of tile i+1 are requested before tile i is converted and stored, so the global-load latency
@@ -679,7 +891,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_tc_kernel(const __grid_c
         const int lh = r / TILE_W, lw = r % TILE_W;
         int stage = 0;
         uint32_t phase = 0;
-        uint32_t cur[KREAL], nxt[KREAL];
+        uint32_t buf[3][KREAL];                 // taps of tiles i, i+1, i+2 (loads two tiles ahead of their use)
         auto fetch = [&](int tile, uint32_t* dst) {
             const TileCoord t = decode_tile(p, tile, BN);
             const int y = t.h0 + lh, x = t.w0 + lw;
@@ -689,26 +901,31 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_tc_kernel(const __grid_c
                 dst[kk] = stem_px_raw<IN_KIND>(sp.in, t.img, c, y + (tap / 3 - 1) * p.dil, x + (tap % 3 - 1) * p.dil, p.H, p.W);
             }
         };
-        if ((int)blockIdx.x < p.total_tiles) fetch(blockIdx.x, cur);
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int next = tile + gridDim.x;
-            if (next < p.total_tiles) fetch(next, nxt);
-            uint32_t pk[NK * 8];
+        const int G = gridDim.x;
+        if ((int)blockIdx.x < p.total_tiles) fetch(blockIdx.x, buf[0]);
+        if ((int)blockIdx.x + G < p.total_tiles) fetch(blockIdx.x + G, buf[1]);
+        for (int base = blockIdx.x; base < p.total_tiles; base += 3 * G) {
 #pragma unroll
-            for (int j = 0; j < NK * 8; ++j)
-                pk[j] = pack_bf16(2 * j < KREAL ? stem_val<IN_KIND>(cur[2 * j]) : 0.f,
-                                  2 * j + 1 < KREAL ? stem_val<IN_KIND>(cur[2 * j + 1]) : 0.f);
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            uint8_t* row = a_ring + stage * A_STAGE_BYTES + r * 128;
+            for (int u = 0; u < 3; ++u) {
+                const int tile = base + u * G;
+                if (tile >= p.total_tiles) break;
+                if (tile + 2 * G < p.total_tiles) fetch(tile + 2 * G, buf[(u + 2) % 3]);
+                const uint32_t* cur = buf[u];
+                uint32_t pk[NK * 8];
 #pragma unroll
-            for (int chunk = 0; chunk < NK * 2; ++chunk)
-                *reinterpret_cast<uint4*>(row + ((chunk ^ (r & 7)) << 4)) =
-                    make_uint4(pk[4 * chunk], pk[4 * chunk + 1], pk[4 * chunk + 2], pk[4 * chunk + 3]);
-            fence_proxy_async();                    // generic-proxy stores -> visible to the tensor core (async proxy)
-            mbar_arrive(&full_bar[stage]);
-            if (++stage == STEM_STAGES) { stage = 0; phase ^= 1u; }
+                for (int j = 0; j < NK * 8; ++j)
+                    pk[j] = pack_bf16(2 * j < KREAL ? stem_val<IN_KIND>(cur[2 * j]) : 0.f,
+                                      2 * j + 1 < KREAL ? stem_val<IN_KIND>(cur[2 * j + 1]) : 0.f);
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                uint8_t* row = a_ring + stage * A_STAGE_BYTES + r * 128;
 #pragma unroll
-            for (int kk = 0; kk < KREAL; ++kk) cur[kk] = nxt[kk];
+                for (int chunk = 0; chunk < NK * 2; ++chunk)
+                    *reinterpret_cast<uint4*>(row + ((chunk ^ (r & 7)) << 4)) =
+                        make_uint4(pk[4 * chunk], pk[4 * chunk + 1], pk[4 * chunk + 2], pk[4 * chunk + 3]);
+                fence_proxy_async();                // generic-proxy stores -> visible to the tensor core (async proxy)
+                mbar_arrive(&full_bar[stage]);
+                if (++stage == STEM_STAGES) { stage = 0; phase ^= 1u; }
+            }
         }
     } else {
         // ------------------------------------------------------------------ MMA issuer (warp-uniform loop)
@@ -779,7 +996,7 @@ template <int BN, int NSTAGES>
 int launch_variant(const ConvParams& p, cudaStream_t stream) {
     constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * KCHUNK * 2;
     constexpr size_t SMEM = (size_t)NSTAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ +
-                            4096 + 256 /* bias (<= 1024 ch) + out_conv weights */;
+                            4096 + 256 /* bias (<= 1024 ch) + out_conv weights */ + EPI_STAGE_TOTAL;
     static_assert(SMEM <= 227 * 1024, "stage ring exceeds shared memory");
     static bool attr_done = false;
     if (!attr_done) {
@@ -833,17 +1050,41 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
 
     // Thin layers (Cout = 64 / 128): one haloed region per tile and chunk; weights resident in shared memory when
     // the whole layer fits, else streamed through a ring of (tap, chunk) slices.
-    bool halo = false, halo_wres = true;
+    bool halo = false, halo_wres = true, halo_pair = false;
     int halo_nhalf = 1;
     size_t halo_smem = 0;
-    if (!up && a->Cout == BN && BN <= 128 && a->dilation <= 4) {
+    const char* pair_env = getenv("DC_CONV_PAIR");               // measurement aid: "0" disables the CTA-pair kernel
+    if (!up && a->Cout == BN && BN <= 128 && a->dilation <= 4 && !(pair_env && pair_env[0] == '0')) {
+        // CTA pair (cta_group::2): half of the weight rows per SM, two-half regions
+        const size_t w_half = (size_t)9 * (a->Cin / KCHUNK) * (BN / 2) * KCHUNK * 2;
+        const size_t budget = 227 * 1024 - 1024 - HALO_BAR_BYTES - 768 - EPI_STAGE_TOTAL;
+        const int rw = HT_W * 2 + 2 * a->dilation, rh = HT_H + 2 * a->dilation;
+        const size_t region_stride = (size_t)rw * rh * KCHUNK * 2;
+        const long long nst = w_half < budget ? (long long)((budget - w_half) / region_stride) : 0;
+        if (nst >= 2) {
+            halo = halo_pair = true;
+            halo_nhalf = 2;
+            p.region_w = rw; p.region_h = rh; p.region_stride = (int)region_stride;
+            p.nstages = nst > HALO_MAX_STAGES ? HALO_MAX_STAGES : (int)nst;
+            halo_smem = w_half + (size_t)p.nstages * region_stride + 1024 + HALO_BAR_BYTES + 768 + EPI_STAGE_TOTAL;
+        }
+    }
+    if (!halo && !up && a->Cout == BN && BN <= 128 && a->dilation <= 4) {
         // TMA and the MMA unit both take the swizzle phase from absolute address bits, so a region only needs
         // TMA's 128 B alignment, not a 1024 B one: regions are packed back to back
         const size_t w_tile = (size_t)BN * KCHUNK * 2;
         const size_t w_bytes = (size_t)9 * (a->Cin / KCHUNK) * w_tile;
-        const size_t budget = 227 * 1024 - 1024 /* alignment slack */ - HALO_BAR_BYTES - 768 /* bias + out_conv */;
-        for (int pass = 0; pass < 2 && !halo; ++pass) {          // pass 0: resident weights, pass 1: streamed
-            for (int nhalf = 2; nhalf >= 1 && !halo; --nhalf) {
+        const size_t budget = 227 * 1024 - 1024 /* alignment slack */ - HALO_BAR_BYTES - 768 /* bias + out_conv */ -
+                              EPI_STAGE_TOTAL /* epilogue transpose buffers */;
+        // Preference order (measured, profiles/): two halves (two independent MMA chains) beat one; resident weights
+        // beat streamed ones, and at BN = 64 a streamed slice carries only 256 MMA-cycles, too little to cover the
+        // L2 latency with the ring that fits -- so BN = 64 takes resident/1 half before anything streamed.
+        static const int order128[4][2] = {{2, 0}, {2, 1}, {1, 0}, {1, 1}};     // {nhalf, pass}; pass 1 = streamed
+        static const int order64[4][2] = {{2, 0}, {1, 0}, {2, 1}, {1, 1}};
+        for (int oi = 0; oi < 4 && !halo; ++oi) {
+            {
+                const int nhalf = (BN == 128 ? order128 : order64)[oi][0];
+                const int pass = (BN == 128 ? order128 : order64)[oi][1];
                 const int rw = HT_W * nhalf + 2 * a->dilation, rh = HT_H + 2 * a->dilation;
                 const size_t region_stride = (size_t)rw * rh * KCHUNK * 2;
                 size_t wsm = w_bytes;
@@ -863,13 +1104,13 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
                     p.region_w = rw; p.region_h = rh; p.region_stride = (int)region_stride;
                     p.nstages = nst > HALO_MAX_STAGES ? HALO_MAX_STAGES : (int)nst;
                     p.nbstages = nb;
-                    halo_smem = wsm + (size_t)p.nstages * region_stride + 1024 + HALO_BAR_BYTES + 768;
+                    halo_smem = wsm + (size_t)p.nstages * region_stride + 1024 + HALO_BAR_BYTES + 768 + EPI_STAGE_TOTAL;
                 }
             }
         }
     }
     if (const char* force = getenv("DC_CONV_PATH")) {        // measurement aid: A/B the two kernels
-        if (!strcmp(force, "generic")) halo = false;
+        if (!strcmp(force, "generic")) halo = halo_pair = false;
     }
     {
         cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B};
@@ -885,7 +1126,7 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
         const int rows = up ? 4 * a->Cout : a->Cout;
         cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)rows};
         cuuint64_t str[1] = {(cuuint64_t)ktot * 2};
-        cuuint32_t box[2] = {KCHUNK, (cuuint32_t)BN};
+        cuuint32_t box[2] = {KCHUNK, (cuuint32_t)(halo_pair ? BN / 2 : BN)};
         int rc = encode_map(&p.tmB, a->weight, 2, dims, str, box);
         if (rc != DC_OK) return rc;
     }
@@ -909,6 +1150,21 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
     p.head_w = a->head_w; p.head_b = a->head_b; p.thresh = a->thresh;
     p.prob_out = a->prob_out; p.mask_out = a->mask_out;
 
+    if (halo_pair) {
+        const int n_pairs = (p.total_tiles + 1) / 2;
+        const int max_clusters = num_sms() / 2;
+        const int grid = 2 * (n_pairs < max_clusters ? n_pairs : max_clusters);
+        static bool attr_done = false;
+        if (!attr_done) {
+            DC_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            DC_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_done = true;
+        }
+        if (BN == 64) conv_halo2_kernel<64><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
+        else          conv_halo2_kernel<128><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
+        DC_CUDA(cudaGetLastError());
+        return DC_OK;
+    }
     if (halo) {
         const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
 #define DC_HALO_CASE(bn, nh, wr)                                                                                     \
@@ -958,7 +1214,7 @@ int launch_stem(const dc_stem_args_t* a, cudaStream_t stream) {
     p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
     p.out_stride = a->out_stride; p.out_offset = a->out_offset;
     sp.in = a->in; sp.weight = a->weight; sp.in_kind = a->in_kind;
-    constexpr size_t SMEM = 64 * 128 + (size_t)STEM_STAGES * A_STAGE_BYTES + 1024 + 256 + 512;
+    constexpr size_t SMEM = 64 * 128 + (size_t)STEM_STAGES * A_STAGE_BYTES + 1024 + 256 + 512 + EPI_STAGE_TOTAL;
     static bool attr_done = false;
     if (!attr_done) {
         DC_CUDA(cudaFuncSetAttribute(stem_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
