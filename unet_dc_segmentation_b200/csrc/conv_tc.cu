@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
 // (A 4 KB + B N/2 x 32 B per MMA), which is what bounds the N = 64 layers.
 // Leader = even CTA: it alone issues the MMAs; both CTAs run a TMA producer (bytes credited to the leader's
 // barriers), both run epilogues on their own TMEM half, commits are multicast to both CTAs' barriers.
-template <int BN>
+template <int BN, bool WRES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv_halo2_kernel(const __grid_constant__ ConvParams p) {
     constexpr int NH = 2;
@@ -650,12 +650,14 @@ conv_halo2_kernel(const __grid_constant__ ConvParams p) {
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int n_wtiles = 9 * p.kchunks;
-    uint8_t* w_res = smem;
+    const int n_wtiles = WRES ? 9 * p.kchunks : p.nbstages;
+    uint8_t* w_res = smem;                                          // resident half-weights, or the weight ring
     uint8_t* a_ring = smem + n_wtiles * W_TILE_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(a_ring + p.nstages * p.region_stride);
     uint64_t* empty_bar = full_bar + HALO_MAX_STAGES;
-    uint64_t* tfull_bar = empty_bar + HALO_MAX_STAGES;
+    uint64_t* bfull_bar = empty_bar + HALO_MAX_STAGES;
+    uint64_t* bempty_bar = bfull_bar + HALO_MAX_STAGES;
+    uint64_t* tfull_bar = bempty_bar + HALO_MAX_STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint64_t* w_bar = tempty_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
@@ -664,6 +666,7 @@ conv_halo2_kernel(const __grid_constant__ ConvParams p) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NST = p.nstages;
+    const int NBS = p.nbstages;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
@@ -675,7 +678,10 @@ conv_halo2_kernel(const __grid_constant__ ConvParams p) {
         tma_prefetch_desc(&p.tmB);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < HALO_MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < HALO_MAX_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1);
+            mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1);
+        }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }   // 4 warps x 2 CTAs
         mbar_init(w_bar, 1);
         fence_barrier_init();
@@ -699,14 +705,16 @@ conv_halo2_kernel(const __grid_constant__ ConvParams p) {
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (one per CTA)
-        if (elect_one()) {
-            if (leader) mbar_expect_tx(w_bar, (uint32_t)(2 * n_wtiles * W_TILE_BYTES));
-            for (int j = 0; j < n_wtiles; ++j)
-                tma_load_2d_2sm(w_res + j * W_TILE_BYTES, &p.tmB, w_bar, j * KCHUNK, (int)rank * (BN / 2));
+        if (WRES) {
+            if (elect_one()) {
+                if (leader) mbar_expect_tx(w_bar, (uint32_t)(2 * n_wtiles * W_TILE_BYTES));
+                for (int j = 0; j < n_wtiles; ++j)
+                    tma_load_2d_2sm(w_res + j * W_TILE_BYTES, &p.tmB, w_bar, j * KCHUNK, (int)rank * (BN / 2));
+            }
+            __syncwarp();
         }
-        __syncwarp();
-        int stage = 0;
-        uint32_t phase = 0;
+        int stage = 0, bstage = 0;
+        uint32_t phase = 0, bphase = 0;
         for (int pair = cluster_id; pair < n_pairs; pair += n_clusters) {
             const TileCoord t = decode_tile<HT_H, HT_TW>(p, pair_tile(pair), BN);
             for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -718,6 +726,18 @@ conv_halo2_kernel(const __grid_constant__ ConvParams p) {
                 }
                 __syncwarp();
                 if (++stage == NST) { stage = 0; phase ^= 1u; }
+                if (!WRES) {
+                    for (int tap = 0; tap < 9; ++tap) {           // this CTA's half of every (tap, chunk) weight slice
+                        mbar_wait(&bempty_bar[bstage], bphase ^ 1u);
+                        if (elect_one()) {
+                            if (leader) mbar_expect_tx(&bfull_bar[bstage], 2 * W_TILE_BYTES);
+                            tma_load_2d_2sm(w_res + bstage * W_TILE_BYTES, &p.tmB, &bfull_bar[bstage],
+                                            (tap * p.kchunks + kc) * KCHUNK, (int)rank * (BN / 2));
+                        }
+                        __syncwarp();
+                        if (++bstage == NBS) { bstage = 0; bphase ^= 1u; }
+                    }
+                }
             }
         }
     } else if (warp == 1) {
@@ -728,10 +748,10 @@ conv_halo2_kernel(const __grid_constant__ ConvParams p) {
             const uint32_t w_addr = smem_u32(w_res);
             const uint32_t tap_dy_bytes = (uint32_t)(p.dil * p.region_w) * 128u;
             const uint32_t tap_dx_bytes = (uint32_t)p.dil * 128u;
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, bstage = 0;
+            uint32_t phase = 0, bphase = 0;
             int it = 0;
-            mbar_wait(w_bar, 0);
+            if (WRES) mbar_wait(w_bar, 0);
             for (int pair = cluster_id; pair < n_pairs; pair += n_clusters, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
@@ -743,29 +763,55 @@ conv_halo2_kernel(const __grid_constant__ ConvParams p) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t region = smem_u32(a_ring + stage * p.region_stride);
-                    const uint32_t w_chunk = w_addr + (uint32_t)(kc * W_TILE_BYTES);
-                    const uint32_t w_tap_stride = (uint32_t)(p.kchunks * W_TILE_BYTES);
-                    if (elect_one()) {
-                        // (no tap skipping here: the two tiles of a pair may sit at different image borders;
-                        //  windows in the padding read TMA's zero fill)
+                    if (WRES) {
+                        const uint32_t w_chunk = w_addr + (uint32_t)(kc * W_TILE_BYTES);
+                        const uint32_t w_tap_stride = (uint32_t)(p.kchunks * W_TILE_BYTES);
+                        if (elect_one()) {
+                            // (no tap skipping here: the two tiles of a pair may sit at different image borders;
+                            //  windows in the padding read TMA's zero fill)
 #pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint32_t a_addr = region + (uint32_t)(tap / 3) * tap_dy_bytes + (uint32_t)(tap % 3) * tap_dx_bytes;
+                                const uint64_t adesc = umma_desc_sw128_strided(a_addr, sbo);
+                                const uint64_t bdesc = umma_desc_sw128(w_chunk + (uint32_t)tap * w_tap_stride);
+#pragma unroll
+                                for (int k = 0; k < KCHUNK / 16; ++k) {
+#pragma unroll
+                                    for (int half = 0; half < NH; ++half)
+                                        umma_bf16_2sm(d_tmem + (uint32_t)(half * BN), adesc + (uint64_t)(2 * k + 64 * half),
+                                                      bdesc + (uint64_t)(2 * k), idesc, accumulate);
+                                    accumulate = 1;
+                                }
+                            }
+                            umma_commit_2sm(&empty_bar[stage]);
+                        }
+                        __syncwarp();
+                        accumulate = 1;
+                    } else {
+#pragma unroll 1
                         for (int tap = 0; tap < 9; ++tap) {
+                            mbar_wait(&bfull_bar[bstage], bphase);
+                            tc_fence_after();
                             const uint32_t a_addr = region + (uint32_t)(tap / 3) * tap_dy_bytes + (uint32_t)(tap % 3) * tap_dx_bytes;
                             const uint64_t adesc = umma_desc_sw128_strided(a_addr, sbo);
-                            const uint64_t bdesc = umma_desc_sw128(w_chunk + (uint32_t)tap * w_tap_stride);
+                            const uint64_t bdesc = umma_desc_sw128(w_addr + (uint32_t)(bstage * W_TILE_BYTES));
+                            if (elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < KCHUNK / 16; ++k) {
+                                for (int k = 0; k < KCHUNK / 16; ++k) {
 #pragma unroll
-                                for (int half = 0; half < NH; ++half)
-                                    umma_bf16_2sm(d_tmem + (uint32_t)(half * BN), adesc + (uint64_t)(2 * k + 64 * half),
-                                                  bdesc + (uint64_t)(2 * k), idesc, accumulate);
-                                accumulate = 1;
+                                    for (int half = 0; half < NH; ++half)
+                                        umma_bf16_2sm(d_tmem + (uint32_t)(half * BN), adesc + (uint64_t)(2 * k + 64 * half),
+                                                      bdesc + (uint64_t)(2 * k), idesc, (k == 0) ? accumulate : 1u);
+                                }
+                                umma_commit_2sm(&bempty_bar[bstage]);
                             }
+                            __syncwarp();
+                            accumulate = 1;
+                            if (++bstage == NBS) { bstage = 0; bphase ^= 1u; }
                         }
-                        umma_commit_2sm(&empty_bar[stage]);
+                        if (elect_one()) umma_commit_2sm(&empty_bar[stage]);
+                        __syncwarp();
                     }
-                    __syncwarp();
-                    accumulate = 1;
                     if (++stage == NST) { stage = 0; phase ^= 1u; }
                 }
                 if (elect_one()) umma_commit_2sm(&tfull_bar[as]);
@@ -1055,18 +1101,33 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
     size_t halo_smem = 0;
     const char* pair_env = getenv("DC_CONV_PAIR");               // measurement aid: "0" disables the CTA-pair kernel
     if (!up && a->Cout == BN && BN <= 128 && a->dilation <= 4 && !(pair_env && pair_env[0] == '0')) {
-        // CTA pair (cta_group::2): half of the weight rows per SM, two-half regions
-        const size_t w_half = (size_t)9 * (a->Cin / KCHUNK) * (BN / 2) * KCHUNK * 2;
+        // CTA pair (cta_group::2): half of the weight rows per SM, two-half regions; weights resident when the
+        // layer's half fits next to two regions, else streamed (BN = 128 only: a BN = 64 slice is too little work
+        // to cover the L2 latency with the ring that fits)
+        const size_t w_tile = (size_t)(BN / 2) * KCHUNK * 2;
+        const size_t w_half = (size_t)9 * (a->Cin / KCHUNK) * w_tile;
         const size_t budget = 227 * 1024 - 1024 - HALO_BAR_BYTES - 768 - EPI_STAGE_TOTAL;
         const int rw = HT_W * 2 + 2 * a->dilation, rh = HT_H + 2 * a->dilation;
         const size_t region_stride = (size_t)rw * rh * KCHUNK * 2;
-        const long long nst = w_half < budget ? (long long)((budget - w_half) / region_stride) : 0;
-        if (nst >= 2) {
-            halo = halo_pair = true;
-            halo_nhalf = 2;
-            p.region_w = rw; p.region_h = rh; p.region_stride = (int)region_stride;
-            p.nstages = nst > HALO_MAX_STAGES ? HALO_MAX_STAGES : (int)nst;
-            halo_smem = w_half + (size_t)p.nstages * region_stride + 1024 + HALO_BAR_BYTES + 768 + EPI_STAGE_TOTAL;
+        for (int pass = 0; pass < (BN == 128 ? 2 : 1) && !halo; ++pass) {
+            size_t wsm = w_half;
+            int nb = 0;
+            if (pass == 1) {
+                if (budget < 2 * region_stride + 4 * w_tile) break;
+                nb = (int)((budget - 2 * region_stride) / w_tile);
+                if (nb > HALO_MAX_STAGES) nb = HALO_MAX_STAGES;
+                wsm = (size_t)nb * w_tile;
+            }
+            const long long nst = wsm < budget ? (long long)((budget - wsm) / region_stride) : 0;
+            if (nst >= 2) {
+                halo = halo_pair = true;
+                halo_wres = pass == 0;
+                halo_nhalf = 2;
+                p.region_w = rw; p.region_h = rh; p.region_stride = (int)region_stride;
+                p.nstages = nst > HALO_MAX_STAGES ? HALO_MAX_STAGES : (int)nst;
+                p.nbstages = nb;
+                halo_smem = wsm + (size_t)p.nstages * region_stride + 1024 + HALO_BAR_BYTES + 768 + EPI_STAGE_TOTAL;
+            }
         }
     }
     if (!halo && !up && a->Cout == BN && BN <= 128 && a->dilation <= 4) {
@@ -1156,12 +1217,14 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
         const int grid = 2 * (n_pairs < max_clusters ? n_pairs : max_clusters);
         static bool attr_done = false;
         if (!attr_done) {
-            DC_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            DC_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            DC_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            DC_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            DC_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             attr_done = true;
         }
-        if (BN == 64) conv_halo2_kernel<64><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
-        else          conv_halo2_kernel<128><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
+        if (BN == 64)       conv_halo2_kernel<64, true><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
+        else if (halo_wres) conv_halo2_kernel<128, true><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
+        else                conv_halo2_kernel<128, false><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
         DC_CUDA(cudaGetLastError());
         return DC_OK;
     }
