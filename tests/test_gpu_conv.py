@@ -49,6 +49,9 @@ CONV_CASES = [
     (1, 40, 40, 64, 128, 2),      # enc2.0 shape: halo kernel, BN = 128, dilation 2
     (1, 32, 16, 64, 64, 4),       # halo kernel, dilation 4
     (2, 16, 8, 64, 64, 1),        # exactly one 16 x 8 halo tile per image
+    (1, 48, 40, 256, 512, 1),     # CTA-pair kernel, BN = 256, two n-tiles, odd number of m-tiles (15)
+    (3, 16, 24, 128, 256, 4),     # CTA-pair kernel, BN = 256, dilation 4
+    (1, 16, 8, 512, 256, 2),      # CTA-pair kernel, a single m-tile (the peer CTA redoes it)
 ]
 
 
@@ -66,10 +69,18 @@ def test_conv3x3_store(cuda_device, B, H, W, cin, cout, d):
     _close(got, want, f"conv {cin}->{cout} d{d} {B}x{H}x{W}")
 
 
-@pytest.mark.parametrize("B,H,W,cin,cout,d", [(2, 16, 32, 64, 64, 1), (1, 24, 40, 64, 128, 2)])
+@pytest.mark.parametrize("B,H,W,cin,cout,d", [(2, 16, 32, 64, 64, 1), (1, 24, 40, 64, 128, 2), (1, 32, 48, 128, 256, 4)])
 def test_conv3x3_generic_path_forced(cuda_device, monkeypatch, B, H, W, cin, cout, d):
-    """Thin layers normally take conv_halo_kernel; DC_CONV_PATH=generic keeps the per-tap kernel covered."""
+    """Most layers take the CTA-pair halo kernel; DC_CONV_PATH=generic keeps the per-tap kernel covered."""
     monkeypatch.setenv("DC_CONV_PATH", "generic")
+    test_conv3x3_store(cuda_device, B, H, W, cin, cout, d)
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,d", [(2, 16, 32, 64, 64, 1), (2, 48, 24, 128, 64, 1), (1, 40, 40, 64, 128, 2),
+                                               (2, 16, 16, 128, 128, 2), (3, 40, 24, 192, 64, 3)])
+def test_conv3x3_single_cta_halo_forced(cuda_device, monkeypatch, B, H, W, cin, cout, d):
+    """DC_CONV_PAIR=0 keeps the single-CTA halo kernel (resident and streamed weights) covered."""
+    monkeypatch.setenv("DC_CONV_PAIR", "0")
     test_conv3x3_store(cuda_device, B, H, W, cin, cout, d)
 
 

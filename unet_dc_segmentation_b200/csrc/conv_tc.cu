@@ -107,6 +107,21 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
     return *reinterpret_cast<uint32_t*>(&r);
 }
 
+// CTA pairs: the two CTAs of a pair work on two different pixel tiles of the SAME n-tile (they share B).
+// pair index -> (m-tile pair, n-tile); tile of CTA `rank` = (2 * mpair + rank) * n_tiles + nt.  An odd m-tile
+// count makes the last peer redo the last m-tile (identical stores).
+__device__ __forceinline__ int pair_count(const ConvParams& p) {
+    const int m_tiles = p.total_tiles / p.n_tiles;
+    return ((m_tiles + 1) >> 1) * p.n_tiles;
+}
+__device__ __forceinline__ int pair_to_tile(const ConvParams& p, int pair, int rank) {
+    const int m_tiles = p.total_tiles / p.n_tiles;
+    const int mpair = pair / p.n_tiles, nt = pair - mpair * p.n_tiles;
+    int m = 2 * mpair + rank;
+    if (m >= m_tiles) m = m_tiles - 1;
+    return m * p.n_tiles + nt;
+}
+
 // tcgen05.wait::ld that also names the registers an earlier tcgen05.ld fills: the compiler must not touch
 // them before this point (the loads are asynchronous; a plain wait carries no data dependency).
 __device__ __forceinline__ void tmem_ld_wait_on(uint32_t* v) {
@@ -147,11 +162,10 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
     // warp-private smem buffer and stored as 8 pixels x 64 contiguous bytes per instruction (4 lanes per pixel).
     for (int it = group;; it += EPI_GROUPS) {
         int tile;
-        if (PAIR) {                     // CTA pair: pair = cluster + it * clusters, this CTA's tile = 2 * pair + rank
+        if (PAIR) {                     // CTA pair: pair = cluster + it * clusters
             const int pair = (int)(blockIdx.x >> 1) + it * (int)(gridDim.x >> 1);
-            if (2 * pair >= p.total_tiles) break;
-            tile = 2 * pair + (int)(blockIdx.x & 1);
-            if (tile >= p.total_tiles) tile = p.total_tiles - 1;
+            if (pair >= pair_count(p)) break;
+            tile = pair_to_tile(p, pair, (int)(blockIdx.x & 1));
         } else {
             tile = blockIdx.x + it * gridDim.x;
             if (tile >= p.total_tiles) break;
@@ -424,6 +438,7 @@ constexpr int HT_H = 16, HT_W = 8;      // 16 x 8 output patch: each 8-pixel row
 // NHALF = 1 is kept for layers whose resident weights leave no room for two 16-wide regions.
 constexpr int HALO_MAX_STAGES = 8;
 constexpr int HALO_BAR_BYTES = 512;     // 4 x 8 stage barriers + TMEM / weight barriers + TMEM slot
+constexpr int HALO_BIAS_BYTES = 4096 + 256;   // bias (<= 1024 channels) + out_conv weights
 
 // K-major SWIZZLE_128B descriptor whose 8-row groups are `sbo_bytes` apart and whose start may sit on any
 // 128 B row of a 1024 B-aligned region.  Measured on B200 (tests/test_gpu_conv.py halo cases): the MMA unit
@@ -463,7 +478,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
     uint64_t* w_bar = tempty_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
     float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + HALO_BAR_BYTES);
-    uint8_t* stg_s = reinterpret_cast<uint8_t*>(full_bar) + HALO_BAR_BYTES + 768;
+    uint8_t* stg_s = reinterpret_cast<uint8_t*>(full_bar) + HALO_BAR_BYTES + HALO_BIAS_BYTES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NST = p.nstages;
@@ -640,10 +655,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
 // (A 4 KB + B N/2 x 32 B per MMA), which is what bounds the N = 64 layers.
 // Leader = even CTA: it alone issues the MMAs; both CTAs run a TMA producer (bytes credited to the leader's
 // barriers), both run epilogues on their own TMEM half, commits are multicast to both CTAs' barriers.
-template <int BN, bool WRES>
+template <int BN, int NH, bool WRES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv_halo2_kernel(const __grid_constant__ ConvParams p) {
-    constexpr int NH = 2;
     constexpr int HT_TW = HT_W * NH;
     constexpr int W_TILE_BYTES = (BN / 2) * KCHUNK * 2;     // this CTA's half of one (tap, chunk) weight slice
     constexpr int TMEM_COLS = 2 * NH * BN;
@@ -662,7 +676,7 @@ conv_halo2_kernel(const __grid_constant__ ConvParams p) {
     uint64_t* w_bar = tempty_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
     float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + HALO_BAR_BYTES);
-    uint8_t* stg_s = reinterpret_cast<uint8_t*>(full_bar) + HALO_BAR_BYTES + 768;
+    uint8_t* stg_s = reinterpret_cast<uint8_t*>(full_bar) + HALO_BAR_BYTES + HALO_BIAS_BYTES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NST = p.nstages;
@@ -670,7 +684,7 @@ conv_halo2_kernel(const __grid_constant__ ConvParams p) {
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-    const int n_pairs = (p.total_tiles + 1) >> 1;
+    const int n_pairs = pair_count(p);
 
     stage_bias(p, bias_s);
     if (warp == 0 && lane == 0) {
@@ -697,11 +711,7 @@ conv_halo2_kernel(const __grid_constant__ ConvParams p) {
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t region_bytes = (uint32_t)(p.region_w * p.region_h * KCHUNK * 2);
 
-    // the pair's tiles: 2*pair + rank; an odd tile count makes the last peer redo the last tile (identical stores)
-    auto pair_tile = [&](int pair) {
-        int tile = 2 * pair + (int)rank;
-        return tile < p.total_tiles ? tile : p.total_tiles - 1;
-    };
+    auto pair_tile = [&](int pair) { return pair_to_tile(p, pair, (int)rank); };
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (one per CTA)
@@ -709,7 +719,7 @@ conv_halo2_kernel(const __grid_constant__ ConvParams p) {
             if (elect_one()) {
                 if (leader) mbar_expect_tx(w_bar, (uint32_t)(2 * n_wtiles * W_TILE_BYTES));
                 for (int j = 0; j < n_wtiles; ++j)
-                    tma_load_2d_2sm(w_res + j * W_TILE_BYTES, &p.tmB, w_bar, j * KCHUNK, (int)rank * (BN / 2));
+                    tma_load_2d_2sm(w_res + j * W_TILE_BYTES, &p.tmB, w_bar, j * KCHUNK, (int)rank * (BN / 2));   // n_tiles == 1
             }
             __syncwarp();
         }
@@ -732,7 +742,7 @@ conv_halo2_kernel(const __grid_constant__ ConvParams p) {
                         if (elect_one()) {
                             if (leader) mbar_expect_tx(&bfull_bar[bstage], 2 * W_TILE_BYTES);
                             tma_load_2d_2sm(w_res + bstage * W_TILE_BYTES, &p.tmB, &bfull_bar[bstage],
-                                            (tap * p.kchunks + kc) * KCHUNK, (int)rank * (BN / 2));
+                                            (tap * p.kchunks + kc) * KCHUNK, t.n0 + (int)rank * (BN / 2));
                         }
                         __syncwarp();
                         if (++bstage == NBS) { bstage = 0; bphase ^= 1u; }
@@ -1099,21 +1109,24 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
     bool halo = false, halo_wres = true, halo_pair = false;
     int halo_nhalf = 1;
     size_t halo_smem = 0;
-    const char* pair_env = getenv("DC_CONV_PAIR");               // measurement aid: "0" disables the CTA-pair kernel
-    if (!up && a->Cout == BN && BN <= 128 && a->dilation <= 4 && !(pair_env && pair_env[0] == '0')) {
-        // CTA pair (cta_group::2): half of the weight rows per SM, two-half regions; weights resident when the
-        // layer's half fits next to two regions, else streamed (BN = 128 only: a BN = 64 slice is too little work
-        // to cover the L2 latency with the ring that fits)
+    const char* pair_env = getenv("DC_CONV_PAIR");               // measurement aid: "0" disables the CTA-pair kernels
+    if (!up && a->dilation <= 4 && !(pair_env && pair_env[0] == '0')) {
+        // CTA pair (cta_group::2): half of the weight rows per SM.  BN <= 128: two 8-wide halves per tile (two MMA
+        // chains); BN = 256: one half (a 128-cycle MMA hides its own latency, and 2 x 2 x 256 columns would not fit
+        // TMEM).  Weights resident when Cout == BN and the layer's half fits next to two regions, else streamed
+        // (not at BN = 64: a 4 KB slice is too little work to cover the L2 latency with the ring that fits).
+        const int nh = BN == 256 ? 1 : 2;
         const size_t w_tile = (size_t)(BN / 2) * KCHUNK * 2;
         const size_t w_half = (size_t)9 * (a->Cin / KCHUNK) * w_tile;
-        const size_t budget = 227 * 1024 - 1024 - HALO_BAR_BYTES - 768 - EPI_STAGE_TOTAL;
-        const int rw = HT_W * 2 + 2 * a->dilation, rh = HT_H + 2 * a->dilation;
+        const size_t budget = 227 * 1024 - 1024 - HALO_BAR_BYTES - HALO_BIAS_BYTES - EPI_STAGE_TOTAL;
+        const int rw = HT_W * nh + 2 * a->dilation, rh = HT_H + 2 * a->dilation;
         const size_t region_stride = (size_t)rw * rh * KCHUNK * 2;
-        for (int pass = 0; pass < (BN == 128 ? 2 : 1) && !halo; ++pass) {
+        for (int pass = 0; pass < 2 && !halo; ++pass) {
             size_t wsm = w_half;
             int nb = 0;
+            if (pass == 0 && (a->Cout != BN || BN == 256)) continue;   // resident: single n-tile, BN <= 128 kernels
             if (pass == 1) {
-                if (budget < 2 * region_stride + 4 * w_tile) break;
+                if (BN == 64 || budget < 2 * region_stride + 4 * w_tile) break;
                 nb = (int)((budget - 2 * region_stride) / w_tile);
                 if (nb > HALO_MAX_STAGES) nb = HALO_MAX_STAGES;
                 wsm = (size_t)nb * w_tile;
@@ -1122,11 +1135,11 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
             if (nst >= 2) {
                 halo = halo_pair = true;
                 halo_wres = pass == 0;
-                halo_nhalf = 2;
+                halo_nhalf = nh;
                 p.region_w = rw; p.region_h = rh; p.region_stride = (int)region_stride;
                 p.nstages = nst > HALO_MAX_STAGES ? HALO_MAX_STAGES : (int)nst;
                 p.nbstages = nb;
-                halo_smem = wsm + (size_t)p.nstages * region_stride + 1024 + HALO_BAR_BYTES + 768 + EPI_STAGE_TOTAL;
+                halo_smem = wsm + (size_t)p.nstages * region_stride + 1024 + HALO_BAR_BYTES + HALO_BIAS_BYTES + EPI_STAGE_TOTAL;
             }
         }
     }
@@ -1135,7 +1148,7 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
         // TMA's 128 B alignment, not a 1024 B one: regions are packed back to back
         const size_t w_tile = (size_t)BN * KCHUNK * 2;
         const size_t w_bytes = (size_t)9 * (a->Cin / KCHUNK) * w_tile;
-        const size_t budget = 227 * 1024 - 1024 /* alignment slack */ - HALO_BAR_BYTES - 768 /* bias + out_conv */ -
+        const size_t budget = 227 * 1024 - 1024 /* alignment slack */ - HALO_BAR_BYTES - HALO_BIAS_BYTES -
                               EPI_STAGE_TOTAL /* epilogue transpose buffers */;
         // Preference order (measured, profiles/): two halves (two independent MMA chains) beat one; resident weights
         // beat streamed ones, and at BN = 64 a streamed slice carries only 256 MMA-cycles, too little to cover the
@@ -1165,7 +1178,7 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
                     p.region_w = rw; p.region_h = rh; p.region_stride = (int)region_stride;
                     p.nstages = nst > HALO_MAX_STAGES ? HALO_MAX_STAGES : (int)nst;
                     p.nbstages = nb;
-                    halo_smem = wsm + (size_t)p.nstages * region_stride + 1024 + HALO_BAR_BYTES + 768 + EPI_STAGE_TOTAL;
+                    halo_smem = wsm + (size_t)p.nstages * region_stride + 1024 + HALO_BAR_BYTES + HALO_BIAS_BYTES + EPI_STAGE_TOTAL;
                 }
             }
         }
@@ -1212,19 +1225,22 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
     p.prob_out = a->prob_out; p.mask_out = a->mask_out;
 
     if (halo_pair) {
-        const int n_pairs = (p.total_tiles + 1) / 2;
+        const int m_tiles = p.total_tiles / p.n_tiles;
+        const int n_pairs = ((m_tiles + 1) / 2) * p.n_tiles;
         const int max_clusters = num_sms() / 2;
         const int grid = 2 * (n_pairs < max_clusters ? n_pairs : max_clusters);
-        static bool attr_done = false;
-        if (!attr_done) {
-            DC_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            DC_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            DC_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr_done = true;
+#define DC_PAIR_CASE(bn, nh, wr)                                                                                      \
+        if (BN == bn && halo_wres == wr) {                                                                            \
+            static bool attr_done = false;                                                                            \
+            if (!attr_done) {                                                                                         \
+                DC_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<bn, nh, wr>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             227 * 1024));                                                            \
+                attr_done = true;                                                                                     \
+            }                                                                                                         \
+            conv_halo2_kernel<bn, nh, wr><<<grid, NUM_THREADS, halo_smem, stream>>>(p);                               \
         }
-        if (BN == 64)       conv_halo2_kernel<64, true><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
-        else if (halo_wres) conv_halo2_kernel<128, true><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
-        else                conv_halo2_kernel<128, false><<<grid, NUM_THREADS, halo_smem, stream>>>(p);
+        DC_PAIR_CASE(64, 2, true) DC_PAIR_CASE(128, 2, true) DC_PAIR_CASE(128, 2, false) DC_PAIR_CASE(256, 1, false)
+#undef DC_PAIR_CASE
         DC_CUDA(cudaGetLastError());
         return DC_OK;
     }
