@@ -660,7 +660,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv_halo2_kernel(const __grid_constant__ ConvParams p) {
     constexpr int HT_TW = HT_W * NH;
     constexpr int W_TILE_BYTES = (BN / 2) * KCHUNK * 2;     // this CTA's half of one (tap, chunk) weight slice
-    constexpr int TMEM_COLS = 2 * NH * BN;
+    constexpr int TMEM_USED = 2 * NH * BN;
+    constexpr int TMEM_COLS = TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512);   // power of two
+    static_assert(TMEM_USED <= 512, "accumulators exceed TMEM");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -1115,10 +1117,14 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
         // chains); BN = 256: one half (a 128-cycle MMA hides its own latency, and 2 x 2 x 256 columns would not fit
         // TMEM).  Weights resident when Cout == BN and the layer's half fits next to two regions, else streamed
         // (not at BN = 64: a 4 KB slice is too little work to cover the L2 latency with the ring that fits).
-        const int nh = BN == 256 ? 1 : 2;
+        // Halves per tile = independent accumulator chains.  Back-to-back MMAs into one accumulator issue ~130 cycles
+        // apart, so a chain needs >= 128 cycles of other work between its MMAs: N = 128 -> 2 halves (64-cycle MMAs),
+        // N = 64 -> 4 halves (32-cycle MMAs; 3 or 2 when the regions would not fit), N = 256 -> 1.
         const size_t w_tile = (size_t)(BN / 2) * KCHUNK * 2;
         const size_t w_half = (size_t)9 * (a->Cin / KCHUNK) * w_tile;
         const size_t budget = 227 * 1024 - 1024 - HALO_BAR_BYTES - HALO_BIAS_BYTES - EPI_STAGE_TOTAL;
+        const int nh_max = BN == 256 ? 1 : (BN == 128 ? 2 : 4);
+        for (int nh = nh_max; nh >= (BN == 64 ? 2 : nh_max) && !halo; --nh) {
         const int rw = HT_W * nh + 2 * a->dilation, rh = HT_H + 2 * a->dilation;
         const size_t region_stride = (size_t)rw * rh * KCHUNK * 2;
         for (int pass = 0; pass < 2 && !halo; ++pass) {
@@ -1141,6 +1147,7 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
                 p.nbstages = nb;
                 halo_smem = wsm + (size_t)p.nstages * region_stride + 1024 + HALO_BAR_BYTES + HALO_BIAS_BYTES + EPI_STAGE_TOTAL;
             }
+        }
         }
     }
     if (!halo && !up && a->Cout == BN && BN <= 128 && a->dilation <= 4) {
@@ -1230,7 +1237,7 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
         const int max_clusters = num_sms() / 2;
         const int grid = 2 * (n_pairs < max_clusters ? n_pairs : max_clusters);
 #define DC_PAIR_CASE(bn, nh, wr)                                                                                      \
-        if (BN == bn && halo_wres == wr) {                                                                            \
+        if (BN == bn && halo_nhalf == nh && halo_wres == wr) {                                                        \
             static bool attr_done = false;                                                                            \
             if (!attr_done) {                                                                                         \
                 DC_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<bn, nh, wr>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -1239,7 +1246,8 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
             }                                                                                                         \
             conv_halo2_kernel<bn, nh, wr><<<grid, NUM_THREADS, halo_smem, stream>>>(p);                               \
         }
-        DC_PAIR_CASE(64, 2, true) DC_PAIR_CASE(128, 2, true) DC_PAIR_CASE(128, 2, false) DC_PAIR_CASE(256, 1, false)
+        DC_PAIR_CASE(64, 4, true) DC_PAIR_CASE(64, 3, true) DC_PAIR_CASE(64, 2, true)
+        DC_PAIR_CASE(128, 2, true) DC_PAIR_CASE(128, 2, false) DC_PAIR_CASE(256, 1, false)
 #undef DC_PAIR_CASE
         DC_CUDA(cudaGetLastError());
         return DC_OK;
