@@ -20,19 +20,20 @@
 //             of tile i overlaps the MMAs of tile i+1.
 // Taps whose shifted patch is wholly outside the image (large dilation on small maps) are skipped.
 //
-// Two kernels share the roles and the epilogue:
-//   conv_tc_kernel    (generic)  one TMA box per (tap, 64-channel chunk): A is re-fetched per tap from L2.
-//                                Right for Cout >= 256 where each A chunk feeds 256 output channels.
-//   conv_halo_kernel  (Cout = 64 / 128, small dilation)  the packed weights of the whole layer stay
-//                                resident in shared memory and ONE haloed activation region
-//                                (16+2d) x (8+2d) pixels x 64 ch is loaded per tile and chunk; the nine taps
-//                                are nine UMMA descriptors into that region (start = base + (ky*d*RW + kx*d)
-//                                rows, stride between 8-pixel groups = RW rows).  L2->SM traffic drops ~9x,
-//                                which is what bounds the thin layers (profiles/r01_*).
+// Kernels (they share the roles and the epilogue; DESIGN.md 3.1 has the measurements):
+//   conv_tc_kernel     generic: one TMA box per (tap, 64-channel chunk), A re-fetched per tap from L2.
+//                      Used for dilation 8 / 16 (enc4, bottleneck) and the transposed convs.
+//   conv_halo_kernel   single CTA: ONE haloed activation region (16+2d) x (8*NH+2d) pixels x 64 ch per tile and
+//                      chunk; the nine taps are nine UMMA descriptors into that region (start = base +
+//                      (ky*d*RW + kx*d) rows, stride between 8-pixel groups = RW rows).  Weights resident in
+//                      shared memory, or streamed per (tap, chunk).  Fallback of the pair kernel.
+//   conv_halo2_kernel  the same on a CTA pair (cta_group::2): M = 256 MMAs over two SMs, each SM holds half of the
+//                      weight rows and its own pixel tile.  Runs every 3x3 layer with dilation <= 4.
+//   stem_tc_kernel     first layer (Cin = 3): im2col tile built by producer warps, K = 9 -> 16 or 27 -> 32.
 //
-// Warp roles (256 threads, 1 CTA / SM, persistent over tiles):
-//   warp 0 lane 0 : TMA producer           warp 1 lane 0 : tcgen05.mma issuer
-//   warp 2        : TMEM alloc / dealloc   warps 4..7    : epilogue (TMEM -> regs -> global)
+// Warp roles (384 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0 : TMA producer           warp 1 : tcgen05.mma issuer       (warp-uniform loops, one elected lane issues)
+//   warp 2 : TMEM alloc / dealloc   warps 4..11 : two epilogue groups (TMEM -> regs -> smem transpose -> global)
 #include "common.cuh"
 
 #include <cuda.h>
