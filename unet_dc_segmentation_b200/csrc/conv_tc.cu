@@ -208,8 +208,8 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                 const size_t ppix = ((size_t)t.img * (p.H >> 1) + (ph >> 1)) * (size_t)(p.W >> 1) + (pw >> 1);
                 pptr = p.pool_out + ppix * p.pool_stride + t.n0 + sq * 8;
             }
-            const bool pool_writer = !(lane & 1) && !(lane & TW);
-            const int pool_row = (TW == 16) ? (lane >> 1) : (((lane >> 4) << 2) | ((lane & 7) >> 1));
+            // first of the four warp-local pixels (index = row * TW + col) of the pooled pixel this lane stores
+            const int pool_r0 = (TW == 16) ? 2 * (lane >> 2) : (16 * (lane >> 4) + 2 * ((lane >> 2) & 3));
             int bias_base = t.n0;
             float head_acc = p.head_b;
 
@@ -273,25 +273,21 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                         const uint4 val = *reinterpret_cast<const uint4*>(stg + stg_off(8 * j + (lane >> 2), sq));
                         if (sval[j]) *reinterpret_cast<uint4*>(sptr[j] + c0) = val;
                     }
-                    __syncwarp();
                     if (p.epilogue == DC_EPI_STORE_POOL) {
-                        // 2x2 window = lanes {l, l^1 (w+1), l^TW (h+1), l^(TW+1)}: all inside this warp
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            uint32_t m = max_bf16x2(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
-                            pk[j] = max_bf16x2(m, __shfl_xor_sync(0xffffffffu, m, TW));
-                        }
-                        if (pool_writer) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                *reinterpret_cast<uint4*>(stg + stg_off(pool_row, q)) =
-                                    make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                        }
-                        __syncwarp();
-                        const uint4 val = *reinterpret_cast<const uint4*>(stg + stg_off(lane >> 2, sq));
-                        if (pval) *reinterpret_cast<uint4*>(pptr + c0) = val;
-                        __syncwarp();
+                        // 2x2 max straight from the staged tile: lane (pp, sq) reads chunk sq of the four pixels of
+                        // pooled pixel pp (the max of bf16-rounded values = the bf16 rounding of the max)
+                        const uint4 a0 = *reinterpret_cast<const uint4*>(stg + stg_off(pool_r0, sq));
+                        const uint4 a1 = *reinterpret_cast<const uint4*>(stg + stg_off(pool_r0 + 1, sq));
+                        const uint4 a2 = *reinterpret_cast<const uint4*>(stg + stg_off(pool_r0 + TW, sq));
+                        const uint4 a3 = *reinterpret_cast<const uint4*>(stg + stg_off(pool_r0 + TW + 1, sq));
+                        uint4 m;
+                        m.x = max_bf16x2(max_bf16x2(a0.x, a1.x), max_bf16x2(a2.x, a3.x));
+                        m.y = max_bf16x2(max_bf16x2(a0.y, a1.y), max_bf16x2(a2.y, a3.y));
+                        m.z = max_bf16x2(max_bf16x2(a0.z, a1.z), max_bf16x2(a2.z, a3.z));
+                        m.w = max_bf16x2(max_bf16x2(a0.w, a1.w), max_bf16x2(a2.w, a3.w));
+                        if (pval) *reinterpret_cast<uint4*>(pptr + c0) = m;
                     }
+                    __syncwarp();
                 }
             }
             if (half == NHALF - 1) {
