@@ -14,6 +14,7 @@
  *                                max_pool2d / cat / sigmoid calls inside that forward
  *                                (models/model_2.py:20-32,40-54,58-80), one layer at a time
  *   dc_rolling_ball              rolling_ball_correction_rgb  utils/data_loader.py:11-24
+ *   dc_resize_linear_u8          the two cv2.resize calls     quantify_droplets_batch.py:44, :57
  *   dc_label_stats               quantify                     quantify_droplets_batch.py:81-95
  *
  * Conventions: every function returns 0 (DC_OK) or a negative DC_E* code and never throws;
@@ -161,6 +162,21 @@ typedef struct dc_rolling_ball_args {
 
 int dc_rolling_ball_workspace_bytes(int B, int H, int W, int C, size_t* bytes);
 int dc_rolling_ball(const dc_rolling_ball_args_t* args, void* stream);
+
+/* ------------------------------------------------------------------ bilinear resize (u8)
+ * The two cv2.resize calls of quantify_droplets_batch.py:44 (frame -> IMG_SIZE x IMG_SIZE) and :57 (mask -> original
+ * size).  Both pass their interpolation flag in cv2.resize's `dst` slot, so both are OpenCV's default INTER_LINEAR
+ * on 8-bit data (11-bit fixed point); this entry point reproduces that bit for bit.
+ * in: u8 [B, src_h, src_w, C] interleaved (C = 1 or 3); out: u8 [B, dst_h, dst_w, C]. */
+typedef struct dc_resize_args {
+    const uint8_t* in;
+    uint8_t* out;
+    int B, C;
+    int src_h, src_w;
+    int dst_h, dst_w;
+} dc_resize_args_t;
+
+int dc_resize_linear_u8(const dc_resize_args_t* args, void* stream);
 
 /* ------------------------------------------------------------------ labelling + droplet table
  * quantify() of quantify_droplets_batch.py:81-95 for a batch of masks: 4-connected labelling,

@@ -48,6 +48,7 @@ def _lib():
         lib.orc_ellipse_rows.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
         lib.orc_rolling_ball_u8.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         lib.orc_label4.argtypes = [i32p, i32p, ctypes.c_int, ctypes.c_int]
+        lib.orc_resize_linear_u8.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, u8p, ctypes.c_int, ctypes.c_int]
         lib.orc_quantify.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_double,
                                      i32p, ctypes.c_int, i64p, f64p, f64p, f64p, f64p, f64p]
         _LIB = lib
@@ -78,6 +79,20 @@ def rolling_ball_correction_rgb(image: np.ndarray, radius: int = 50) -> np.ndarr
     rc = _lib().orc_rolling_ball_u8(_ptr(image, ctypes.c_uint8), _ptr(out, ctypes.c_uint8), H, W, C, int(radius))
     if rc != 0:
         raise RuntimeError(f"orc_rolling_ball_u8 failed: {rc}")
+    return out
+
+
+def resize_linear_u8(src: np.ndarray, dsize) -> np.ndarray:
+    """cv2.resize(src, dsize) with the default INTER_LINEAR on u8 -- what reference qdb:44 and qdb:57 effectively
+    call (their interpolation flag lands in the `dst` slot).  dsize = (width, height) as in cv2."""
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    dw, dh = int(dsize[0]), int(dsize[1])
+    sh, sw = src.shape[:2]
+    cn = 1 if src.ndim == 2 else src.shape[2]
+    out = np.empty((dh, dw) if src.ndim == 2 else (dh, dw, cn), np.uint8)
+    rc = _lib().orc_resize_linear_u8(_ptr(src, ctypes.c_uint8), sh, sw, cn, _ptr(out, ctypes.c_uint8), dh, dw)
+    if rc != 0:
+        raise RuntimeError(f"orc_resize_linear_u8 failed: {rc}")
     return out
 
 

@@ -19,6 +19,7 @@
  *                         reference quantify_droplets_batch.py:82 and :86
  *   orc_quantify          reference quantify_droplets_batch.py:81-95 (label, min_area
  *                         filter, relabel, regionprops_table, micron columns)
+ *   orc_resize_linear_u8  the two cv2.resize calls, reference quantify_droplets_batch.py:44 and :57
  *
  * Third-party arithmetic restated here (not vendored in /root/reference; requirements.txt
  * pins nothing): opencv-python (probe: 4.13.0 in this image) and scikit-image (absent in
@@ -208,4 +209,54 @@ int orc_quantify(const uint8_t *mask, int H, int W, int64_t min_area, double px_
     if (labels_out) memcpy(labels_out, img, sizeof(int32_t) * n);
     free(sr); free(sc); free(ar); free(img); free(lbl);
     return n2;
+}
+
+/* ------------------------------------------------------------------ bilinear resize (u8)
+ * cv2.resize(src, (dw, dh)) with INTER_LINEAR on 8-bit data, which is what BOTH resize calls of the reference
+ * do: quantify_droplets_batch.py:44 passes cv2.INTER_AREA and :57 passes cv2.INTER_NEAREST in the `dst` slot, so
+ * the interpolation stays at its default (pinned by tests/golden/resize.npz, generated with the
+ * reference's exact call form).  OpenCV (opencv-python 4.13, imgproc resize.cpp, not vendored in /root/reference):
+ *   fx = (float)((dx + 0.5) * scale - 0.5); sx = floor(fx); fx -= sx          (scale = 1 / (dsize / ssize), double)
+ *   x: sx < 0 -> sx = 0, fx = 0;  sx >= sw - 1 -> sx = sw - 1, fx = 0;  taps sx and min(sx + 1, sw - 1)
+ *   y: weights are NOT clamped; the two row indices sy, sy + 1 are clipped to [0, sh - 1]
+ *   coefficients: short(lrintf((1 - f) * 2048)), short(lrintf(f * 2048))
+ *   horizontal: S = s[sx] * a0 + s[sx + 1] * a1            (int)
+ *   vertical:   dst = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2
+ * src: u8 [sh, sw, cn] interleaved; dst: u8 [dh, dw, cn]. */
+static void orc_lin_coeff(int d, int dn, int sn, int clamp_frac, int *i0, int *i1, int *a0, int *a1)
+{
+    double scale = 1.0 / ((double)dn / (double)sn);
+    float f = (float)(((double)d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= (float)s;
+    if (clamp_frac) {
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= sn - 1) { s = sn - 1; f = 0.f; }
+        *i0 = s; *i1 = s + 1 < sn ? s + 1 : sn - 1;
+    } else {
+        *i0 = s < 0 ? 0 : (s > sn - 1 ? sn - 1 : s);
+        *i1 = s + 1 < 0 ? 0 : (s + 1 > sn - 1 ? sn - 1 : s + 1);
+    }
+    *a0 = (int)lrintf((1.f - f) * 2048.f);
+    *a1 = (int)lrintf(f * 2048.f);
+}
+
+int orc_resize_linear_u8(const uint8_t *src, int sh, int sw, int cn, uint8_t *dst, int dh, int dw)
+{
+    if (sh <= 0 || sw <= 0 || dh <= 0 || dw <= 0 || cn <= 0) return -1;
+    for (int y = 0; y < dh; ++y) {
+        int y0, y1, b0, b1;
+        orc_lin_coeff(y, dh, sh, 0, &y0, &y1, &b0, &b1);
+        for (int x = 0; x < dw; ++x) {
+            int x0, x1, a0, a1;
+            orc_lin_coeff(x, dw, sw, 1, &x0, &x1, &a0, &a1);
+            for (int c = 0; c < cn; ++c) {
+                int S0 = src[((size_t)y0 * sw + x0) * cn + c] * a0 + src[((size_t)y0 * sw + x1) * cn + c] * a1;
+                int S1 = src[((size_t)y1 * sw + x0) * cn + c] * a0 + src[((size_t)y1 * sw + x1) * cn + c] * a1;
+                int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+                dst[((size_t)y * dw + x) * cn + c] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+            }
+        }
+    }
+    return 0;
 }

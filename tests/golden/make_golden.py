@@ -263,6 +263,26 @@ def main():
             print("e2e image", i, "droplets", len(df), "fg", float(mask.mean()))
     np.savez_compressed(HERE / "end_to_end.npz", **e2e)
 
+    # ---- the two resizes exactly as the reference calls them (interpolation flag in the `dst` slot, qdb:44,57)
+    import cv2
+    rs = np.random.RandomState(21)
+    rz = {}
+    for name, shape, dsize in (("rgb_69x102_to_128", (69, 102, 3), (128, 128)), ("rgb_64_to_128", (64, 64, 3), (128, 128)),
+                               ("rgb_96_to_96", (96, 96, 3), (96, 96)), ("rgb_175x250_to_128", (175, 250, 3), (128, 128)),
+                               ("rgb_17x23_to_64", (17, 23, 3), (64, 64))):
+        im = rs.randint(0, 256, shape).astype(np.uint8)
+        rz[f"{name}/in"] = im
+        rz[f"{name}/dsize"] = np.array(dsize, np.int64)
+        rz[f"{name}/out"] = cv2.resize(im, dsize, cv2.INTER_AREA)              # qdb:44, verbatim call form
+    for name, shape, dsize in (("mask_128_to_102x69", (128, 128), (102, 69)), ("mask_128_to_64", (128, 128), (64, 64)),
+                               ("mask_128_to_250x175", (128, 128), (250, 175)), ("mask_64_to_23x17", (64, 64), (23, 17))):
+        m = (rs.rand(*shape) < 0.3).astype(np.uint8)
+        rz[f"{name}/in"] = m
+        rz[f"{name}/dsize"] = np.array(dsize, np.int64)
+        rz[f"{name}/out"] = cv2.resize(m, dsize, cv2.INTER_NEAREST)            # qdb:57, verbatim call form
+    np.savez_compressed(HERE / "resize.npz", **rz)
+    print("resize.npz", len(rz) // 3, "cases")
+
     # ---- the reference's shipped sample outputs: formula / column known answers
     import pandas as pd
     df = pd.read_csv(REF / "outputs" / "all_droplets.csv")

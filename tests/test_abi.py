@@ -40,7 +40,8 @@ def test_ctypes_structs_match_c_layout(tmp_path):
     """sizeof / offsetof of every argument struct, as gcc lays them out, equals the ctypes mirror."""
     from unet_dc_segmentation_b200 import _lib
     structs = {"dc_conv_args_t": _lib.ConvArgs, "dc_stem_args_t": _lib.StemArgs, "dc_model_desc_t": _lib.ModelDesc,
-               "dc_rolling_ball_args_t": _lib.RollingBallArgs, "dc_label_args_t": _lib.LabelArgs}
+               "dc_rolling_ball_args_t": _lib.RollingBallArgs, "dc_label_args_t": _lib.LabelArgs,
+               "dc_resize_args_t": _lib.ResizeArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]
     for cname, cls in structs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')

@@ -35,6 +35,16 @@ def test_quantify_matches_reference(case):
     assert labels.max() == len(cols["label"])
 
 
+RZ = load_golden("resize.npz")
+
+
+@pytest.mark.parametrize("case", golden_cases(RZ))
+def test_resize_matches_reference_call_form(case):
+    """The reference's resize calls (flag in the dst slot => bilinear) against the fixed-point restatement."""
+    src, dsize, want = RZ[f"{case}/in"], tuple(int(v) for v in RZ[f"{case}/dsize"]), RZ[f"{case}/out"]
+    np.testing.assert_array_equal(oracle.resize_linear_u8(src, dsize), want)
+
+
 def test_quantify_empty_frame_contract():
     df = oracle.quantify(np.zeros((8, 8), np.uint8), 1, 3.45)
     assert df.empty and len(df.columns) == 0            # qdb:87-88

@@ -11,9 +11,9 @@ All compute goes through lib/libunetdc_b200.so (C ABI: include/unetdc_b200.h).  
 PyTorch fallback: without the library or an sm_100 GPU the calls raise.
 """
 from .model import UNet, UNetDC  # noqa: F401
-from .morphology import rolling_ball_correction_rgb, rolling_ball_device  # noqa: F401
+from .morphology import resize_linear_u8_device, rolling_ball_correction_rgb, rolling_ball_device  # noqa: F401
 from .pipeline import DropletPipeline  # noqa: F401
 from .quantify import label_stats_device, quantify, quantify_arrays  # noqa: F401
 
-__all__ = ["UNetDC", "UNet", "rolling_ball_correction_rgb", "rolling_ball_device", "quantify", "quantify_arrays",
+__all__ = ["UNetDC", "UNet", "rolling_ball_correction_rgb", "rolling_ball_device", "resize_linear_u8_device", "quantify", "quantify_arrays",
            "label_stats_device", "DropletPipeline"]

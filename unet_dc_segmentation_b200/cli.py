@@ -7,9 +7,10 @@ Function-for-function (reference file:line):
     load_model   qdb:34-37     preprocess  qdb:40-46     run_batch  qdb:48-79     quantify  qdb:81-95
     main         qdb:100-201   (argparse flags qdb:101-128; report files qdb:163-199, read back by gui_qt.py:470-589)
 
-What stays on the host, exactly as in the reference: PIL decode, the two cv2.resize calls (which are bilinear --
-the reference passes the interpolation flag in the `dst` slot, SURVEY.md 0.2 -- and the identity when the frame
-is already IMG_SIZE), PNG / CSV / XLSX writing, overlays.  `--img_size` (default 512 = the reference's IMG_SIZE
+On the device: rolling ball, both resizes (cv2.resize at qdb:44 and qdb:57 is bilinear -- the reference passes the
+interpolation flag in the `dst` slot, SURVEY.md 0.2 -- reproduced bit for bit by dc_resize_linear_u8; the identity
+when the frame is already IMG_SIZE), the network, the threshold, labelling and the table.  On the host, exactly as
+in the reference: PIL decode, PNG / CSV / XLSX writing, overlays.  `--img_size` (default 512 = the reference's IMG_SIZE
 constant) and `--gpus` are the only additions; with `--gpus N` (under torchrun) frames are sharded i -> rank
 i mod N and the tables are gathered on rank 0.
 """
@@ -23,7 +24,7 @@ import numpy as np
 import torch
 
 from .model import UNetDC
-from .morphology import rolling_ball_correction_rgb
+from .morphology import resize_linear_u8_device, rolling_ball_device
 from .quantify import quantify
 
 IMG_SIZE = 512                     # qdb:30
@@ -45,17 +46,19 @@ def load_model(ckpt) -> UNetDC:
 
 
 def preprocess(path, background_radius: int, img_size: int | None = None):
-    """qdb:40-46: decode to RGB, rolling-ball correct, resize to the network size, /255, HWC -> CHW."""
-    import cv2
+    """qdb:40-46: decode to RGB, rolling-ball correct, resize to the network size, /255, HWC -> CHW.
+    Returns (f32 [3,S,S] tensor on the GPU, (oh, ow))."""
     from PIL import Image
     size = IMG_SIZE if img_size is None else int(img_size)
     im = np.array(Image.open(path).convert("RGB"))
     oh, ow = im.shape[:2]
-    im = rolling_ball_correction_rgb(im, background_radius)
+    x = torch.from_numpy(im).to(_device())[None]                               # u8 [1,oh,ow,3]
+    x = rolling_ball_device(x, background_radius)                             # qdb:43
     if (oh, ow) != (size, size):
-        im = cv2.resize(im, (size, size), interpolation=cv2.INTER_LINEAR)      # what qdb:44 effectively does
-    im = im.astype(np.float32) / 255.0
-    return torch.from_numpy(im).permute(2, 0, 1), (oh, ow)
+        x = resize_linear_u8_device(x, (size, size))                          # qdb:44 (effectively INTER_LINEAR)
+    # IEEE division as numpy does it at qdb:45 (torch turns `/ python_scalar` into a multiply by the reciprocal)
+    scale = torch.full((), 255.0, dtype=torch.float32, device=x.device)
+    return torch.div(x[0].to(torch.float32), scale).permute(2, 0, 1), (oh, ow)    # qdb:45-46
 
 
 @torch.no_grad()
@@ -64,14 +67,15 @@ def run_batch(tensors, meta, model, mask_dir, overlay_dir, thresh, min_area, px_
     import cv2
     dev = next(model.parameters()).device
     batch = torch.stack(tensors).to(dev)
-    probs = model(batch)
-    masks = (probs[:, 0] > thresh).to(torch.uint8).cpu().numpy()
+    probs = model(batch.contiguous())
+    masks_dev = (probs[:, 0] > thresh).to(torch.uint8)                        # qdb:56
     for i in range(len(tensors)):
         fpath, (oh, ow) = meta[i]
         name = Path(fpath).stem
-        mask = masks[i]
-        if mask.shape != (oh, ow):
-            mask = cv2.resize(mask, (ow, oh), interpolation=cv2.INTER_LINEAR)   # what qdb:57 effectively does
+        m = masks_dev[i:i + 1]
+        if tuple(m.shape[1:]) != (oh, ow):
+            m = resize_linear_u8_device(m, (ow, oh))                          # qdb:57 (effectively INTER_LINEAR)
+        mask = m[0].cpu().numpy()
         cv2.imwrite(str(Path(mask_dir) / f"{name}_pred.png"), mask * 255)
         df = quantify(mask, min_area, px_per_um)
         df.insert(0, "filename", Path(fpath).name)

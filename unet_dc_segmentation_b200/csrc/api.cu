@@ -139,6 +139,12 @@ int dc_rolling_ball(const dc_rolling_ball_args_t* args, void* stream) {
     return launch_rolling_ball(args, (cudaStream_t)stream);
 }
 
+int dc_resize_linear_u8(const dc_resize_args_t* args, void* stream) {
+    int rc = check_current_device(nullptr);
+    if (rc != DC_OK) return rc;
+    return launch_resize_linear_u8(args, (cudaStream_t)stream);
+}
+
 int dc_label_workspace_bytes(int B, int H, int W, size_t* bytes) {
     DC_REQUIRE(bytes && B > 0 && H > 0 && W > 0, DC_EINVAL, "dc_label_workspace_bytes: bad argument");
     *bytes = label_workspace_bytes(B, H, W);

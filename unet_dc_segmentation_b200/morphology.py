@@ -62,3 +62,25 @@ def rolling_ball_correction_rgb(image: np.ndarray, radius: int = 50, device: str
     t = torch.from_numpy(arr).to(device)[None]
     out = rolling_ball_device(t, radius)[0].cpu().numpy()
     return out[:, :, 0] if squeeze else out
+
+
+def resize_linear_u8_device(images: torch.Tensor, dsize, out: torch.Tensor | None = None) -> torch.Tensor:
+    """cv2.resize(img, dsize) with the default INTER_LINEAR on u8, bit-exact, for a device batch -- what the two
+    resize calls of reference quantify_droplets_batch.py:44 and :57 effectively do (flag in the `dst` slot).
+    images: CUDA u8 [B,H,W] or [B,H,W,3]; dsize = (width, height) as in cv2.  Returns [B,dh,dw(,3)]."""
+    _lib.require_cuda(images, "images")
+    if images.dtype != torch.uint8 or images.dim() not in (3, 4):
+        raise TypeError("resize works on uint8 [B,H,W] or [B,H,W,3]")
+    images = images.contiguous()
+    B, sh, sw = images.shape[:3]
+    cn = 1 if images.dim() == 3 else images.shape[3]
+    dw, dh = int(dsize[0]), int(dsize[1])
+    shape = (B, dh, dw) if images.dim() == 3 else (B, dh, dw, cn)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.uint8, device=images.device)
+    elif tuple(out.shape) != shape or out.dtype != torch.uint8 or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous uint8 tensor of shape {shape}")
+    args = _lib.ResizeArgs(images.data_ptr(), out.data_ptr(), B, cn, sh, sw, dh, dw)
+    with torch.cuda.device(images.device):
+        _lib.check(_lib.load().dc_resize_linear_u8(C.byref(args), _lib.stream_ptr(images.device)))
+    return out

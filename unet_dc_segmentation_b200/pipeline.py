@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 from .model import UNetDC
-from .morphology import rolling_ball_device, rolling_ball_workspace_bytes
+from .morphology import resize_linear_u8_device, rolling_ball_device, rolling_ball_workspace_bytes
 from .quantify import DEFAULT_CAPACITY, DropletTables, alloc_tables, label_stats_device, label_workspace_bytes
 
 
@@ -34,8 +34,14 @@ class BatchResult:
 
 class DropletPipeline:
     def __init__(self, model: UNetDC, background_radius: int | None = 50, prob_thresh: float = 0.3,
-                 min_area: int = 1, px_per_micron: float | None = None, capacity: int = DEFAULT_CAPACITY):
+                 min_area: int = 1, px_per_micron: float | None = None, capacity: int = DEFAULT_CAPACITY,
+                 img_size: int | None = None):
+        """img_size: network input size.  None = native resolution (frames must be multiples of 16; both resizes of
+        the reference are then the identity).  An integer reproduces the as-shipped flow (IMG_SIZE = 512, qdb:30):
+        corrected frames are resized to img_size x img_size (qdb:44) and the mask is resized back to the frame size
+        (qdb:57), both with cv2's effective INTER_LINEAR, on the device."""
         self.model = model
+        self.img_size = img_size
         self.background_radius = background_radius
         self.prob_thresh = float(prob_thresh)
         self.min_area = int(min_area)
@@ -60,7 +66,14 @@ class DropletPipeline:
                 need = rolling_ball_workspace_bytes(x.shape[0], x.shape[1], x.shape[2], 1 if x.dim() == 3 else x.shape[3])
                 self._rb_ws = torch.empty(need, dtype=torch.uint8, device=x.device)
             x = rolling_ball_device(x, self.background_radius, out=self._rb_out, workspace=self._rb_ws)
-        masks, probs = self.model.predict_u8(x, self.prob_thresh, return_prob=return_prob, mask_out=mask_out)
+        oh, ow = int(images.shape[1]), int(images.shape[2])
+        resized = self.img_size is not None and (oh, ow) != (self.img_size, self.img_size)
+        if resized:
+            x = resize_linear_u8_device(x, (self.img_size, self.img_size))                     # qdb:44
+            masks, probs = self.model.predict_u8(x, self.prob_thresh, return_prob=return_prob)
+            masks = resize_linear_u8_device(masks, (ow, oh), out=mask_out)                     # qdb:57
+        else:
+            masks, probs = self.model.predict_u8(x, self.prob_thresh, return_prob=return_prob, mask_out=mask_out)
         need = label_workspace_bytes(*masks.shape)
         if self._ccl_ws is None or self._ccl_ws.device != masks.device or self._ccl_ws.numel() < need:
             self._ccl_ws = torch.empty(need, dtype=torch.uint8, device=masks.device)
