@@ -51,6 +51,8 @@ class DropletPipeline:
         self._rb_out = None
         self._ccl_ws = None
         self._staging = None
+        self._slots = [None, None]       # run_host_pipelined's device / pinned buffers, kept across calls
+        self._streams = None
 
     # ------------------------------------------------------------------ device-resident entry
     def run_device(self, images: torch.Tensor, return_prob: bool = False, want_labels: bool = False,
@@ -115,8 +117,11 @@ class DropletPipeline:
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
         it = iter(batches)
-        s_in, s_run, s_out = (torch.cuda.Stream(dev) for _ in range(3))
-        slots = [None, None]
+        if self._streams is None or self._streams[0].device != dev:
+            self._streams = tuple(torch.cuda.Stream(dev) for _ in range(3))
+            self._slots = [None, None]
+        s_in, s_run, s_out = self._streams
+        slots = self._slots              # pinned allocations cost milliseconds: made once, reused by later calls
         micron = bool(self.px_per_micron)
 
         def make_slot(shape):
@@ -135,7 +140,8 @@ class DropletPipeline:
         def stage(k, host):
             host = torch.from_numpy(np.ascontiguousarray(host)) if isinstance(host, np.ndarray) else host
             sl = slots[k % 2]
-            if sl is None or sl["dev_in"].shape != host.shape:
+            if (sl is None or sl["dev_in"].shape != host.shape or sl["tables"].capacity != self.capacity
+                    or (sl["tables"].area_um2 is not None) != micron):
                 sl = slots[k % 2] = make_slot(tuple(host.shape))
             with torch.cuda.stream(s_in):
                 s_in.wait_event(sl["ev_free"])            # the slot's previous batch has been computed and read back
