@@ -110,7 +110,8 @@ class DropletPipeline:
         """Generator over host batches (each u8 [B,H,W] or [B,H,W,3], ideally pinned; all the same shape):
         yields (masks u8 numpy [B,H,W], list of per-image column dicts) per batch, in order.
 
-        Three streams and two buffer slots: the H2D copy of batch k+1 and the D2H copy of batch k-1 run while
+        Four streams (copy-in, compute, one read-back stream per slot) and two buffer slots: the H2D copy of batch
+        k+1 and the D2H copy of batch k-1 run while
         batch k computes, so the steady-state rate is the device rate, not device + PCIe.  Outputs land in
         pinned host buffers owned by the pipeline (copy them if you keep more than two batches alive)."""
         dev = torch.device(device)
@@ -118,9 +119,12 @@ class DropletPipeline:
             dev = torch.device("cuda", torch.cuda.current_device())
         it = iter(batches)
         if self._streams is None or self._streams[0].device != dev:
-            self._streams = tuple(torch.cuda.Stream(dev) for _ in range(3))
+            self._streams = tuple(torch.cuda.Stream(dev) for _ in range(4))
             self._slots = [None, None]
-        s_in, s_run, s_out = self._streams
+        # one read-back stream PER SLOT: finishing batch k-1 must not wait behind batch k's mask copy, which is
+        # queued as soon as batch k is launched and cannot start before batch k has been computed
+        s_in, s_run, s_out0, s_out1 = self._streams
+        s_outs = (s_out0, s_out1)
         slots = self._slots              # pinned allocations cost milliseconds: made once, reused by later calls
         micron = bool(self.px_per_micron)
 
@@ -150,6 +154,7 @@ class DropletPipeline:
 
         def compute(k):
             sl = slots[k % 2]
+            s_out = s_outs[k % 2]
             with torch.cuda.stream(s_run):
                 s_run.wait_event(sl["ev_in"])
                 self.run_device(sl["dev_in"], mask_out=sl["masks"], tables_out=sl["tables"])
@@ -162,6 +167,7 @@ class DropletPipeline:
 
         def finish(k):
             sl = slots[k % 2]
+            s_out = s_outs[k % 2]
             t = sl["tables"]
             sl["ev_counts"].synchronize()
             counts = sl["h_counts"].numpy().copy()
