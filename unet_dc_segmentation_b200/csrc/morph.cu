@@ -39,13 +39,6 @@ __device__ __forceinline__ unsigned vop(unsigned a, unsigned b) {
     return IS_MAX ? __vmaxu4(a, b) : __vminu4(a, b);
 }
 
-// 4 bytes starting at byte offset `off` of a word-aligned shared array
-__device__ __forceinline__ unsigned ld4_unaligned(const unsigned* base, int off) {
-    int w = off >> 2;
-    unsigned lo = base[w], hi = base[w + 1];
-    return __funnelshift_r(lo, hi, (off & 3) * 8);
-}
-
 // One morphology pass over planes addressed as in[((p/C)*H*W + y*W + x)*C + p%C] (in_c = C) and
 // written planar.  SUBTRACT: out = saturate(orig - result), plus a per-plane min/max reduction.
 template <bool IS_MAX, bool SUBTRACT>
@@ -67,6 +60,18 @@ __global__ void __launch_bounds__(512) morph_pass_kernel(const uint8_t* __restri
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const int nthreads = blockDim.x * blockDim.y;
 
+    __shared__ int2 rowtab[MAX_RADIUS];
+    __shared__ int nrows_s;
+    if (tid == 0) {
+        int n = 0;
+        for (int i = 0; i < k; ++i) {
+            const int l = se.lvl[i];
+            if (l == 255) continue;
+            const int base = (l * level_words + i * pitch) * 4;
+            rowtab[n++] = make_int2(base + se.j1[i], base + se.j2m[i]);
+        }
+        nrows_s = n;
+    }
     // ---- stage level 0 (tile + halo), identity outside the image ----
     uint8_t* s8 = reinterpret_cast<uint8_t*>(smem);
     const uint8_t* src = in + (size_t)b * H * W * in_c + c;
@@ -98,16 +103,29 @@ __global__ void __launch_bounds__(512) morph_pass_kernel(const uint8_t* __restri
         __syncthreads();
     }
     // ---- combine the element rows ----
+    // sm_100a has no byte-lane SIMD min/max (__vminu4 expands to 7 instructions) but it has the DPX 16-bit-lane
+    // three-operand form (VIMNMX3.U16x2).  The accumulator is kept as two words of 16-bit lanes (even / odd
+    // pixels); each fetched u8x4 window is split with two PRMTs, so a row costs 4 PRMT + 2 VIMNMX3 instead of 14.
+    // rowtab: per non-empty element row, the byte offsets of its two windows inside the level tables (one
+    // broadcast LDS.64 instead of three dependent constant-bank loads plus address arithmetic).
     const int lx4 = threadIdx.x * 4, ly = threadIdx.y;
-    unsigned acc = ident;
-    for (int i = 0; i < k; ++i) {
-        const int l = se.lvl[i];
-        if (l == 255) continue;
-        const unsigned* row = smem + l * level_words + (ly + i) * pitch;
-        unsigned a = ld4_unaligned(row, lx4 + se.j1[i]);
-        unsigned bb = ld4_unaligned(row, lx4 + se.j2m[i]);
-        acc = vop<IS_MAX>(acc, vop<IS_MAX>(a, bb));
+    const uint8_t* tbase = reinterpret_cast<const uint8_t*>(smem) + (ly * pitch) * 4 + lx4;
+    const unsigned id16 = IS_MAX ? 0u : 0x00ff00ffu;
+    unsigned acc_e = id16, acc_o = id16;
+    const int nrows = nrows_s;
+#pragma unroll 4
+    for (int n = 0; n < nrows; ++n) {
+        const int2 t = rowtab[n];
+        const unsigned* ra = reinterpret_cast<const unsigned*>(tbase + (t.x & ~3));
+        const unsigned* rb = reinterpret_cast<const unsigned*>(tbase + (t.y & ~3));
+        const unsigned a = __funnelshift_r(ra[0], ra[1], (t.x & 3) * 8);
+        const unsigned bb = __funnelshift_r(rb[0], rb[1], (t.y & 3) * 8);
+        const unsigned a_e = __byte_perm(a, 0, 0x4240), a_o = __byte_perm(a, 0, 0x4341);
+        const unsigned b_e = __byte_perm(bb, 0, 0x4240), b_o = __byte_perm(bb, 0, 0x4341);
+        acc_e = IS_MAX ? __vimax3_u16x2(acc_e, a_e, b_e) : __vimin3_u16x2(acc_e, a_e, b_e);
+        acc_o = IS_MAX ? __vimax3_u16x2(acc_o, a_o, b_o) : __vimin3_u16x2(acc_o, a_o, b_o);
     }
+    const unsigned acc = __byte_perm(acc_e, acc_o, 0x6240);     // bytes: e.lo, o.lo, e.hi, o.hi
     // ---- write (and, for the second pass, subtract + reduce) ----
     const int gx = blockIdx.x * TW + lx4, gy = blockIdx.y * TH + ly;
     int mn = 255, mx = 0;
@@ -225,11 +243,11 @@ int launch_rolling_ball(const dc_rolling_ball_args_t* a, cudaStream_t stream) {
 
     const int RW = TW + se.k, pitch = ((RW + 3) >> 2) + 1, RH = TH + se.k - 1;
     const size_t smem = (size_t)se.nlevels * pitch * RH * 4;
-    DC_REQUIRE(smem <= 227 * 1024, DC_EINVAL, "dc_rolling_ball: radius %d needs %zu B of shared memory", a->radius, smem);
+    DC_REQUIRE(smem <= 226 * 1024, DC_EINVAL, "dc_rolling_ball: radius %d needs %zu B of shared memory", a->radius, smem);
     static bool attr_done = false;
     if (!attr_done) {
-        DC_CUDA(cudaFuncSetAttribute(morph_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        DC_CUDA(cudaFuncSetAttribute(morph_pass_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DC_CUDA(cudaFuncSetAttribute(morph_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));   // + 816 B static (rowtab)
+        DC_CUDA(cudaFuncSetAttribute(morph_pass_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));   // + 816 B static (rowtab)
         attr_done = true;
     }
     dim3 block(TW / 4, TH);
