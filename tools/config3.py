@@ -1,0 +1,70 @@
+"""BASELINE config 3: rolling ball (radius 50) and labelling + droplet table on 2048x2048 frames / masks with
+~10k droplets each, measured on a batch of 64 (a single frame is microseconds of work), against HBM.
+
+    python tools/config3.py [--batch 64] [--out profiles/r01_config3.md]
+"""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO))
+from unet_dc_segmentation_b200 import label_stats_device, rolling_ball_device, workload as wl   # noqa: E402
+from unet_dc_segmentation_b200.morphology import rolling_ball_workspace_bytes   # noqa: E402
+from unet_dc_segmentation_b200.quantify import alloc_tables, label_workspace_bytes   # noqa: E402
+from unet_dc_segmentation_b200.synth import synthetic_image, synthetic_mask   # noqa: E402
+
+
+def timed(fn, n=5, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--size", type=int, default=2048)
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    B, S = a.batch, a.size
+    peaks = json.loads((REPO / "MEASURED_PEAKS.json").read_text()) if (REPO / "MEASURED_PEAKS.json").exists() else {}
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    dev = torch.device("cuda", 0)
+    base_f = [synthetic_image(S, i) for i in range(4)]
+    base_m = [synthetic_mask(S, 14000, seed=i, rmin=2, rmax=5) for i in range(4)]       # ~10k droplets each
+    frames = torch.from_numpy(np.stack([np.roll(base_f[i % 4], 31 * (i // 4), axis=1) for i in range(B)])).to(dev)
+    masks = torch.from_numpy(np.stack([np.roll(base_m[i % 4], 31 * (i // 4), axis=1) for i in range(B)])).to(dev)
+    px = B * S * S
+    out = torch.empty_like(frames)
+    ws = torch.empty(rolling_ball_workspace_bytes(B, S, S, 1), dtype=torch.uint8, device=dev)
+    ms_rb = timed(lambda: rolling_ball_device(frames, 50, out=out, workspace=ws))
+    cws = torch.empty(label_workspace_bytes(B, S, S), dtype=torch.uint8, device=dev)
+    tabs = alloc_tables(B, 16384, True, dev)
+    ms_ccl = timed(lambda: label_stats_device(masks, 1, 3.45, 16384, workspace=cws, out=tabs))
+    n = tabs.counts.cpu().numpy()
+    rb_bytes = px * wl.ROLLING_BALL_BYTES_PER_PX
+    ccl_bytes = px * (wl.LABEL_BYTES_PER_PX + wl.STATS_BYTES_PER_PX) + int(n.sum()) * wl.STATS_BYTES_PER_DROPLET
+    rows = [f"config 3 on B200: batch {B} of {S}x{S}, droplets per mask {n.mean():.0f} (min {n.min()}, max {n.max()}); HBM peak {hbm} GB/s (measured copy)",
+            "", "| stage | ms / batch | frames/s | algorithmic GB/s | of HBM peak | bound |", "|---|---|---|---|---|---|",
+            f"| rolling ball radius 50 (dc_rolling_ball, 4 launches) | {ms_rb:.2f} | {B / ms_rb * 1e3:.0f} | {rb_bytes / ms_rb / 1e6:.0f} | {rb_bytes / ms_rb / 1e6 / hbm:.4f} | instructions (1995-tap exact ellipse) |",
+            f"| labelling + droplet table (dc_label_stats, 8 launches) | {ms_ccl:.2f} | {B / ms_ccl * 1e3:.0f} | {ccl_bytes / ms_ccl / 1e6:.0f} | {ccl_bytes / ms_ccl / 1e6 / hbm:.4f} | latency / atomics |"]
+    text = "\n".join(rows)
+    print(text)
+    if a.out:
+        Path(a.out).write_text(text + "\n")
+
+
+if __name__ == "__main__":
+    main()
