@@ -1053,11 +1053,8 @@ int launch_variant(const ConvParams& p, cudaStream_t stream) {
     constexpr size_t SMEM = (size_t)NSTAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ +
                             4096 + 256 /* bias (<= 1024 ch) + out_conv weights */ + EPI_STAGE_TOTAL;
     static_assert(SMEM <= 227 * 1024, "stage ring exceeds shared memory");
-    static bool attr_done = false;
-    if (!attr_done) {
-        DC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        attr_done = true;
-    }
+    // function attributes are per device: set on every launch (a host-side call of well under a microsecond)
+    DC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
     conv_tc_kernel<BN, NSTAGES><<<grid, NUM_THREADS, SMEM, stream>>>(p);
     DC_CUDA(cudaGetLastError());
@@ -1235,12 +1232,9 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
         const int grid = 2 * (n_pairs < max_clusters ? n_pairs : max_clusters);
 #define DC_PAIR_CASE(bn, nh, wr)                                                                                      \
         if (BN == bn && halo_nhalf == nh && halo_wres == wr) {                                                        \
-            static bool attr_done = false;                                                                            \
-            if (!attr_done) {                                                                                         \
-                DC_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<bn, nh, wr>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             227 * 1024));                                                            \
-                attr_done = true;                                                                                     \
-            }                                                                                                         \
+            /* function attributes are per device: set on every launch (sub-microsecond host call) */                 \
+            DC_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<bn, nh, wr>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                         227 * 1024));                                                                \
             conv_halo2_kernel<bn, nh, wr><<<grid, NUM_THREADS, halo_smem, stream>>>(p);                               \
         }
         DC_PAIR_CASE(64, 4, true) DC_PAIR_CASE(64, 3, true) DC_PAIR_CASE(64, 2, true)
@@ -1253,12 +1247,8 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
         const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
 #define DC_HALO_CASE(bn, nh, wr)                                                                                     \
         if (BN == bn && halo_nhalf == nh && halo_wres == wr) {                                                       \
-            static bool attr_done = false;                                                                           \
-            if (!attr_done) {                                                                                        \
-                DC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<bn, nh, wr>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             227 * 1024));                                                           \
-                attr_done = true;                                                                                    \
-            }                                                                                                        \
+            DC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<bn, nh, wr>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                         227 * 1024));                                                               \
             conv_halo_kernel<bn, nh, wr><<<grid, NUM_THREADS, halo_smem, stream>>>(p);                               \
         }
         DC_HALO_CASE(64, 1, true) DC_HALO_CASE(64, 2, true) DC_HALO_CASE(128, 1, true) DC_HALO_CASE(128, 2, true)
@@ -1299,13 +1289,10 @@ int launch_stem(const dc_stem_args_t* a, cudaStream_t stream) {
     p.out_stride = a->out_stride; p.out_offset = a->out_offset;
     sp.in = a->in; sp.weight = a->weight; sp.in_kind = a->in_kind;
     constexpr size_t SMEM = 64 * 128 + (size_t)STEM_STAGES * A_STAGE_BYTES + 1024 + 256 + 512 + EPI_STAGE_TOTAL;
-    static bool attr_done = false;
-    if (!attr_done) {
-        DC_CUDA(cudaFuncSetAttribute(stem_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        DC_CUDA(cudaFuncSetAttribute(stem_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        DC_CUDA(cudaFuncSetAttribute(stem_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        attr_done = true;
-    }
+    // function attributes are per device: set on every launch (a host-side call of well under a microsecond)
+    DC_CUDA(cudaFuncSetAttribute(stem_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    DC_CUDA(cudaFuncSetAttribute(stem_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    DC_CUDA(cudaFuncSetAttribute(stem_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
     switch (a->in_kind) {
         case 0: stem_tc_kernel<0><<<grid, STEM_THREADS, SMEM, stream>>>(sp); break;

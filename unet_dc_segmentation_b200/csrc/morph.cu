@@ -244,12 +244,9 @@ int launch_rolling_ball(const dc_rolling_ball_args_t* a, cudaStream_t stream) {
     const int RW = TW + se.k, pitch = ((RW + 3) >> 2) + 1, RH = TH + se.k - 1;
     const size_t smem = (size_t)se.nlevels * pitch * RH * 4;
     DC_REQUIRE(smem <= 226 * 1024, DC_EINVAL, "dc_rolling_ball: radius %d needs %zu B of shared memory", a->radius, smem);
-    static bool attr_done = false;
-    if (!attr_done) {
-        DC_CUDA(cudaFuncSetAttribute(morph_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));   // + 816 B static (rowtab)
-        DC_CUDA(cudaFuncSetAttribute(morph_pass_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));   // + 816 B static (rowtab)
-        attr_done = true;
-    }
+    // function attributes are per device: set on every launch (a host-side call of well under a microsecond)
+    DC_CUDA(cudaFuncSetAttribute(morph_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));   // + 816 B static (rowtab)
+    DC_CUDA(cudaFuncSetAttribute(morph_pass_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));   // + 816 B static (rowtab)
     dim3 block(TW / 4, TH);
     dim3 grid(ceil_div(W, TW), ceil_div(H, TH), planes);
     init_minmax_kernel<<<ceil_div(planes, 256), 256, 0, stream>>>(minmax, planes);
