@@ -1,19 +1,18 @@
 #!/bin/bash
-# ncu evidence for one round: launch list of the bench command + full captures of chosen conv launches.
-# usage (under gpurun, repo root): bash tools/profile.sh <tag> [extra bench args]
-TAG=${1:-r01}; shift
-ARGS="--steps 2 --warmup 3 --no-cpu-baseline $@"
+# ncu evidence for one round, small enough to come back through gpurun_out/ (< 64 MiB): the launch list of the bench
+# command plus per-launch metric CSVs for every launch of one warm step.  Summarise with tools/summarize_profiles.py
+# and tools/metrics_table.py (see profiles/README.md).
+# usage (under gpurun, repo root): bash tools/profile.sh <tag>
+TAG=${1:-r01}
+ARGS="--steps 2 --warmup 3 --no-cpu-baseline"
+M="gpu__time_duration.sum,launch__grid_size,launch__block_size,launch__registers_per_thread,launch__shared_mem_per_block_dynamic,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__throughput.avg.pct_of_peak_sustained_elapsed,l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed,l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum,l1tex__m_xbar2l1tex_read_bytes.sum,lts__t_sector_hit_rate.pct,sm__cycles_elapsed.avg,smsp__inst_executed.sum"
 mkdir -p gpurun_out
 python bench.py $ARGS > gpurun_out/plain_$TAG.json 2> gpurun_out/plain_$TAG.err || { echo "plain run failed"; tail gpurun_out/plain_$TAG.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_$TAG.csv \
-    python bench.py $ARGS > gpurun_out/ncu_launch_$TAG.log 2>&1
-echo "launch list rc=$?"
-# conv_tc launches per forward (in order): enc1.3 enc2.0 enc2.3 enc3.0 enc3.3 enc4.0 enc4.3 bott.0 bott.3 up4 dec4.0 dec4.3 up3
-# dec3.0 dec3.3 up2 dec2.0 dec2.3 up1 dec1.0 dec1.3 = 21; skip 3 warm-up forwards (63) then take dec4.0 (idx 10), dec1.0, dec1.3
-ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 73 -c 1 -o gpurun_out/prof_dec40_$TAG -f \
-    python bench.py $ARGS > gpurun_out/ncu_full1_$TAG.log 2>&1
-echo "full dec4.0 rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 82 -c 2 -o gpurun_out/prof_dec1_$TAG -f \
-    python bench.py $ARGS > gpurun_out/ncu_full2_$TAG.log 2>&1
-echo "full dec1.x rc=$?"
-ls -la gpurun_out | tail -20
+    python bench.py $ARGS > /dev/null 2>&1; echo "launch list rc=$?"
+# one warm forward = 22 launches (stem + 21 conv); 3 warm-up steps precede it
+ncu --metrics $M --clock-control none -k regex:'conv_|stem_' -s 66 -c 22 --csv --log-file gpurun_out/fwd_metrics_$TAG.csv \
+    python bench.py $ARGS > /dev/null 2>&1; echo "forward metrics rc=$?"
+ncu --metrics $M --clock-control none -k regex:'morph_|stretch_|ccl_|init_minmax' -s 36 -c 12 --csv --log-file gpurun_out/aux_metrics_$TAG.csv \
+    python bench.py $ARGS > /dev/null 2>&1; echo "aux metrics rc=$?"
+du -sh gpurun_out
