@@ -112,3 +112,21 @@ def test_reference_sample_outputs_known_answers():
         sel = g["filename"] == fn
         assert sel.sum() == cnt and area[sel].sum() == tot
         assert g["label"][sel].tolist() == list(range(1, int(cnt) + 1))
+
+
+@pytest.mark.parametrize("shape,p", [((64, 64), 0.5), ((97, 131), 0.6), ((200, 300), 0.4), ((33, 7), 0.7)])
+def test_labelling_matches_opencv_connected_components(shape, p):
+    """scikit-image is not in this image, so `label` / `regionprops_table` semantics are also pinned against a real
+    third-party implementation: cv2.connectedComponentsWithStats(connectivity=4) numbers components in raster order of
+    their first pixel exactly as skimage.measure.label(connectivity=1) does, and reports pixel-count
+    areas and mean-coordinate centroids in f64."""
+    import cv2
+    rs = np.random.RandomState(shape[0] * 7 + shape[1])
+    mask = (rs.rand(*shape) < p).astype(np.uint8)
+    n_cv, lab_cv, stats, cent = cv2.connectedComponentsWithStats(mask, connectivity=4, ltype=cv2.CV_32S)
+    lab, cols = oracle.quantify_arrays(mask, 1, None)
+    assert n_cv - 1 == len(cols["label"])
+    np.testing.assert_array_equal(lab, lab_cv)
+    np.testing.assert_array_equal(cols["area"], stats[1:, cv2.CC_STAT_AREA])
+    np.testing.assert_array_equal(cols["centroid-0"], cent[1:, 1])        # cv2 centroids are (x, y)
+    np.testing.assert_array_equal(cols["centroid-1"], cent[1:, 0])
