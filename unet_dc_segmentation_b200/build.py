@@ -32,12 +32,23 @@ def find_nvcc() -> str:
     return cand
 
 
+HASH_PATH = LIB_DIR / "libunetdc_b200.so.srchash"
+
+
+def source_hash() -> str:
+    """Content hash of everything that goes into the library (file times do not survive a repo snapshot)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in [CSRC / s for s in SOURCES] + HEADERS:
+        h.update(d.name.encode())
+        h.update(d.read_bytes())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
-    if not LIB_PATH.exists():
+    if not LIB_PATH.exists() or not HASH_PATH.exists():
         return True
-    t = LIB_PATH.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + HEADERS
-    return any(d.stat().st_mtime > t for d in deps)
+    return HASH_PATH.read_text().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
@@ -46,8 +57,22 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB_PATH
     nvcc = find_nvcc()
     LIB_DIR.mkdir(exist_ok=True)
-    obj_dir = PKG / "build"
-    obj_dir.mkdir(exist_ok=True)
+    # several ranks may import the package at once (torchrun): one builds, the others wait and then find it fresh
+    import fcntl
+    lock = open(LIB_DIR / ".build.lock", "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and not is_stale():
+            return LIB_PATH
+        return _build_locked(nvcc, verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(nvcc: str, verbose: bool) -> Path:
+    obj_dir = PKG / "build" / f"obj_{os.getpid()}"
+    obj_dir.mkdir(parents=True, exist_ok=True)
     procs = []
     objs = []
     for s in SOURCES:
@@ -69,6 +94,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
     os.replace(tmp, LIB_PATH)
+    HASH_PATH.write_text(source_hash() + "\n")
+    shutil.rmtree(obj_dir, ignore_errors=True)
     return LIB_PATH
 
 
