@@ -188,6 +188,8 @@ def run_b200(args):
     from unet_dc_segmentation_b200 import workload as wl
 
     B, S, K, Wm = args.batch, args.size, args.steps, args.warmup
+    # torchrun pins OMP_NUM_THREADS=1; the one-off CPU calibration of the synthetic checkpoint can use this rank's share
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(1, world)))
     sd = calibrated_state_dict(seed=0)
     model = UNetDC(3, 1)
     model.load_state_dict(sd)
