@@ -11,8 +11,8 @@ On the device: rolling ball, both resizes (cv2.resize at qdb:44 and qdb:57 is bi
 interpolation flag in the `dst` slot, SURVEY.md 0.2 -- reproduced bit for bit by dc_resize_linear_u8; the identity
 when the frame is already IMG_SIZE), the network, the threshold, labelling and the table.  On the host, exactly as
 in the reference: PIL decode, PNG / CSV / XLSX writing, overlays.  `--img_size` (default 512 = the reference's IMG_SIZE
-constant) and `--gpus` are the only additions; with `--gpus N` (under torchrun) frames are sharded i -> rank
-i mod N and the tables are gathered on rank 0.
+constant) is the only added flag.  Under torchrun (one rank per GPU) frames are sharded i -> rank i mod N, every
+rank writes the per-image files of its own frames, and the tables are gathered on rank 0, which writes the reports.
 """
 from __future__ import annotations
 
