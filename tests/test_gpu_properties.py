@@ -1,0 +1,55 @@
+"""GPU: randomized (hypothesis) parity of the integer stages against the oracle / OpenCV on small inputs --
+ragged shapes, every radius, min_area filters, empty and full masks."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+COMMON = dict(deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow], derandomize=True)
+
+
+@settings(max_examples=60, **COMMON)
+@given(h=st.integers(1, 70), w=st.integers(1, 70), p=st.floats(0.0, 1.0), min_area=st.integers(1, 6),
+       seed=st.integers(0, 10 ** 6), px=st.sampled_from([None, 2.0, 3.45]))
+def test_label_stats_random(cuda_device, h, w, p, min_area, seed, px):
+    import torch
+    from unet_dc_segmentation_b200 import quantify_arrays
+    mask = (np.random.RandomState(seed).rand(h, w) < p).astype(np.uint8)
+    tables, labels = quantify_arrays(torch.from_numpy(mask[None]).cuda(), min_area, px, want_labels=True)
+    want_l, want = oracle.quantify_arrays(mask, min_area, px)
+    np.testing.assert_array_equal(labels[0].cpu().numpy(), want_l)
+    assert set(tables[0]) == set(want)
+    for c, v in want.items():
+        np.testing.assert_array_equal(np.asarray(tables[0][c]), v, err_msg=c)
+
+
+@settings(max_examples=30, **COMMON)
+@given(h=st.integers(1, 90), w=st.integers(1, 90), radius=st.integers(1, 70), seed=st.integers(0, 10 ** 6),
+       smooth=st.booleans())
+def test_rolling_ball_random(cuda_device, h, w, radius, seed, smooth):
+    import torch
+    from unet_dc_segmentation_b200 import rolling_ball_device
+    rs = np.random.RandomState(seed)
+    img = rs.randint(0, 256, (h, w)).astype(np.uint8)
+    if smooth:
+        img = (np.add.outer(np.arange(h), np.arange(w)) % 256).astype(np.uint8) // 2 + img // 8
+    got = rolling_ball_device(torch.from_numpy(img[None]).cuda(), radius)[0].cpu().numpy()
+    want = oracle.rolling_ball_correction_rgb(img[:, :, None], radius)[:, :, 0]
+    np.testing.assert_array_equal(got, want)
+
+
+@settings(max_examples=40, **COMMON)
+@given(sh=st.integers(1, 80), sw=st.integers(1, 80), dh=st.integers(1, 120), dw=st.integers(1, 120),
+       cn=st.sampled_from([1, 3]), seed=st.integers(0, 10 ** 6))
+def test_resize_random_vs_cv2(cuda_device, sh, sw, dh, dw, cn, seed):
+    import cv2
+    import torch
+    from unet_dc_segmentation_b200 import resize_linear_u8_device
+    shape = (sh, sw, 3) if cn == 3 else (sh, sw)
+    src = np.random.RandomState(seed).randint(0, 256, shape).astype(np.uint8)
+    got = resize_linear_u8_device(torch.from_numpy(src[None]).cuda(), (dw, dh))[0].cpu().numpy()
+    np.testing.assert_array_equal(got, cv2.resize(src, (dw, dh)).reshape(got.shape))
+    np.testing.assert_array_equal(got, oracle.resize_linear_u8(src, (dw, dh)))
