@@ -53,3 +53,26 @@ def test_resize_random_vs_cv2(cuda_device, sh, sw, dh, dw, cn, seed):
     got = resize_linear_u8_device(torch.from_numpy(src[None]).cuda(), (dw, dh))[0].cpu().numpy()
     np.testing.assert_array_equal(got, cv2.resize(src, (dw, dh)).reshape(got.shape))
     np.testing.assert_array_equal(got, oracle.resize_linear_u8(src, (dw, dh)))
+
+
+@settings(max_examples=30, **COMMON)
+@given(B=st.integers(1, 3), H=st.integers(1, 40), W=st.integers(1, 40), cin=st.sampled_from([64, 128, 192, 256]),
+       cout=st.sampled_from([64, 128, 256, 512]), d=st.integers(1, 6), relu=st.booleans(), seed=st.integers(0, 10 ** 6))
+def test_conv3x3_random_shapes(cuda_device, B, H, W, cin, cout, d, relu, seed):
+    """Ragged frame sizes and every (Cin, Cout, dilation) family: CTA-pair halo (resident / streamed weights, 1-4
+    halves), and the generic per-tap kernel (dilation > 4), against fp32 conv2d on the same bf16 operands."""
+    import torch
+    import torch.nn.functional as F
+    from unet_dc_segmentation_b200 import layers
+    from unet_dc_segmentation_b200.model import pack_conv3x3
+    g = torch.Generator().manual_seed(seed)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (3.0 * cin ** 0.5)).bfloat16().float()
+    b = torch.randn(cout, generator=g) * 0.1
+    x = torch.randn(B, H, W, cin, generator=g).bfloat16()
+    want = F.conv2d(x.float().permute(0, 3, 1, 2), w, b, padding=d, dilation=d)
+    if relu:
+        want = F.relu(want)
+    want = want.permute(0, 2, 3, 1)
+    got = layers.conv3x3(x.cuda(), pack_conv3x3(w).cuda(), b.cuda(), dilation=d, relu=relu).float().cpu()
+    err = (got - want).abs()
+    assert bool((err <= 1e-2 * want.abs().clamp(min=1.0)).all()), f"max err {float(err.max()):.4g}"
