@@ -135,21 +135,45 @@ __device__ __forceinline__ void tmem_ld_wait_on(uint32_t* v) {
                  : "memory");
 }
 
-// Epilogue: EPI_GROUPS groups of 4 warps; group g owns accumulator stage g and every EPI_GROUPS-th tile of the
-// CTA, so two tiles drain concurrently while the MMA warp fills the next.  Within a group the 4 x 32 threads are
-// the 128 TMEM lanes: thread L owns pixel (L / TW, L % TW) of the tile.  TMEM -> registers (next 32-column chunk
-// in flight while this one is processed) -> +bias (staged in smem), ReLU -> bf16 NHWC stores, with the fused
-// 2x2 max-pool, the transposed-conv parity scatter or the out_conv + sigmoid + threshold head as `p.epilogue` says.
+// Epilogue: EPI_GROUPS groups of 4 warps work on the SAME tile (both wait for the accumulator stage the MMA warp
+// just committed).  Within a group the 4 x 32 threads are the 128 TMEM lanes: thread L owns pixel (L / TW, L % TW).
+// The groups split the tile's columns: group g drains the 32-column chunks c = g (mod 2) of every half (for the
+// HEAD epilogue, whose per-pixel dot product needs all 64 channels in one thread, group g takes the halves
+// g (mod 2)).  Draining a stage with all eight warps halves the time the MMA warp waits for it; the stage is
+// handed back as soon as a warp's last tcgen05.ld has landed, before that chunk is processed.
+// TMEM -> registers (next chunk in flight while this one is processed) -> +bias (staged in smem) -> bf16 with the
+// ReLU folded into the conversion -> a warp-private smem tile -> NHWC stores of 8 pixels x 64 B per instruction
+// (measured: a thread writing its own pixel's 64 B directly, even as two st.global.v8.b32 sectors, is slower --
+// 32 lines per instruction instead of 8).  STORE_POOL also writes the 2x2 max from the staged tile; UPSCATTER
+// sends each chunk to its output parity.
 // NHALF > 1: the tile is NHALF side-by-side TW-wide patches, each with its own BN-column accumulator.
 constexpr int EPI_GROUPS = 2;
 constexpr int EPI_STAGE_BYTES = 32 * 64;                    // per warp: 32 pixels x 32 channels bf16
 constexpr int EPI_STAGE_TOTAL = EPI_GROUPS * 4 * EPI_STAGE_BYTES;
 
-// Staging slot of 16-byte chunk q (0..3) of pixel row r in a warp's 32 x 64 B buffer (bank-conflict-free for
-// both the per-pixel writes and the 4-lanes-per-pixel reads).
-__device__ __forceinline__ uint32_t stg_off(int r, int q) { return (uint32_t)(r * 64 + ((q ^ ((r >> 1) & 3)) << 4)); }
+// Staging slot of 16-byte chunk q (0..3) of pixel row r in a warp's 32 x 64 B buffer: rows 2k, 2k+1 share a
+// 128-byte line, (r ^ r>>1) & 1 picks the half and the chunk is rotated by k, so the per-pixel writes (32 rows,
+// one q) and the pooled reads (rows r, r+1, r+TW, r+TW+1 for even r; 4 lanes per row) are both conflict-free.
+__device__ __forceinline__ uint32_t stg_off(int r, int q) {
+    return (uint32_t)(((r >> 1) << 7) | (((r ^ (r >> 1)) & 1) << 6) | ((q ^ ((r >> 1) & 3)) << 4));
+}
 
-template <int BN, int TH, int TW, int NHALF = 1, bool PAIR = false>
+__device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {      // max(., 0) folded into the conversion
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+template <bool PAIR>
+__device__ __forceinline__ void release_accumulator(uint64_t* bar, int lane) {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(bar);      // the leader's MMA warp waits for both CTAs
+        else mbar_arrive(bar);
+    }
+}
+
+template <int BN, int TH, int TW, int NHALF = 1, bool PAIR = false, bool COOP = true>
 __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, const int lane, const int group,
                                              const uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                              const float* bias_s, uint8_t* stg_all) {
@@ -157,11 +181,16 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
     const int lh = L / TW, lw = L % TW;
     const float* head_s = bias_s + p.Cout;                     // out_conv weights follow the bias (HEAD only)
     uint8_t* stg = stg_all + (group * 4 + e) * EPI_STAGE_BYTES;
-    const int sq = lane & 3;                                   // the 16-byte chunk this lane stores after the transpose
-    // Stores go out transposed: a thread computes 32 channels of ONE pixel (64 B), but writing that directly makes
-    // every store instruction touch 32 different lines.  Each 32-pixel x 32-channel chunk is staged in a
-    // warp-private smem buffer and stored as 8 pixels x 64 contiguous bytes per instruction (4 lanes per pixel).
-    for (int it = group;; it += EPI_GROUPS) {
+    const int sq = lane & 3;                                   // the 16-byte chunk this lane handles of a pooled pixel
+    // first of the four warp-local pixels (index = row * TW + col) of the pooled pixel this lane stores
+    const int pool_r0 = (TW == 16) ? 2 * (lane >> 2) : (16 * (lane >> 4) + 2 * ((lane >> 2) & 3));
+    // COOP = false (the stem, whose MMA is a single instruction per tile): the groups take alternate tiles instead,
+    // group g owning accumulator stage g, so that a warp always has a second chunk to prefetch.
+    constexpr int CPG = COOP ? BN / 64 : BN / 32;              // chunks per half per group
+    constexpr int CSTEP = COOP ? 64 : 32;                      // column distance between a group's chunks
+    constexpr int NI = NHALF * CPG;                            // chunks per tile per group
+    const int cgrp = COOP ? group * 32 : 0;                    // first column of this group's first chunk
+    for (int it = COOP ? 0 : group;; it += COOP ? 1 : EPI_GROUPS) {
         int tile;
         if (PAIR) {                     // CTA pair: pair = cluster + it * clusters
             const int pair = (int)(blockIdx.x >> 1) + it * (int)(gridDim.x >> 1);
@@ -172,139 +201,147 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
             if (tile >= p.total_tiles) break;
         }
         const TileCoord t = decode_tile<TH, TW * NHALF>(p, tile, BN);
-        const int as = it & 1;                                 // == group
+        const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
-#pragma unroll 1
-        for (int half = 0; half < NHALF; ++half) {
-            const int h = t.h0 + lh, w = t.w0 + half * TW + lw;
-            const bool valid = (h < p.H) && (w < p.W);
-            // pixels this lane stores for (4 rounds x 8 pixels): pr = 8 j + lane / 4 of the warp's 32
-            int sh[4], sw[4];
-            bool sval[4];
-            __nv_bfloat16* sptr[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int pL = e * 32 + 8 * j + (lane >> 2);
-                sh[j] = t.h0 + pL / TW;
-                sw[j] = t.w0 + half * TW + pL % TW;
-                sval[j] = (sh[j] < p.H) && (sw[j] < p.W);
-                sptr[j] = nullptr;
-                if (p.epilogue == DC_EPI_STORE || p.epilogue == DC_EPI_STORE_POOL) {
-                    const size_t opix = ((size_t)t.img * p.H + sh[j]) * (size_t)p.W + sw[j];
-                    sptr[j] = p.out + opix * p.out_stride + p.out_offset + t.n0 + sq * 8;
-                }
-            }
-            // pooled pixel this lane stores: pp = lane / 4 of the warp's 8 (2x2 windows of its 32 pixels)
-            __nv_bfloat16* pptr = nullptr;
-            bool pval = false;
-            if (p.epilogue == DC_EPI_STORE_POOL) {
-                const int pp = lane >> 2;
-                const int ph_l = (TW == 16) ? 0 : 2 * (pp >> 2);
-                const int pw_l = (TW == 16) ? 2 * pp : 2 * (pp & 3);
-                const int ph = t.h0 + e * (32 / TW) + ph_l, pw = t.w0 + half * TW + pw_l;
-                pval = (ph < p.H) && (pw < p.W);
-                const size_t ppix = ((size_t)t.img * (p.H >> 1) + (ph >> 1)) * (size_t)(p.W >> 1) + (pw >> 1);
-                pptr = p.pool_out + ppix * p.pool_stride + t.n0 + sq * 8;
-            }
-            // first of the four warp-local pixels (index = row * TW + col) of the pooled pixel this lane stores
-            const int pool_r0 = (TW == 16) ? 2 * (lane >> 2) : (16 * (lane >> 4) + 2 * ((lane >> 2) & 3));
-            int bias_base = t.n0;
-            float head_acc = p.head_b;
+        const uint32_t tstage = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(as * NHALF * BN);
 
-            const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)((as * NHALF + half) * BN);
-            uint32_t vbuf[2][32];
-            tmem_ld32(taddr, vbuf[0]);
+        if (p.epilogue == DC_EPI_HEAD) {
+#pragma unroll 1
+            for (int half = COOP ? group : 0; half < NHALF; half += COOP ? EPI_GROUPS : 1) {
+                const int h = t.h0 + lh, w = t.w0 + half * TW + lw;
+                float head_acc = p.head_b;
+                const uint32_t taddr = tstage + (uint32_t)(half * BN);
+                uint32_t vbuf[2][32];
+                tmem_ld32(taddr, vbuf[0]);
 #pragma unroll
-            for (int c = 0; c < BN / 32; ++c) {
-                const int c0 = c * 32;
-                uint32_t* v = vbuf[c & 1];
-                tmem_ld_wait_on(v);
-                if (c + 1 < BN / 32) tmem_ld32(taddr + (uint32_t)(c0 + 32), vbuf[(c + 1) & 1]);
-                if (p.epilogue == DC_EPI_UPSCATTER) {
-                    // GEMM column n = (a*2 + b)*Cout + co  ->  output pixel (2h + a, 2w + b), channel co
-                    const int n = t.n0 + c0;
-                    const int q = n / p.Cout;
-                    const int co = n - q * p.Cout;
-                    bias_base = co - c0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const size_t opix = ((size_t)t.img * (2 * p.H) + (2 * sh[j] + (q >> 1))) * (size_t)(2 * p.W) +
-                                            (2 * sw[j] + (q & 1));
-                        sptr[j] = p.out + opix * p.out_stride + p.out_offset + co - c0 + sq * 8;
-                    }
-                }
-                const float4* b4 = reinterpret_cast<const float4*>(bias_s + bias_base + c0);
-                float x[32];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 b = b4[j];
-                    x[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
-                    x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-                    x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
-                    x[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
-                }
-                if (p.relu) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
-                }
-                if (p.epilogue == DC_EPI_HEAD) {
-                    const float4* w4 = reinterpret_cast<const float4*>(head_s + c0);
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t* v = vbuf[c & 1];
+                    tmem_ld_wait_on(v);
+                    if (c + 1 < BN / 32) tmem_ld32(taddr + (uint32_t)(c * 32 + 32), vbuf[(c + 1) & 1]);
+                    else if (half + (COOP ? EPI_GROUPS : 1) >= NHALF) release_accumulator<PAIR>(&tempty_bar[as], lane);
+                    const float4* b4 = reinterpret_cast<const float4*>(bias_s + t.n0 + c * 32);
+                    const float4* w4 = reinterpret_cast<const float4*>(head_s + c * 32);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4 hw = w4[j];
-                        head_acc = fmaf(x[4 * j + 0], hw.x, head_acc);
-                        head_acc = fmaf(x[4 * j + 1], hw.y, head_acc);
-                        head_acc = fmaf(x[4 * j + 2], hw.z, head_acc);
-                        head_acc = fmaf(x[4 * j + 3], hw.w, head_acc);
+                        const float4 b = b4[j], hw = w4[j];
+                        float x0 = __uint_as_float(v[4 * j + 0]) + b.x, x1 = __uint_as_float(v[4 * j + 1]) + b.y;
+                        float x2 = __uint_as_float(v[4 * j + 2]) + b.z, x3 = __uint_as_float(v[4 * j + 3]) + b.w;
+                        if (p.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+                        head_acc = fmaf(x0, hw.x, head_acc);
+                        head_acc = fmaf(x1, hw.y, head_acc);
+                        head_acc = fmaf(x2, hw.z, head_acc);
+                        head_acc = fmaf(x3, hw.w, head_acc);
                     }
-                } else {
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
-                    // transpose through smem: row = pixel (lane), then 4 lanes per pixel read 16 B each
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        *reinterpret_cast<uint4*>(stg + stg_off(lane, q)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint4 val = *reinterpret_cast<const uint4*>(stg + stg_off(8 * j + (lane >> 2), sq));
-                        if (sval[j]) *reinterpret_cast<uint4*>(sptr[j] + c0) = val;
-                    }
-                    if (p.epilogue == DC_EPI_STORE_POOL) {
-                        // 2x2 max straight from the staged tile: lane (pp, sq) reads chunk sq of the four pixels of
-                        // pooled pixel pp (the max of bf16-rounded values = the bf16 rounding of the max)
-                        const uint4 a0 = *reinterpret_cast<const uint4*>(stg + stg_off(pool_r0, sq));
-                        const uint4 a1 = *reinterpret_cast<const uint4*>(stg + stg_off(pool_r0 + 1, sq));
-                        const uint4 a2 = *reinterpret_cast<const uint4*>(stg + stg_off(pool_r0 + TW, sq));
-                        const uint4 a3 = *reinterpret_cast<const uint4*>(stg + stg_off(pool_r0 + TW + 1, sq));
-                        uint4 m;
-                        m.x = max_bf16x2(max_bf16x2(a0.x, a1.x), max_bf16x2(a2.x, a3.x));
-                        m.y = max_bf16x2(max_bf16x2(a0.y, a1.y), max_bf16x2(a2.y, a3.y));
-                        m.z = max_bf16x2(max_bf16x2(a0.z, a1.z), max_bf16x2(a2.z, a3.z));
-                        m.w = max_bf16x2(max_bf16x2(a0.w, a1.w), max_bf16x2(a2.w, a3.w));
-                        if (pval) *reinterpret_cast<uint4*>(pptr + c0) = m;
-                    }
-                    __syncwarp();
+                }
+                if ((h < p.H) && (w < p.W)) {
+                    const float prob = 1.0f / (1.0f + expf(-head_acc));              // torch.sigmoid, fp32
+                    const size_t opix = ((size_t)t.img * p.H + h) * (size_t)p.W + w;
+                    if (p.prob_out) p.prob_out[opix] = prob;
+                    if (p.mask_out) p.mask_out[opix] = prob > p.thresh ? 1 : 0;      // qdb:56
                 }
             }
-            if (half == NHALF - 1) {
-                // accumulators fully read: hand them back to the MMA warp
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (PAIR) mbar_arrive_leader(&tempty_bar[as]);      // the leader's MMA warp waits for both CTAs
-                    else mbar_arrive(&tempty_bar[as]);
+            if (COOP && group >= NHALF) release_accumulator<PAIR>(&tempty_bar[as], lane);     // a group with no half of its own
+            continue;
+        }
+
+        const uint32_t tbase = tstage + (uint32_t)cgrp;
+        uint32_t vbuf[2][32];
+        tmem_ld32(tbase, vbuf[0]);
+        bool pval = false;
+        // pixels this lane stores after the transpose (4 rounds x 8 pixels): pr = 8 r + lane / 4 of the warp's 32
+        int sh[4], sw[4];
+        bool sval[4];
+        __nv_bfloat16* sptr[4];                                // channel t.n0 + 8 sq of those pixels
+        __nv_bfloat16* pptr = nullptr;                         // pooled pixel (lane / 4), channel t.n0 + 8 sq
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+            const int half = j / CPG, cc = j % CPG;            // compile-time
+            const int c0 = cc * CSTEP + cgrp;                  // first GEMM column of this chunk within the n-tile
+            uint32_t* v = vbuf[j & 1];
+            tmem_ld_wait_on(v);
+            if (j + 1 < NI) tmem_ld32(tbase + (uint32_t)(((j + 1) / CPG) * BN + ((j + 1) % CPG) * CSTEP), vbuf[(j + 1) & 1]);
+            else release_accumulator<PAIR>(&tempty_bar[as], lane);            // this warp has read all it will
+            if (cc == 0) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int pL = e * 32 + 8 * r + (lane >> 2);
+                    sh[r] = t.h0 + pL / TW;
+                    sw[r] = t.w0 + half * TW + pL % TW;
+                    sval[r] = (sh[r] < p.H) && (sw[r] < p.W);
+                    const size_t opix = ((size_t)t.img * p.H + sh[r]) * (size_t)p.W + sw[r];
+                    sptr[r] = p.out + opix * p.out_stride + p.out_offset + t.n0 + sq * 8;
+                }
+                if (p.epilogue == DC_EPI_STORE_POOL) {
+                    const int pp = lane >> 2;
+                    const int ph_l = (TW == 16) ? 0 : 2 * (pp >> 2);
+                    const int pw_l = (TW == 16) ? 2 * pp : 2 * (pp & 3);
+                    const int ph = t.h0 + e * (32 / TW) + ph_l, pw = t.w0 + half * TW + pw_l;
+                    pval = (ph < p.H) && (pw < p.W);
+                    const size_t ppix = ((size_t)t.img * (p.H >> 1) + (ph >> 1)) * (size_t)(p.W >> 1) + (pw >> 1);
+                    pptr = p.pool_out + ppix * p.pool_stride + t.n0 + sq * 8;
                 }
             }
-            if (p.epilogue == DC_EPI_HEAD && valid) {
-                const float prob = 1.0f / (1.0f + expf(-head_acc));              // torch.sigmoid, fp32
-                const size_t opix = ((size_t)t.img * p.H + h) * (size_t)p.W + w;
-                if (p.prob_out) p.prob_out[opix] = prob;
-                if (p.mask_out) p.mask_out[opix] = prob > p.thresh ? 1 : 0;      // qdb:56
+            int bias_at = t.n0 + c0;
+            int dst_at = c0;                                   // element offset from sptr[r]
+            if (p.epilogue == DC_EPI_UPSCATTER) {
+                // GEMM column n = (a*2 + b)*Cout + co  ->  output pixel (2h + a, 2w + b), channel co
+                const int n = t.n0 + c0;
+                const int q = n / p.Cout;
+                bias_at = n - q * p.Cout;
+                dst_at = 0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const size_t opix = ((size_t)t.img * (2 * p.H) + (2 * sh[r] + (q >> 1))) * (size_t)(2 * p.W) + (2 * sw[r] + (q & 1));
+                    sptr[r] = p.out + opix * p.out_stride + p.out_offset + bias_at + sq * 8;
+                }
             }
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + bias_at);
+            float x[32];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float4 b = b4[k];
+                x[4 * k + 0] = __uint_as_float(v[4 * k + 0]) + b.x;
+                x[4 * k + 1] = __uint_as_float(v[4 * k + 1]) + b.y;
+                x[4 * k + 2] = __uint_as_float(v[4 * k + 2]) + b.z;
+                x[4 * k + 3] = __uint_as_float(v[4 * k + 3]) + b.w;
+            }
+            uint32_t pk[16];
+            if (p.relu) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) pk[k] = pack_bf16_relu(x[2 * k], x[2 * k + 1]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) pk[k] = pack_bf16(x[2 * k], x[2 * k + 1]);
+            }
+            // Stores go out transposed: a thread holds 32 channels of ONE pixel (64 B); written directly, every store
+            // instruction would touch 32 different lines.  The chunk is staged in a warp-private smem tile and stored
+            // as 8 pixels x 64 contiguous bytes per instruction (4 lanes per pixel).
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(stg + stg_off(lane, q)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint4 val = *reinterpret_cast<const uint4*>(stg + stg_off(8 * r + (lane >> 2), sq));
+                if (sval[r]) *reinterpret_cast<uint4*>(sptr[r] + dst_at) = val;
+            }
+            if (p.epilogue == DC_EPI_STORE_POOL) {
+                // 2x2 max straight from the staged tile: lane (pp, sq) reads chunk sq of the four pixels of pooled
+                // pixel pp (the max of bf16-rounded values = the bf16 rounding of the max)
+                const uint4 a0 = *reinterpret_cast<const uint4*>(stg + stg_off(pool_r0, sq));
+                const uint4 a1 = *reinterpret_cast<const uint4*>(stg + stg_off(pool_r0 + 1, sq));
+                const uint4 a2 = *reinterpret_cast<const uint4*>(stg + stg_off(pool_r0 + TW, sq));
+                const uint4 a3 = *reinterpret_cast<const uint4*>(stg + stg_off(pool_r0 + TW + 1, sq));
+                uint4 m;
+                m.x = max_bf16x2(max_bf16x2(a0.x, a1.x), max_bf16x2(a2.x, a3.x));
+                m.y = max_bf16x2(max_bf16x2(a0.y, a1.y), max_bf16x2(a2.y, a3.y));
+                m.z = max_bf16x2(max_bf16x2(a0.z, a1.z), max_bf16x2(a2.z, a3.z));
+                m.w = max_bf16x2(max_bf16x2(a0.w, a1.w), max_bf16x2(a2.w, a3.w));
+                if (pval) *reinterpret_cast<uint4*>(pptr + c0) = m;
+            }
+            __syncwarp();
         }
     }
 }
@@ -341,7 +378,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < NSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4 * EPI_GROUPS); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -491,7 +528,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
             mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1);
             mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1);
         }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4 * EPI_GROUPS); }
         mbar_init(w_bar, 1);
         fence_barrier_init();
     }
@@ -695,7 +732,7 @@ conv_halo2_kernel(const __grid_constant__ ConvParams p) {
             mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1);
             mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1);
         }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }   // 4 warps x 2 CTAs
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8 * EPI_GROUPS); }   // 4 x EPI_GROUPS warps x 2 CTAs
         mbar_init(w_bar, 1);
         fence_barrier_init();
     }
@@ -899,7 +936,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_tc_kernel(const __grid_c
     stage_bias(p, bias_s);
     if (threadIdx.x == 0) {
         for (int s = 0; s < STEM_STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }          // groups take alternate tiles
         fence_barrier_init();
     }
     if (warp == 12) {
@@ -937,7 +974,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_tc_kernel(const __grid_c
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 8) {
-        run_epilogue<BN, TILE_H, TILE_W>(p, warp & 3, lane, warp >> 2, tmem_base, tfull_bar, tempty_bar, bias_s, stg_s);
+        run_epilogue<BN, TILE_H, TILE_W, 1, false, false>(p, warp & 3, lane, warp >> 2, tmem_base, tfull_bar, tempty_bar, bias_s, stg_s);
     } else if (warp < 12) {
         // ------------------------------------------------------------------ im2col producers: one tile row each
         // The taps of tile i+1 are requested before tile i is converted and stored, so the global-load latency
