@@ -199,9 +199,11 @@ __device__ __forceinline__ void tma_load_4d_2sm(void* dst, const void* tmap, uin
         "r"(c2), "r"(c3)
         : "memory");
 }
-// arrive on the leader CTA's copy of `bar` (from either CTA of the pair)
+// arrive on the leader CTA's copy of `bar` (from either CTA of the pair).  Relaxed: what it orders is TMEM reads
+// (tcgen05.wait::ld + fence::before_thread_sync), not memory; a release at cluster scope costs MEMBAR.GPU + ERRBAR,
+// i.e. a wait for every global store the warp has in flight (13 % of enc1.3's samples).
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {   // one full warp in EACH CTA
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
