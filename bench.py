@@ -77,6 +77,15 @@ class ClockSampler:
         self.thread = threading.Thread(target=self._pump, daemon=True)
         self.thread.start()
 
+    def wait_ready(self, timeout: float = 15.0):
+        """Block until nvidia-smi has initialised (NVML start-up takes 0.2-2 s on a fresh box and, overlapping the
+        timed region, was measured to stretch it by 10-30 %) and is delivering samples."""
+        if self.proc is None:
+            return
+        t0 = time.time()
+        while len(self.lines) < 2 and time.time() - t0 < timeout and self.proc.poll() is None:
+            time.sleep(0.05)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
@@ -222,7 +231,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.3)
+    sampler.wait_ready()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
     barrier(); torch.cuda.synchronize()
     t_wall0 = time.time()

@@ -190,6 +190,19 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
     constexpr int CSTEP = COOP ? 64 : 32;                      // column distance between a group's chunks
     constexpr int NI = NHALF * CPG;                            // chunks per tile per group
     const int cgrp = COOP ? group * 32 : 0;                    // first column of this group's first chunk
+    // Output addressing, split into a per-lane part fixed for the whole kernel and warp-uniform parts per tile /
+    // half / chunk (the address arithmetic used to cost more instructions than the arithmetic on the data).
+    // After the transpose this lane stores chunk sq of pixels pL0 + 8 r (r = 0..3) of its warp's 32.
+    const bool up = p.epilogue == DC_EPI_UPSCATTER;
+    const int pL0 = e * 32 + (lane >> 2);
+    const int row0 = pL0 / TW, col0 = pL0 % TW;
+    const long long cs = (long long)p.out_stride * (up ? 2 : 1);                 // elements per tile column
+    const long long rs = (long long)p.out_stride * (up ? 4 : 1) * p.W;           // elements per tile row
+    __nv_bfloat16* const lane_ptr = p.out + (row0 * rs + col0 * cs + p.out_offset + sq * 8);
+    // pooled pixel of this lane: lane / 4 of the 8 the warp's 32 pixels pool into
+    const int prow = (TW == 16) ? e : 2 * e + (lane >> 4);
+    const int pcol = (TW == 16) ? (lane >> 2) : ((lane >> 2) & 3);
+    __nv_bfloat16* const pool_lane_ptr = p.pool_out + (((long long)prow * (p.W >> 1) + pcol) * p.pool_stride + sq * 8);
     for (int it = COOP ? 0 : group;; it += COOP ? 1 : EPI_GROUPS) {
         int tile;
         if (PAIR) {                     // CTA pair: pair = cluster + it * clusters
@@ -249,12 +262,16 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
         const uint32_t tbase = tstage + (uint32_t)cgrp;
         uint32_t vbuf[2][32];
         tmem_ld32(tbase, vbuf[0]);
+        // warp-uniform offsets of this tile
+        const long long tile_off = up ? (((long long)t.img * (2 * p.H) + 2 * t.h0) * (2 * p.W) + 2 * t.w0) * p.out_stride
+                                      : (((long long)t.img * p.H + t.h0) * p.W + t.w0) * p.out_stride + t.n0;
+        const long long ptile_off = (((long long)t.img * (p.H >> 1) + (t.h0 >> 1)) * (p.W >> 1) + (t.w0 >> 1)) * p.pool_stride + t.n0;
+        const int hmax = p.H - t.h0;
+        int q0 = 0, rem0 = 0;                                  // UPSCATTER: n0 = q0 * Cout + rem0
+        if (up) { q0 = t.n0 / p.Cout; rem0 = t.n0 - q0 * p.Cout; }
+        uint32_t vmask = 0;                                    // bit r: pixel pL0 + 8 r of this half is inside the image
         bool pval = false;
-        // pixels this lane stores after the transpose (4 rounds x 8 pixels): pr = 8 r + lane / 4 of the warp's 32
-        int sh[4], sw[4];
-        bool sval[4];
-        __nv_bfloat16* sptr[4];                                // channel t.n0 + 8 sq of those pixels
-        __nv_bfloat16* pptr = nullptr;                         // pooled pixel (lane / 4), channel t.n0 + 8 sq
+        long long half_off = 0, phalf_off = 0;
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
             const int half = j / CPG, cc = j % CPG;            // compile-time
@@ -264,39 +281,27 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
             if (j + 1 < NI) tmem_ld32(tbase + (uint32_t)(((j + 1) / CPG) * BN + ((j + 1) % CPG) * CSTEP), vbuf[(j + 1) & 1]);
             else release_accumulator<PAIR>(&tempty_bar[as], lane);            // this warp has read all it will
             if (cc == 0) {
+                const int wmax = p.W - t.w0 - half * TW;
+                vmask = 0;
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    const int pL = e * 32 + 8 * r + (lane >> 2);
-                    sh[r] = t.h0 + pL / TW;
-                    sw[r] = t.w0 + half * TW + pL % TW;
-                    sval[r] = (sh[r] < p.H) && (sw[r] < p.W);
-                    const size_t opix = ((size_t)t.img * p.H + sh[r]) * (size_t)p.W + sw[r];
-                    sptr[r] = p.out + opix * p.out_stride + p.out_offset + t.n0 + sq * 8;
+                    const int row = row0 + (TW == 16 ? (r >> 1) : r), col = col0 + (TW == 16 ? (r & 1) * 8 : 0);
+                    vmask |= (uint32_t)((row < hmax) && (col < wmax)) << r;
                 }
-                if (p.epilogue == DC_EPI_STORE_POOL) {
-                    const int pp = lane >> 2;
-                    const int ph_l = (TW == 16) ? 0 : 2 * (pp >> 2);
-                    const int pw_l = (TW == 16) ? 2 * pp : 2 * (pp & 3);
-                    const int ph = t.h0 + e * (32 / TW) + ph_l, pw = t.w0 + half * TW + pw_l;
-                    pval = (ph < p.H) && (pw < p.W);
-                    const size_t ppix = ((size_t)t.img * (p.H >> 1) + (ph >> 1)) * (size_t)(p.W >> 1) + (pw >> 1);
-                    pptr = p.pool_out + ppix * p.pool_stride + t.n0 + sq * 8;
-                }
+                pval = (2 * prow < hmax) && (2 * pcol < wmax);
+                half_off = half * TW * cs;
+                phalf_off = (long long)(half * (TW / 2)) * p.pool_stride;
             }
             int bias_at = t.n0 + c0;
-            int dst_at = c0;                                   // element offset from sptr[r]
-            if (p.epilogue == DC_EPI_UPSCATTER) {
+            long long chunk_off = c0;
+            if (up) {
                 // GEMM column n = (a*2 + b)*Cout + co  ->  output pixel (2h + a, 2w + b), channel co
-                const int n = t.n0 + c0;
-                const int q = n / p.Cout;
-                bias_at = n - q * p.Cout;
-                dst_at = 0;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const size_t opix = ((size_t)t.img * (2 * p.H) + (2 * sh[r] + (q >> 1))) * (size_t)(2 * p.W) + (2 * sw[r] + (q & 1));
-                    sptr[r] = p.out + opix * p.out_stride + p.out_offset + bias_at + sq * 8;
-                }
+                int co = rem0 + c0, q = q0;
+                while (co >= p.Cout) { co -= p.Cout; ++q; }
+                bias_at = co;
+                chunk_off = ((long long)(q >> 1) * (2 * p.W) + (q & 1)) * p.out_stride + co;
             }
+            __nv_bfloat16* const dst = lane_ptr + (tile_off + half_off + chunk_off);
             const float4* b4 = reinterpret_cast<const float4*>(bias_s + bias_at);
             float x[32];
 #pragma unroll
@@ -325,7 +330,8 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const uint4 val = *reinterpret_cast<const uint4*>(stg + stg_off(8 * r + (lane >> 2), sq));
-                if (sval[r]) *reinterpret_cast<uint4*>(sptr[r] + dst_at) = val;
+                const long long d = (TW == 16) ? (r & 1) * 8 * cs + (r >> 1) * rs : r * rs;      // pixel pL0 + 8 r
+                if (vmask & (1u << r)) *reinterpret_cast<uint4*>(dst + d) = val;
             }
             if (p.epilogue == DC_EPI_STORE_POOL) {
                 // 2x2 max straight from the staged tile: lane (pp, sq) reads chunk sq of the four pixels of pooled
@@ -339,7 +345,7 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                 m.y = max_bf16x2(max_bf16x2(a0.y, a1.y), max_bf16x2(a2.y, a3.y));
                 m.z = max_bf16x2(max_bf16x2(a0.z, a1.z), max_bf16x2(a2.z, a3.z));
                 m.w = max_bf16x2(max_bf16x2(a0.w, a1.w), max_bf16x2(a2.w, a3.w));
-                if (pval) *reinterpret_cast<uint4*>(pptr + c0) = m;
+                if (pval) *reinterpret_cast<uint4*>(pool_lane_ptr + (ptile_off + phalf_off + c0)) = m;
             }
             __syncwarp();
         }
