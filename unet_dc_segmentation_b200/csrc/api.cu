@@ -59,6 +59,10 @@ struct dc_model {
     int device;
     dc_model_desc_t desc;
     float head_b;
+    // host copies of the biases of the 64-channel layers (enc1.0, enc1.3, upconv1, dec1.0): their kernels take the
+    // bias as kernel parameters (constant-bank operands) instead of staging it in shared memory
+    float bias64[DC_NUM_LAYERS][64];
+    bool has_bias64[DC_NUM_LAYERS];
 };
 
 namespace {
@@ -180,6 +184,15 @@ int dc_model_create(dc_model_t** out, int device, const dc_model_desc_t* desc) {
         delete m;
         return cuda_fail(e, "cudaMemcpy(out_conv.bias)");
     }
+    memset(m->has_bias64, 0, sizeof(m->has_bias64));
+    for (int layer : {0, 1, 19, 20}) {
+        e = cudaMemcpy(m->bias64[layer], desc->bias[layer], 64 * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            delete m;
+            return cuda_fail(e, "cudaMemcpy(bias of a 64-channel layer)");
+        }
+        m->has_bias64[layer] = true;
+    }
     *out = m;
     return DC_OK;
 }
@@ -240,7 +253,7 @@ static int forward_impl(dc_model_t* m, int in_kind, const void* in, int B, int H
             a.prob_out = prob_out;
             a.mask_out = mask_out;
         }
-        return launch_conv_tc(&a, stream);
+        return launch_conv_tc(&a, stream, m->has_bias64[layer] ? m->bias64[layer] : nullptr);
     };
     int launch_no = 0;
 #define DC_TRY(x)                                                        \
@@ -259,7 +272,7 @@ static int forward_impl(dc_model_t* m, int in_kind, const void* in, int B, int H
         s.in_kind = in_kind; s.B = B; s.H = H; s.W = W; s.Cout = 64; s.dilation = d.dilations[0];
         s.in = in; s.weight = (const float*)d.weight[0]; s.bias = d.bias[0];
         s.out = f.a[0]; s.out_stride = 64; s.out_offset = 0;
-        DC_TRY(launch_stem(&s, stream));
+        DC_TRY(launch_stem(&s, stream, m->has_bias64[0] ? m->bias64[0] : nullptr));
     }
     DC_TRY(conv(1, DC_KIND_CONV3X3, DC_EPI_STORE_POOL, 1, H, W, 64, 64, d.dilations[0], f.a[0], 64, f.cat[0], 128, 64,
                 f.pool[0]));

@@ -27,8 +27,10 @@ int  cuda_fail(cudaError_t e, const char* what);
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------- launchers implemented per .cu
-int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream);
-int launch_stem(const dc_stem_args_t* a, cudaStream_t stream);
+// bias_host: optional HOST copy of a->bias (dc_model_create keeps one); layers with Cout == 64 then take their bias
+// from the kernel parameters (constant-bank operands) instead of shared memory.
+int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream, const float* bias_host = nullptr);
+int launch_stem(const dc_stem_args_t* a, cudaStream_t stream, const float* bias_host = nullptr);
 int launch_label_stats(const dc_label_args_t* a, cudaStream_t stream);
 int launch_rolling_ball(const dc_rolling_ball_args_t* a, cudaStream_t stream);
 int launch_resize_linear_u8(const dc_resize_args_t* a, cudaStream_t stream);

@@ -58,6 +58,8 @@ struct alignas(64) ConvParams {
     int tiles_w, tiles_h, n_tiles, total_tiles;
     int epilogue, relu;
     const float* bias;
+    int bias_const;                 // Cout == 64 and the host knows the values: bias_c[] below, read as c[0][..] operands
+    float bias_c[64];
     __nv_bfloat16* out;
     int out_stride, out_offset;
     __nv_bfloat16* pool_out;
@@ -302,15 +304,28 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                 chunk_off = ((long long)(q >> 1) * (2 * p.W) + (q & 1)) * p.out_stride + co;
             }
             __nv_bfloat16* const dst = lane_ptr + (tile_off + half_off + chunk_off);
-            const float4* b4 = reinterpret_cast<const float4*>(bias_s + bias_at);
             float x[32];
+            if (p.bias_const) {
+                // Cout == 64: this chunk's 32 biases are kernel parameters at a compile-time offset, i.e. constant-bank
+                // operands of the FADDs (the smem path below costs 16 of a chunk's ~64 LSU wavefronts, and the
+                // store-heavy layers run at 85 % of the LSU data pipe)
+                if ((COOP ? group : (cc & 1)) == 0) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float4 b = b4[k];
-                x[4 * k + 0] = __uint_as_float(v[4 * k + 0]) + b.x;
-                x[4 * k + 1] = __uint_as_float(v[4 * k + 1]) + b.y;
-                x[4 * k + 2] = __uint_as_float(v[4 * k + 2]) + b.z;
-                x[4 * k + 3] = __uint_as_float(v[4 * k + 3]) + b.w;
+                    for (int k = 0; k < 32; ++k) x[k] = __uint_as_float(v[k]) + p.bias_c[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) x[k] = __uint_as_float(v[k]) + p.bias_c[32 + k];
+                }
+            } else {
+                const float4* b4 = reinterpret_cast<const float4*>(bias_s + bias_at);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4 b = b4[k];
+                    x[4 * k + 0] = __uint_as_float(v[4 * k + 0]) + b.x;
+                    x[4 * k + 1] = __uint_as_float(v[4 * k + 1]) + b.y;
+                    x[4 * k + 2] = __uint_as_float(v[4 * k + 2]) + b.z;
+                    x[4 * k + 3] = __uint_as_float(v[4 * k + 3]) + b.w;
+                }
             }
             uint32_t pk[16];
             if (p.relu) {
@@ -1106,7 +1121,7 @@ int launch_variant(const ConvParams& p, cudaStream_t stream) {
 
 }  // namespace
 
-int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
+int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream, const float* bias_host) {
     DC_REQUIRE(a && a->in && a->weight && a->bias, DC_EINVAL, "dc_conv_tc: null pointer argument");
     DC_REQUIRE(a->kind == DC_KIND_CONV3X3 || a->kind == DC_KIND_UPCONV2, DC_EINVAL, "dc_conv_tc: kind %d", a->kind);
     DC_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0, DC_EINVAL, "dc_conv_tc: bad shape %d x %d x %d", a->B, a->H, a->W);
@@ -1261,6 +1276,10 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
     p.epilogue = a->epilogue;
     p.relu = up ? 0 : (a->relu != 0);
     p.bias = a->bias;
+    if (bias_host && a->Cout == 64 && a->epilogue != DC_EPI_HEAD) {
+        p.bias_const = 1;
+        memcpy(p.bias_c, bias_host, sizeof(p.bias_c));
+    }
     p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
     p.out_stride = a->out_stride; p.out_offset = a->out_offset;
     p.pool_out = reinterpret_cast<__nv_bfloat16*>(a->pool_out);
@@ -1307,7 +1326,7 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream) {
     }
 }
 
-int launch_stem(const dc_stem_args_t* a, cudaStream_t stream) {
+int launch_stem(const dc_stem_args_t* a, cudaStream_t stream, const float* bias_host) {
     DC_REQUIRE(a && a->in && a->weight && a->bias && a->out, DC_EINVAL, "dc_stem: null pointer argument");
     DC_REQUIRE(a->Cout == 64, DC_EINVAL, "dc_stem: Cout must be 64 (got %d)", a->Cout);
     DC_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0 && a->dilation >= 1, DC_EINVAL, "dc_stem: bad shape");
@@ -1328,6 +1347,10 @@ int launch_stem(const dc_stem_args_t* a, cudaStream_t stream) {
     p.total_tiles = (int)total;
     p.epilogue = DC_EPI_STORE; p.relu = 1;
     p.bias = a->bias;
+    if (bias_host) {
+        p.bias_const = 1;
+        memcpy(p.bias_c, bias_host, sizeof(p.bias_c));
+    }
     p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
     p.out_stride = a->out_stride; p.out_offset = a->out_offset;
     sp.in = a->in; sp.weight = a->weight; sp.in_kind = a->in_kind;
