@@ -16,6 +16,8 @@
  *   dc_rolling_ball              rolling_ball_correction_rgb  utils/data_loader.py:11-24
  *   dc_resize_linear_u8          the two cv2.resize calls     quantify_droplets_batch.py:44, :57
  *   dc_label_stats               quantify                     quantify_droplets_batch.py:81-95
+ *   dc_overlay_stencil           cv2.findContours + cv2.drawContours of the overlays
+ *                                                           quantify_droplets_batch.py:74-79
  *
  * Conventions: every function returns 0 (DC_OK) or a negative DC_E* code and never throws;
  * dc_last_error() gives the message of the calling thread's last failure.  All data pointers
@@ -203,6 +205,24 @@ typedef struct dc_label_args {
 
 int dc_label_workspace_bytes(int B, int H, int W, size_t* bytes);
 int dc_label_stats(const dc_label_args_t* args, void* stream);
+
+/* ---- overlay stencil --------------------------------------------------------------------------
+ * stencil[b,y,x] = 1 exactly where
+ *     cnts, _ = cv2.findContours(mask, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+ *     cv2.drawContours(img, cnts, -1, (0, 255, 0), 2)        (quantify_droplets_batch.py:76-77)
+ * changes img, else 0: the caller paints those pixels (0, 255, 0) in the BGR frame it read (qdb:75,78).
+ * Only top-level borders (droplets nested inside a hole of another are not outlined), thickness 2 as
+ * OpenCV rasterises it.  mask: u8 [B,H,W], non-zero = foreground.  Bit-exact against OpenCV 4.x. */
+typedef struct dc_overlay_args {
+    const uint8_t* mask;
+    int B, H, W;
+    uint8_t* stencil;    /* u8 [B,H,W], {0,1} */
+    void* workspace;
+    size_t workspace_bytes;
+} dc_overlay_args_t;
+
+int dc_overlay_workspace_bytes(int B, int H, int W, size_t* bytes);
+int dc_overlay_stencil(const dc_overlay_args_t* args, void* stream);
 
 #ifdef __cplusplus
 }

@@ -49,6 +49,7 @@ def _lib():
         lib.orc_rolling_ball_u8.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         lib.orc_label4.argtypes = [i32p, i32p, ctypes.c_int, ctypes.c_int]
         lib.orc_resize_linear_u8.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, u8p, ctypes.c_int, ctypes.c_int]
+        lib.orc_overlay_stencil.argtypes = [u8p, ctypes.c_int, ctypes.c_int, u8p]
         lib.orc_quantify.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_double,
                                      i32p, ctypes.c_int, i64p, f64p, f64p, f64p, f64p, f64p]
         _LIB = lib
@@ -93,6 +94,18 @@ def resize_linear_u8(src: np.ndarray, dsize) -> np.ndarray:
     rc = _lib().orc_resize_linear_u8(_ptr(src, ctypes.c_uint8), sh, sw, cn, _ptr(out, ctypes.c_uint8), dh, dw)
     if rc != 0:
         raise RuntimeError(f"orc_resize_linear_u8 failed: {rc}")
+    return out
+
+
+def overlay_stencil(mask: np.ndarray) -> np.ndarray:
+    """Pixels painted by cv2.drawContours(img, cv2.findContours(mask, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE)[0], -1,
+    color, 2) -- reference qdb:76-77 -- as a u8 {0,1} map."""
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    H, W = mask.shape
+    out = np.empty((H, W), np.uint8)
+    rc = _lib().orc_overlay_stencil(_ptr(mask, ctypes.c_uint8), H, W, _ptr(out, ctypes.c_uint8))
+    if rc != 0:
+        raise RuntimeError(f"orc_overlay_stencil failed: {rc}")
     return out
 
 

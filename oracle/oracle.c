@@ -20,6 +20,8 @@
  *   orc_quantify          reference quantify_droplets_batch.py:81-95 (label, min_area
  *                         filter, relabel, regionprops_table, micron columns)
  *   orc_resize_linear_u8  the two cv2.resize calls, reference quantify_droplets_batch.py:44 and :57
+ *   orc_overlay_stencil   cv2.findContours(RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) + cv2.drawContours(thickness 2),
+ *                         reference quantify_droplets_batch.py:76-77, as the set of painted pixels
  *
  * Third-party arithmetic restated here (not vendored in /root/reference; requirements.txt
  * pins nothing): opencv-python (probe: 4.13.0 in this image) and scikit-image (absent in
@@ -258,5 +260,75 @@ int orc_resize_linear_u8(const uint8_t *src, int sh, int sw, int cn, uint8_t *ds
             }
         }
     }
+    return 0;
+}
+
+
+/* ---------------------------------------------------------------------------------------------
+ * Overlay stencil: which pixels reference quantify_droplets_batch.py:76-77 paints,
+ *     cnts, _ = cv2.findContours(mask, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+ *     cv2.drawContours(img, cnts, -1, (0, 255, 0), 2)
+ * restated without border following (OpenCV 4.x semantics; tests/test_oracle_golden.py pins it against cv2):
+ *  - RETR_EXTERNAL keeps the outer borders of the 8-connected non-zero components that face the background
+ *    connected (4-connectivity, through zero pixels) to the image frame; a component inside a hole of another
+ *    has a hole border as parent and is dropped.
+ *  - The points of such a border are the component's pixels with a 4-neighbour in that outer background
+ *    (Suzuki-Abe border points for 8-connected foreground); CHAIN_APPROX_SIMPLE only drops collinear ones.
+ *  - drawContours thickness 2: ThickLine per polyline segment = a filled radius-1 circle (a plus) at both end
+ *    points + FillConvexPoly of the band p +- dp, |dp| = 1.  For horizontal / vertical segments that is the pixel
+ *    row / column on either side; for diagonal segments dp = (+-0.707, -+0.707) and the polygon OUTLINE, drawn
+ *    with a fixed-point line, rounds onto the two diagonals one step to either side of the segment.
+ *    A diagonal step p -> q exists where p, q are diagonal neighbours and the 4-neighbour they share on one side
+ *    is outer background.
+ * out[y*W+x] = 1 where painted.  Returns 0, or -1 on bad arguments / allocation failure. */
+int orc_overlay_stencil(const uint8_t *mask, int H, int W, uint8_t *out)
+{
+    if (H <= 0 || W <= 0 || !mask || !out) return -1;
+    const int P = 3, PH = H + 2 * P, PW = W + 2 * P;        /* padded frame: zeros = outer background */
+    uint8_t *fg = (uint8_t *)calloc((size_t)PH * PW, 1);
+    uint8_t *outer = (uint8_t *)calloc((size_t)PH * PW, 1);
+    uint8_t *ct = (uint8_t *)calloc((size_t)PH * PW, 1);
+    int *stack = (int *)malloc(sizeof(int) * (size_t)PH * PW);
+    if (!fg || !outer || !ct || !stack) { free(fg); free(outer); free(ct); free(stack); return -1; }
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) fg[(y + P) * PW + x + P] = mask[y * W + x] != 0;
+    /* flood the zero pixels from the frame corner, 4-connectivity */
+    int sp = 0;
+    stack[sp++] = 0;
+    outer[0] = 1;
+    while (sp) {
+        const int i = stack[--sp], y = i / PW, x = i % PW;
+        const int ny[4] = {y - 1, y + 1, y, y}, nx[4] = {x, x, x - 1, x + 1};
+        for (int k = 0; k < 4; ++k) {
+            if (ny[k] < 0 || ny[k] >= PH || nx[k] < 0 || nx[k] >= PW) continue;
+            const int j = ny[k] * PW + nx[k];
+            if (!fg[j] && !outer[j]) { outer[j] = 1; stack[sp++] = j; }
+        }
+    }
+    for (int y = 1; y < PH - 1; ++y)
+        for (int x = 1; x < PW - 1; ++x) {
+            const int i = y * PW + x;
+            ct[i] = fg[i] && (outer[i - PW] || outer[i + PW] || outer[i - 1] || outer[i + 1]);
+        }
+#define ORC_PAINT(yy, xx)                                                                             \
+    do {                                                                                              \
+        const int y_ = (yy) - P, x_ = (xx) - P;                                                       \
+        if (y_ >= 0 && y_ < H && x_ >= 0 && x_ < W) out[y_ * W + x_] = 1;                             \
+    } while (0)
+    for (int i = 0; i < H * W; ++i) out[i] = 0;
+    for (int y = 1; y < PH - 2; ++y)
+        for (int x = 1; x < PW - 1; ++x) {
+            const int i = y * PW + x;
+            if (ct[i]) { ORC_PAINT(y, x); ORC_PAINT(y - 1, x); ORC_PAINT(y + 1, x); ORC_PAINT(y, x - 1); ORC_PAINT(y, x + 1); }
+            if (!fg[i]) continue;
+            if (fg[i + PW + 1] && (outer[i + 1] || outer[i + PW])) {        /* step to (y+1, x+1) */
+                ORC_PAINT(y - 1, x + 1); ORC_PAINT(y + 1, x - 1); ORC_PAINT(y, x + 2); ORC_PAINT(y + 2, x);
+            }
+            if (fg[i + PW - 1] && (outer[i - 1] || outer[i + PW])) {        /* step to (y+1, x-1) */
+                ORC_PAINT(y + 1, x + 1); ORC_PAINT(y - 1, x - 1); ORC_PAINT(y + 2, x); ORC_PAINT(y, x - 2);
+            }
+        }
+#undef ORC_PAINT
+    free(fg); free(outer); free(ct); free(stack);
     return 0;
 }

@@ -40,7 +40,13 @@ def test_cli_native_size_outputs(cuda_device, workdir):
         mask = cv2.imread(str(out / "predicted_masks" / f"{n}_pred.png"), cv2.IMREAD_GRAYSCALE)
         assert mask is not None and set(np.unique(mask)) <= {0, 255}
         assert mask.shape == ((80, 112) if n == "wide" else (96, 96))
-        assert (out / "overlays" / f"{n}_overlay.png").exists()
+        # overlay = the reference's own three calls (qdb:75-77) on the frame and the mask that were written
+        ov = cv2.imread(str(out / "overlays" / f"{n}_overlay.png"))
+        src = [f for f in (workdir / "in").iterdir() if f.stem == n][0]
+        want_ov = cv2.imread(str(src))
+        cnts, _ = cv2.findContours(mask // 255, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+        cv2.drawContours(want_ov, cnts, -1, (0, 255, 0), 2)
+        np.testing.assert_array_equal(ov, want_ov, err_msg=f"{n} overlay")
         df = pd.read_csv(out / f"{n}_droplets.csv", float_precision="round_trip")   # the default parser is 1 ulp sloppy
         want = oracle.quantify(mask // 255, 1, 3.45)
         if want.empty:

@@ -130,3 +130,23 @@ def test_labelling_matches_opencv_connected_components(shape, p):
     np.testing.assert_array_equal(cols["area"], stats[1:, cv2.CC_STAT_AREA])
     np.testing.assert_array_equal(cols["centroid-0"], cent[1:, 1])        # cv2 centroids are (x, y)
     np.testing.assert_array_equal(cols["centroid-1"], cent[1:, 0])
+
+
+# ----------------------------------------------------------------------------- overlay stencil (qdb:74-79)
+from overlay_cases import _cv2_overlay_stencil, _overlay_cases  # noqa: E402
+
+
+def test_overlay_stencil_matches_opencv_contours():
+    """oracle.overlay_stencil (no border following) paints exactly the pixels of cv2.findContours(RETR_EXTERNAL,
+    CHAIN_APPROX_SIMPLE) + cv2.drawContours(thickness 2): nested components, frame-touching ones, thin diagonals,
+    checkerboards, random and blob-like masks."""
+    for m in _overlay_cases():
+        np.testing.assert_array_equal(oracle.overlay_stencil(m), _cv2_overlay_stencil(m), err_msg=f"mask {m.shape}")
+
+
+def test_overlay_stencil_on_droplet_like_mask():
+    from unet_dc_segmentation_b200.synth import synthetic_image
+    img = synthetic_image(256, 3)
+    m = (img > 60).astype(np.uint8)
+    assert 0 < m.mean() < 0.5
+    np.testing.assert_array_equal(oracle.overlay_stencil(m * 255), _cv2_overlay_stencil(m))

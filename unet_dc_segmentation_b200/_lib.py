@@ -20,7 +20,7 @@ EXPORTS = [
     "dc_last_error", "dc_version", "dc_device_check", "dc_conv_tc", "dc_stem", "dc_model_create",
     "dc_model_destroy", "dc_forward_workspace_bytes", "dc_forward", "dc_forward_num_launches", "dc_forward_profile",
     "dc_rolling_ball_workspace_bytes", "dc_rolling_ball", "dc_label_workspace_bytes", "dc_label_stats",
-    "dc_resize_linear_u8",
+    "dc_resize_linear_u8", "dc_overlay_workspace_bytes", "dc_overlay_stencil",
 ]
 
 
@@ -85,6 +85,13 @@ class LabelArgs(Structure):
     ]
 
 
+class OverlayArgs(Structure):
+    _fields_ = [
+        ("mask", c_void_p), ("B", c_int), ("H", c_int), ("W", c_int), ("stencil", c_void_p),
+        ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+    ]
+
+
 _LIB = None
 
 
@@ -124,6 +131,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.dc_label_workspace_bytes.argtypes = [c_int, c_int, c_int, POINTER(c_size_t)]
     lib.dc_label_stats.argtypes = [POINTER(LabelArgs), c_void_p]
     lib.dc_resize_linear_u8.argtypes = [POINTER(ResizeArgs), c_void_p]
+    lib.dc_overlay_workspace_bytes.argtypes = [c_int, c_int, c_int, POINTER(c_size_t)]
+    lib.dc_overlay_stencil.argtypes = [POINTER(OverlayArgs), c_void_p]
     for name in EXPORTS:
         if name not in ("dc_last_error",):
             getattr(lib, name).restype = c_int

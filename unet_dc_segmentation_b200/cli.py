@@ -9,8 +9,9 @@ Function-for-function (reference file:line):
 
 On the device: rolling ball, both resizes (cv2.resize at qdb:44 and qdb:57 is bilinear -- the reference passes the
 interpolation flag in the `dst` slot, SURVEY.md 0.2 -- reproduced bit for bit by dc_resize_linear_u8; the identity
-when the frame is already IMG_SIZE), the network, the threshold, labelling and the table.  On the host, exactly as
-in the reference: PIL decode, PNG / CSV / XLSX writing, overlays.  `--img_size` (default 512 = the reference's IMG_SIZE
+when the frame is already IMG_SIZE), the network, the threshold, labelling, the table and the overlay contours (qdb:76-77,
+bit-exact against OpenCV's findContours + drawContours).  On the host, exactly as in the reference: PIL / cv2 decode,
+PNG / CSV / XLSX writing.  `--img_size` (default 512 = the reference's IMG_SIZE
 constant) is the only added flag.  Under torchrun (one rank per GPU) frames are sharded i -> rank i mod N, every
 rank writes the per-image files of its own frames, and the tables are gathered on rank 0, which writes the reports.
 """
@@ -25,6 +26,7 @@ import torch
 
 from .model import UNetDC
 from .morphology import resize_linear_u8_device, rolling_ball_device
+from .overlay import draw_overlay, overlay_stencil_device
 from .quantify import quantify
 
 IMG_SIZE = 512                     # qdb:30
@@ -84,11 +86,11 @@ def run_batch(tensors, meta, model, mask_dir, overlay_dir, thresh, min_area, px_
         per_image_rows.append({"filename": Path(fpath).name, "droplet_count": len(df),
                                "total_area_px": df["area"].sum() if not df.empty else 0})
         if overlay_dir is not None:
-            img = cv2.imread(str(fpath))
+            img = cv2.imread(str(fpath))                                              # qdb:75
             if img is not None:
-                cnts, _ = cv2.findContours(mask, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
-                cv2.drawContours(img, cnts, -1, (0, 255, 0), 2)
-                cv2.imwrite(str(Path(overlay_dir) / f"{name}_overlay.png"), img)
+                # qdb:76-77: the pixels findContours(RETR_EXTERNAL) + drawContours(thickness 2) paint, from the GPU
+                draw_overlay(img, overlay_stencil_device(m)[0].cpu().numpy())
+                cv2.imwrite(str(Path(overlay_dir) / f"{name}_overlay.png"), img)      # qdb:78
 
 
 def write_reports(out_dir: Path, per_image_rows, all_props, skip_excel: bool, skip_histogram: bool) -> None:

@@ -161,6 +161,18 @@ int dc_label_stats(const dc_label_args_t* args, void* stream) {
     return launch_label_stats(args, (cudaStream_t)stream);
 }
 
+int dc_overlay_workspace_bytes(int B, int H, int W, size_t* bytes) {
+    DC_REQUIRE(bytes && B > 0 && H > 0 && W > 0, DC_EINVAL, "dc_overlay_workspace_bytes: bad argument");
+    *bytes = overlay_workspace_bytes(B, H, W);
+    return DC_OK;
+}
+
+int dc_overlay_stencil(const dc_overlay_args_t* args, void* stream) {
+    int rc = check_current_device(nullptr);
+    if (rc != DC_OK) return rc;
+    return launch_overlay_stencil(args, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------ whole network
 
 int dc_model_create(dc_model_t** out, int device, const dc_model_desc_t* desc) {

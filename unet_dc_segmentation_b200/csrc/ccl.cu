@@ -47,15 +47,16 @@ __device__ __forceinline__ void union_min(int* L, int a, int b) {
 }
 
 // ---- K1: per 32x32 tile union-find in shared memory; rows are merged with a warp ballot ----
+// invert != 0 labels the ZERO pixels instead (the background components the overlay stencil needs).
 __global__ void __launch_bounds__(TILE* TILE) ccl_local_kernel(const uint8_t* __restrict__ mask, int* __restrict__ L,
-                                                              int H, int W) {
+                                                              int H, int W, int invert) {
     __shared__ int s[TILE * TILE];
     __shared__ unsigned rowbits[TILE];
     const int lx = threadIdx.x, ly = threadIdx.y;
     const int x = blockIdx.x * TILE + lx, y = blockIdx.y * TILE + ly;
     const size_t img = (size_t)blockIdx.z * H * W;
     const bool inb = (x < W) && (y < H);
-    const bool fg = inb && mask[img + (size_t)y * W + x] != 0;
+    const bool fg = inb && ((mask[img + (size_t)y * W + x] != 0) != (invert != 0));
     const unsigned bits = __ballot_sync(0xffffffffu, fg);
     const int tid = ly * TILE + lx;
     int lab = -1;
@@ -285,6 +286,89 @@ struct Workspace {
     int* blockoff;
 };
 
+// ------------------------------------------------------------------------------------------------ overlay stencil
+// The pixels that cv2.drawContours(img, findContours(mask, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE), -1, color, 2)
+// paints (reference quantify_droplets_batch.py:74-79), derived without tracing (the rule is pinned against cv2
+// itself on adversarial and random masks by the CPU and GPU overlay tests under tests/):
+//   outer background = zero pixels 4-connected to the image frame (holes are not);
+//   contour          = non-zero pixels with a 4-neighbour in the outer background or outside the image
+//                      (exactly the point set of the external contours: only top-level borders are retrieved);
+//   thickness 2      = every contour pixel plus its 4-neighbours (cv2's radius-1 caps and 3-wide bands), plus, for
+//                      every diagonal step of a border -- two diagonal non-zero pixels whose common 4-neighbour on
+//                      one side is outer background -- the pixels one step to either side of both ends, which the
+//                      outline of cv2's rotated band quad rounds onto.
+
+// frame-touching background components: flag their roots
+__global__ void ovl_mark_kernel(const int* __restrict__ L, uint8_t* __restrict__ flag, int H, int W) {
+    const int per = 2 * W + 2 * H;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per) return;
+    int y, x;
+    if (t < W) { y = 0; x = t; }
+    else if (t < 2 * W) { y = H - 1; x = t - W; }
+    else if (t < 2 * W + H) { y = t - 2 * W; x = 0; }
+    else { y = t - 2 * W - H; x = W - 1; }
+    const size_t img = (size_t)blockIdx.y * H * W;
+    const int i = y * W + x;
+    if (L[img + i] >= 0) flag[img + find_root(L + img, i)] = 1;
+}
+
+// outer[i] = 1 for zero pixels whose component reaches the frame
+__global__ void ovl_outer_kernel(const int* __restrict__ L, const uint8_t* __restrict__ flag, uint8_t* __restrict__ outer,
+                                 int HW) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= HW) return;
+    const size_t img = (size_t)blockIdx.y * HW;
+    uint8_t o = 0;
+    if (L[img + i] >= 0) o = flag[img + find_root(L + img, i)];
+    outer[img + i] = o;
+}
+
+constexpr int OVL_T = 32;         // output tile edge
+constexpr int OVL_R = 3;          // halo: contour test at distance <= 2 needs `outer` at distance <= 3
+__global__ void __launch_bounds__(OVL_T* OVL_T) ovl_stencil_kernel(const uint8_t* __restrict__ mask,
+                                                                  const uint8_t* __restrict__ outer,
+                                                                  uint8_t* __restrict__ stencil, int H, int W) {
+    constexpr int S = OVL_T + 2 * OVL_R;
+    __shared__ uint8_t fg_s[S][S + 2], out_s[S][S + 2], ct_s[S][S + 2];
+    const size_t img = (size_t)blockIdx.z * H * W;
+    const int x0 = blockIdx.x * OVL_T - OVL_R, y0 = blockIdx.y * OVL_T - OVL_R;
+    const int tid = threadIdx.y * OVL_T + threadIdx.x;
+    for (int i = tid; i < S * S; i += OVL_T * OVL_T) {
+        const int ly = i / S, lx = i % S;
+        const int y = y0 + ly, x = x0 + lx;
+        const bool inb = y >= 0 && y < H && x >= 0 && x < W;
+        fg_s[ly][lx] = inb && mask[img + (size_t)y * W + x] != 0;
+        out_s[ly][lx] = inb ? outer[img + (size_t)y * W + x] : 1;     // outside the image = the frame
+    }
+    __syncthreads();
+    for (int i = tid; i < S * S; i += OVL_T * OVL_T) {
+        const int ly = i / S, lx = i % S;
+        uint8_t c = 0;
+        if (fg_s[ly][lx] && ly > 0 && ly < S - 1 && lx > 0 && lx < S - 1)
+            c = out_s[ly - 1][lx] | out_s[ly + 1][lx] | out_s[ly][lx - 1] | out_s[ly][lx + 1];
+        ct_s[ly][lx] = c;
+    }
+    __syncthreads();
+    const int x = blockIdx.x * OVL_T + threadIdx.x, y = blockIdx.y * OVL_T + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int ly = threadIdx.y + OVL_R, lx = threadIdx.x + OVL_R;
+    uint8_t v = ct_s[ly][lx] | ct_s[ly - 1][lx] | ct_s[ly + 1][lx] | ct_s[ly][lx - 1] | ct_s[ly][lx + 1];
+    // diagonal step p -> p + (1, 1) (rows, cols): both non-zero, (p.y, p.x + 1) or (p.y + 1, p.x) outer background;
+    // paints p + (-1, +1), p + (+1, -1), p + (0, +2), p + (+2, 0)
+    auto step_dr = [&](int py, int px) -> uint8_t {
+        return fg_s[py][px] & fg_s[py + 1][px + 1] & (out_s[py][px + 1] | out_s[py + 1][px]);
+    };
+    // anti-diagonal step p -> p + (1, -1): (p.y, p.x - 1) or (p.y + 1, p.x) outer background;
+    // paints p + (+1, +1), p + (-1, -1), p + (+2, 0), p + (0, -2)
+    auto step_dl = [&](int py, int px) -> uint8_t {
+        return fg_s[py][px] & fg_s[py + 1][px - 1] & (out_s[py][px - 1] | out_s[py + 1][px]);
+    };
+    v |= step_dr(ly + 1, lx - 1) | step_dr(ly - 1, lx + 1) | step_dr(ly, lx - 2) | step_dr(ly - 2, lx);
+    v |= step_dl(ly - 1, lx - 1) | step_dl(ly + 1, lx + 1) | step_dl(ly - 2, lx) | step_dl(ly, lx + 2);
+    stencil[img + (size_t)y * W + x] = v ? 1 : 0;
+}
+
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
@@ -318,7 +402,7 @@ int launch_label_stats(const dc_label_args_t* a, cudaStream_t stream) {
 
     dim3 tb(TILE, TILE);
     dim3 tg(ceil_div(W, TILE), ceil_div(H, TILE), B);
-    ccl_local_kernel<<<tg, tb, 0, stream>>>(a->mask, ws.L, H, W);
+    ccl_local_kernel<<<tg, tb, 0, stream>>>(a->mask, ws.L, H, W, 0);
 
     long long nborder = (long long)((H - 1) / TILE) * W + (long long)((W - 1) / TILE) * H;
     if (nborder > 0) {
@@ -347,6 +431,44 @@ int launch_label_stats(const dc_label_args_t* a, cudaStream_t stream) {
                                                (unsigned long long*)s1);
     ccl_finalize_kernel<<<zg, 256, 0, stream>>>(a->counts, a->capacity, (const long long*)a->area, a->centroid0,
                                                 a->centroid1, a->eq_diam, a->area_um2, a->diam_um, a->px_per_um);
+    DC_CUDA(cudaGetLastError());
+    return DC_OK;
+}
+
+size_t overlay_workspace_bytes(int B, int H, int W) {
+    size_t hw = (size_t)H * W;
+    return align256(sizeof(int) * hw * B) + 2 * align256(hw * B);
+}
+
+int launch_overlay_stencil(const dc_overlay_args_t* a, cudaStream_t stream) {
+    DC_REQUIRE(a && a->mask && a->stencil, DC_EINVAL, "dc_overlay_stencil: null pointer argument");
+    DC_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0, DC_EINVAL, "dc_overlay_stencil: bad shape %d %d %d", a->B, a->H, a->W);
+    DC_REQUIRE((long long)a->H * a->W < (1ll << 31), DC_EINVAL, "dc_overlay_stencil: image too large for int32 indices");
+    DC_REQUIRE(a->B <= 65535, DC_EINVAL, "dc_overlay_stencil: batch > 65535");
+    const int B = a->B, H = a->H, W = a->W, HW = H * W;
+    DC_REQUIRE(a->workspace && a->workspace_bytes >= overlay_workspace_bytes(B, H, W), DC_EWORKSPACE,
+               "dc_overlay_stencil: workspace too small (%zu < %zu)", a->workspace_bytes, overlay_workspace_bytes(B, H, W));
+    char* p = (char*)a->workspace;
+    int* L = (int*)p;             p += align256(sizeof(int) * (size_t)HW * B);
+    uint8_t* flag = (uint8_t*)p;  p += align256((size_t)HW * B);
+    uint8_t* outer = (uint8_t*)p;
+
+    dim3 tb(TILE, TILE);
+    dim3 tg(ceil_div(W, TILE), ceil_div(H, TILE), B);
+    ccl_local_kernel<<<tg, tb, 0, stream>>>(a->mask, L, H, W, 1);          // label the background
+    long long nborder = (long long)((H - 1) / TILE) * W + (long long)((W - 1) / TILE) * H;
+    if (nborder > 0) {
+        dim3 bg((unsigned)((nborder + 255) / 256), B);
+        ccl_border_kernel<<<bg, 256, 0, stream>>>(L, H, W);
+    }
+    DC_CUDA(cudaMemsetAsync(flag, 0, (size_t)HW * B, stream));
+    dim3 mg(ceil_div(2 * W + 2 * H, 256), B);
+    ovl_mark_kernel<<<mg, 256, 0, stream>>>(L, flag, H, W);
+    dim3 og(ceil_div(HW, 256), B);
+    ovl_outer_kernel<<<og, 256, 0, stream>>>(L, flag, outer, HW);
+    dim3 sb(OVL_T, OVL_T);
+    dim3 sg(ceil_div(W, OVL_T), ceil_div(H, OVL_T), B);
+    ovl_stencil_kernel<<<sg, sb, 0, stream>>>(a->mask, outer, a->stencil, H, W);
     DC_CUDA(cudaGetLastError());
     return DC_OK;
 }

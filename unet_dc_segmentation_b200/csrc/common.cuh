@@ -35,6 +35,8 @@ int launch_label_stats(const dc_label_args_t* a, cudaStream_t stream);
 int launch_rolling_ball(const dc_rolling_ball_args_t* a, cudaStream_t stream);
 int launch_resize_linear_u8(const dc_resize_args_t* a, cudaStream_t stream);
 size_t label_workspace_bytes(int B, int H, int W);
+int launch_overlay_stencil(const dc_overlay_args_t* a, cudaStream_t stream);
+size_t overlay_workspace_bytes(int B, int H, int W);
 size_t rolling_ball_workspace_bytes(int planes, int H, int W);
 int num_sms();
 
