@@ -13,7 +13,8 @@ import torch
 
 REPO = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(REPO))
-from unet_dc_segmentation_b200 import label_stats_device, rolling_ball_device, workload as wl   # noqa: E402
+from unet_dc_segmentation_b200 import label_stats_device, overlay_stencil_device, rolling_ball_device, workload as wl   # noqa: E402
+from unet_dc_segmentation_b200.overlay import overlay_workspace_bytes   # noqa: E402
 from unet_dc_segmentation_b200.morphology import rolling_ball_workspace_bytes   # noqa: E402
 from unet_dc_segmentation_b200.quantify import alloc_tables, label_workspace_bytes   # noqa: E402
 from unet_dc_segmentation_b200.synth import synthetic_image, synthetic_mask   # noqa: E402
@@ -54,12 +55,17 @@ def main():
     tabs = alloc_tables(B, 16384, True, dev)
     ms_ccl = timed(lambda: label_stats_device(masks, 1, 3.45, 16384, workspace=cws, out=tabs))
     n = tabs.counts.cpu().numpy()
+    ows = torch.empty(overlay_workspace_bytes(B, S, S), dtype=torch.uint8, device=dev)
+    sten = torch.empty_like(masks)
+    ms_ov = timed(lambda: overlay_stencil_device(masks, out=sten, workspace=ows))
+    ov_bytes = px * 2          # u8 mask read + u8 stencil write
     rb_bytes = px * wl.ROLLING_BALL_BYTES_PER_PX
     ccl_bytes = px * (wl.LABEL_BYTES_PER_PX + wl.STATS_BYTES_PER_PX) + int(n.sum()) * wl.STATS_BYTES_PER_DROPLET
     rows = [f"config 3 on B200: batch {B} of {S}x{S}, droplets per mask {n.mean():.0f} (min {n.min()}, max {n.max()}); HBM peak {hbm} GB/s (measured copy)",
             "", "| stage | ms / batch | frames/s | algorithmic GB/s | of HBM peak | bound |", "|---|---|---|---|---|---|",
             f"| rolling ball radius 50 (dc_rolling_ball, 4 launches) | {ms_rb:.2f} | {B / ms_rb * 1e3:.0f} | {rb_bytes / ms_rb / 1e6:.0f} | {rb_bytes / ms_rb / 1e6 / hbm:.4f} | instructions (1995-tap exact ellipse) |",
-            f"| labelling + droplet table (dc_label_stats, 8 launches) | {ms_ccl:.2f} | {B / ms_ccl * 1e3:.0f} | {ccl_bytes / ms_ccl / 1e6:.0f} | {ccl_bytes / ms_ccl / 1e6 / hbm:.4f} | latency / atomics |"]
+            f"| labelling + droplet table (dc_label_stats, 8 launches) | {ms_ccl:.2f} | {B / ms_ccl * 1e3:.0f} | {ccl_bytes / ms_ccl / 1e6:.0f} | {ccl_bytes / ms_ccl / 1e6 / hbm:.4f} | latency / atomics |",
+            f"| overlay stencil (dc_overlay_stencil, 6 launches) | {ms_ov:.2f} | {B / ms_ov * 1e3:.0f} | {ov_bytes / ms_ov / 1e6:.0f} | {ov_bytes / ms_ov / 1e6 / hbm:.4f} | background labelling (same union-find) |"]
     text = "\n".join(rows)
     print(text)
     if a.out:

@@ -50,12 +50,30 @@ constexpr int A_STAGE_BYTES = TILE_M * KCHUNK * 2;   // 16 KB
 constexpr int NUM_THREADS = 384;      // 4 role warps + 2 epilogue groups x 4 warps
 constexpr int EPI_WARP0 = 4;
 
+// floor(n / d) for 0 <= n < 2^31 as one widening multiply and a shift (Granlund-Montgomery round-up magic number):
+// s = ceil(log2 d), m = floor(2^(31+s) / d) + 1 < 2^32.
+struct FastDiv {
+    uint32_t mul, shift;
+};
+inline FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    uint32_t s = 0;
+    while ((1ll << s) < d) ++s;
+    f.shift = 31 + s;
+    f.mul = (uint32_t)(((1ull << f.shift) / (uint32_t)d) + 1ull);
+    return f;
+}
+__device__ __forceinline__ int fast_div(int n, const FastDiv& f) {
+    return (int)(((unsigned long long)(uint32_t)n * f.mul) >> f.shift);
+}
+
 struct alignas(64) ConvParams {
     CUtensorMap tmA;
     CUtensorMap tmB;
     int B, H, W, Cin, Cout;
     int dil, ntaps, kchunks;
-    int tiles_w, tiles_h, n_tiles, total_tiles;
+    int tiles_w, tiles_h, n_tiles, total_tiles, m_tiles;      // m_tiles = pixel tiles = total_tiles / n_tiles
+    FastDiv fd_ntiles, fd_per_img, fd_tiles_w;      // exact division of tile indices (< 2^31) without the ~20-instruction IDIV
     int epilogue, relu;
     const float* bias;
     int bias_const;                 // Cout == 64 and the host knows the values: bias_c[] below, read as c[0][..] operands
@@ -79,12 +97,12 @@ struct TileCoord {
 template <int TH = TILE_H, int TW = TILE_W>
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, int BN) {
     TileCoord t;
-    int nt = tile % p.n_tiles;
-    int m = tile / p.n_tiles;
+    int m = fast_div(tile, p.fd_ntiles);
+    int nt = tile - m * p.n_tiles;
     int per_img = p.tiles_h * p.tiles_w;
-    t.img = m / per_img;
+    t.img = fast_div(m, p.fd_per_img);
     int r = m - t.img * per_img;
-    int th = r / p.tiles_w;
+    int th = fast_div(r, p.fd_tiles_w);
     t.h0 = th * TH;
     t.w0 = (r - th * p.tiles_w) * TW;
     t.n0 = nt * BN;
@@ -114,12 +132,11 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
 // pair index -> (m-tile pair, n-tile); tile of CTA `rank` = (2 * mpair + rank) * n_tiles + nt.  An odd m-tile
 // count makes the last peer redo the last m-tile (identical stores).
 __device__ __forceinline__ int pair_count(const ConvParams& p) {
-    const int m_tiles = p.total_tiles / p.n_tiles;
-    return ((m_tiles + 1) >> 1) * p.n_tiles;
+    return ((p.m_tiles + 1) >> 1) * p.n_tiles;
 }
 __device__ __forceinline__ int pair_to_tile(const ConvParams& p, int pair, int rank) {
-    const int m_tiles = p.total_tiles / p.n_tiles;
-    const int mpair = pair / p.n_tiles, nt = pair - mpair * p.n_tiles;
+    const int m_tiles = p.m_tiles;
+    const int mpair = fast_div(pair, p.fd_ntiles), nt = pair - mpair * p.n_tiles;
     int m = 2 * mpair + rank;
     if (m >= m_tiles) m = m_tiles - 1;
     return m * p.n_tiles + nt;
@@ -1273,6 +1290,8 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream, const float* bi
     const long long total = (long long)a->B * p.tiles_w * p.tiles_h * p.n_tiles;
     DC_REQUIRE(total < (1ll << 31), DC_EINVAL, "dc_conv_tc: too many tiles");
     p.total_tiles = (int)total;
+    p.m_tiles = p.total_tiles / p.n_tiles;
+    p.fd_ntiles = make_fastdiv(p.n_tiles); p.fd_per_img = make_fastdiv(p.tiles_h * p.tiles_w); p.fd_tiles_w = make_fastdiv(p.tiles_w);
     p.epilogue = a->epilogue;
     p.relu = up ? 0 : (a->relu != 0);
     p.bias = a->bias;
@@ -1345,6 +1364,8 @@ int launch_stem(const dc_stem_args_t* a, cudaStream_t stream, const float* bias_
     const long long total = (long long)a->B * p.tiles_w * p.tiles_h;
     DC_REQUIRE(total < (1ll << 31), DC_EINVAL, "dc_stem: too many tiles");
     p.total_tiles = (int)total;
+    p.m_tiles = p.total_tiles / p.n_tiles;
+    p.fd_ntiles = make_fastdiv(p.n_tiles); p.fd_per_img = make_fastdiv(p.tiles_h * p.tiles_w); p.fd_tiles_w = make_fastdiv(p.tiles_w);
     p.epilogue = DC_EPI_STORE; p.relu = 1;
     p.bias = a->bias;
     if (bias_host) {
