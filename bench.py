@@ -314,8 +314,8 @@ def run_b200(args):
     ccl_gbs = ccl_bytes / (stage_ms[2] * 1e-3) / 1e9
     launches_per_step = 4 + n_launch + 8
     # DRAM bytes of the 22 forward launches, from the committed ncu capture of this exact configuration
-    # (profiles/r01c_forward_per_launch.md: sum of dram__bytes_read.sum + dram__bytes_write.sum); null elsewhere
-    traffic = 76.7e9 if (B, S) == (32, 1024) and tuple(model.dilations) == (1, 2, 4, 8, 16) else None
+    # (profiles/r01e_forward_per_launch.md: sum of dram__bytes_read.sum + dram__bytes_write.sum); null elsewhere
+    traffic = 77.4e9 if (B, S) == (32, 1024) and tuple(model.dilations) == (1, 2, 4, 8, 16) else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -326,7 +326,7 @@ def run_b200(args):
                    "droplets_per_image": float(counts.mean())},
         "roofline": {"kernel": "conv_tc_kernel (21 tcgen05 launches) + stem_kernel = dc_forward", "bound": "tensor",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                     "traffic_note": "DRAM bytes per dc_forward (22 launches), ncu, profiles/r01c_forward_per_launch.md; "
+                     "traffic_note": "DRAM bytes per dc_forward (22 launches), ncu, profiles/r01e_forward_per_launch.md; "
                                      "activations written once + read once would be ~84 GB unfused (SURVEY 8d)",
                      "peak_source": f"{ptype} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
                      "flops_per_launch_group": fwd_flops, "flops_model": "in-bounds taps (conservative), SURVEY.md 8d",
