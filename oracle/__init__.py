@@ -244,3 +244,145 @@ def run_path(state_dict, images_u8, radius=50, prob_thresh=0.3, min_area=1, px_p
     masks = (probs > prob_thresh).astype(np.uint8)
     tables = [quantify(m, min_area, px_per_um) for m in masks]
     return probs, masks, tables
+
+
+# ----------------------------------------------------------------------------- density maps (quantify_pipline.py)
+# numpy restatement of the alternate front end's per-image maps.  Third-party arithmetic restated:
+# OpenCV's u8 cvtColor / GaussianBlur / Otsu / rectangular morphology / moments and scipy.ndimage.gaussian_filter
+# (neither vendored in /root/reference); pinned in tests/test_oracle_golden.py against cv2 / scipy themselves and
+# against the reference's own functions (tests/golden/density.npz).
+
+_GAUSS15_Q8 = np.array([1, 3, 6, 12, 20, 30, 36, 40, 36, 30, 20, 12, 6, 3, 1], np.int64)   # sums to 256
+
+
+def _reflect101(i, n):
+    """cv2 BORDER_REFLECT_101 (gfedcb|abcdefgh|gfedcba)."""
+    if n == 1:
+        return np.zeros_like(i)
+    p = 2 * (n - 1)
+    i = np.mod(i, p)
+    return np.where(i >= n, p - i, i)
+
+
+def _rect15(a, op, pad):
+    """15x15 rectangular erode (np.minimum, pad 255) / dilate (np.maximum, pad 0), out-of-image taps ignored."""
+    H, W = a.shape
+    e = np.pad(a, ((0, 0), (7, 7)), constant_values=pad)
+    h = e[:, 0:W].copy()
+    for j in range(1, 15):
+        h = op(h, e[:, j:j + W])
+    e = np.pad(h, ((7, 7), (0, 0)), constant_values=pad)
+    v = e[0:H].copy()
+    for j in range(1, 15):
+        v = op(v, e[j:j + H])
+    return v
+
+
+def otsu_threshold_u8(a: np.ndarray) -> int:
+    """cv2.threshold(..., THRESH_OTSU)'s threshold for a u8 image (OpenCV getThreshVal_Otsu_8u, f64, same order)."""
+    h = np.bincount(np.ascontiguousarray(a, dtype=np.uint8).ravel(), minlength=256)
+    scale = 1.0 / a.size
+    mu = 0.0
+    for i in range(256):
+        mu += i * float(h[i])
+    mu *= scale
+    mu1 = q1 = max_sigma = 0.0
+    max_val = 0
+    eps = float(np.finfo(np.float32).eps)
+    for i in range(256):
+        p_i = float(h[i]) * scale
+        mu1 *= q1
+        q1 += p_i
+        q2 = 1.0 - q1
+        if min(q1, q2) < eps or max(q1, q2) > 1.0 - eps:
+            continue
+        mu1 = (mu1 + i * p_i) / q1
+        mu2 = (mu - q1 * mu1) / q2
+        sigma = q1 * q2 * (mu1 - mu2) * (mu1 - mu2)
+        if sigma > max_sigma:
+            max_sigma, max_val = sigma, i
+    return max_val
+
+
+def roi_blurred_gray(img_rgb: np.ndarray) -> np.ndarray:
+    """cv2.GaussianBlur(cv2.cvtColor(img, COLOR_RGB2GRAY), (15, 15), 0)  (quantify_pipline.py:45-46): 15-bit gray
+    coefficients, the 8-bit error-diffused kernel of sigma 2.6, rows then columns in integers, one rounding."""
+    img = np.ascontiguousarray(img_rgb, dtype=np.uint8)
+    r, g, b = (img[..., c].astype(np.int64) for c in range(3))
+    gray = (r * 9798 + g * 19235 + b * 3735 + (1 << 14)) >> 15
+    H, W = gray.shape
+    e = gray[:, _reflect101(np.arange(-7, W + 7), W)]
+    h = sum(e[:, j:j + W] * _GAUSS15_Q8[j] for j in range(15))
+    e = h[_reflect101(np.arange(-7, H + 7), H), :]
+    v = sum(e[j:j + H, :] * _GAUSS15_Q8[j] for j in range(15))
+    return ((v + (1 << 15)) >> 16).astype(np.uint8)
+
+
+def roi_mask(img_rgb: np.ndarray):
+    """generate_roi_mask (quantify_pipline.py:44-51) + the centroid of quantify_pipline.py:134-137.
+    Returns (u8 {0,1} [H,W], cy, cx)."""
+    b = roi_blurred_gray(img_rgb)
+    m = np.where(b > otsu_threshold_u8(b), 255, 0).astype(np.uint8)                 # :47
+    m = _rect15(_rect15(m, np.maximum, 0), np.minimum, 255)                          # :49 MORPH_CLOSE
+    m = _rect15(_rect15(m, np.minimum, 255), np.maximum, 0)                          # :50 MORPH_OPEN
+    roi = (m > 0).astype(np.uint8)                                                   # :51
+    H, W = roi.shape
+    ys, xs = np.nonzero(roi)
+    m00 = float(len(ys))
+    cx = int(float(xs.sum()) / m00) if m00 else W // 2                               # :135
+    cy = int(float(ys.sum()) / m00) if m00 else H // 2                               # :136
+    return roi, cy, cx
+
+
+def radial_density(mask: np.ndarray, roi: np.ndarray, nb_layers: int, cy: int, cx: int) -> np.ndarray:
+    """get_targets (quantify_pipline.py:61-91): droplets per concentric ring painted onto the ring's ROI pixels."""
+    _, cols = quantify_arrays(np.ascontiguousarray(mask, dtype=np.uint8), 1, None)   # :66-68 label + centroids
+    c0, c1 = np.asarray(cols["centroid-0"], np.float64), np.asarray(cols["centroid-1"], np.float64)
+    out = np.zeros(mask.shape, np.float32)
+    ys, xs = np.nonzero(roi)
+    if len(ys) == 0 or len(c0) == 0:                                                 # :71-72
+        return out
+    d = np.sqrt(((xs - cx) ** 2 + (ys - cy) ** 2).astype(np.float64))                # :75
+    bounds = np.linspace(0, d.max(), nb_layers + 1)                                  # :76-77
+    dc = np.sqrt((c1 - cx) ** 2 + (c0 - cy) ** 2)                                    # :80
+    for i in range(nb_layers):                                                       # :83-90
+        ring = (bounds[i] < d) & (d <= bounds[i + 1])
+        if ring.any():
+            out[ys[ring], xs[ring]] = np.sum((bounds[i] < dc) & (dc <= bounds[i + 1]))
+    return out
+
+
+def gaussian_weights(sigma: float, truncate: float = 4.0):
+    """scipy.ndimage._filters._gaussian_kernel1d (order 0)."""
+    radius = int(truncate * float(sigma) + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    return phi / phi.sum(), radius
+
+
+def gaussian_filter_f32(a: np.ndarray, sigma: float) -> np.ndarray:
+    """scipy.ndimage.gaussian_filter(float32 image, sigma) with the default mode='reflect': axis 0 then axis 1, each
+    pass accumulated in f64 in NI_Correlate1D's symmetric order (centre, then tap pairs from the outside in) and
+    rounded to f32."""
+    w, r = gaussian_weights(sigma)
+    out = np.ascontiguousarray(a, dtype=np.float32)
+    for axis in (0, 1):
+        x = np.moveaxis(out, axis, -1).astype(np.float64)
+        n = x.shape[-1]
+        idx = np.mod(np.arange(-r, n + r), 2 * n)
+        idx = np.where(idx >= n, 2 * n - 1 - idx, idx)                               # (d c b a | a b c d | d c b a)
+        e = x[..., idx]
+        acc = e[..., r:r + n] * w[r]
+        for jj in range(-r, 0):
+            acc = acc + (e[..., r + jj:r + jj + n] + e[..., r - jj:r - jj + n]) * w[r + jj]
+        out = np.moveaxis(acc.astype(np.float32), -1, axis)
+    return np.ascontiguousarray(out)
+
+
+def spatial_density(mask: np.ndarray, roi: np.ndarray, kernel_size: int = 21) -> np.ndarray:
+    """density_maps (quantify_pipline.py:93-97)."""
+    sigma = kernel_size / 6
+    d = gaussian_filter_f32(mask.astype(np.float32), sigma)
+    d = d / (gaussian_filter_f32(roi.astype(np.float32), sigma) + np.float32(1e-5))
+    d *= np.float32(100)
+    return d

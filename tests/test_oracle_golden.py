@@ -150,3 +150,52 @@ def test_overlay_stencil_on_droplet_like_mask():
     m = (img > 60).astype(np.uint8)
     assert 0 < m.mean() < 0.5
     np.testing.assert_array_equal(oracle.overlay_stencil(m * 255), _cv2_overlay_stencil(m))
+
+
+# ----------------------------------------------------------------------------- density maps (quantify_pipline.py, N4)
+DENSITY_CASES = ["tissue_96x128", "border_128x128", "wide_64x200", "small_33x29", "flat_image", "no_droplets"]
+
+
+@pytest.mark.parametrize("name", DENSITY_CASES)
+def test_density_maps_match_the_reference_functions(name):
+    """oracle.roi_mask / radial_density / spatial_density against generate_roi_mask, the cv2.moments centroid,
+    get_targets and density_maps of the reference's quantify_pipline.py (tests/golden/make_golden_density.py)."""
+    g = load_golden("density.npz")
+    img, mask = g[f"{name}/img"], g[f"{name}/mask"]
+    roi, cy, cx = oracle.roi_mask(img)
+    np.testing.assert_array_equal(roi, g[f"{name}/roi"])
+    assert [cy, cx] == list(g[f"{name}/centroid"])
+    np.testing.assert_array_equal(oracle.radial_density(mask, roi, 10, cy, cx), g[f"{name}/radial"])
+    np.testing.assert_array_equal(oracle.spatial_density(mask, roi), g[f"{name}/spatial"])          # bit for bit
+
+
+def test_roi_mask_steps_match_opencv():
+    """Each OpenCV call of generate_roi_mask on its own: gray + 15x15 Gaussian (fixed point), the Otsu threshold, and
+    the close / open pair, on random sizes down to 1 pixel."""
+    import cv2
+    from scipy import ndimage as ndi
+    rs = np.random.RandomState(3)
+    kernel = np.ones((15, 15), np.uint8)
+    for it in range(40):
+        H, W = rs.randint(1, 90, 2) if it % 4 else rs.randint(90, 260, 2)
+        base = ndi.gaussian_filter(rs.rand(H, W), rs.choice([2, 5, 12]))
+        base = (base - base.min()) / max(float(np.ptp(base)), 1e-9)
+        img = np.clip(base[..., None] * rs.randint(100, 256, 3)[None, None] + rs.randn(H, W, 3) * 8, 0, 255).astype(np.uint8)
+        blurred = cv2.GaussianBlur(cv2.cvtColor(img, cv2.COLOR_RGB2GRAY), (15, 15), 0)
+        np.testing.assert_array_equal(oracle.roi_blurred_gray(img), blurred, err_msg=f"blur {H}x{W}")
+        t, m = cv2.threshold(blurred, 0, 255, cv2.THRESH_BINARY + cv2.THRESH_OTSU)
+        assert oracle.otsu_threshold_u8(blurred) == int(t)
+        m = cv2.morphologyEx(cv2.morphologyEx(m, cv2.MORPH_CLOSE, kernel), cv2.MORPH_OPEN, kernel)
+        roi, cy, cx = oracle.roi_mask(img)
+        np.testing.assert_array_equal(roi, (m > 0).astype(np.uint8), err_msg=f"roi {H}x{W}")
+        M = cv2.moments(roi)
+        assert (cy, cx) == ((int(M["m01"] / M["m00"]), int(M["m10"] / M["m00"])) if M["m00"] else (H // 2, W // 2))
+
+
+def test_gaussian_filter_restatement_matches_scipy_bitwise():
+    from scipy.ndimage import gaussian_filter
+    rs = np.random.RandomState(4)
+    for shape in [(64, 80), (7, 9), (200, 33), (1, 40), (29, 1)]:
+        for sigma in (21 / 6, 1.0, 7.5):
+            a = (rs.rand(*shape) < 0.3).astype(np.float32)
+            np.testing.assert_array_equal(oracle.gaussian_filter_f32(a, sigma), gaussian_filter(a, sigma=sigma))
