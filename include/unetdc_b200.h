@@ -18,6 +18,9 @@
  *   dc_label_stats               quantify                     quantify_droplets_batch.py:81-95
  *   dc_overlay_stencil           cv2.findContours + cv2.drawContours of the overlays
  *                                                           quantify_droplets_batch.py:74-79
+ *   dc_roi_mask / dc_radial_density / dc_spatial_density
+ *                                generate_roi_mask, get_targets, density_maps of the alternate
+ *                                front end                   quantify_pipline.py:44-51, :61-91, :93-97
  *
  * Conventions: every function returns 0 (DC_OK) or a negative DC_E* code and never throws;
  * dc_last_error() gives the message of the calling thread's last failure.  All data pointers
@@ -223,6 +226,64 @@ typedef struct dc_overlay_args {
 
 int dc_overlay_workspace_bytes(int B, int H, int W, size_t* bytes);
 int dc_overlay_stencil(const dc_overlay_args_t* args, void* stream);
+
+/* ---- density maps of quantify_pipline.py (the reference's alternate front end) ---------------------------
+ * All three are bit-exact against the OpenCV / numpy / scipy calls they replace.
+ *
+ * dc_roi_mask: generate_roi_mask(img) (quantify_pipline.py:44-51: RGB2GRAY, GaussianBlur 15x15, Otsu,
+ *   15x15 close, 15x15 open, > 0) and the centroid of quantify_pipline.py:133-136
+ *   (cx = int(m10/m00), cy = int(m01/m00) of cv2.moments, image centre when the mask is empty).
+ *   rgb: u8 [B,H,W,3]; roi: u8 [B,H,W] {0,1}; centroid: int32 [B][2] = (cy, cx). */
+typedef struct dc_roi_args {
+    const uint8_t* rgb;
+    int B, H, W;
+    uint8_t* roi;
+    int* centroid;
+    void* workspace;
+    size_t workspace_bytes;
+} dc_roi_args_t;
+
+int dc_roi_workspace_bytes(int B, int H, int W, size_t* bytes);
+int dc_roi_mask(const dc_roi_args_t* args, void* stream);
+
+/* dc_radial_density: get_targets(mask, roi, nb_layers, cy, cx) (quantify_pipline.py:61-91).  The droplet
+ *   centroids are the centroid0 / centroid1 / counts columns dc_label_stats wrote for the same masks with
+ *   min_area = 1 (the reference labels the mask again without a size filter, :66-68).  out: f32 [B,H,W]. */
+typedef struct dc_radial_args {
+    const uint8_t* roi;
+    int B, H, W;
+    const int* centroid;        /* [B][2] = (cy, cx) */
+    const int* counts;          /* [B] */
+    const double* centroid0;    /* [B,capacity] row */
+    const double* centroid1;    /* [B,capacity] col */
+    int capacity;
+    int nb_layers;              /* 1..64; the reference uses 10 (:138) */
+    float* out;
+    void* workspace;
+    size_t workspace_bytes;
+} dc_radial_args_t;
+
+int dc_radial_workspace_bytes(int B, size_t* bytes);
+int dc_radial_density(const dc_radial_args_t* args, void* stream);
+
+/* dc_spatial_density: density_maps(mask, roi, kernel_size) (quantify_pipline.py:93-97):
+ *   100 * gaussian_filter(mask) / (gaussian_filter(roi) + 1e-5), scipy.ndimage.gaussian_filter on float32 with
+ *   mode='reflect'.  weights: HOST pointer to the 2*radius+1 normalised f64 taps scipy builds for the sigma
+ *   (sigma = kernel_size / 6, radius = int(4*sigma + 0.5)); read during the call.  out: f32 [B,H,W]. */
+#define DC_GAUSS_MAX_RADIUS 64
+typedef struct dc_spatial_args {
+    const uint8_t* mask;
+    const uint8_t* roi;
+    int B, H, W;
+    int radius;
+    const double* weights;
+    float* out;
+    void* workspace;
+    size_t workspace_bytes;
+} dc_spatial_args_t;
+
+int dc_spatial_workspace_bytes(int B, int H, int W, size_t* bytes);
+int dc_spatial_density(const dc_spatial_args_t* args, void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,8 @@ EXPORTS = [
     "dc_model_destroy", "dc_forward_workspace_bytes", "dc_forward", "dc_forward_num_launches", "dc_forward_profile",
     "dc_rolling_ball_workspace_bytes", "dc_rolling_ball", "dc_label_workspace_bytes", "dc_label_stats",
     "dc_resize_linear_u8", "dc_overlay_workspace_bytes", "dc_overlay_stencil",
+    "dc_roi_workspace_bytes", "dc_roi_mask", "dc_radial_workspace_bytes", "dc_radial_density",
+    "dc_spatial_workspace_bytes", "dc_spatial_density",
 ]
 
 
@@ -92,6 +94,28 @@ class OverlayArgs(Structure):
     ]
 
 
+class RoiArgs(Structure):
+    _fields_ = [
+        ("rgb", c_void_p), ("B", c_int), ("H", c_int), ("W", c_int), ("roi", c_void_p), ("centroid", c_void_p),
+        ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+    ]
+
+
+class RadialArgs(Structure):
+    _fields_ = [
+        ("roi", c_void_p), ("B", c_int), ("H", c_int), ("W", c_int), ("centroid", c_void_p), ("counts", c_void_p),
+        ("centroid0", c_void_p), ("centroid1", c_void_p), ("capacity", c_int), ("nb_layers", c_int), ("out", c_void_p),
+        ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+    ]
+
+
+class SpatialArgs(Structure):
+    _fields_ = [
+        ("mask", c_void_p), ("roi", c_void_p), ("B", c_int), ("H", c_int), ("W", c_int), ("radius", c_int),
+        ("weights", c_void_p), ("out", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+    ]
+
+
 _LIB = None
 
 
@@ -133,6 +157,12 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.dc_resize_linear_u8.argtypes = [POINTER(ResizeArgs), c_void_p]
     lib.dc_overlay_workspace_bytes.argtypes = [c_int, c_int, c_int, POINTER(c_size_t)]
     lib.dc_overlay_stencil.argtypes = [POINTER(OverlayArgs), c_void_p]
+    lib.dc_roi_workspace_bytes.argtypes = [c_int, c_int, c_int, POINTER(c_size_t)]
+    lib.dc_roi_mask.argtypes = [POINTER(RoiArgs), c_void_p]
+    lib.dc_radial_workspace_bytes.argtypes = [c_int, POINTER(c_size_t)]
+    lib.dc_radial_density.argtypes = [POINTER(RadialArgs), c_void_p]
+    lib.dc_spatial_workspace_bytes.argtypes = [c_int, c_int, c_int, POINTER(c_size_t)]
+    lib.dc_spatial_density.argtypes = [POINTER(SpatialArgs), c_void_p]
     for name in EXPORTS:
         if name not in ("dc_last_error",):
             getattr(lib, name).restype = c_int

@@ -173,6 +173,42 @@ int dc_overlay_stencil(const dc_overlay_args_t* args, void* stream) {
     return launch_overlay_stencil(args, (cudaStream_t)stream);
 }
 
+int dc_roi_workspace_bytes(int B, int H, int W, size_t* bytes) {
+    DC_REQUIRE(bytes && B > 0 && H > 0 && W > 0, DC_EINVAL, "dc_roi_workspace_bytes: bad argument");
+    *bytes = roi_workspace_bytes(B, H, W);
+    return DC_OK;
+}
+
+int dc_roi_mask(const dc_roi_args_t* args, void* stream) {
+    int rc = check_current_device(nullptr);
+    if (rc != DC_OK) return rc;
+    return launch_roi_mask(args, (cudaStream_t)stream);
+}
+
+int dc_radial_workspace_bytes(int B, size_t* bytes) {
+    DC_REQUIRE(bytes && B > 0, DC_EINVAL, "dc_radial_workspace_bytes: bad argument");
+    *bytes = radial_workspace_bytes(B);
+    return DC_OK;
+}
+
+int dc_radial_density(const dc_radial_args_t* args, void* stream) {
+    int rc = check_current_device(nullptr);
+    if (rc != DC_OK) return rc;
+    return launch_radial_density(args, (cudaStream_t)stream);
+}
+
+int dc_spatial_workspace_bytes(int B, int H, int W, size_t* bytes) {
+    DC_REQUIRE(bytes && B > 0 && H > 0 && W > 0, DC_EINVAL, "dc_spatial_workspace_bytes: bad argument");
+    *bytes = spatial_workspace_bytes(B, H, W);
+    return DC_OK;
+}
+
+int dc_spatial_density(const dc_spatial_args_t* args, void* stream) {
+    int rc = check_current_device(nullptr);
+    if (rc != DC_OK) return rc;
+    return launch_spatial_density(args, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------ whole network
 
 int dc_model_create(dc_model_t** out, int device, const dc_model_desc_t* desc) {

@@ -37,6 +37,12 @@ int launch_resize_linear_u8(const dc_resize_args_t* a, cudaStream_t stream);
 size_t label_workspace_bytes(int B, int H, int W);
 int launch_overlay_stencil(const dc_overlay_args_t* a, cudaStream_t stream);
 size_t overlay_workspace_bytes(int B, int H, int W);
+int launch_roi_mask(const dc_roi_args_t* a, cudaStream_t stream);
+size_t roi_workspace_bytes(int B, int H, int W);
+int launch_radial_density(const dc_radial_args_t* a, cudaStream_t stream);
+size_t radial_workspace_bytes(int B);
+int launch_spatial_density(const dc_spatial_args_t* a, cudaStream_t stream);
+size_t spatial_workspace_bytes(int B, int H, int W);
 size_t rolling_ball_workspace_bytes(int planes, int H, int W);
 int num_sms();
 
