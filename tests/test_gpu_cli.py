@@ -31,7 +31,8 @@ def test_cli_native_size_outputs(cuda_device, workdir):
     from unet_dc_segmentation_b200 import cli
     out = workdir / "out_native"
     rc = cli.main(["--img_dir", str(workdir / "in"), "--ckpt_path", str(workdir / "ckpt.pth"), "--out_dir", str(out),
-                   "--batch", "2", "--px_per_micron", "3.45", "--save_overlays", "--skip_histogram", "--img_size", "96"])
+                   "--batch", "2", "--px_per_micron", "3.45", "--save_overlays", "--skip_histogram", "--img_size", "96",
+                   "--density_maps"])
     assert rc == 0
     names = ["frame0", "frame1", "frame2", "wide"]
     ref_cols = list(load_golden("reference_outputs.npz")["columns"])          # the reference's own all_droplets.csv header
@@ -47,6 +48,12 @@ def test_cli_native_size_outputs(cuda_device, workdir):
         cnts, _ = cv2.findContours(mask // 255, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
         cv2.drawContours(want_ov, cnts, -1, (0, 255, 0), 2)
         np.testing.assert_array_equal(ov, want_ov, err_msg=f"{n} overlay")
+        # density maps (quantify_pipline.py:131-141) = the restated reference functions on the same frame and mask
+        from PIL import Image
+        rgb = np.array(Image.open(src).convert("RGB"))
+        roi, cy, cx = oracle.roi_mask(rgb)
+        np.testing.assert_array_equal(np.load(out / f"{n}_radial_density.npy"), oracle.radial_density(mask // 255, roi, 10, cy, cx))
+        np.testing.assert_array_equal(np.load(out / f"{n}_spatial_density.npy"), oracle.spatial_density(mask // 255, roi))
         df = pd.read_csv(out / f"{n}_droplets.csv", float_precision="round_trip")   # the default parser is 1 ulp sloppy
         want = oracle.quantify(mask // 255, 1, 3.45)
         if want.empty:

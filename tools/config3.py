@@ -15,6 +15,7 @@ REPO = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(REPO))
 from unet_dc_segmentation_b200 import label_stats_device, overlay_stencil_device, rolling_ball_device, workload as wl   # noqa: E402
 from unet_dc_segmentation_b200.overlay import overlay_workspace_bytes   # noqa: E402
+from unet_dc_segmentation_b200 import density   # noqa: E402
 from unet_dc_segmentation_b200.morphology import rolling_ball_workspace_bytes   # noqa: E402
 from unet_dc_segmentation_b200.quantify import alloc_tables, label_workspace_bytes   # noqa: E402
 from unet_dc_segmentation_b200.synth import synthetic_image, synthetic_mask   # noqa: E402
@@ -59,13 +60,25 @@ def main():
     sten = torch.empty_like(masks)
     ms_ov = timed(lambda: overlay_stencil_device(masks, out=sten, workspace=ows))
     ov_bytes = px * 2          # u8 mask read + u8 stencil write
+    # density maps of quantify_pipline.py on a smaller batch (the RGB frames and three f32 planes per frame add up)
+    Bd = min(B, 16)
+    rgb = frames[:Bd, :, :, None].expand(Bd, S, S, 3).contiguous()
+    ms_roi = timed(lambda: density.roi_mask_device(rgb))
+    roi, cen = density.roi_mask_device(rgb)
+    tabs_d = label_stats_device(masks[:Bd], 1, None, 16384)
+    ms_rad = timed(lambda: density.radial_density_device(roi, cen, tabs_d, 10))
+    ms_spa = timed(lambda: density.spatial_density_device(masks[:Bd], roi, 21))
+    pxd = Bd * S * S
     rb_bytes = px * wl.ROLLING_BALL_BYTES_PER_PX
     ccl_bytes = px * (wl.LABEL_BYTES_PER_PX + wl.STATS_BYTES_PER_PX) + int(n.sum()) * wl.STATS_BYTES_PER_DROPLET
     rows = [f"config 3 on B200: batch {B} of {S}x{S}, droplets per mask {n.mean():.0f} (min {n.min()}, max {n.max()}); HBM peak {hbm} GB/s (measured copy)",
             "", "| stage | ms / batch | frames/s | algorithmic GB/s | of HBM peak | bound |", "|---|---|---|---|---|---|",
             f"| rolling ball radius 50 (dc_rolling_ball, 4 launches) | {ms_rb:.2f} | {B / ms_rb * 1e3:.0f} | {rb_bytes / ms_rb / 1e6:.0f} | {rb_bytes / ms_rb / 1e6 / hbm:.4f} | instructions (1995-tap exact ellipse) |",
             f"| labelling + droplet table (dc_label_stats, 8 launches) | {ms_ccl:.2f} | {B / ms_ccl * 1e3:.0f} | {ccl_bytes / ms_ccl / 1e6:.0f} | {ccl_bytes / ms_ccl / 1e6 / hbm:.4f} | latency / atomics |",
-            f"| overlay stencil (dc_overlay_stencil, 6 launches) | {ms_ov:.2f} | {B / ms_ov * 1e3:.0f} | {ov_bytes / ms_ov / 1e6:.0f} | {ov_bytes / ms_ov / 1e6 / hbm:.4f} | background labelling (same union-find) |"]
+            f"| overlay stencil (dc_overlay_stencil, 6 launches) | {ms_ov:.2f} | {B / ms_ov * 1e3:.0f} | {ov_bytes / ms_ov / 1e6:.0f} | {ov_bytes / ms_ov / 1e6 / hbm:.4f} | background labelling (same union-find) |",
+            f"| ROI mask (dc_roi_mask, 14 launches; batch {Bd}) | {ms_roi:.2f} | {Bd / ms_roi * 1e3:.0f} | {pxd * 4 / ms_roi / 1e6:.0f} | {pxd * 4 / ms_roi / 1e6 / hbm:.4f} | 10 separable u8 passes (3 B/px in, 1 B/px out algorithmic) |",
+            f"| radial ring counts (dc_radial_density, 3 launches; batch {Bd}) | {ms_rad:.2f} | {Bd / ms_rad * 1e3:.0f} | {pxd * 6 / ms_rad / 1e6:.0f} | {pxd * 6 / ms_rad / 1e6 / hbm:.4f} | f64 sqrt per pixel (2 x 1 B in, 4 B out) |",
+            f"| spatial density (dc_spatial_density, 5 launches; batch {Bd}) | {ms_spa:.2f} | {Bd / ms_spa * 1e3:.0f} | {pxd * 6 / ms_spa / 1e6:.0f} | {pxd * 6 / ms_spa / 1e6 / hbm:.4f} | f64 accumulation of 29 taps x 4 passes (2 B in, 4 B out) |"]
     text = "\n".join(rows)
     print(text)
     if a.out:

@@ -6,6 +6,7 @@
     quantify                       <- quantify_droplets_batch.py:81                 (quantify.py)
     load_model / preprocess / run_batch / main  <- quantify_droplets_batch.py       (cli.py)
     overlay_stencil_device         <- findContours + drawContours, qdb:74-79        (overlay.py)
+    generate_roi_mask / get_targets / density_maps  <- quantify_pipline.py:44,61,93 (density.py)
     DropletPipeline                fused batched device path                        (pipeline.py)
 
 All compute goes through lib/libunetdc_b200.so (C ABI: include/unetdc_b200.h).  There is no CPU or

@@ -11,8 +11,8 @@ On the device: rolling ball, both resizes (cv2.resize at qdb:44 and qdb:57 is bi
 interpolation flag in the `dst` slot, SURVEY.md 0.2 -- reproduced bit for bit by dc_resize_linear_u8; the identity
 when the frame is already IMG_SIZE), the network, the threshold, labelling, the table and the overlay contours (qdb:76-77,
 bit-exact against OpenCV's findContours + drawContours).  On the host, exactly as in the reference: PIL / cv2 decode,
-PNG / CSV / XLSX writing.  `--img_size` (default 512 = the reference's IMG_SIZE
-constant) is the only added flag.  Under torchrun (one rank per GPU) frames are sharded i -> rank i mod N, every
+PNG / CSV / XLSX writing.  Added flags: `--img_size` (default 512 = the reference's
+IMG_SIZE constant) and `--density_maps` (the per-image maps of the reference's second front end, quantify_pipline.py:131-141).  Under torchrun (one rank per GPU) frames are sharded i -> rank i mod N, every
 rank writes the per-image files of its own frames, and the tables are gathered on rank 0, which writes the reports.
 """
 from __future__ import annotations
@@ -26,7 +26,9 @@ import torch
 
 from .model import UNetDC
 from .morphology import resize_linear_u8_device, rolling_ball_device
+from .density import normalize, radial_density_device, roi_mask_device, spatial_density_device
 from .overlay import draw_overlay, overlay_stencil_device
+from .quantify import label_stats_device
 from .quantify import quantify
 
 IMG_SIZE = 512                     # qdb:30
@@ -64,8 +66,10 @@ def preprocess(path, background_radius: int, img_size: int | None = None):
 
 
 @torch.no_grad()
-def run_batch(tensors, meta, model, mask_dir, overlay_dir, thresh, min_area, px_per_um, per_image_rows, all_props):
-    """qdb:48-79: forward one batch, then per image: mask, PNG, droplet table, CSV, summary row, overlay."""
+def run_batch(tensors, meta, model, mask_dir, overlay_dir, thresh, min_area, px_per_um, per_image_rows, all_props,
+              density_dir=None):
+    """qdb:48-79: forward one batch, then per image: mask, PNG, droplet table, CSV, summary row, overlay.
+    density_dir: also write the radial / spatial density maps of the reference's quantify_pipline.py:131-141."""
     import cv2
     dev = next(model.parameters()).device
     batch = torch.stack(tensors).to(dev)
@@ -91,6 +95,33 @@ def run_batch(tensors, meta, model, mask_dir, overlay_dir, thresh, min_area, px_
                 # qdb:76-77: the pixels findContours(RETR_EXTERNAL) + drawContours(thickness 2) paint, from the GPU
                 draw_overlay(img, overlay_stencil_device(m)[0].cpu().numpy())
                 cv2.imwrite(str(Path(overlay_dir) / f"{name}_overlay.png"), img)      # qdb:78
+        if density_dir is not None:
+            save_density_maps(fpath, name, m, density_dir)
+
+
+def save_density_maps(fpath, name, mask_dev, density_dir) -> None:
+    """quantify_pipline.py:131-141 for one image: ROI mask of the ORIGINAL frame, its centroid, droplets per concentric
+    ring and the Gaussian droplet density, all on the device.  Writes {name}_radial_density.npy / _spatial_density.npy
+    (the exact f32 maps) and, when matplotlib is installed, the reference's two 'hot' PNGs of the normalised maps."""
+    from PIL import Image
+    orig = np.array(Image.open(fpath).convert("RGB"))                                  # qpl:131
+    roi, cen = roi_mask_device(torch.from_numpy(orig).to(mask_dev.device)[None])       # qpl:132-136
+    t = label_stats_device(mask_dev, 1, None)                                          # qpl:66-68 (no size filter)
+    n = int(t.counts.max().item())
+    if n > t.capacity:
+        t = label_stats_device(mask_dev, 1, None, n)
+    radial = radial_density_device(roi, cen, t, 10)[0].cpu().numpy()                   # qpl:138
+    spatial = spatial_density_device(mask_dev, roi)[0].cpu().numpy()                   # qpl:139
+    np.save(Path(density_dir) / f"{name}_radial_density.npy", radial)
+    np.save(Path(density_dir) / f"{name}_spatial_density.npy", spatial)
+    try:
+        import matplotlib
+        matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+    except ImportError:
+        return
+    plt.imsave(Path(density_dir) / f"{name}_radial_density.png", normalize(radial), cmap="hot")      # qpl:140
+    plt.imsave(Path(density_dir) / f"{name}_spatial_density.png", normalize(spatial), cmap="hot")    # qpl:141
 
 
 def write_reports(out_dir: Path, per_image_rows, all_props, skip_excel: bool, skip_histogram: bool) -> None:
@@ -146,6 +177,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--background_radius", type=int, default=50, help="radius for rolling ball background correction")
     p.add_argument("--skip_excel", action="store_true", help="skip generation of the Excel workbook")
     p.add_argument("--skip_histogram", action="store_true", help="skip histogram plot generation")
+    p.add_argument("--density_maps", action="store_true",
+                   help="also write the radial / spatial droplet-density maps of the reference's quantify_pipline.py")
     p.add_argument("--img_size", type=int, default=IMG_SIZE,
                    help="network input size (reference constant IMG_SIZE = 512); use the frame size for native-resolution inference")
     return p
@@ -180,7 +213,7 @@ def main(argv=None) -> int:
 
     def flush():
         run_batch(tensors, meta, model, mask_dir, overlay_dir, args.prob_thresh, args.min_area, args.px_per_micron,
-                  per_image_rows, all_props)
+                  per_image_rows, all_props, density_dir=out_dir if args.density_maps else None)
         tensors.clear()
         meta.clear()
 
