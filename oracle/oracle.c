@@ -176,7 +176,7 @@ int orc_quantify(const uint8_t *mask, int H, int W, int64_t min_area, double px_
                  double *area_um2, double *diam_um)
 {
     size_t n = (size_t)H * W;
-    int32_t *img = (int32_t *)malloc(sizeof(int32_t) * (n ? n : 1));
+    int32_t *img = (int32_t *)calloc(n ? n : 1, sizeof(int32_t));
     int32_t *lbl = (int32_t *)malloc(sizeof(int32_t) * (n ? n : 1));
     if (!img || !lbl) { free(img); free(lbl); return -2; }
     for (size_t i = 0; i < n; ++i) img[i] = mask[i] ? 1 : 0;
