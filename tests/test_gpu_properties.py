@@ -76,3 +76,43 @@ def test_conv3x3_random_shapes(cuda_device, B, H, W, cin, cout, d, relu, seed):
     got = layers.conv3x3(x.cuda(), pack_conv3x3(w).cuda(), b.cuda(), dilation=d, relu=relu).float().cpu()
     err = (got - want).abs()
     assert bool((err <= 1e-2 * want.abs().clamp(min=1.0)).all()), f"max err {float(err.max()):.4g}"
+
+
+@settings(max_examples=40, **COMMON)
+@given(B=st.integers(1, 3), H=st.integers(1, 70), W=st.integers(1, 70), p=st.sampled_from([0.1, 0.4, 0.6, 0.9]),
+       blur=st.sampled_from([0.0, 1.0, 2.0]), seed=st.integers(0, 10 ** 6))
+def test_overlay_stencil_random_vs_opencv(cuda_device, B, H, W, p, blur, seed):
+    import cv2
+    import torch
+    from scipy import ndimage as ndi
+    from unet_dc_segmentation_b200 import overlay_stencil_device
+    rs = np.random.RandomState(seed)
+    f = rs.rand(B, H, W)
+    if blur:
+        f = np.stack([ndi.gaussian_filter(x, blur) for x in f])
+        f = (f - f.min()) / max(float(np.ptp(f)), 1e-9)
+    masks = ((f > 0.5) if blur else (f < p)).astype(np.uint8)
+    got = overlay_stencil_device(torch.from_numpy(masks).cuda()).cpu().numpy()
+    for b in range(B):
+        img = np.zeros((H, W, 3), np.uint8)
+        cnts, _ = cv2.findContours(masks[b], cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+        cv2.drawContours(img, cnts, -1, (0, 255, 0), 2)
+        np.testing.assert_array_equal(got[b], (img[..., 1] > 0).astype(np.uint8))
+
+
+@settings(max_examples=25, **COMMON)
+@given(H=st.integers(1, 80), W=st.integers(1, 80), nb=st.integers(1, 20), ks=st.sampled_from([3, 9, 21, 45]),
+       seed=st.integers(0, 10 ** 6))
+def test_density_maps_random_vs_oracle(cuda_device, H, W, nb, ks, seed):
+    from scipy import ndimage as ndi
+    from unet_dc_segmentation_b200 import density
+    rs = np.random.RandomState(seed)
+    base = ndi.gaussian_filter(rs.rand(H, W), 4.0)
+    base = (base - base.min()) / max(float(np.ptp(base)), 1e-9)
+    img = np.clip(base[..., None] * rs.randint(60, 256, 3)[None, None] + rs.randn(H, W, 3) * 6, 0, 255).astype(np.uint8)
+    mask = (rs.rand(H, W) < 0.06).astype(np.uint8)
+    roi_want, cy, cx = oracle.roi_mask(img)
+    roi = density.generate_roi_mask(img)
+    np.testing.assert_array_equal(roi, roi_want)
+    np.testing.assert_array_equal(density.get_targets(mask, roi, nb, cy, cx), oracle.radial_density(mask, roi, nb, cy, cx))
+    np.testing.assert_array_equal(density.density_maps(mask, roi, ks), oracle.spatial_density(mask, roi, ks))
