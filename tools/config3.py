@@ -76,9 +76,9 @@ def main():
             f"| rolling ball radius 50 (dc_rolling_ball, 4 launches) | {ms_rb:.2f} | {B / ms_rb * 1e3:.0f} | {rb_bytes / ms_rb / 1e6:.0f} | {rb_bytes / ms_rb / 1e6 / hbm:.4f} | instructions (1995-tap exact ellipse) |",
             f"| labelling + droplet table (dc_label_stats, 8 launches) | {ms_ccl:.2f} | {B / ms_ccl * 1e3:.0f} | {ccl_bytes / ms_ccl / 1e6:.0f} | {ccl_bytes / ms_ccl / 1e6 / hbm:.4f} | latency / atomics |",
             f"| overlay stencil (dc_overlay_stencil, 6 launches) | {ms_ov:.2f} | {B / ms_ov * 1e3:.0f} | {ov_bytes / ms_ov / 1e6:.0f} | {ov_bytes / ms_ov / 1e6 / hbm:.4f} | background labelling (same union-find) |",
-            f"| ROI mask (dc_roi_mask, 14 launches; batch {Bd}) | {ms_roi:.2f} | {Bd / ms_roi * 1e3:.0f} | {pxd * 4 / ms_roi / 1e6:.0f} | {pxd * 4 / ms_roi / 1e6 / hbm:.4f} | 10 separable u8 passes (3 B/px in, 1 B/px out algorithmic) |",
+            f"| ROI mask (dc_roi_mask, 11 launches; batch {Bd}) | {ms_roi:.2f} | {Bd / ms_roi * 1e3:.0f} | {pxd * 4 / ms_roi / 1e6:.0f} | {pxd * 4 / ms_roi / 1e6 / hbm:.4f} | tiled gray + 15x15 blur, then bit-packed morphology (3 B/px in, 1 B/px out algorithmic) |",
             f"| radial ring counts (dc_radial_density, 3 launches; batch {Bd}) | {ms_rad:.2f} | {Bd / ms_rad * 1e3:.0f} | {pxd * 6 / ms_rad / 1e6:.0f} | {pxd * 6 / ms_rad / 1e6 / hbm:.4f} | f64 sqrt per pixel (2 x 1 B in, 4 B out) |",
-            f"| spatial density (dc_spatial_density, 5 launches; batch {Bd}) | {ms_spa:.2f} | {Bd / ms_spa * 1e3:.0f} | {pxd * 6 / ms_spa / 1e6:.0f} | {pxd * 6 / ms_spa / 1e6 / hbm:.4f} | f64 accumulation of 29 taps x 4 passes (2 B in, 4 B out) |"]
+            f"| spatial density (dc_spatial_density, 2 launches; batch {Bd}) | {ms_spa:.2f} | {Bd / ms_spa * 1e3:.0f} | {pxd * 6 / ms_spa / 1e6:.0f} | {pxd * 6 / ms_spa / 1e6 / hbm:.4f} | f64 accumulation, 29 taps x 2 planes x 2 axes (2 B in, 4 B out) |"]
     text = "\n".join(rows)
     print(text)
     if a.out:
