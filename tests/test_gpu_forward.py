@@ -171,3 +171,22 @@ def test_config1_eight_256_images(cuda_device):
         _, cols = oracle.quantify_arrays(masks[i], 1, None)
         cols["n"] = len(cols["label"])
         assert_table_equal(tables[i], cols, f"image {i}")
+
+
+@pytest.mark.parametrize("dil", [(1, 2, 2, 4, 4), (2, 4, 8, 16, 32), (3, 1, 5, 2, 7)])
+def test_forward_other_dilation_sets(cuda_device, dil):
+    """BASELINE config 5 sweeps dilation sets: each moves layers between kernel families (halo regions for dilation
+    <= 4 at every level, the per-tap kernel above that, dilation 32 on an 8x8 bottleneck = centre tap only)."""
+    import torch
+    import unet_dc_segmentation_b200 as pkg
+    from unet_dc_segmentation_b200.synth import calibrated_state_dict, synthetic_image
+    sd = calibrated_state_dict(seed=1, calib_size=64, n_calib=2, dilations=dil)
+    cls = type("UNetDCx", (pkg.UNetDC,), {"dilations": dil})
+    m = cls(3, 1)
+    m.load_state_dict(sd)
+    m = m.to(cuda_device).eval()
+    imgs = np.stack([synthetic_image(128, 700 + b) for b in range(2)])
+    x = torch.from_numpy(np.repeat(imgs[:, None], 3, 1).astype(np.float32) / 255.0)
+    want = oracle.unetdc_forward(sd, x, dil).numpy()
+    emu = oracle.unetdc_forward(sd, x, dil, emulate_bf16=True).numpy()
+    _check_probs(m(x.to(cuda_device)).cpu().numpy(), want, emu, f"dilations {dil}")
