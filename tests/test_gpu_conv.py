@@ -84,6 +84,17 @@ def test_conv3x3_single_cta_halo_forced(cuda_device, monkeypatch, B, H, W, cin, 
     test_conv3x3_store(cuda_device, B, H, W, cin, cout, d)
 
 
+@pytest.mark.parametrize("env", [("DC_CONV_PATH", "generic"), ("DC_CONV_PAIR", "0")])
+def test_fused_epilogues_on_the_fallback_kernels(cuda_device, monkeypatch, env):
+    """Pool, head and transposed-conv epilogues through the per-tap kernel and the single-CTA halo kernel (one or two
+    halves per tile: an epilogue group can be left without a half of its own in the head epilogue)."""
+    monkeypatch.setenv(*env)
+    test_conv3x3_store_pool(cuda_device, 1, 16, 32, 64, 1)
+    test_conv3x3_store_pool(cuda_device, 2, 24, 48, 128, 2)
+    test_head_epilogue(cuda_device)
+    test_upconv2x2(cuda_device, 1, 8, 16, 128, 64)
+
+
 def test_conv3x3_no_relu_and_channel_slices(cuda_device):
     """Reads channels [0,64) of a 128-wide buffer and writes channels [64,128) of another (the concat layout)."""
     import torch
