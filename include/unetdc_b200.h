@@ -47,6 +47,10 @@ extern "C" {
 #define DC_ECAPACITY (-4) /* droplet table capacity exceeded (counts are still exact) */
 #define DC_EWORKSPACE (-5)
 
+/* Bumped whenever a struct or signature in this header changes; dc_version() returns the value the library was
+ * built with and the Python binding refuses to load a library that disagrees. */
+#define DC_ABI_VERSION 200
+
 const char* dc_last_error(void);
 int dc_version(void);
 /* 0 when `device` is usable (compute capability 10.x); fills *sm_count when non-NULL. */
@@ -96,6 +100,12 @@ typedef struct dc_conv_args {
 } dc_conv_args_t;
 
 int dc_conv_tc(const dc_conv_args_t* args, void* stream);
+
+/* TEST AID, never called on the product path: pins which kernel family dc_conv_tc picks for layers that have a
+ * choice, so that the fallback kernels stay under test.  AUTO (the default): CTA-pair halo kernel where it fits,
+ * else single-CTA halo, else per-tap.  Process-wide; not thread-safe against concurrent launches. */
+enum { DC_CONV_FAMILY_AUTO = 0, DC_CONV_FAMILY_NO_PAIR = 1, DC_CONV_FAMILY_GENERIC = 2 };
+int dc_debug_set_conv_family(int family);
 
 /* First layer (Cin = 3, models/model_2.py:10 first conv) + BatchNorm + ReLU on tcgen05: the im2col tile is
  * built in shared memory by producer warps (K = 27 -> 32, or 9 -> 16 for grayscale where the three identical

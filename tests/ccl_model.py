@@ -1,0 +1,175 @@
+"""Pure-Python model of the run-based labelling scheme of csrc/ccl.cu (test infrastructure, CPU only).
+
+It mirrors the kernels phase by phase -- 64 x 128 tiles, runs clipped at 64-pixel words, union-find over run starts
+with min-index roots, the packed per-tile accumulators, border merges, kept-root numbering by popcount prefix -- so
+that the DESIGN of the GPU algorithm (bit tricks, field widths, offsets) is checked against the oracle on the CPU,
+where there is no GPU to run the kernels themselves.  Sequential: no atomics, no barriers."""
+from __future__ import annotations
+
+import numpy as np
+
+TILE_W, TILE_H = 64, 128
+M64 = (1 << 64) - 1
+
+
+def bits_below(b):
+    return M64 if b >= 64 else (1 << b) - 1
+
+
+def bits_upto(b):
+    return M64 if b >= 63 else (2 << b) - 1
+
+
+def ffs(w):            # 0-based index of the lowest set bit
+    return (w & -w).bit_length() - 1
+
+
+def run_start(w, b):
+    z = ~w & M64 & bits_below(b)
+    return z.bit_length() if z else 0          # 64 - clz(z)
+
+
+def run_end(w, b):
+    z = ~w & M64 & ~bits_upto(b) & M64
+    return ffs(z) - 1 if z else 63
+
+
+def merge_rows(dn, up, unite):
+    ov = dn & up
+    while ov:
+        b = ffs(ov)
+        unite(run_start(dn, b), run_start(up, b))
+        ov &= ~bits_upto(min(run_end(dn, b), run_end(up, b))) & M64
+
+
+def nz4(v):
+    h = (v | (((v | 0x80808080) - 0x01010101) & 0xFFFFFFFF)) & 0x80808080
+    return ((((h >> 7) * 0x01020408) & 0xFFFFFFFF) >> 24) & 0xF
+
+
+def find(P, x):
+    while P[x] != x:
+        x = P[x]
+    return x
+
+
+def union_min(P, a, b):
+    a, b = find(P, a), find(P, b)
+    if a < b:
+        P[b] = a
+    elif b < a:
+        P[a] = b
+
+
+def label_stats(mask: np.ndarray, min_area: int = 1, invert: bool = False):
+    """Returns (labels int32 [H,W], area, sum_row, sum_col) following csrc/ccl.cu."""
+    H, W = mask.shape
+    WW = (W + 63) // 64
+    fgm = (mask != 0) != invert
+    bits = [[0] * WW for _ in range(H)]
+    for y in range(H):
+        for wx in range(WW):
+            seg = fgm[y, wx * 64:min(W, wx * 64 + 64)]
+            w = 0
+            for k, v in enumerate(seg):
+                if v:
+                    w |= 1 << k
+            bits[y][wx] = w
+    P, ACC, AUX = {}, {}, {}
+    rootbits = [[0] * WW for _ in range(H)]
+    # K1: tiles
+    for ty0 in range(0, H, TILE_H):
+        for wx in range(WW):
+            x0 = wx * 64
+            par = {}
+            rows = [bits[ty0 + t][wx] if ty0 + t < H else 0 for t in range(TILE_H)]
+            for t, w in enumerate(rows):
+                s = w & ~(w << 1) & M64
+                while s:
+                    b = ffs(s)
+                    par[t * 64 + b] = t * 64 + b
+                    s &= s - 1
+            for t in range(1, TILE_H):
+                merge_rows(rows[t], rows[t - 1], lambda sd, su, t=t: union_min(par, t * 64 + sd, (t - 1) * 64 + su))
+            for t, w in enumerate(rows):
+                s = w & ~(w << 1) & M64
+                gbase = (ty0 + t) * W + x0
+                while s:
+                    b = ffs(s)
+                    e = run_end(w, b)
+                    ln = e - b + 1
+                    pk = ln | (((b + e) * ln // 2) << 16) | ((t * ln) << 36)
+                    r = find(par, t * 64 + b)
+                    groot = (ty0 + (r >> 6)) * W + x0 + (r & 63)
+                    if r == t * 64 + b:
+                        ACC[gbase + b] = ACC.get(gbase + b, 0) + pk
+                        P[gbase + b] = gbase + b
+                        AUX[gbase + b] = 0
+                        rootbits[ty0 + t][wx] |= 1 << b
+                    else:
+                        P[gbase + b] = groot
+                        ACC[groot] = ACC.get(groot, 0) + pk
+                    s &= s - 1
+    for g, pk in ACC.items():      # field widths: no carries between the packed fields
+        assert (pk & 0xFFFF) <= 8192 and ((pk >> 16) & 0xFFFFF) <= 258048 and (pk >> 36) <= 520192
+    # K2: borders
+    for y in range(TILE_H, H, TILE_H):
+        for wx in range(WW):
+            g = y * W + wx * 64
+            merge_rows(bits[y][wx], bits[y - 1][wx], lambda sd, su, g=g: union_min(P, g + sd, g - W + su))
+    for y in range(H):
+        for wx in range(1, WW):
+            a, b = bits[y][wx - 1], bits[y][wx]
+            if (a >> 63) & b & 1:
+                g = y * W + wx * 64
+                union_min(P, g, g - 64 + run_start(a, 63))
+    # K2b: areas
+    roots = [(y, wx) for y in range(H) for wx in range(WW) if rootbits[y][wx]]
+    if min_area > 1:
+        for y, wx in roots:
+            s = rootbits[y][wx]
+            while s:
+                gi = y * W + wx * 64 + ffs(s)
+                AUX[find(P, gi)] += ACC[gi] & 0xFFFF
+                s &= s - 1
+    # K3-K5: kept roots, ids in raster order
+    n = 0
+    for y, wx in roots:
+        s = rootbits[y][wx]
+        while s:
+            gi = y * W + wx * 64 + ffs(s)
+            if P[gi] == gi:
+                if min_area <= 1 or AUX[gi] >= min_area:
+                    n += 1
+                    AUX[gi] = n
+                else:
+                    AUX[gi] = 0
+            s &= s - 1
+    area = np.zeros(n, np.int64)
+    s0 = np.zeros(n, np.int64)
+    s1 = np.zeros(n, np.int64)
+    # K6
+    for y, wx in roots:
+        s = rootbits[y][wx]
+        while s:
+            gi = y * W + wx * 64 + ffs(s)
+            i = AUX[find(P, gi)]
+            if i:
+                pk = ACC[gi]
+                a, sc, sr = pk & 0xFFFF, (pk >> 16) & 0xFFFFF, pk >> 36
+                area[i - 1] += a
+                s0[i - 1] += sr + a * ((y // TILE_H) * TILE_H)
+                s1[i - 1] += sc + a * (wx * 64)
+            s &= s - 1
+    # K8
+    labels = np.zeros((H, W), np.int32)
+    for y in range(H):
+        for wx in range(WW):
+            w = bits[y][wx]
+            s = w & ~(w << 1) & M64
+            while s:
+                b = ffs(s)
+                e = run_end(w, b)
+                labels[y, wx * 64 + b:wx * 64 + e + 1] = AUX[find(P, y * W + wx * 64 + b)]
+                s &= s - 1
+    return labels, area, s0, s1

@@ -10,6 +10,16 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture
+def conv_family():
+    """dc_debug_set_conv_family for the duration of one test (the product path never calls it)."""
+    from unet_dc_segmentation_b200 import _lib
+    lib = _lib.load()
+    codes = {"auto": _lib.DC_CONV_FAMILY_AUTO, "no_pair": _lib.DC_CONV_FAMILY_NO_PAIR, "generic": _lib.DC_CONV_FAMILY_GENERIC}
+    yield lambda name: _lib.check(lib.dc_debug_set_conv_family(codes[name]))
+    _lib.check(lib.dc_debug_set_conv_family(_lib.DC_CONV_FAMILY_AUTO))
+
+
 def _close(got, want, what=""):
     import torch
     got = got.float().cpu()
@@ -52,6 +62,10 @@ CONV_CASES = [
     (1, 48, 40, 256, 512, 1),     # CTA-pair kernel, BN = 256, two n-tiles, odd number of m-tiles (15)
     (3, 16, 24, 128, 256, 4),     # CTA-pair kernel, BN = 256, dilation 4
     (1, 16, 8, 512, 256, 2),      # CTA-pair kernel, a single m-tile (the peer CTA redoes it)
+    (1, 64, 64, 512, 1024, 16),   # bottleneck.0 of a 1024^2 frame (model_2.py:16): dilation 16 with every tap in bounds
+    (1, 48, 80, 1024, 1024, 16),  # bottleneck.3: ragged map, taps partly in the padding
+    (2, 32, 48, 256, 512, 8),     # enc4.0 (model_2.py:13): dilation 8, non-centre taps in bounds
+    (1, 128, 128, 512, 512, 8),   # enc4.3 at its 1024^2-frame size
 ]
 
 
@@ -70,25 +84,25 @@ def test_conv3x3_store(cuda_device, B, H, W, cin, cout, d):
 
 
 @pytest.mark.parametrize("B,H,W,cin,cout,d", [(2, 16, 32, 64, 64, 1), (1, 24, 40, 64, 128, 2), (1, 32, 48, 128, 256, 4)])
-def test_conv3x3_generic_path_forced(cuda_device, monkeypatch, B, H, W, cin, cout, d):
-    """Most layers take the CTA-pair halo kernel; DC_CONV_PATH=generic keeps the per-tap kernel covered."""
-    monkeypatch.setenv("DC_CONV_PATH", "generic")
+def test_conv3x3_generic_path_forced(cuda_device, conv_family, B, H, W, cin, cout, d):
+    """Most layers take the CTA-pair halo kernel; the test-only family switch keeps the per-tap kernel covered."""
+    conv_family("generic")
     test_conv3x3_store(cuda_device, B, H, W, cin, cout, d)
 
 
 @pytest.mark.parametrize("B,H,W,cin,cout,d", [(2, 16, 32, 64, 64, 1), (2, 48, 24, 128, 64, 1), (1, 40, 40, 64, 128, 2),
                                                (2, 16, 16, 128, 128, 2), (3, 40, 24, 192, 64, 3)])
-def test_conv3x3_single_cta_halo_forced(cuda_device, monkeypatch, B, H, W, cin, cout, d):
-    """DC_CONV_PAIR=0 keeps the single-CTA halo kernel (resident and streamed weights) covered."""
-    monkeypatch.setenv("DC_CONV_PAIR", "0")
+def test_conv3x3_single_cta_halo_forced(cuda_device, conv_family, B, H, W, cin, cout, d):
+    """DC_CONV_FAMILY_NO_PAIR keeps the single-CTA halo kernel (resident and streamed weights) covered."""
+    conv_family("no_pair")
     test_conv3x3_store(cuda_device, B, H, W, cin, cout, d)
 
 
-@pytest.mark.parametrize("env", [("DC_CONV_PATH", "generic"), ("DC_CONV_PAIR", "0")])
-def test_fused_epilogues_on_the_fallback_kernels(cuda_device, monkeypatch, env):
+@pytest.mark.parametrize("family", ["generic", "no_pair"])
+def test_fused_epilogues_on_the_fallback_kernels(cuda_device, conv_family, family):
     """Pool, head and transposed-conv epilogues through the per-tap kernel and the single-CTA halo kernel (one or two
     halves per tile: an epilogue group can be left without a half of its own in the head epilogue)."""
-    monkeypatch.setenv(*env)
+    conv_family(family)
     test_conv3x3_store_pool(cuda_device, 1, 16, 32, 64, 1)
     test_conv3x3_store_pool(cuda_device, 2, 24, 48, 128, 2)
     test_head_epilogue(cuda_device)

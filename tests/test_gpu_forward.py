@@ -14,6 +14,14 @@ bf16 and accumulates in fp32; the reference is fp32 throughout.  Two checks:
     single bf16 roundings: max |dp| <= EMU_TOL = 0.02, mean |dp| <= EMU_MEAN_TOL = 0.001 (measured on B200:
     max 0.013, mean 0.0003).  This is the check that says the kernels compute the network they claim to.
 
+THE STATED TOLERANCE: |dp| <= 0.03 on the survey's checkpoint -- default init + BatchNorm
+calibration + an out_conv bias shift (``calibrated_state_dict(fit_head=False)``, logit std ~0.4) -- and masks may
+differ from the reference's only where |p_ref - thresh| <= 0.03: test_survey_checkpoint_stated_tolerance.  The bench
+and most tests use the fitted-head checkpoint (``fit_head=True``: out_conv is least-squares fitted so that the masks
+look like droplets; its logits span -6..+4, ~10x the gain), for which the same bf16 noise in the last feature map
+becomes up to 0.06-0.07 of probability at the steepest pixels: PROB_TOL = 0.08 applies to THAT checkpoint only, and
+bench.py reports how many mask pixels / droplets actually differ from the fp32 reference on the bench frames.
+
 Droplet tables are bit-exact GIVEN THE SAME MASK, so every table check feeds the oracle the kernel's own mask."""
 import numpy as np
 import pytest
@@ -26,6 +34,10 @@ PROB_TOL = 0.08
 MEAN_TOL = 0.004
 EMU_MEAN_TOL = 0.001
 EMU_TOL = 0.02
+
+
+SURVEY_TOL = 0.03          # the stated bf16 tolerance, on the survey's checkpoint
+SURVEY_MEAN_TOL = 0.002
 
 
 def _check_probs(got, ref_fp32, emu=None, what=""):
@@ -147,6 +159,11 @@ def test_whole_path_vs_reference_golden(cuda_device):
         n += 1
     assert n == 5
     assert list(pipe.run_host_pipelined(iter(()))) == []
+    # results are owned by the caller: holding ALL of them (not just the latest) must keep every batch intact
+    held = list(pipe.run_host_pipelined(seq[k % 2] for k in range(5)))
+    for k, (mk, tb) in enumerate(held):
+        np.testing.assert_array_equal(mk, masks if k % 2 == 0 else want_f_masks, err_msg=f"held batch {k}")
+    assert not np.shares_memory(held[0][0], held[2][0])
 
 
 def test_config1_eight_256_images(cuda_device):
@@ -190,3 +207,31 @@ def test_forward_other_dilation_sets(cuda_device, dil):
     want = oracle.unetdc_forward(sd, x, dil).numpy()
     emu = oracle.unetdc_forward(sd, x, dil, emulate_bf16=True).numpy()
     _check_probs(m(x.to(cuda_device)).cpu().numpy(), want, emu, f"dilations {dil}")
+
+
+def test_survey_checkpoint_stated_tolerance(cuda_device):
+    """SURVEY.md 8(d)'s checkpoint and bar: |dp| <= 0.03 against the fp32 reference path (cv2 rolling ball + the
+    reference network), mask mismatches only within 0.03 of prob_thresh, tables bit-exact given the kernel's mask."""
+    import torch
+    from unet_dc_segmentation_b200 import DropletPipeline
+    from unet_dc_segmentation_b200.synth import calibrated_state_dict, synthetic_image
+    sd = calibrated_state_dict(seed=0, fit_head=False)
+    m = _model("UNetDC", sd, cuda_device)
+    imgs = np.stack([synthetic_image(256, 40 + i) for i in range(4)])
+    probs_ref, masks_ref, _ = oracle.run_path(sd, [np.repeat(im[:, :, None], 3, 2) for im in imgs], radius=50,
+                                              prob_thresh=0.3, min_area=1, px_per_um=None, use_cv2=True)
+    pipe = DropletPipeline(m, 50, 0.3, 1, None, capacity=32768)
+    res = pipe.run_device(torch.from_numpy(imgs).to(cuda_device), return_prob=True)
+    probs = res.probs[:, 0].cpu().numpy()
+    masks = res.masks.cpu().numpy()
+    err = np.abs(probs - probs_ref)
+    diff = masks != masks_ref
+    print(f"survey checkpoint: max |dp| {err.max():.4f} mean {err.mean():.5f}; mask pixels differing {int(diff.sum())} "
+          f"({100.0 * diff.mean():.3f} %)")
+    assert err.max() <= SURVEY_TOL and err.mean() <= SURVEY_MEAN_TOL
+    assert int((diff & (np.abs(probs_ref - 0.3) > SURVEY_TOL)).sum()) == 0
+    tables = res.tables.to_host()
+    for i in range(4):
+        _, cols = oracle.quantify_arrays(masks[i], 1, None)
+        cols["n"] = len(cols["label"])
+        assert_table_equal(tables[i], cols, f"image {i}")

@@ -91,3 +91,39 @@ def test_rolling_ball_stage_matches_cv2_at_full_size(run):
         f = run["frames"][b]
         want = cv2.normalize(cv2.subtract(f, cv2.morphologyEx(f, cv2.MORPH_OPEN, k)), None, 0, 255, cv2.NORM_MINMAX)
         np.testing.assert_array_equal(got[b], want, err_msg=f"frame {b}")
+
+
+def test_forward_parity_at_full_size(run):
+    """The benchmarked shape itself (BASELINE configs[1]: 1024 x 1024 frames, batch 32): frames 0 and 17 of the batch
+    against the fp32 reference network (oracle.unetdc_forward restates models/model_2.py:56-80) and against the bf16
+    emulation.  At this size the bottleneck map is 64 x 64, so dilation 16 (model_2.py:16) and dilation 8
+    (model_2.py:13) run with all nine taps in bounds, and every layer runs its full multi-tile schedule.
+    Tolerances: tests/test_gpu_forward.py (PROB_TOL / EMU_TOL); masks may differ from the reference's only inside
+    the PROB_TOL band around prob_thresh, and the droplet table is bit-exact given the kernel's mask."""
+    import torch
+    from test_gpu_forward import EMU_MEAN_TOL, EMU_TOL, MEAN_TOL, PROB_TOL
+    from unet_dc_segmentation_b200 import rolling_ball_device
+    from unet_dc_segmentation_b200.synth import calibrated_state_dict
+    sd = calibrated_state_dict(seed=0)
+    idx = [0, 17]
+    pre = rolling_ball_device(run["dev_frames"][idx], 50).cpu().numpy()          # bit-exact vs cv2 (test above)
+    x = torch.from_numpy(np.repeat(pre[:, None], 3, 1).astype(np.float32) / 255.0)
+    ref = oracle.unetdc_forward(sd, x).numpy()[:, 0]
+    emu = oracle.unetdc_forward(sd, x, emulate_bf16=True, gray_input=True).numpy()[:, 0]
+    got = run["probs"][idx, 0].cpu().numpy()
+    masks = run["masks"][idx].cpu().numpy()
+    e_ref, e_emu = np.abs(got - ref), np.abs(got - emu)
+    ref_mask = (ref > 0.3).astype(np.uint8)
+    diff = masks != ref_mask
+    in_band = np.abs(ref - 0.3) <= PROB_TOL
+    n_ref = [len(oracle.quantify_arrays(m, 1, None)[1]["label"]) for m in ref_mask]
+    n_got = [len(run["tables"][i]["label"]) for i in idx]
+    print(f"1024^2: vs fp32 max {e_ref.max():.4f} mean {e_ref.mean():.5f}; vs bf16 emulation max {e_emu.max():.4f} "
+          f"mean {e_emu.mean():.5f}; mask pixels differing {int(diff.sum())} of {diff.size} "
+          f"({int((diff & ~in_band).sum())} outside the band); droplets {n_got} vs reference {n_ref}")
+    assert e_ref.max() <= PROB_TOL and e_ref.mean() <= MEAN_TOL
+    assert e_emu.max() <= EMU_TOL and e_emu.mean() <= EMU_MEAN_TOL
+    assert int((diff & ~in_band).sum()) == 0
+    assert diff.mean() < 0.005
+    for a, b in zip(n_got, n_ref):
+        assert abs(a - b) <= 0.03 * b, f"droplet count {a} vs reference {b}"

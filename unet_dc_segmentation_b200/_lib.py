@@ -15,9 +15,11 @@ DC_EINVAL, DC_ECUDA, DC_EDEVICE, DC_ECAPACITY, DC_EWORKSPACE = -1, -2, -3, -4, -
 DC_KIND_CONV3X3, DC_KIND_UPCONV2 = 0, 1
 DC_EPI_STORE, DC_EPI_STORE_POOL, DC_EPI_HEAD, DC_EPI_UPSCATTER = 0, 1, 2, 3
 DC_NUM_LAYERS = 23
+DC_CONV_FAMILY_AUTO, DC_CONV_FAMILY_NO_PAIR, DC_CONV_FAMILY_GENERIC = 0, 1, 2
+ABI_VERSION = 200          # DC_ABI_VERSION of include/unetdc_b200.h these ctypes structures mirror
 
 EXPORTS = [
-    "dc_last_error", "dc_version", "dc_device_check", "dc_conv_tc", "dc_stem", "dc_model_create",
+    "dc_last_error", "dc_version", "dc_device_check", "dc_conv_tc", "dc_debug_set_conv_family", "dc_stem", "dc_model_create",
     "dc_model_destroy", "dc_forward_workspace_bytes", "dc_forward", "dc_forward_num_launches", "dc_forward_profile",
     "dc_rolling_ball_workspace_bytes", "dc_rolling_ball", "dc_label_workspace_bytes", "dc_label_stats",
     "dc_resize_linear_u8", "dc_overlay_workspace_bytes", "dc_overlay_stencil",
@@ -128,19 +130,25 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     if build_if_missing and _build.is_stale():
         try:
             _build.build()
-        except Exception as exc:  # stale-but-present is still usable; missing is fatal
-            if not path.exists():
-                raise RuntimeError(
-                    f"{path} is missing and could not be built ({exc}); unet_dc_segmentation_b200 has "
-                    "no CPU or PyTorch fallback") from exc
+        except Exception as exc:
+            # a stale library may have been built against other struct layouts: loading it would corrupt memory
+            what = "is out of date with its sources" if path.exists() else "is missing"
+            raise RuntimeError(
+                f"{path} {what} and could not be rebuilt ({exc}); unet_dc_segmentation_b200 has "
+                "no CPU or PyTorch fallback") from exc
     if not path.exists():
         raise RuntimeError(f"{path} is missing; run `python -m unet_dc_segmentation_b200.build`")
     lib = C.CDLL(str(path))
     lib.dc_last_error.restype = C.c_char_p
     lib.dc_last_error.argtypes = []
     lib.dc_version.restype = c_int
+    lib.dc_version.argtypes = []
+    if lib.dc_version() != ABI_VERSION:
+        raise RuntimeError(f"{path} reports ABI version {lib.dc_version()}, this binding is for {ABI_VERSION}: "
+                           "rebuild with `python -m unet_dc_segmentation_b200.build --force`")
     lib.dc_device_check.argtypes = [c_int, POINTER(c_int)]
     lib.dc_conv_tc.argtypes = [POINTER(ConvArgs), c_void_p]
+    lib.dc_debug_set_conv_family.argtypes = [c_int]
     lib.dc_stem.argtypes = [POINTER(StemArgs), c_void_p]
     lib.dc_model_create.argtypes = [POINTER(c_void_p), c_int, POINTER(ModelDesc)]
     lib.dc_model_destroy.argtypes = [c_void_p]

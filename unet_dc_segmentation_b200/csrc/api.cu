@@ -69,7 +69,8 @@ namespace {
 
 // Activation buffers of one forward, carved out of the caller's workspace (all bf16 NHWC).
 struct ForwardBuffers {
-    char* a[5];      // first-conv output of enc1..enc4 / bottleneck; reused as dec{l}.0 output for l < 4
+    char* a[5];      // first-conv output of enc1..enc4 / bottleneck
+    char* ad[4];     // dec{l}.0 output
     char* cat[4];    // [B,Hl,Wl,2*Cl]: channels [0,Cl) <- upconv, [Cl,2Cl) <- encoder skip (torch.cat order)
     char* pool[4];   // 2x2 max-pooled encoder output
     char* bott;      // bottleneck.3 output
@@ -77,28 +78,57 @@ struct ForwardBuffers {
     size_t total;
 };
 
+// Buffers are placed by lifetime: [t0, t1] = first launch that writes .. last launch that reads (launch numbers of
+// forward_impl below); two buffers may share memory when their lifetimes do not intersect.  Largest first, each at
+// the lowest offset that is free for its whole lifetime.  At 32 x 1024^2 this is 15.6 GB (the skip halves of cat[0..3]
+// have to survive the whole bottom of the U) instead of the 30.5 GB of one private buffer per tensor.
 ForwardBuffers carve(char* base, int B, int H, int W) {
     ForwardBuffers f;
     memset(&f, 0, sizeof(f));
-    size_t off = 0;
-    auto take = [&](size_t elems) {
-        char* p = base ? base + off : nullptr;
-        off += align256(elems * 2);
-        return p;
+    struct Item { size_t bytes; int t0, t1; char** slot; size_t off; };
+    Item items[24];
+    int n = 0;
+    auto add = [&](char** slot, size_t elems, int t0, int t1) {
+        Item it = {align256(elems * 2), t0, t1, slot, 0};
+        items[n++] = it;
     };
     for (int l = 0; l < 5; ++l) {
         const size_t px = (size_t)B * (H >> l) * (W >> l);
         const size_t C = (size_t)64 << l;
-        f.a[l] = take(px * C);
+        add(&f.a[l], px * C, 2 * l, 2 * l + 1);
         if (l < 4) {
-            f.cat[l] = take(px * 2 * C);
-            f.pool[l] = take(px / 4 * C);
-            if (l > 0) f.db[l] = take(px * C);
+            add(&f.cat[l], px * 2 * C, 2 * l + 1, 20 - 3 * l);
+            add(&f.pool[l], px / 4 * C, 2 * l + 1, 2 * l + 2);
+            add(&f.ad[l], px * C, 20 - 3 * l, 21 - 3 * l);
+            if (l > 0) add(&f.db[l], px * C, 21 - 3 * l, 22 - 3 * l);
         } else {
-            f.bott = take(px * C);
+            add(&f.bott, px * C, 9, 10);
         }
     }
-    f.total = off;
+    int order[24];
+    for (int i = 0; i < n; ++i) order[i] = i;
+    for (int i = 1; i < n; ++i)                              // insertion sort, bytes descending (stable)
+        for (int j = i; j > 0 && items[order[j]].bytes > items[order[j - 1]].bytes; --j) {
+            int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t;
+        }
+    size_t total = 0;
+    for (int oi = 0; oi < n; ++oi) {
+        Item& it = items[order[oi]];
+        size_t best = 0;
+        bool moved = true;
+        while (moved) {                                       // lowest offset with no live neighbour overlapping it
+            moved = false;
+            for (int oj = 0; oj < oi; ++oj) {
+                const Item& o = items[order[oj]];
+                if (o.t1 < it.t0 || it.t1 < o.t0) continue;   // never alive together
+                if (best < o.off + o.bytes && o.off < best + it.bytes) { best = o.off + o.bytes; moved = true; }
+            }
+        }
+        it.off = best;
+        if (best + it.bytes > total) total = best + it.bytes;
+    }
+    for (int i = 0; i < n; ++i) *items[i].slot = base ? base + items[i].off : nullptr;
+    f.total = total;
     return f;
 }
 
@@ -108,7 +138,9 @@ extern "C" {
 
 const char* dc_last_error(void) { return g_err; }
 
-int dc_version(void) { return 100; }
+int dc_version(void) { return DC_ABI_VERSION; }
+
+int dc_debug_set_conv_family(int family) { return set_conv_family(family); }
 
 int dc_device_check(int device, int* sm_count) {
     cudaDeviceProp prop;
@@ -343,13 +375,13 @@ static int forward_impl(dc_model_t* m, int in_kind, const void* in, int B, int H
         const int base = 10 + 3 * (3 - l);
         DC_TRY(conv(base, DC_KIND_UPCONV2, DC_EPI_UPSCATTER, 0, h / 2, w / 2, 2 * c, c, 1, src, 2 * c, f.cat[l], 2 * c, 0,
                     nullptr));
-        DC_TRY(conv(base + 1, DC_KIND_CONV3X3, DC_EPI_STORE, 1, h, w, 2 * c, c, 1, f.cat[l], 2 * c, f.a[l], c, 0, nullptr));
+        DC_TRY(conv(base + 1, DC_KIND_CONV3X3, DC_EPI_STORE, 1, h, w, 2 * c, c, 1, f.cat[l], 2 * c, f.ad[l], c, 0, nullptr));
         if (l > 0) {
-            DC_TRY(conv(base + 2, DC_KIND_CONV3X3, DC_EPI_STORE, 1, h, w, c, c, 1, f.a[l], c, f.db[l], c, 0, nullptr));
+            DC_TRY(conv(base + 2, DC_KIND_CONV3X3, DC_EPI_STORE, 1, h, w, c, c, 1, f.ad[l], c, f.db[l], c, 0, nullptr));
             src = f.db[l];
         } else {
             // dec1.3 + out_conv + sigmoid + threshold (model_2.py:79-80, qdb:56)
-            DC_TRY(conv(base + 2, DC_KIND_CONV3X3, DC_EPI_HEAD, 1, h, w, c, c, 1, f.a[l], c, nullptr, 0, 0, nullptr));
+            DC_TRY(conv(base + 2, DC_KIND_CONV3X3, DC_EPI_HEAD, 1, h, w, c, c, 1, f.ad[l], c, nullptr, 0, 0, nullptr));
         }
     }
 #undef DC_TRY

@@ -1,24 +1,40 @@
-// ccl.cu -- 4-connected labelling + per-droplet statistics on the GPU.
+// ccl.cu -- 4-connected labelling + per-droplet statistics on the GPU, run-based on a bit-packed mask.
 //
 // Replaces the device-side work of quantify() (reference quantify_droplets_batch.py:81-95):
-//   label(mask, connectivity=1)            -> ccl_local_kernel + ccl_border_kernel (union-find,
+//   label(mask, connectivity=1)            -> ccl_tile_kernel + ccl_border_kernel (union-find over RUN STARTS,
 //                                             root = smallest raster index of the component)
-//   per-label `< min_area` filter (:83-85) -> ccl_flatten_area_kernel + the keep predicate
-//   label(lbl) again = compaction (:86)    -> ccl_count / ccl_scan / ccl_assign (prefix sum over
-//                                             kept roots in raster order = skimage's numbering)
-//   regionprops_table + micron columns     -> ccl_moments_kernel (warp-aggregated 64-bit integer
-//                                             atomics) + ccl_finalize_kernel (IEEE f64 divide/sqrt)
+//   per-label `< min_area` filter (:83-85) -> ccl_area_kernel + the keep predicate of ccl_mark_kernel
+//   label(lbl) again = compaction (:86)    -> ccl_mark / ccl_scan / ccl_ids (prefix sum over kept roots in raster
+//                                             order = skimage's numbering)
+//   regionprops_table + micron columns     -> per-run moments (closed form per run, no per-pixel work) summed per
+//                                             tile-local component, ccl_accumulate_kernel (one 64-bit atomic triple
+//                                             per tile-local component) + ccl_finalize_kernel (IEEE f64 divide/sqrt)
 //
-// Everything is integer until the last kernel, so labels / counts / areas are bit-exact and the
-// centroids are the exact integer sums divided once in f64, as numpy does.
+// Data layout.  The u8 mask is read ONCE (1 B/px) and packed to 1 bit/px (`bits`, 64-px words, row pitch
+// WW = ceil(W/64) words).  Everything after that works on runs (maximal horizontal stretches of set bits inside one
+// 64-px word): a 1024^2 frame with ~3 k droplets has ~30 k runs, so the int32 label plane of a per-pixel algorithm
+// (4 B/px written, then re-read by every later pass) never exists.  Union-find state lives in planes indexed by the
+// pixel index of a run's FIRST pixel and is touched only there (sparse: a few sectors per droplet):
+//   P   int32  parent (pixel index of another run start of the same component, smaller or equal)
+//   ACC u64    per tile-local root: area | sum(col - tile_x0) << 16 | sum(row - tile_y0) << 36 of its tile-local
+//              component (field maxima for a 64 x 128 tile: 8192, 258 048, 520 192: no carries between fields)
+//   AUX u32    per final root: total area (min_area > 1), then the final label id (0 = filtered out)
+// `rootbits` marks the run starts that are tile-local roots, `keptbits` the final roots that survive min_area.
+// The int32 label image is written only when the caller asks for it (labels_out), straight from the runs.
+//
+// Everything is integer until the last kernel, so labels / counts / areas are bit-exact and the centroids are the
+// exact integer sums divided once in f64, as numpy does.
 #include "common.cuh"
 
 namespace dc {
 
 namespace {
 
-constexpr int TILE = 32;          // ccl_local tile edge (one warp per tile row)
-constexpr int SCAN_BLOCK = 1024;  // pixels per compaction block
+typedef unsigned long long u64;
+
+constexpr int TILE_W = 64;        // one 64-bit word
+constexpr int TILE_H = 128;       // rows per tile = threads per block (one thread per word-row)
+constexpr int WORDS_PER_BLOCK = 256;   // compaction granularity of the kept-root scan
 
 __device__ __forceinline__ int find_root(const volatile int* L, int x) {
     int p = L[x];
@@ -46,110 +62,221 @@ __device__ __forceinline__ void union_min(int* L, int a, int b) {
     } while (!done);
 }
 
-// ---- K1: per 32x32 tile union-find in shared memory; rows are merged with a warp ballot ----
-// invert != 0 labels the ZERO pixels instead (the background components the overlay stencil needs).
-__global__ void __launch_bounds__(TILE* TILE) ccl_local_kernel(const uint8_t* __restrict__ mask, int* __restrict__ L,
-                                                              int H, int W, int invert) {
-    __shared__ int s[TILE * TILE];
-    __shared__ unsigned rowbits[TILE];
-    const int lx = threadIdx.x, ly = threadIdx.y;
-    const int x = blockIdx.x * TILE + lx, y = blockIdx.y * TILE + ly;
-    const size_t img = (size_t)blockIdx.z * H * W;
-    const bool inb = (x < W) && (y < H);
-    const bool fg = inb && ((mask[img + (size_t)y * W + x] != 0) != (invert != 0));
-    const unsigned bits = __ballot_sync(0xffffffffu, fg);
-    const int tid = ly * TILE + lx;
-    int lab = -1;
-    if (fg) {
-        unsigned below = (1u << lx) - 1u;
-        unsigned zeros = ~bits & below;                 // background pixels left of me in this row
-        int start = zeros ? (32 - __clz(zeros)) : 0;    // first pixel of my horizontal run
-        lab = ly * TILE + start;
+__device__ __forceinline__ u64 bits_below(int b) { return b >= 64 ? ~0ull : ((1ull << b) - 1ull); }   // bits [0, b)
+__device__ __forceinline__ u64 bits_upto(int b) { return b >= 63 ? ~0ull : ((2ull << b) - 1ull); }    // bits [0, b]
+
+// first / last bit of the run of ones of `w` that contains bit b (bit b is set)
+__device__ __forceinline__ int run_start(u64 w, int b) {
+    const u64 z = ~w & bits_below(b);
+    return z ? 64 - __clzll((long long)z) : 0;
+}
+__device__ __forceinline__ int run_end(u64 w, int b) {
+    const u64 z = ~w & ~bits_upto(b);
+    return z ? __ffsll((long long)z) - 2 : 63;
+}
+
+// For every pair (run of `dn`, run of `up`) that overlaps in x: unite(start of the dn run, start of the up run).
+// A maximal stretch of dn & up lies inside exactly one run of each word, and two stretches never share both runs,
+// so every overlapping pair is visited exactly once.
+template <class U>
+__device__ __forceinline__ void merge_rows(u64 dn, u64 up, U&& unite) {
+    u64 ov = dn & up;
+    while (ov) {
+        const int b = __ffsll((long long)ov) - 1;
+        unite(run_start(dn, b), run_start(up, b));
+        ov &= ~bits_upto(min(run_end(dn, b), run_end(up, b)));
     }
-    s[tid] = lab;
-    if (lx == 0) rowbits[ly] = bits;
+}
+
+// bit k = (byte k of v != 0)
+__device__ __forceinline__ unsigned nz4(unsigned v) {
+    const unsigned h = (v | ((v | 0x80808080u) - 0x01010101u)) & 0x80808080u;   // bit 7 of every non-zero byte
+    return (((h >> 7) * 0x01020408u) >> 24) & 0xFu;
+}
+
+__device__ __forceinline__ u64 pack_acc(unsigned len, unsigned srow, unsigned scol) {
+    return (u64)len | ((u64)scol << 16) | ((u64)srow << 36);
+}
+
+// ---- K1: one 64 x 128 tile per block: pack the mask to bits, union-find over the tile's runs in shared memory,
+//          per-run moments summed into the tile-local roots.  invert != 0 labels the ZERO pixels instead (the
+//          background components the overlay stencil needs).
+__global__ void __launch_bounds__(TILE_H) ccl_tile_kernel(const uint8_t* __restrict__ mask, u64* __restrict__ bits,
+                                                          u64* __restrict__ rootbits, int* __restrict__ P,
+                                                          u64* __restrict__ ACC, unsigned* __restrict__ AUX, int H, int W,
+                                                          int WW, int invert, int zero_aux) {
+    __shared__ int par[TILE_W * TILE_H];
+    __shared__ u64 rowbits[TILE_H];
+    const int t = threadIdx.x;
+    const int wx = blockIdx.x, ty0 = blockIdx.y * TILE_H, img = blockIdx.z;
+    const size_t HW = (size_t)H * W;
+    const uint8_t* m = mask + (size_t)img * HW;
+    const int x0 = wx * TILE_W;
+
+    // ---- pack: 4 lanes per row, 16 pixels (one 16-byte load) per lane
+    if (((W & 15) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = t + j * TILE_H;
+            const int row = c >> 2, q = c & 3;
+            const int y = ty0 + row, x = x0 + q * 16;
+            unsigned b16 = 0;
+            if (y < H && x < W) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(m + (size_t)y * W + x));
+                b16 = nz4(v.x) | (nz4(v.y) << 4) | (nz4(v.z) << 8) | (nz4(v.w) << 12);
+                if (invert) b16 ^= 0xFFFFu;
+            }
+            u64 part = (u64)b16 << (16 * q);
+            part |= __shfl_xor_sync(0xffffffffu, part, 1);
+            part |= __shfl_xor_sync(0xffffffffu, part, 2);
+            if (q == 0) rowbits[row] = part;
+        }
+    } else {
+        const int y = ty0 + t;
+        u64 w = 0;
+        if (y < H) {
+            const int n = min(TILE_W, W - x0);
+            const uint8_t* r = m + (size_t)y * W + x0;
+            for (int k = 0; k < n; ++k) w |= (u64)((r[k] != 0) != (invert != 0)) << k;
+        }
+        rowbits[t] = w;
+    }
     __syncthreads();
-    if (fg && ly > 0) {
-        unsigned up = rowbits[ly - 1];
-        if ((up >> lx) & 1u) {
-            // one union per overlapping run pair: skip when the pixel to the left already links them
-            bool left_links = lx > 0 && ((bits >> (lx - 1)) & 1u) && ((up >> (lx - 1)) & 1u);
-            if (!left_links) union_min(s, tid, tid - TILE);
-        }
+
+    const int y = ty0 + t;
+    const bool inb = y < H;
+    const u64 w = rowbits[t];                              // 0 for rows below the image
+    const u64 up = t > 0 ? rowbits[t - 1] : 0ull;
+    const size_t word_idx = ((size_t)img * H + (inb ? y : 0)) * WW + wx;
+    if (__syncthreads_or(w != 0ull) == 0) {                // empty tile: nothing to label
+        if (inb) { bits[word_idx] = 0ull; rootbits[word_idx] = 0ull; }
+        return;
+    }
+    if (inb) bits[word_idx] = w;
+    const u64 starts = w & ~(w << 1);
+    for (u64 s = starts; s; s &= s - 1) {
+        const int b = __ffsll((long long)s) - 1;
+        par[t * TILE_W + b] = t * TILE_W + b;
     }
     __syncthreads();
-    if (inb) {
-        int out = -1;
-        if (fg) {
-            int r = find_root(s, tid);
-            int ry = r / TILE, rx = r % TILE;
-            out = (blockIdx.y * TILE + ry) * W + (blockIdx.x * TILE + rx);
-        }
-        L[img + (size_t)y * W + x] = out;
-    }
-}
+    merge_rows(w, up, [&](int sd, int su) { union_min(par, t * TILE_W + sd, (t - 1) * TILE_W + su); });
+    __syncthreads();
 
-// ---- K2: merge across tile borders in global memory ----
-__global__ void ccl_border_kernel(int* L, int H, int W) {
-    const int nbr = (H - 1) / TILE;   // horizontal borders: rows y = TILE*k, k = 1..nbr
-    const int nbc = (W - 1) / TILE;   // vertical borders:   cols x = TILE*k
-    const long long nh = (long long)nbr * W, nv = (long long)nbc * H;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int* Li = L + (size_t)blockIdx.y * H * W;
-    if (t < nh) {
-        int y = (int)(t / W + 1) * TILE, x = (int)(t % W);
-        int i = y * W + x;
-        if (Li[i] >= 0 && Li[i - W] >= 0) {
-            bool left_links = (x % TILE != 0) && Li[i - 1] >= 0 && Li[i - W - 1] >= 0;
-            if (!left_links) union_min(Li, i, i - W);
-        }
-    } else if (t < nh + nv) {
-        t -= nh;
-        int x = (int)(t / H + 1) * TILE, y = (int)(t % H);
-        int i = y * W + x;
-        if (Li[i] >= 0 && Li[i - 1] >= 0) {
-            bool up_links = (y % TILE != 0) && Li[i - W] >= 0 && Li[i - W - 1] >= 0;
-            if (!up_links) union_min(Li, i, i - 1);
+    // ---- tile-local roots publish their own run; every run start gets its parent in the global plane
+    int* Pi = P + (size_t)img * HW;
+    u64* Ai = ACC + (size_t)img * HW;
+    unsigned* Xi = AUX + (size_t)img * HW;
+    const int gbase = y * W + x0;                          // pixel index of bit 0 of this word (H*W < 2^31)
+    u64 rootw = 0;
+    for (u64 s = starts; s; s &= s - 1) {
+        const int b = __ffsll((long long)s) - 1;
+        const int self = t * TILE_W + b;
+        const int r = find_root(par, self);
+        if (r == self) {
+            const int e = run_end(w, b);
+            const unsigned len = (unsigned)(e - b + 1);
+            Ai[gbase + b] = pack_acc(len, (unsigned)t * len, (unsigned)(b + e) * len / 2u);
+            Pi[gbase + b] = gbase + b;
+            if (zero_aux) Xi[gbase + b] = 0u;
+            rootw |= 1ull << b;
+        } else {
+            Pi[gbase + b] = (ty0 + (r >> 6)) * W + x0 + (r & 63);
         }
     }
-}
-
-// ---- K3 (only when min_area > 1): flatten + per-root pixel count ----
-__global__ void ccl_flatten_area_kernel(int* L, int* area, int HW) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int* Li = L + (size_t)blockIdx.y * HW;
-    int* Ai = area + (size_t)blockIdx.y * HW;
-    int r = -1;
-    if (i < HW && Li[i] >= 0) {
-        r = find_root(Li, i);
-        Li[i] = r;
-    }
-    unsigned act = __ballot_sync(0xffffffffu, r >= 0);
-    if (r >= 0) {
-        unsigned peers = __match_any_sync(act, r);
-        if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&Ai[r], __popc(peers));
+    if (inb) rootbits[word_idx] = rootw;
+    __syncthreads();                                       // the roots' records are visible to the whole block
+    for (u64 s = starts & ~rootw; s; s &= s - 1) {
+        const int b = __ffsll((long long)s) - 1;
+        const int r = find_root(par, t * TILE_W + b);
+        const int e = run_end(w, b);
+        const unsigned len = (unsigned)(e - b + 1);
+        atomicAdd(&Ai[(ty0 + (r >> 6)) * W + x0 + (r & 63)], pack_acc(len, (unsigned)t * len, (unsigned)(b + e) * len / 2u));
     }
 }
 
-__device__ __forceinline__ bool keep_root(const int* Li, const int* Ai, int i, int HW, long long min_area) {
-    if (i >= HW || Li[i] != i) return false;
-    return min_area <= 1 || (long long)Ai[i] >= min_area;
+// ---- K2: merge across tile borders (runs are clipped at tile borders, so every start has a P entry)
+__global__ void ccl_border_kernel(const u64* __restrict__ bits, int* P, int H, int W, int WW) {
+    const int nbr = (H - 1) / TILE_H;                      // horizontal borders: rows y = TILE_H * k, k = 1..nbr
+    const long long nh = (long long)nbr * WW, nv = (long long)H * (WW - 1);
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64* Bi = bits + (size_t)blockIdx.y * H * WW;
+    int* Pi = P + (size_t)blockIdx.y * H * W;
+    if (i < nh) {
+        const int k = (int)(i / WW) + 1, wx = (int)(i % WW);
+        const int y = k * TILE_H;
+        const u64 dn = Bi[(size_t)y * WW + wx], up = Bi[(size_t)(y - 1) * WW + wx];
+        const int g = y * W + wx * TILE_W;
+        merge_rows(dn, up, [&](int sd, int su) { union_min(Pi, g + sd, g - W + su); });
+    } else if (i < nh + nv) {
+        i -= nh;
+        const int y = (int)(i / (WW - 1)), wx = (int)(i % (WW - 1)) + 1;
+        const u64 a = Bi[(size_t)y * WW + wx - 1], b = Bi[(size_t)y * WW + wx];
+        if ((a >> 63) & b & 1ull) {
+            const int g = y * W + wx * TILE_W;
+            union_min(Pi, g, g - TILE_W + run_start(a, 63));
+        }
+    }
 }
 
-// ---- K4a: kept roots per SCAN_BLOCK pixels ----
-__global__ void __launch_bounds__(SCAN_BLOCK) ccl_count_kernel(const int* __restrict__ L, const int* __restrict__ aux,
-                                                               int* __restrict__ blockcnt, int HW, int nblk,
-                                                               long long min_area) {
-    const int* Li = L + (size_t)blockIdx.y * HW;
-    const int* Ai = aux + (size_t)blockIdx.y * HW;
-    int i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
-    int c = __syncthreads_count(keep_root(Li, Ai, i, HW, min_area));
-    if (threadIdx.x == 0) blockcnt[(size_t)blockIdx.y * nblk + blockIdx.x] = c;
+// ---- K2b (only when min_area > 1): total pixel count per final root
+__global__ void ccl_area_kernel(const u64* __restrict__ rootbits, const int* __restrict__ P, const u64* __restrict__ ACC,
+                                unsigned* __restrict__ AUX, int H, int W, int WW) {
+    const long long NW = (long long)H * WW;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NW) return;
+    const u64 rw = rootbits[(size_t)blockIdx.y * NW + i];
+    if (!rw) return;
+    const size_t HW = (size_t)H * W;
+    const int* Pi = P + blockIdx.y * HW;
+    const int gbase = (int)(i / WW) * W + (int)(i % WW) * TILE_W;
+    for (u64 s = rw; s; s &= s - 1) {
+        const int gi = gbase + __ffsll((long long)s) - 1;
+        atomicAdd(&AUX[blockIdx.y * HW + find_root(Pi, gi)], (unsigned)(ACC[blockIdx.y * HW + gi] & 0xFFFFull));
+    }
 }
 
-// ---- K4b: exclusive scan of the block counts of one image (one block per image) ----
+// ---- K3: final roots that survive the min_area filter -> keptbits, and their count per WORDS_PER_BLOCK words
+__global__ void __launch_bounds__(WORDS_PER_BLOCK) ccl_mark_kernel(const u64* __restrict__ rootbits, const int* __restrict__ P,
+                                                                   unsigned* __restrict__ AUX, u64* __restrict__ keptbits,
+                                                                   int* __restrict__ blockcnt, int H, int W, int WW, int nblk,
+                                                                   long long min_area) {
+    const long long NW = (long long)H * WW;
+    const long long i = (long long)blockIdx.x * WORDS_PER_BLOCK + threadIdx.x;
+    const size_t HW = (size_t)H * W;
+    u64 kept = 0;
+    if (i < NW) {
+        const u64 rw = rootbits[(size_t)blockIdx.y * NW + i];
+        if (rw) {
+            const int* Pi = P + blockIdx.y * HW;
+            unsigned* Xi = AUX + blockIdx.y * HW;
+            const int gbase = (int)(i / WW) * W + (int)(i % WW) * TILE_W;
+            for (u64 s = rw; s; s &= s - 1) {
+                const int b = __ffsll((long long)s) - 1;
+                const int gi = gbase + b;
+                if (Pi[gi] != gi) continue;                           // merged into a component with an earlier first pixel
+                if (min_area <= 1 || (long long)Xi[gi] >= min_area) kept |= 1ull << b;
+                else Xi[gi] = 0u;                                     // label 0: filtered out (qdb:83-85)
+            }
+        }
+        keptbits[(size_t)blockIdx.y * NW + i] = kept;
+    }
+    // block sum of the popcounts
+    __shared__ int warp_sum[WORDS_PER_BLOCK / 32];
+    int v = __popcll(kept);
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int k = 0; k < WORDS_PER_BLOCK / 32; ++k) tot += warp_sum[k];
+        blockcnt[(size_t)blockIdx.y * nblk + blockIdx.x] = tot;
+    }
+}
+
+// ---- K4: exclusive scan of the block counts of one image (one block per image); zeroes the table rows in use
 __global__ void __launch_bounds__(1024) ccl_scan_kernel(const int* __restrict__ blockcnt, int* __restrict__ blockoff,
-                                                        int* __restrict__ counts, int nblk) {
+                                                        int* __restrict__ counts, int nblk, int capacity, long long* area,
+                                                        long long* s0, long long* s1) {
     __shared__ int warp_sum[32];
     __shared__ int carry_s;
     const int* c = blockcnt + (size_t)blockIdx.x * nblk;
@@ -182,81 +309,68 @@ __global__ void __launch_bounds__(1024) ccl_scan_kernel(const int* __restrict__ 
         if (threadIdx.x == 1023) carry_s = carry + warp_sum[wid] + incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) counts[blockIdx.x] = carry_s;
+    const int total = carry_s;
+    if (threadIdx.x == 0) counts[blockIdx.x] = total;
+    const int n = min(total, capacity);
+    for (int r = threadIdx.x; r < n; r += 1024) {
+        const size_t q = (size_t)blockIdx.x * capacity + r;
+        area[q] = 0; s0[q] = 0; s1[q] = 0;
+    }
 }
 
-// ---- K4c: consecutive ids (1..n, raster order of first pixel) written at the root positions ----
-__global__ void __launch_bounds__(SCAN_BLOCK) ccl_assign_kernel(const int* __restrict__ L, int* __restrict__ aux,
-                                                                const int* __restrict__ blockoff, int HW, int nblk,
-                                                                long long min_area) {
-    __shared__ int warp_cnt[SCAN_BLOCK / 32];
-    const int* Li = L + (size_t)blockIdx.y * HW;
-    int* Ai = aux + (size_t)blockIdx.y * HW;
-    int i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+// ---- K5: consecutive ids (1..n, raster order of first pixel) written at the kept roots
+__global__ void __launch_bounds__(WORDS_PER_BLOCK) ccl_ids_kernel(const u64* __restrict__ keptbits, const int* __restrict__ blockoff,
+                                                                  unsigned* __restrict__ AUX, int H, int W, int WW, int nblk) {
+    __shared__ int warp_cnt[WORDS_PER_BLOCK / 32];
+    const long long NW = (long long)H * WW;
+    const long long i = (long long)blockIdx.x * WORDS_PER_BLOCK + threadIdx.x;
+    const u64 kw = i < NW ? keptbits[(size_t)blockIdx.y * NW + i] : 0ull;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    bool is_root = (i < HW) && Li[i] == i;
-    bool keep = keep_root(Li, Ai, i, HW, min_area);
-    unsigned b = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) warp_cnt[wid] = __popc(b);
+    const int c = __popcll(kw);
+    int incl = c;
+    for (int d = 1; d < 32; d <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += n;
+    }
+    if (lane == 31) warp_cnt[wid] = incl;
     __syncthreads();
-    if (wid == 0) {
-        int w = warp_cnt[lane], wi = w;
-        for (int d = 1; d < 32; d <<= 1) {
-            int n = __shfl_up_sync(0xffffffffu, wi, d);
-            if (lane >= d) wi += n;
-        }
-        warp_cnt[lane] = wi - w;
-    }
-    __syncthreads();
-    if (is_root) {
-        int id = 0;
-        if (keep) id = blockoff[(size_t)blockIdx.y * nblk + blockIdx.x] + warp_cnt[wid] + __popc(b & ((1u << lane) - 1u)) + 1;
-        Ai[i] = id;   // aux now holds the final label of every root (0 = filtered out)
+    int before = 0;
+    for (int k = 0; k < wid; ++k) before += warp_cnt[k];
+    if (!kw) return;
+    unsigned id = (unsigned)(blockoff[(size_t)blockIdx.y * nblk + blockIdx.x] + before + incl - c);
+    unsigned* Xi = AUX + (size_t)blockIdx.y * H * W;
+    const int gbase = (int)(i / WW) * W + (int)(i % WW) * TILE_W;
+    for (u64 s = kw; s; s &= s - 1) Xi[gbase + __ffsll((long long)s) - 1] = ++id;
+}
+
+// ---- K6: every tile-local component adds its moments to the table row of its final root
+__global__ void ccl_accumulate_kernel(const u64* __restrict__ rootbits, const int* __restrict__ P, const u64* __restrict__ ACC,
+                                      const unsigned* __restrict__ AUX, int H, int W, int WW, int capacity,
+                                      u64* __restrict__ area, u64* __restrict__ s0, u64* __restrict__ s1) {
+    const long long NW = (long long)H * WW;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NW) return;
+    const u64 rw = rootbits[(size_t)blockIdx.y * NW + i];
+    if (!rw) return;
+    const size_t HW = (size_t)H * W;
+    const int* Pi = P + blockIdx.y * HW;
+    const int y = (int)(i / WW), x0 = (int)(i % WW) * TILE_W;
+    const u64 ty0 = (u64)((y / TILE_H) * TILE_H);
+    const int gbase = y * W + x0;
+    for (u64 s = rw; s; s &= s - 1) {
+        const int gi = gbase + __ffsll((long long)s) - 1;
+        const unsigned id = AUX[blockIdx.y * HW + find_root(Pi, gi)];
+        if (id == 0u || id > (unsigned)capacity) continue;
+        const u64 pk = ACC[blockIdx.y * HW + gi];
+        const u64 a = pk & 0xFFFFull, sc = (pk >> 16) & 0xFFFFFull, sr = pk >> 36;
+        const size_t q = (size_t)blockIdx.y * capacity + (id - 1);
+        atomicAdd(&area[q], a);
+        atomicAdd(&s0[q], sr + a * ty0);
+        atomicAdd(&s1[q], sc + a * (u64)x0);
     }
 }
 
-// ---- zero the accumulator rows that will be used ----
-__global__ void ccl_zero_rows_kernel(const int* __restrict__ counts, int capacity, long long* area, long long* s0,
-                                     long long* s1) {
-    int b = blockIdx.y;
-    int n = min(counts[b], capacity);
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n) {
-        size_t o = (size_t)b * capacity + r;
-        area[o] = 0; s0[o] = 0; s1[o] = 0;
-    }
-}
-
-// ---- K5: final label image + area / sum(row) / sum(col) per droplet ----
-__global__ void ccl_moments_kernel(const int* __restrict__ L, const int* __restrict__ aux, int* __restrict__ labels_out,
-                                   int H, int W, int capacity, unsigned long long* __restrict__ area,
-                                   unsigned long long* __restrict__ s0, unsigned long long* __restrict__ s1) {
-    const int HW = H * W;
-    const int b = blockIdx.y;
-    const int* Li = L + (size_t)b * HW;
-    const int* Ai = aux + (size_t)b * HW;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int id = 0;
-    if (i < HW && Li[i] >= 0) id = Ai[find_root(Li, i)];
-    if (labels_out && i < HW) labels_out[(size_t)b * HW + i] = id;
-    const bool acc = id > 0 && id <= capacity;
-    unsigned act = __ballot_sync(0xffffffffu, acc);
-    if (acc) {
-        const int lane = threadIdx.x & 31;
-        const int py = i / W, px = i - py * W;
-        unsigned peers = __match_any_sync(act, id);
-        unsigned sr = __reduce_add_sync(peers, (unsigned)py);   // REDUX.SUM over the peer set
-        unsigned sc = __reduce_add_sync(peers, (unsigned)px);
-        if ((__ffs(peers) - 1) == lane) {
-            size_t o = (size_t)b * capacity + (id - 1);
-            atomicAdd(&area[o], (unsigned long long)__popc(peers));
-            atomicAdd(&s0[o], (unsigned long long)sr);
-            atomicAdd(&s1[o], (unsigned long long)sc);
-        }
-    }
-}
-
-// ---- K6: integer sums -> f64 columns (IEEE divide / sqrt, as numpy evaluates them) ----
+// ---- K7: integer sums -> f64 columns (IEEE divide / sqrt, as numpy evaluates them) ----
 __global__ void ccl_finalize_kernel(const int* __restrict__ counts, int capacity, const long long* __restrict__ area,
                                     double* c0, double* c1, double* diam, double* area_um2, double* diam_um,
                                     double px_per_um) {
@@ -279,12 +393,76 @@ __global__ void ccl_finalize_kernel(const int* __restrict__ counts, int capacity
     }
 }
 
+// ---- K8 (only when the caller wants the label image): 4 pixels per thread, straight from the runs
+__global__ void ccl_labels_kernel(const u64* __restrict__ bits, const int* __restrict__ P, const unsigned* __restrict__ AUX,
+                                  int* __restrict__ labels_out, int H, int W, int WW) {
+    const int W4 = (W + 3) >> 2;
+    const long long n = (long long)H * W4;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int y = (int)(i / W4), x = (int)(i % W4) * 4;
+    const size_t HW = (size_t)H * W;
+    const u64 w = bits[((size_t)blockIdx.y * H + y) * WW + (x >> 6)];
+    const int sh = x & 63;
+    int out[4] = {0, 0, 0, 0};
+    if ((w >> sh) & 0xFull) {
+        const int* Pi = P + blockIdx.y * HW;
+        const int gbase = y * W + (x & ~63);
+        int prev_start = -1, prev_id = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!((w >> (sh + k)) & 1ull)) continue;
+            const int st = run_start(w, sh + k);
+            if (st != prev_start) {
+                prev_start = st;
+                prev_id = (int)AUX[blockIdx.y * HW + find_root(Pi, gbase + st)];
+            }
+            out[k] = prev_id;
+        }
+    }
+    int* dst = labels_out + blockIdx.y * HW + (size_t)y * W + x;
+    if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(labels_out) & 15) == 0) {
+        *reinterpret_cast<int4*>(dst) = make_int4(out[0], out[1], out[2], out[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (x + k < W) dst[k] = out[k];
+    }
+}
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
 struct Workspace {
-    int* L;
-    int* aux;
-    int* blockcnt;
-    int* blockoff;
+    u64 *bits, *rootbits, *keptbits;
+    int* P;
+    u64* ACC;
+    unsigned* AUX;
+    int *blockcnt, *blockoff;
+    size_t total;
 };
+
+Workspace carve_ws(char* base, int B, int H, int W) {
+    Workspace ws;
+    const size_t hw = (size_t)H * W * B;
+    const size_t nw = (size_t)H * ceil_div(W, TILE_W) * B;
+    const size_t nblk = (size_t)ceil_div(H * ceil_div(W, TILE_W), WORDS_PER_BLOCK) * B;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char* p = base ? base + off : nullptr;
+        off += align256(bytes);
+        return p;
+    };
+    ws.bits = (u64*)take(nw * 8);
+    ws.rootbits = (u64*)take(nw * 8);
+    ws.keptbits = (u64*)take(nw * 8);
+    ws.P = (int*)take(hw * 4);
+    ws.ACC = (u64*)take(hw * 8);
+    ws.AUX = (unsigned*)take(hw * 4);
+    ws.blockcnt = (int*)take(nblk * 4);
+    ws.blockoff = (int*)take(nblk * 4);
+    ws.total = off;
+    return ws;
+}
 
 // ------------------------------------------------------------------------------------------------ overlay stencil
 // The pixels that cv2.drawContours(img, findContours(mask, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE), -1, color, 2)
@@ -297,9 +475,13 @@ struct Workspace {
 //                      every diagonal step of a border -- two diagonal non-zero pixels whose common 4-neighbour on
 //                      one side is outer background -- the pixels one step to either side of both ends, which the
 //                      outline of cv2's rotated band quad rounds onto.
+// Everything runs on the bit planes: the BACKGROUND is labelled with the run-based kernels above (a handful of long
+// runs per row, so the one huge outer component costs little), frame-touching roots are flagged, and the rule is
+// evaluated 64 pixels at a time with shifts and ANDs.
 
-// frame-touching background components: flag their roots
-__global__ void ovl_mark_kernel(const int* __restrict__ L, uint8_t* __restrict__ flag, int H, int W) {
+// frame-touching background components: flag their roots (AUX = 1; the tile kernel zeroed it at every tile-local root)
+__global__ void ovl_mark_kernel(const u64* __restrict__ bits, const int* __restrict__ P, unsigned* __restrict__ AUX, int H,
+                                int W, int WW) {
     const int per = 2 * W + 2 * H;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= per) return;
@@ -308,76 +490,105 @@ __global__ void ovl_mark_kernel(const int* __restrict__ L, uint8_t* __restrict__
     else if (t < 2 * W) { y = H - 1; x = t - W; }
     else if (t < 2 * W + H) { y = t - 2 * W; x = 0; }
     else { y = t - 2 * W - H; x = W - 1; }
-    const size_t img = (size_t)blockIdx.y * H * W;
-    const int i = y * W + x;
-    if (L[img + i] >= 0) flag[img + find_root(L + img, i)] = 1;
+    const size_t HW = (size_t)H * W;
+    const u64 w = bits[((size_t)blockIdx.y * H + y) * WW + (x >> 6)];
+    if (!((w >> (x & 63)) & 1ull)) return;
+    const int g = y * W + (x & ~63) + run_start(w, x & 63);
+    AUX[blockIdx.y * HW + find_root(P + blockIdx.y * HW, g)] = 1u;
 }
 
-// outer[i] = 1 for zero pixels whose component reaches the frame
-__global__ void ovl_outer_kernel(const int* __restrict__ L, const uint8_t* __restrict__ flag, uint8_t* __restrict__ outer,
-                                 int HW) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= HW) return;
-    const size_t img = (size_t)blockIdx.y * HW;
-    uint8_t o = 0;
-    if (L[img + i] >= 0) o = flag[img + find_root(L + img, i)];
-    outer[img + i] = o;
+// outer word = the background runs whose component reaches the frame
+__global__ void ovl_outer_kernel(const u64* __restrict__ bits, const int* __restrict__ P, const unsigned* __restrict__ AUX,
+                                 u64* __restrict__ outer, int H, int W, int WW) {
+    const long long NW = (long long)H * WW;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NW) return;
+    const size_t HW = (size_t)H * W;
+    const u64 w = bits[(size_t)blockIdx.y * NW + i];
+    u64 o = 0;
+    if (w) {
+        const int* Pi = P + blockIdx.y * HW;
+        const int gbase = (int)(i / WW) * W + (int)(i % WW) * TILE_W;
+        for (u64 s = w & ~(w << 1); s; s &= s - 1) {
+            const int b = __ffsll((long long)s) - 1;
+            if (AUX[blockIdx.y * HW + find_root(Pi, gbase + b)]) o |= bits_upto(run_end(w, b)) & ~bits_below(b);
+        }
+    }
+    outer[(size_t)blockIdx.y * NW + i] = o;
 }
 
-constexpr int OVL_T = 32;         // output tile edge
-constexpr int OVL_R = 3;          // halo: contour test at distance <= 2 needs `outer` at distance <= 3
-__global__ void __launch_bounds__(OVL_T* OVL_T) ovl_stencil_kernel(const uint8_t* __restrict__ mask,
-                                                                  const uint8_t* __restrict__ outer,
-                                                                  uint8_t* __restrict__ stencil, int H, int W) {
-    constexpr int S = OVL_T + 2 * OVL_R;
-    __shared__ uint8_t fg_s[S][S + 2], out_s[S][S + 2], ct_s[S][S + 2];
-    const size_t img = (size_t)blockIdx.z * H * W;
-    const int x0 = blockIdx.x * OVL_T - OVL_R, y0 = blockIdx.y * OVL_T - OVL_R;
-    const int tid = threadIdx.y * OVL_T + threadIdx.x;
-    for (int i = tid; i < S * S; i += OVL_T * OVL_T) {
-        const int ly = i / S, lx = i % S;
-        const int y = y0 + ly, x = x0 + lx;
-        const bool inb = y >= 0 && y < H && x >= 0 && x < W;
-        fg_s[ly][lx] = inb && mask[img + (size_t)y * W + x] != 0;
-        out_s[ly][lx] = inb ? outer[img + (size_t)y * W + x] : 1;     // outside the image = the frame
+// Row accessor for the stencil: word wx of row y of a bit plane, `fill` outside the image; `pad` = value of the
+// bits of the last word beyond column W.
+struct PlaneRow {
+    const u64* row;       // nullptr: outside the image
+    int WW;
+    u64 fill, tailmask;   // tailmask: valid bits of the last word
+    __device__ __forceinline__ u64 word(int wx) const {
+        if (!row || wx < 0 || wx >= WW) return fill;
+        u64 v = row[wx];
+        if (wx == WW - 1) v = (v & tailmask) | (fill & ~tailmask);
+        return v;
     }
-    __syncthreads();
-    for (int i = tid; i < S * S; i += OVL_T * OVL_T) {
-        const int ly = i / S, lx = i % S;
-        uint8_t c = 0;
-        if (fg_s[ly][lx] && ly > 0 && ly < S - 1 && lx > 0 && lx < S - 1)
-            c = out_s[ly - 1][lx] | out_s[ly + 1][lx] | out_s[ly][lx - 1] | out_s[ly][lx + 1];
-        ct_s[ly][lx] = c;
+    // bit x of the result = plane[x + dx] for the 64 columns of word wx (|dx| <= 3)
+    __device__ __forceinline__ u64 shifted(int wx, int dx) const {
+        const u64 c = word(wx);
+        if (dx == 0) return c;
+        if (dx > 0) return (c >> dx) | (word(wx + 1) << (64 - dx));
+        return (c << -dx) | (word(wx - 1) >> (64 + dx));
     }
-    __syncthreads();
-    const int x = blockIdx.x * OVL_T + threadIdx.x, y = blockIdx.y * OVL_T + threadIdx.y;
-    if (x >= W || y >= H) return;
-    const int ly = threadIdx.y + OVL_R, lx = threadIdx.x + OVL_R;
-    uint8_t v = ct_s[ly][lx] | ct_s[ly - 1][lx] | ct_s[ly + 1][lx] | ct_s[ly][lx - 1] | ct_s[ly][lx + 1];
+};
+
+__device__ __forceinline__ u64 spread8(unsigned b) {       // 8 bits -> 8 bytes of 0 / 1
+    u64 v = ((u64)b * 0x0101010101010101ull) & 0x8040201008040201ull;
+    return ((v + 0x7F7F7F7F7F7F7F7Full) >> 7) & 0x0101010101010101ull;
+}
+
+__global__ void ovl_stencil_kernel(const u64* __restrict__ bg, const u64* __restrict__ outer, uint8_t* __restrict__ stencil,
+                                   int H, int W, int WW) {
+    const long long NW = (long long)H * WW;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NW) return;
+    const int y = (int)(i / WW), wx = (int)(i % WW);
+    const u64* bgi = bg + (size_t)blockIdx.y * NW;
+    const u64* oui = outer + (size_t)blockIdx.y * NW;
+    const u64 tailmask = (W & 63) ? bits_below(W & 63) : ~0ull;
+    // FG(r): foreground = not background, 0 outside the image.  OUT(r): outer background, 1 outside the image.
+    auto BG = [&](int r) { return PlaneRow{(r >= 0 && r < H) ? bgi + (size_t)r * WW : nullptr, WW, ~0ull, tailmask}; };
+    auto OUT = [&](int r) { return PlaneRow{(r >= 0 && r < H) ? oui + (size_t)r * WW : nullptr, WW, ~0ull, tailmask}; };
+    auto fg = [&](int r, int dx) { return ~BG(r).shifted(wx, dx); };          // background is 1 outside the image
+    auto out = [&](int r, int dx) { return OUT(r).shifted(wx, dx); };
+    // contour pixels of row r, shifted by dx
+    auto ct = [&](int r, int dx) {
+        return fg(r, dx) & (out(r - 1, dx) | out(r + 1, dx) | out(r, dx - 1) | out(r, dx + 1));
+    };
+    u64 v = ct(y, 0) | ct(y - 1, 0) | ct(y + 1, 0) | ct(y, -1) | ct(y, 1);
     // diagonal step p -> p + (1, 1) (rows, cols): both non-zero, (p.y, p.x + 1) or (p.y + 1, p.x) outer background;
     // paints p + (-1, +1), p + (+1, -1), p + (0, +2), p + (+2, 0)
-    auto step_dr = [&](int py, int px) -> uint8_t {
-        return fg_s[py][px] & fg_s[py + 1][px + 1] & (out_s[py][px + 1] | out_s[py + 1][px]);
-    };
+    auto step_dr = [&](int r, int dx) { return fg(r, dx) & fg(r + 1, dx + 1) & (out(r, dx + 1) | out(r + 1, dx)); };
     // anti-diagonal step p -> p + (1, -1): (p.y, p.x - 1) or (p.y + 1, p.x) outer background;
     // paints p + (+1, +1), p + (-1, -1), p + (+2, 0), p + (0, -2)
-    auto step_dl = [&](int py, int px) -> uint8_t {
-        return fg_s[py][px] & fg_s[py + 1][px - 1] & (out_s[py][px - 1] | out_s[py + 1][px]);
-    };
-    v |= step_dr(ly + 1, lx - 1) | step_dr(ly - 1, lx + 1) | step_dr(ly, lx - 2) | step_dr(ly - 2, lx);
-    v |= step_dl(ly - 1, lx - 1) | step_dl(ly + 1, lx + 1) | step_dl(ly - 2, lx) | step_dl(ly, lx + 2);
-    stencil[img + (size_t)y * W + x] = v ? 1 : 0;
+    auto step_dl = [&](int r, int dx) { return fg(r, dx) & fg(r + 1, dx - 1) & (out(r, dx - 1) | out(r + 1, dx)); };
+    v |= step_dr(y + 1, -1) | step_dr(y - 1, 1) | step_dr(y, -2) | step_dr(y - 2, 0);
+    v |= step_dl(y - 1, -1) | step_dl(y + 1, 1) | step_dl(y - 2, 0) | step_dl(y, 2);
+    v &= (wx == WW - 1) ? tailmask : ~0ull;
+    uint8_t* dst = stencil + (size_t)blockIdx.y * H * W + (size_t)y * W + (size_t)wx * TILE_W;
+    const int n = min(TILE_W, W - wx * TILE_W);
+    if (n == TILE_W && (W & 15) == 0 && (reinterpret_cast<uintptr_t>(stencil) & 15) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned h = (unsigned)(v >> (16 * k)) & 0xFFFFu;
+            const u64 lo = spread8(h & 0xFFu), hi = spread8(h >> 8);
+            *reinterpret_cast<uint4*>(dst + 16 * k) =
+                make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
+        }
+    } else {
+        for (int k = 0; k < n; ++k) dst[k] = (uint8_t)((v >> k) & 1ull);
+    }
 }
-
-size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
-size_t label_workspace_bytes(int B, int H, int W) {
-    size_t hw = (size_t)H * W;
-    int nblk = (int)((hw + SCAN_BLOCK - 1) / SCAN_BLOCK);
-    return 2 * align256(sizeof(int) * hw * B) + 2 * align256(sizeof(int) * (size_t)nblk * B);
-}
+size_t label_workspace_bytes(int B, int H, int W) { return carve_ws(nullptr, B, H, W).total; }
 
 int launch_label_stats(const dc_label_args_t* a, cudaStream_t stream) {
     DC_REQUIRE(a && a->mask && a->counts && a->area && a->centroid0 && a->centroid1 && a->eq_diam, DC_EINVAL,
@@ -387,88 +598,74 @@ int launch_label_stats(const dc_label_args_t* a, cudaStream_t stream) {
     DC_REQUIRE((long long)a->H * a->W < (1ll << 31), DC_EINVAL, "dc_label_stats: image too large for int32 indices");
     DC_REQUIRE(a->px_per_um <= 0.0 || (a->area_um2 && a->diam_um), DC_EINVAL,
                "dc_label_stats: px_per_um given but micron columns are NULL");
-    const int B = a->B, H = a->H, W = a->W, HW = H * W;
-    const int nblk = ceil_div(HW, SCAN_BLOCK);
+    const int B = a->B, H = a->H, W = a->W;
     DC_REQUIRE(a->workspace && a->workspace_bytes >= label_workspace_bytes(B, H, W), DC_EWORKSPACE,
                "dc_label_stats: workspace too small (%zu < %zu)", a->workspace_bytes, label_workspace_bytes(B, H, W));
+    DC_REQUIRE(((uintptr_t)a->workspace & 7) == 0, DC_EINVAL, "dc_label_stats: workspace must be 8-byte aligned");
     DC_REQUIRE(B <= 65535, DC_EINVAL, "dc_label_stats: batch > 65535");
+    const int WW = ceil_div(W, TILE_W);
+    const long long NW = (long long)H * WW;
+    const int nblk = (int)((NW + WORDS_PER_BLOCK - 1) / WORDS_PER_BLOCK);
+    DC_REQUIRE(ceil_div(H, TILE_H) <= 65535, DC_EINVAL, "dc_label_stats: image too tall");
+    const Workspace ws = carve_ws((char*)a->workspace, B, H, W);
+    const int filter = a->min_area > 1;
 
-    char* p = (char*)a->workspace;
-    Workspace ws;
-    ws.L = (int*)p;        p += align256(sizeof(int) * (size_t)HW * B);
-    ws.aux = (int*)p;      p += align256(sizeof(int) * (size_t)HW * B);
-    ws.blockcnt = (int*)p; p += align256(sizeof(int) * (size_t)nblk * B);
-    ws.blockoff = (int*)p;
-
-    dim3 tb(TILE, TILE);
-    dim3 tg(ceil_div(W, TILE), ceil_div(H, TILE), B);
-    ccl_local_kernel<<<tg, tb, 0, stream>>>(a->mask, ws.L, H, W, 0);
-
-    long long nborder = (long long)((H - 1) / TILE) * W + (long long)((W - 1) / TILE) * H;
-    if (nborder > 0) {
-        dim3 bg((unsigned)((nborder + 255) / 256), B);
-        ccl_border_kernel<<<bg, 256, 0, stream>>>(ws.L, H, W);
-    }
-    if (a->min_area > 1) {
-        DC_CUDA(cudaMemsetAsync(ws.aux, 0, sizeof(int) * (size_t)HW * B, stream));
-        dim3 fg(ceil_div(HW, 256), B);
-        ccl_flatten_area_kernel<<<fg, 256, 0, stream>>>(ws.L, ws.aux, HW);
-    }
-    dim3 sg(nblk, B);
-    ccl_count_kernel<<<sg, SCAN_BLOCK, 0, stream>>>(ws.L, ws.aux, ws.blockcnt, HW, nblk, a->min_area);
-    ccl_scan_kernel<<<B, 1024, 0, stream>>>(ws.blockcnt, ws.blockoff, a->counts, nblk);
-    ccl_assign_kernel<<<sg, SCAN_BLOCK, 0, stream>>>(ws.L, ws.aux, ws.blockoff, HW, nblk, a->min_area);
-
+    ccl_tile_kernel<<<dim3(WW, ceil_div(H, TILE_H), B), TILE_H, 0, stream>>>(a->mask, ws.bits, ws.rootbits, ws.P, ws.ACC,
+                                                                            ws.AUX, H, W, WW, 0, filter);
+    const long long nborder = (long long)((H - 1) / TILE_H) * WW + (long long)H * (WW - 1);
+    if (nborder > 0)
+        ccl_border_kernel<<<dim3((unsigned)((nborder + 255) / 256), B), 256, 0, stream>>>(ws.bits, ws.P, H, W, WW);
+    const dim3 wg((unsigned)((NW + 255) / 256), B);
+    if (filter) ccl_area_kernel<<<wg, 256, 0, stream>>>(ws.rootbits, ws.P, ws.ACC, ws.AUX, H, W, WW);
+    ccl_mark_kernel<<<dim3(nblk, B), WORDS_PER_BLOCK, 0, stream>>>(ws.rootbits, ws.P, ws.AUX, ws.keptbits, ws.blockcnt, H, W,
+                                                                  WW, nblk, a->min_area);
     // accumulators live in the caller's table: area (i64) and, until finalize, centroid0/1 reused as i64 sums
     long long* s0 = reinterpret_cast<long long*>(a->centroid0);
     long long* s1 = reinterpret_cast<long long*>(a->centroid1);
-    int maxrows = a->capacity < (HW + 1) / 2 ? a->capacity : (HW + 1) / 2;
-    dim3 zg(ceil_div(maxrows, 256), B);
-    ccl_zero_rows_kernel<<<zg, 256, 0, stream>>>(a->counts, a->capacity, (long long*)a->area, s0, s1);
-    dim3 mg(ceil_div(HW, 256), B);
-    ccl_moments_kernel<<<mg, 256, 0, stream>>>(ws.L, ws.aux, a->labels_out, H, W, a->capacity,
-                                               (unsigned long long*)a->area, (unsigned long long*)s0,
-                                               (unsigned long long*)s1);
-    ccl_finalize_kernel<<<zg, 256, 0, stream>>>(a->counts, a->capacity, (const long long*)a->area, a->centroid0,
-                                                a->centroid1, a->eq_diam, a->area_um2, a->diam_um, a->px_per_um);
+    ccl_scan_kernel<<<B, 1024, 0, stream>>>(ws.blockcnt, ws.blockoff, a->counts, nblk, a->capacity, (long long*)a->area, s0, s1);
+    ccl_ids_kernel<<<dim3(nblk, B), WORDS_PER_BLOCK, 0, stream>>>(ws.keptbits, ws.blockoff, ws.AUX, H, W, WW, nblk);
+    ccl_accumulate_kernel<<<wg, 256, 0, stream>>>(ws.rootbits, ws.P, ws.ACC, ws.AUX, H, W, WW, a->capacity, (u64*)a->area,
+                                                  (u64*)s0, (u64*)s1);
+    const long long hw = (long long)H * W;
+    const int maxrows = (int)(a->capacity < (hw + 1) / 2 ? a->capacity : (hw + 1) / 2);
+    ccl_finalize_kernel<<<dim3(ceil_div(maxrows, 256), B), 256, 0, stream>>>(a->counts, a->capacity, (const long long*)a->area,
+                                                                            a->centroid0, a->centroid1, a->eq_diam,
+                                                                            a->area_um2, a->diam_um, a->px_per_um);
+    if (a->labels_out) {
+        const long long n4 = (long long)H * ((W + 3) >> 2);
+        ccl_labels_kernel<<<dim3((unsigned)((n4 + 255) / 256), B), 256, 0, stream>>>(ws.bits, ws.P, ws.AUX, a->labels_out, H, W,
+                                                                                    WW);
+    }
     DC_CUDA(cudaGetLastError());
     return DC_OK;
 }
 
-size_t overlay_workspace_bytes(int B, int H, int W) {
-    size_t hw = (size_t)H * W;
-    return align256(sizeof(int) * hw * B) + 2 * align256(hw * B);
-}
+size_t overlay_workspace_bytes(int B, int H, int W) { return carve_ws(nullptr, B, H, W).total; }
 
 int launch_overlay_stencil(const dc_overlay_args_t* a, cudaStream_t stream) {
     DC_REQUIRE(a && a->mask && a->stencil, DC_EINVAL, "dc_overlay_stencil: null pointer argument");
     DC_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0, DC_EINVAL, "dc_overlay_stencil: bad shape %d %d %d", a->B, a->H, a->W);
     DC_REQUIRE((long long)a->H * a->W < (1ll << 31), DC_EINVAL, "dc_overlay_stencil: image too large for int32 indices");
     DC_REQUIRE(a->B <= 65535, DC_EINVAL, "dc_overlay_stencil: batch > 65535");
-    const int B = a->B, H = a->H, W = a->W, HW = H * W;
+    const int B = a->B, H = a->H, W = a->W;
     DC_REQUIRE(a->workspace && a->workspace_bytes >= overlay_workspace_bytes(B, H, W), DC_EWORKSPACE,
                "dc_overlay_stencil: workspace too small (%zu < %zu)", a->workspace_bytes, overlay_workspace_bytes(B, H, W));
-    char* p = (char*)a->workspace;
-    int* L = (int*)p;             p += align256(sizeof(int) * (size_t)HW * B);
-    uint8_t* flag = (uint8_t*)p;  p += align256((size_t)HW * B);
-    uint8_t* outer = (uint8_t*)p;
+    DC_REQUIRE(((uintptr_t)a->workspace & 7) == 0, DC_EINVAL, "dc_overlay_stencil: workspace must be 8-byte aligned");
+    DC_REQUIRE(ceil_div(H, TILE_H) <= 65535, DC_EINVAL, "dc_overlay_stencil: image too tall");
+    const int WW = ceil_div(W, TILE_W);
+    const long long NW = (long long)H * WW;
+    const Workspace ws = carve_ws((char*)a->workspace, B, H, W);
 
-    dim3 tb(TILE, TILE);
-    dim3 tg(ceil_div(W, TILE), ceil_div(H, TILE), B);
-    ccl_local_kernel<<<tg, tb, 0, stream>>>(a->mask, L, H, W, 1);          // label the background
-    long long nborder = (long long)((H - 1) / TILE) * W + (long long)((W - 1) / TILE) * H;
-    if (nborder > 0) {
-        dim3 bg((unsigned)((nborder + 255) / 256), B);
-        ccl_border_kernel<<<bg, 256, 0, stream>>>(L, H, W);
-    }
-    DC_CUDA(cudaMemsetAsync(flag, 0, (size_t)HW * B, stream));
-    dim3 mg(ceil_div(2 * W + 2 * H, 256), B);
-    ovl_mark_kernel<<<mg, 256, 0, stream>>>(L, flag, H, W);
-    dim3 og(ceil_div(HW, 256), B);
-    ovl_outer_kernel<<<og, 256, 0, stream>>>(L, flag, outer, HW);
-    dim3 sb(OVL_T, OVL_T);
-    dim3 sg(ceil_div(W, OVL_T), ceil_div(H, OVL_T), B);
-    ovl_stencil_kernel<<<sg, sb, 0, stream>>>(a->mask, outer, a->stencil, H, W);
+    // label the background (runs of zero pixels); AUX is zeroed at every tile-local root
+    ccl_tile_kernel<<<dim3(WW, ceil_div(H, TILE_H), B), TILE_H, 0, stream>>>(a->mask, ws.bits, ws.rootbits, ws.P, ws.ACC,
+                                                                            ws.AUX, H, W, WW, 1, 1);
+    const long long nborder = (long long)((H - 1) / TILE_H) * WW + (long long)H * (WW - 1);
+    if (nborder > 0)
+        ccl_border_kernel<<<dim3((unsigned)((nborder + 255) / 256), B), 256, 0, stream>>>(ws.bits, ws.P, H, W, WW);
+    ovl_mark_kernel<<<dim3(ceil_div(2 * W + 2 * H, 256), B), 256, 0, stream>>>(ws.bits, ws.P, ws.AUX, H, W, WW);
+    const dim3 wg((unsigned)((NW + 255) / 256), B);
+    ovl_outer_kernel<<<wg, 256, 0, stream>>>(ws.bits, ws.P, ws.AUX, ws.keptbits, H, W, WW);
+    ovl_stencil_kernel<<<wg, 256, 0, stream>>>(ws.bits, ws.keptbits, a->stencil, H, W, WW);
     DC_CUDA(cudaGetLastError());
     return DC_OK;
 }

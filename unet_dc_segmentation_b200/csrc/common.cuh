@@ -31,6 +31,7 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // from the kernel parameters (constant-bank operands) instead of shared memory.
 int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream, const float* bias_host = nullptr);
 int launch_stem(const dc_stem_args_t* a, cudaStream_t stream, const float* bias_host = nullptr);
+int set_conv_family(int family);
 int launch_label_stats(const dc_label_args_t* a, cudaStream_t stream);
 int launch_rolling_ball(const dc_rolling_ball_args_t* a, cudaStream_t stream);
 int launch_resize_linear_u8(const dc_resize_args_t* a, cudaStream_t stream);

@@ -50,6 +50,22 @@ constexpr int A_STAGE_BYTES = TILE_M * KCHUNK * 2;   // 16 KB
 constexpr int NUM_THREADS = 384;      // 4 role warps + 2 epilogue groups x 4 warps
 constexpr int EPI_WARP0 = 4;
 
+// Kernel-family override for the tests (dc_debug_set_conv_family): the product path never changes it.
+int g_kernel_family = DC_CONV_FAMILY_AUTO;
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): set once per device, not per launch.
+template <class K>
+int set_max_smem_once(K kernel, int bytes, unsigned long long* done_mask) {
+    int dev = 0;
+    DC_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(__atomic_load_n(done_mask, __ATOMIC_ACQUIRE) & bit)) {
+        DC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        __atomic_fetch_or(done_mask, bit, __ATOMIC_RELEASE);
+    }
+    return DC_OK;
+}
+
 // floor(n / d) for 0 <= n < 2^31 as one widening multiply and a shift (Granlund-Montgomery round-up magic number):
 // s = ceil(log2 d), m = floor(2^(31+s) / d) + 1 < 2^32.
 struct FastDiv {
@@ -1128,8 +1144,8 @@ int launch_variant(const ConvParams& p, cudaStream_t stream) {
     constexpr size_t SMEM = (size_t)NSTAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ +
                             4096 + 256 /* bias (<= 1024 ch) + out_conv weights */ + EPI_STAGE_TOTAL;
     static_assert(SMEM <= 227 * 1024, "stage ring exceeds shared memory");
-    // function attributes are per device: set on every launch (a host-side call of well under a microsecond)
-    DC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    static unsigned long long attr_done = 0;
+    { int rc = set_max_smem_once(conv_tc_kernel<BN, NSTAGES>, (int)SMEM, &attr_done); if (rc != DC_OK) return rc; }
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
     conv_tc_kernel<BN, NSTAGES><<<grid, NUM_THREADS, SMEM, stream>>>(p);
     DC_CUDA(cudaGetLastError());
@@ -1180,8 +1196,7 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream, const float* bi
     bool halo = false, halo_wres = true, halo_pair = false;
     int halo_nhalf = 1;
     size_t halo_smem = 0;
-    const char* pair_env = getenv("DC_CONV_PAIR");               // measurement aid: "0" disables the CTA-pair kernels
-    if (!up && a->dilation <= 4 && !(pair_env && pair_env[0] == '0')) {
+    if (!up && a->dilation <= 4 && g_kernel_family == DC_CONV_FAMILY_AUTO) {
         // CTA pair (cta_group::2): half of the weight rows per SM.  BN <= 128: two 8-wide halves per tile (two MMA
         // chains); BN = 256: one half (a 128-cycle MMA hides its own latency, and 2 x 2 x 256 columns would not fit
         // TMEM).  Weights resident when Cout == BN and the layer's half fits next to two regions, else streamed
@@ -1259,9 +1274,7 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream, const float* bi
             }
         }
     }
-    if (const char* force = getenv("DC_CONV_PATH")) {        // measurement aid: A/B the two kernels
-        if (!strcmp(force, "generic")) halo = halo_pair = false;
-    }
+    if (g_kernel_family == DC_CONV_FAMILY_GENERIC) halo = halo_pair = false;      // test-only override (dc_debug_set_conv_family)
     {
         cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B};
         cuuint64_t str[3] = {(cuuint64_t)a->in_stride * 2, (cuuint64_t)a->W * a->in_stride * 2,
@@ -1313,9 +1326,9 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream, const float* bi
         const int grid = 2 * (n_pairs < max_clusters ? n_pairs : max_clusters);
 #define DC_PAIR_CASE(bn, nh, wr)                                                                                      \
         if (BN == bn && halo_nhalf == nh && halo_wres == wr) {                                                        \
-            /* function attributes are per device: set on every launch (sub-microsecond host call) */                 \
-            DC_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<bn, nh, wr>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                         227 * 1024));                                                                \
+            static unsigned long long attr_done = 0;                                                                  \
+            int rc_ = set_max_smem_once(conv_halo2_kernel<bn, nh, wr>, 227 * 1024, &attr_done);                       \
+            if (rc_ != DC_OK) return rc_;                                                                             \
             conv_halo2_kernel<bn, nh, wr><<<grid, NUM_THREADS, halo_smem, stream>>>(p);                               \
         }
         DC_PAIR_CASE(64, 4, true) DC_PAIR_CASE(64, 3, true) DC_PAIR_CASE(64, 2, true)
@@ -1328,8 +1341,9 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream, const float* bi
         const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
 #define DC_HALO_CASE(bn, nh, wr)                                                                                     \
         if (BN == bn && halo_nhalf == nh && halo_wres == wr) {                                                       \
-            DC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<bn, nh, wr>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                         227 * 1024));                                                               \
+            static unsigned long long attr_done = 0;                                                                 \
+            int rc_ = set_max_smem_once(conv_halo_kernel<bn, nh, wr>, 227 * 1024, &attr_done);                       \
+            if (rc_ != DC_OK) return rc_;                                                                            \
             conv_halo_kernel<bn, nh, wr><<<grid, NUM_THREADS, halo_smem, stream>>>(p);                               \
         }
         DC_HALO_CASE(64, 1, true) DC_HALO_CASE(64, 2, true) DC_HALO_CASE(128, 1, true) DC_HALO_CASE(128, 2, true)
@@ -1343,6 +1357,12 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream, const float* bi
         case 128: return launch_variant<128, 6>(p, stream);
         default:  return launch_variant<64, 8>(p, stream);
     }
+}
+
+int set_conv_family(int family) {
+    DC_REQUIRE(family >= DC_CONV_FAMILY_AUTO && family <= DC_CONV_FAMILY_GENERIC, DC_EINVAL, "dc_debug_set_conv_family: %d", family);
+    g_kernel_family = family;
+    return DC_OK;
 }
 
 int launch_stem(const dc_stem_args_t* a, cudaStream_t stream, const float* bias_host) {
@@ -1376,10 +1396,13 @@ int launch_stem(const dc_stem_args_t* a, cudaStream_t stream, const float* bias_
     p.out_stride = a->out_stride; p.out_offset = a->out_offset;
     sp.in = a->in; sp.weight = a->weight; sp.in_kind = a->in_kind;
     constexpr size_t SMEM = 64 * 128 + (size_t)STEM_STAGES * A_STAGE_BYTES + 1024 + 256 + 512 + EPI_STAGE_TOTAL;
-    // function attributes are per device: set on every launch (a host-side call of well under a microsecond)
-    DC_CUDA(cudaFuncSetAttribute(stem_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    DC_CUDA(cudaFuncSetAttribute(stem_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    DC_CUDA(cudaFuncSetAttribute(stem_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    static unsigned long long attr_done[3] = {0, 0, 0};
+    {
+        int rc = set_max_smem_once(stem_tc_kernel<0>, (int)SMEM, &attr_done[0]);
+        if (rc == DC_OK) rc = set_max_smem_once(stem_tc_kernel<1>, (int)SMEM, &attr_done[1]);
+        if (rc == DC_OK) rc = set_max_smem_once(stem_tc_kernel<2>, (int)SMEM, &attr_done[2]);
+        if (rc != DC_OK) return rc;
+    }
     const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
     switch (a->in_kind) {
         case 0: stem_tc_kernel<0><<<grid, STEM_THREADS, SMEM, stream>>>(sp); break;

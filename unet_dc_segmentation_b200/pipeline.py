@@ -106,14 +106,18 @@ class DropletPipeline:
         return masks.numpy(), tables.to_host()
 
     # ------------------------------------------------------------------ pipelined host entry
-    def run_host_pipelined(self, batches, device: torch.device | str = "cuda"):
+    def run_host_pipelined(self, batches, device: torch.device | str = "cuda", copy: bool = True):
         """Generator over host batches (each u8 [B,H,W] or [B,H,W,3], ideally pinned; all the same shape):
         yields (masks u8 numpy [B,H,W], list of per-image column dicts) per batch, in order.
 
         Four streams (copy-in, compute, one read-back stream per slot) and two buffer slots: the H2D copy of batch
         k+1 and the D2H copy of batch k-1 run while
-        batch k computes, so the steady-state rate is the device rate, not device + PCIe.  Outputs land in
-        pinned host buffers owned by the pipeline (copy them if you keep more than two batches alive)."""
+        batch k computes, so the steady-state rate is the device rate, not device + PCIe.
+
+        Everything yielded is owned by the caller (``list(pipe.run_host_pipelined(...))`` is safe).  ``copy=False``
+        yields the masks as a VIEW of the pipeline's two-slot pinned read-back buffer instead: that view is valid
+        only until the generator is advanced again (the next batch's read-back is queued into the other slot and the
+        one after that into this one)."""
         dev = torch.device(device)
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
@@ -190,6 +194,8 @@ class DropletPipeline:
                 sl["ev_free"].record(s_out)
             s_out.synchronize()
             masks = sl["h_masks"].numpy()
+            if copy:
+                masks = masks.copy()
             out = []
             for b, n in enumerate(counts):
                 n = int(n)
