@@ -177,6 +177,11 @@ typedef struct dc_rolling_ball_args {
 
 int dc_rolling_ball_workspace_bytes(int B, int H, int W, int C, size_t* bytes);
 int dc_rolling_ball(const dc_rolling_ball_args_t* args, void* stream);
+/* Largest `radius` dc_rolling_ball accepts (the haloed tile of the element has to fit in shared memory). */
+int dc_rolling_ball_max_radius(void);
+/* TEST AID (host only, no GPU needed): dumps the chord plan the kernel would run for `radius` with tiles of
+ * `tile_h` rows; returns the number of ints written (layout: csrc/morph.cu) or a negative DC_E* code. */
+int dc_debug_rolling_ball_plan(int radius, int tile_h, int* out, int cap);
 
 /* ------------------------------------------------------------------ bilinear resize (u8)
  * The two cv2.resize calls of quantify_droplets_batch.py:44 (frame -> IMG_SIZE x IMG_SIZE) and :57 (mask -> original

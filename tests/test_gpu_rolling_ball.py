@@ -83,3 +83,30 @@ def test_config3_size_2048_properties(cuda_device):
         assert lut.setdefault(c, g) == g
     keys = sorted(lut)
     assert all(lut[a] <= lut[b] for a, b in zip(keys, keys[1:]))
+
+
+@pytest.mark.parametrize("shape,radius", [((1, 200, 260), 128), ((2, 150, 90), 150), ((1, 300, 300), 177), ((1, 64, 64), 120)])
+def test_large_radii_vs_cv2(cuda_device, shape, radius):
+    """Radii beyond 100 (the reference CLI takes any --background_radius): shorter tiles, more chord levels;
+    against OpenCV itself with the reference's four calls (utils/data_loader.py:17-21)."""
+    import cv2
+    import torch
+    from unet_dc_segmentation_b200 import rolling_ball_device
+    rs = np.random.RandomState(radius)
+    B, H, W = shape
+    imgs = rs.randint(0, 256, (B, H, W)).astype(np.uint8)
+    imgs[:, H // 3:H // 2, W // 4:W // 2] //= 4
+    got = rolling_ball_device(torch.from_numpy(imgs).cuda(), radius).cpu().numpy()
+    k = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (radius, radius))
+    for b in range(B):
+        want = cv2.normalize(cv2.subtract(imgs[b], cv2.morphologyEx(imgs[b], cv2.MORPH_OPEN, k)), None, 0, 255,
+                             cv2.NORM_MINMAX)
+        np.testing.assert_array_equal(got[b], want, err_msg=f"image {b}")
+
+
+def test_radius_limit_is_reported(cuda_device):
+    import torch
+    from unet_dc_segmentation_b200 import rolling_ball_device
+    from unet_dc_segmentation_b200.morphology import max_radius
+    with pytest.raises(ValueError, match="radius must be in"):
+        rolling_ball_device(torch.zeros((1, 32, 32), dtype=torch.uint8).cuda(), max_radius() + 1)

@@ -8,7 +8,7 @@ rc=0
 for f in $FILES; do
   n=$(basename $f .py)
   echo "=== $f"
-  timeout 900 python -m pytest $f -q -m gpu --tb=short --maxfail=8 > gpurun_out/$n.log 2>&1
+  timeout 900 python -m pytest $f -q -rP -m gpu --tb=short --maxfail=8 > gpurun_out/$n.log 2>&1
   r=$?
   tail -n 25 gpurun_out/$n.log
   if [ $r -ne 0 ]; then rc=1; fi

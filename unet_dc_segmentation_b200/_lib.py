@@ -21,7 +21,7 @@ ABI_VERSION = 200          # DC_ABI_VERSION of include/unetdc_b200.h these ctype
 EXPORTS = [
     "dc_last_error", "dc_version", "dc_device_check", "dc_conv_tc", "dc_debug_set_conv_family", "dc_stem", "dc_model_create",
     "dc_model_destroy", "dc_forward_workspace_bytes", "dc_forward", "dc_forward_num_launches", "dc_forward_profile",
-    "dc_rolling_ball_workspace_bytes", "dc_rolling_ball", "dc_label_workspace_bytes", "dc_label_stats",
+    "dc_rolling_ball_workspace_bytes", "dc_rolling_ball", "dc_rolling_ball_max_radius", "dc_debug_rolling_ball_plan", "dc_label_workspace_bytes", "dc_label_stats",
     "dc_resize_linear_u8", "dc_overlay_workspace_bytes", "dc_overlay_stencil",
     "dc_roi_workspace_bytes", "dc_roi_mask", "dc_radial_workspace_bytes", "dc_radial_density",
     "dc_spatial_workspace_bytes", "dc_spatial_density",
@@ -160,6 +160,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
                                        c_void_p, c_size_t, c_void_p, POINTER(c_float)]
     lib.dc_rolling_ball_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, POINTER(c_size_t)]
     lib.dc_rolling_ball.argtypes = [POINTER(RollingBallArgs), c_void_p]
+    lib.dc_rolling_ball_max_radius.argtypes = []
+    lib.dc_debug_rolling_ball_plan.argtypes = [c_int, c_int, POINTER(c_int), c_int]
     lib.dc_label_workspace_bytes.argtypes = [c_int, c_int, c_int, POINTER(c_size_t)]
     lib.dc_label_stats.argtypes = [POINTER(LabelArgs), c_void_p]
     lib.dc_resize_linear_u8.argtypes = [POINTER(ResizeArgs), c_void_p]

@@ -169,6 +169,10 @@ int dc_rolling_ball_workspace_bytes(int B, int H, int W, int C, size_t* bytes) {
     return DC_OK;
 }
 
+int dc_rolling_ball_max_radius(void) { return rolling_ball_max_radius(); }
+
+int dc_debug_rolling_ball_plan(int radius, int tile_h, int* out, int cap) { return rolling_ball_plan_dump(radius, tile_h, out, cap); }
+
 int dc_rolling_ball(const dc_rolling_ball_args_t* args, void* stream) {
     int rc = check_current_device(nullptr);
     if (rc != DC_OK) return rc;

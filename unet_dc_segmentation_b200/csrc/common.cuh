@@ -45,6 +45,8 @@ size_t radial_workspace_bytes(int B);
 int launch_spatial_density(const dc_spatial_args_t* a, cudaStream_t stream);
 size_t spatial_workspace_bytes(int B, int H, int W);
 size_t rolling_ball_workspace_bytes(int planes, int H, int W);
+int rolling_ball_max_radius();
+int rolling_ball_plan_dump(int radius, int th, int* out, int cap);
 int num_sms();
 
 #ifdef __CUDACC__

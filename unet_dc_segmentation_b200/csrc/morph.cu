@@ -6,176 +6,255 @@
 //   corr    = cv2.subtract(channel, bg)                       saturating u8       :20
 //   out     = cv2.normalize(corr, None, 0, 255, NORM_MINMAX)                      :21
 //
-// The element is a radius x radius flat ellipse (NOT separable, not symmetric for even sizes):
-// row i covers columns [j1[i], j2[i]).  erode(y,x) = min_i min_{j in row i} src[y+i-an, x+j-an],
-// dilate uses max over the SAME offsets, taps outside the image are ignored (OpenCV semantics).
+// The element is a radius x radius flat ellipse (NOT separable, not symmetric for even sizes): row i covers the
+// columns [j1[i], j2[i]).  erode(y,x) = min_i min_{j in row i} src[y+i-an, x+j-an], dilate uses max over the SAME
+// offsets, taps outside the image are ignored (OpenCV semantics).
 //
-// Kernel plan: a block stages its tile + halo in shared memory, builds a power-of-two
-// range-min (or max) table along x (levels 2^0..2^L), then every thread owns 4 adjacent pixels
-// and combines, for each of the `radius` element rows, two overlapping 2^l windows with byte-SIMD
-// __vminu4 / __vmaxu4.  All arithmetic is u8, so the result is bit-exact.
+// Kernel plan (chord tables, after Urbach & Wilkinson 2008, with centred chords).  The rows of the ellipse are
+// NESTED intervals [lo_m, hi_m] (M distinct ones: 16 at radius 50), so the horizontal range-min over the m-th chord,
+//   H_m[r][x] = min(H_{m-1}[r][x], min over [lo_m, lo_{m-1}) , min over (hi_{m-1}, hi_m]),
+// is one step away from the previous chord's: two side windows of 1..12 pixels, each read from a power-of-two
+// range table of the staged tile (2 fetches, tables of 1/2/4/8 pixels only).  Each chord table is then consumed at
+// the SAME x by every element row of that width:  out[y][x] = min_m min_{dy in rows(m)} H_m[y+dy][x] -- aligned
+// 4-pixel words, no shifts.  Per output word that is ~32 unaligned fetches (x 1.4 for the row halo) + 50 aligned
+// ones, against 100 unaligned fetches for the row-by-row form, and only 3 small range tables instead of 6.
+// A block owns a 64 x 128 tile; chord tables are double-buffered in shared memory with one barrier per chord.
+// All arithmetic is u8 (as 16-bit lanes for the DPX min/max), so the result is bit-exact.
 #include "common.cuh"
 #include <math.h>
+#include <string.h>
 
 namespace dc {
 
 namespace {
 
-constexpr int TW = 64;           // tile width  (16 threads x 4 pixels)
-constexpr int TH = 64;           // tile height (64: the 49-row halo costs 1.8x the tile, not 2.5x; 2 blocks of 1024 threads per SM)
-constexpr int MAX_RADIUS = 100;
-constexpr int MAX_LEVELS = 7;    // windows up to 64 wide
+constexpr int TW = 64;            // tile width: 16 words of 4 pixels (a half-warp per tile row)
+constexpr int TH_MAX = 128;       // tile height
+constexpr int NT = 512;           // threads per block: 16 warps, each handling tile rows w and w + 16 of a 32-row group
+constexpr int MAX_CHORDS = 64;    // distinct row widths (radius 150 has 45)
+constexpr int MAX_ROWS = 256;     // element rows
+constexpr int MAX_TABLES = 5;     // range tables of 1, 2, 4, 8, 16 pixels
+constexpr int HP = 17;            // chord-table pitch in words: rows r and r + 16 land 16 banks apart
+constexpr int A_ITS = 8;         // 32-row groups of the haloed region: tile rows + element rows - 1 <= 256
+constexpr int B_ITS = TH_MAX / 32;
 
-struct SERows {
-    int k;                        // element size (= radius), anchor = k/2
-    int nlevels;                  // levels 0..nlevels-1 are built
-    unsigned char j1[MAX_RADIUS]; // first column of row i
-    unsigned char j2m[MAX_RADIUS];// j2 - 2^level: start of the second window
-    unsigned char lvl[MAX_RADIUS];// level used by row i; 255 = empty row
+struct Fetch {
+    int woff;                     // word offset of the window inside the range tables (table base + column)
+    int shift;                    // bit shift of the window inside that word pair (0, 8, 16, 24)
+};
+struct Chord {
+    Fetch f[4];                   // left window (1-2 fetches) then right window (0-2 fetches)
+    int nf;
+    int row_begin, row_end;       // element rows of this width: indices into SEPlan::rowoff
+};
+struct SEPlan {
+    int k, an, pad, pitch, RH, level_words, ntables, nchords, th;
+    Chord chord[MAX_CHORDS];
+    short rowoff[MAX_ROWS];       // (dy + an) * HP for the rows, grouped by chord
 };
 
 template <bool IS_MAX>
 __device__ __forceinline__ unsigned vop(unsigned a, unsigned b) {
     return IS_MAX ? __vmaxu4(a, b) : __vminu4(a, b);
 }
+template <bool IS_MAX>
+__device__ __forceinline__ unsigned vop3_16(unsigned acc, unsigned a, unsigned b) {       // DPX: 16-bit lanes
+    return IS_MAX ? __vimax3_u16x2(acc, a, b) : __vimin3_u16x2(acc, a, b);
+}
+// u8x4 -> the even pixels / the odd pixels as two 16-bit lanes (sm_100a has no byte-lane SIMD min/max)
+__device__ __forceinline__ unsigned even16(unsigned v) { return __byte_perm(v, 0, 0x4240); }
+__device__ __forceinline__ unsigned odd16(unsigned v) { return __byte_perm(v, 0, 0x4341); }
 
 // One morphology pass over planes addressed as in[((p/C)*H*W + y*W + x)*C + p%C] (in_c = C) and
 // written planar.  SUBTRACT: out = saturate(orig - result), plus a per-plane min/max reduction.
 template <bool IS_MAX, bool SUBTRACT>
-__global__ void __launch_bounds__(TW / 4 * TH) morph_pass_kernel(const uint8_t* __restrict__ in, int in_c,
-                                                         uint8_t* __restrict__ out, const uint8_t* __restrict__ orig,
-                                                         int orig_c, int H, int W, int* __restrict__ minmax,
-                                                         const __grid_constant__ SERows se) {
+__global__ void __launch_bounds__(NT, 2) morph_chord_kernel(const uint8_t* __restrict__ in, int in_c,
+                                                            uint8_t* __restrict__ out, const uint8_t* __restrict__ orig,
+                                                            int orig_c, int H, int W, int* __restrict__ minmax,
+                                                            const __grid_constant__ SEPlan se) {
     extern __shared__ unsigned smem[];
-    const int k = se.k, an = k / 2;
-    const int pad = (4 - (an & 3)) & 3;          // extra columns on the left: the region starts on a 4-pixel boundary
-    const int RW = TW + k + pad;                 // region width in bytes (tile + halo), halo = k-1 (+1 pad)
-    const int pitch = ((RW + 3) >> 2) + 1;       // words per region row (+1 so unaligned fetches stay in-row)
-    const int RH = TH + k - 1;
-    const int level_words = pitch * RH;
+    const int an = se.an, pad = se.pad, pitch = se.pitch, RH = se.RH, level_words = se.level_words, TH = se.th;
     const unsigned ident = IS_MAX ? 0u : 0xffffffffu;
+    unsigned* hbuf = smem + se.ntables * level_words;          // two chord tables of RH x HP words
+    const int hwords = RH * HP;
 
     const int plane = blockIdx.z;
     const int b = plane / in_c, c = plane % in_c;
     const int x0 = blockIdx.x * TW - an - pad, y0 = blockIdx.y * TH - an;   // region origin in the image (x0 % 4 == 0)
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    const int nthreads = blockDim.x * blockDim.y;
-
-    __shared__ int2 rowtab[MAX_RADIUS];
-    __shared__ int nrows_s;
-    if (tid == 0) {
-        int n = 0;
-        for (int i = 0; i < k; ++i) {
-            const int l = se.lvl[i];
-            if (l == 255) continue;
-            const int base = (l * level_words + i * pitch) * 4;
-            rowtab[n++] = make_int2(base + se.j1[i] + pad, base + se.j2m[i] + pad);
-        }
-        nrows_s = n;
+    const int tid = threadIdx.x;
+    if (!SUBTRACT && minmax && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+        minmax[2 * plane] = 255;                 // the dilate pass (a later launch) reduces into these
+        minmax[2 * plane + 1] = 0;
     }
-    // ---- stage level 0 (tile + halo), identity outside the image ----
+
+    // ---- stage the tile + halo (range table 0), identity outside the image ----
     uint8_t* s8 = reinterpret_cast<uint8_t*>(smem);
     const uint8_t* src = in + (size_t)b * H * W * in_c + c;
     if (in_c == 1 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0) {
         // planar input with 4-pixel-aligned rows: one aligned word per 4 region bytes (x0 % 4 == 0 and W % 4 == 0,
         // so a word lies wholly inside or wholly outside the image)
-        for (int i = tid; i < level_words; i += nthreads) {
+        for (int i = tid; i < level_words; i += NT) {
             const int ry = i / pitch, rxw = i - ry * pitch;
             const int gy = y0 + ry, gx = x0 + 4 * rxw;
             unsigned v = ident;
-            if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = *reinterpret_cast<const unsigned*>(src + (size_t)gy * W + gx);
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(reinterpret_cast<const unsigned*>(src + (size_t)gy * W + gx));
             smem[i] = v;
         }
     } else {
-        for (int i = tid; i < RH * pitch * 4; i += nthreads) {
-            int ry = i / (pitch * 4), rx = i - ry * (pitch * 4);
-            int gy = y0 + ry, gx = x0 + rx;
+        for (int i = tid; i < level_words * 4; i += NT) {
+            const int ry = i / (pitch * 4), rx = i - ry * (pitch * 4);
+            const int gy = y0 + ry, gx = x0 + rx;
             uint8_t v = IS_MAX ? 0 : 255;
-            if (rx < RW && gy >= 0 && gy < H && gx >= 0 && gx < W) v = src[((size_t)gy * W + gx) * in_c];
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = src[((size_t)gy * W + gx) * in_c];
             s8[i] = v;
         }
     }
     __syncthreads();
-    // ---- levels 1..: T_l[x] = op(T_{l-1}[x], T_{l-1}[x + 2^(l-1)]) ----
-    for (int l = 1; l < se.nlevels; ++l) {
+    // ---- range tables: T_l[x] = op(T_{l-1}[x], T_{l-1}[x + 2^(l-1)]) ----
+    for (int l = 1; l < se.ntables; ++l) {
         const unsigned* prev = smem + (l - 1) * level_words;
         unsigned* cur = smem + l * level_words;
         const int step = 1 << (l - 1);           // bytes
-        for (int i = tid; i < level_words; i += nthreads) {
-            int rx = i % pitch;
-            unsigned a = prev[i], bb;
+        for (int i = tid; i < level_words; i += NT) {
+            const int rx = i % pitch;
+            const unsigned a = prev[i];
+            unsigned bb;
             if (step < 4) {
-                unsigned nxt = (rx + 1 < pitch) ? prev[i + 1] : ident;
+                const unsigned nxt = (rx + 1 < pitch) ? prev[i + 1] : ident;
                 bb = __funnelshift_r(a, nxt, step * 8);
             } else {
-                int ws = step >> 2;
+                const int ws = step >> 2;
                 bb = (rx + ws < pitch) ? prev[i + ws] : ident;
             }
             cur[i] = vop<IS_MAX>(a, bb);
         }
         __syncthreads();
     }
-    // ---- combine the element rows ----
-    // sm_100a has no byte-lane SIMD min/max (__vminu4 expands to 7 instructions) but it has the DPX 16-bit-lane
-    // three-operand form (VIMNMX3.U16x2).  The accumulator is kept as two words of 16-bit lanes (even / odd
-    // pixels); each fetched u8x4 window is split with two PRMTs, so a row costs 4 PRMT + 2 VIMNMX3 instead of 14.
-    // rowtab: per non-empty element row, the byte offsets of its two windows inside the level tables (one
-    // broadcast LDS.64 instead of three dependent constant-bank loads plus address arithmetic).
-    const int lx4 = threadIdx.x * 4, ly = threadIdx.y;
-    const uint8_t* tbase = reinterpret_cast<const uint8_t*>(smem) + (ly * pitch) * 4 + lx4;
+
+    // ---- chords ----
+    // lane -> (row within a 32-row group, word of the row): half-warps work on rows 16 apart, which an odd table
+    // pitch and the chord-table pitch of 17 words put on disjoint banks
+    const int lane = tid & 31, warp = tid >> 5;
+    const int xw = lane & 15;
+    const int row0 = warp + 16 * (lane >> 4);
     const unsigned id16 = IS_MAX ? 0u : 0x00ff00ffu;
-    unsigned acc_e = id16, acc_o = id16;
-    const int nrows = nrows_s;
-#pragma unroll 4
-    for (int n = 0; n < nrows; ++n) {
-        const int2 t = rowtab[n];
-        const unsigned* ra = reinterpret_cast<const unsigned*>(tbase + (t.x & ~3));
-        const unsigned* rb = reinterpret_cast<const unsigned*>(tbase + (t.y & ~3));
-        const unsigned a = __funnelshift_r(ra[0], ra[1], (t.x & 3) * 8);
-        const unsigned bb = __funnelshift_r(rb[0], rb[1], (t.y & 3) * 8);
-        const unsigned a_e = __byte_perm(a, 0, 0x4240), a_o = __byte_perm(a, 0, 0x4341);
-        const unsigned b_e = __byte_perm(bb, 0, 0x4240), b_o = __byte_perm(bb, 0, 0x4341);
-        acc_e = IS_MAX ? __vimax3_u16x2(acc_e, a_e, b_e) : __vimin3_u16x2(acc_e, a_e, b_e);
-        acc_o = IS_MAX ? __vimax3_u16x2(acc_o, a_o, b_o) : __vimin3_u16x2(acc_o, a_o, b_o);
-    }
-    const unsigned acc = __byte_perm(acc_e, acc_o, 0x6240);     // bytes: e.lo, o.lo, e.hi, o.hi
-    // ---- write (and, for the second pass, subtract + reduce) ----
-    const int gx = blockIdx.x * TW + lx4, gy = blockIdx.y * TH + ly;
-    int mn = 255, mx = 0;
-    if (gy < H && gx < W) {
-        uint8_t* dst = out + ((size_t)plane * H + gy) * W + gx;
-        unsigned res = acc;
-        if (SUBTRACT) {
-            const int ob = plane / orig_c, oc = plane % orig_c;
-            const uint8_t* o = orig + ((size_t)ob * H * W + (size_t)gy * W + gx) * orig_c + oc;
-            unsigned ov = 0;
+    unsigned he[A_ITS], ho[A_ITS];                // running chord minimum of this thread's region rows (16-bit lanes)
+    unsigned ae[B_ITS], ao[B_ITS];                // result of this thread's output rows
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (gx + j < W) ov |= (unsigned)o[(size_t)j * orig_c] << (8 * j);
-            res = __vsubus4(ov, acc);            // cv2.subtract saturates at 0
+    for (int it = 0; it < A_ITS; ++it) he[it] = ho[it] = id16;
+#pragma unroll
+    for (int it = 0; it < B_ITS; ++it) ae[it] = ao[it] = id16;
+    const unsigned* tbase = smem + row0 * pitch + xw;
+    const int nchords = se.nchords;
+    for (int m = 0; m < nchords; ++m) {
+        const Chord& ch = se.chord[m];
+        unsigned* buf = hbuf + (m & 1) * hwords;
+        const int nf = ch.nf;
+        const int w0 = ch.f[0].woff, s0 = ch.f[0].shift, w1 = ch.f[1].woff, s1 = ch.f[1].shift;
+        const int w2 = ch.f[2].woff, s2 = ch.f[2].shift, w3 = ch.f[3].woff, s3 = ch.f[3].shift;
+#pragma unroll
+        for (int it = 0; it < A_ITS; ++it) {
+            const int r = it * 32 + row0;
+            if (r < RH) {
+                const unsigned* p = tbase + it * 32 * pitch;
+                // (fetch slots beyond nf repeat an earlier window on the host side, so all four are always valid)
+                const unsigned a = __funnelshift_r(p[w0], p[w0 + 1], s0);
+                const unsigned bq = __funnelshift_r(p[w1], p[w1 + 1], s1);
+                he[it] = vop3_16<IS_MAX>(he[it], even16(a), even16(bq));
+                ho[it] = vop3_16<IS_MAX>(ho[it], odd16(a), odd16(bq));
+                if (nf > 2) {
+                    const unsigned cq = __funnelshift_r(p[w2], p[w2 + 1], s2);
+                    const unsigned dq = __funnelshift_r(p[w3], p[w3 + 1], s3);
+                    he[it] = vop3_16<IS_MAX>(he[it], even16(cq), even16(dq));
+                    ho[it] = vop3_16<IS_MAX>(ho[it], odd16(cq), odd16(dq));
+                }
+                buf[r * HP + xw] = __byte_perm(he[it], ho[it], 0x6240);     // bytes: e.lo, o.lo, e.hi, o.hi
+            }
         }
+        __syncthreads();
+        // every element row of this width, at the same x: aligned words of the chord table
+        const unsigned* hb = buf + row0 * HP + xw;
+        int j = ch.row_begin;
+        const int jend = ch.row_end;
+        for (; j + 1 < jend; j += 2) {
+            const int o0 = se.rowoff[j], o1 = se.rowoff[j + 1];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (gx + j < W) {
-                int v = (res >> (8 * j)) & 0xff;
-                dst[j] = (uint8_t)v;
-                mn = min(mn, v); mx = max(mx, v);
+            for (int it = 0; it < B_ITS; ++it) {
+                if (it * 32 + row0 < TH) {
+                    const unsigned v0 = hb[it * 32 * HP + o0], v1 = hb[it * 32 * HP + o1];
+                    ae[it] = vop3_16<IS_MAX>(ae[it], even16(v0), even16(v1));
+                    ao[it] = vop3_16<IS_MAX>(ao[it], odd16(v0), odd16(v1));
+                }
+            }
+        }
+        if (j < jend) {
+            const int o0 = se.rowoff[j];
+#pragma unroll
+            for (int it = 0; it < B_ITS; ++it) {
+                if (it * 32 + row0 < TH) {
+                    const unsigned v0 = hb[it * 32 * HP + o0];
+                    ae[it] = vop3_16<IS_MAX>(ae[it], even16(v0), ae[it]);
+                    ao[it] = vop3_16<IS_MAX>(ao[it], odd16(v0), ao[it]);
+                }
+            }
+        }
+        // (no second barrier: the next chord writes the other buffer, and the one after that is behind the
+        //  next chord's barrier)
+    }
+
+    // ---- write (and, for the second pass, subtract + reduce) ----
+    int mn = 255, mx = 0;
+    const int gx = blockIdx.x * TW + 4 * xw;
+#pragma unroll
+    for (int it = 0; it < B_ITS; ++it) {
+        const int ly = it * 32 + row0;
+        const int gy = blockIdx.y * TH + ly;
+        if (ly < TH && gy < H && gx < W) {
+            const unsigned acc = __byte_perm(ae[it], ao[it], 0x6240);
+            uint8_t* dst = out + ((size_t)plane * H + gy) * W + gx;
+            unsigned res = acc;
+            if (SUBTRACT) {
+                const int ob = plane / orig_c, oc = plane % orig_c;
+                const uint8_t* o = orig + ((size_t)ob * H * W + (size_t)gy * W + gx) * orig_c + oc;
+                unsigned ov = 0;
+                if (orig_c == 1 && gx + 3 < W && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
+                    ov = __ldg(reinterpret_cast<const unsigned*>(o));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (gx + q < W) ov |= (unsigned)o[(size_t)q * orig_c] << (8 * q);
+                }
+                res = __vsubus4(ov, acc);            // cv2.subtract saturates at 0
+            }
+            if (gx + 3 < W && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0)) {
+                *reinterpret_cast<unsigned*>(dst) = res;
+                if (SUBTRACT) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int v = (res >> (8 * q)) & 0xff;
+                        mn = min(mn, v); mx = max(mx, v);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (gx + q < W) {
+                        const int v = (res >> (8 * q)) & 0xff;
+                        dst[q] = (uint8_t)v;
+                        mn = min(mn, v); mx = max(mx, v);
+                    }
+                }
             }
         }
     }
     if (SUBTRACT) {
         mn = __reduce_min_sync(0xffffffffu, mn);
         mx = __reduce_max_sync(0xffffffffu, mx);
-        if ((tid & 31) == 0) {
+        if (lane == 0) {
             atomicMin(&minmax[2 * plane], mn);
             atomicMax(&minmax[2 * plane + 1], mx);
         }
     }
-}
-
-__global__ void init_minmax_kernel(int* minmax, int planes) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < planes) { minmax[2 * i] = 255; minmax[2 * i + 1] = 0; }
 }
 
 // cv2.normalize(NORM_MINMAX, 0..255) on u8: scale = 255 * (1/(max-min)) and shift = -min*scale in
@@ -197,37 +276,113 @@ __global__ void __launch_bounds__(256) stretch_kernel(const uint8_t* __restrict_
     const size_t HW = (size_t)H * W;
     const uint8_t* src = corr + (size_t)plane * HW;
     uint8_t* dst = out + (size_t)b * HW * out_c + c;
+    if (out_c == 1 && (HW & 15) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+        // planar: 16 pixels per thread and iteration
+        const size_t n16 = HW >> 4;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+            const unsigned in4[4] = {v.x, v.y, v.z, v.w};
+            unsigned o4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                o4[q] = (unsigned)lut[in4[q] & 0xff] | ((unsigned)lut[(in4[q] >> 8) & 0xff] << 8) |
+                        ((unsigned)lut[(in4[q] >> 16) & 0xff] << 16) | ((unsigned)lut[in4[q] >> 24] << 24);
+            reinterpret_cast<uint4*>(dst)[i] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        }
+        return;
+    }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (size_t)gridDim.x * blockDim.x)
         dst[i * out_c] = lut[src[i]];
 }
 
-int build_rows(int radius, SERows* se) {
-    const int k = radius;
-    se->k = k;
-    int r = k / 2, c = k / 2;
-    double inv_r2 = r ? 1.0 / ((double)r * r) : 0.0;
-    int maxw = 1;
+// Element rows of cv2.getStructuringElement(MORPH_ELLIPSE, (k, k)) (OpenCV: dx = cvRound(c * sqrt((r^2 - dy^2) / r^2)),
+// j1 = max(c - dx, 0), j2 = min(c + dx + 1, k)) turned into the chord plan of morph_chord_kernel.
+int build_plan(int k, int th, SEPlan* se) {
+    memset(se, 0, sizeof(*se));
+    const int r = k / 2, c = k / 2;
+    const double inv_r2 = r ? 1.0 / ((double)r * r) : 0.0;
+    int lo[MAX_ROWS], hi[MAX_ROWS];
+    if (k > MAX_ROWS) return -1;
     for (int i = 0; i < k; ++i) {
-        int dy = i - r, j1 = 0, j2 = 0;
-        if (abs(dy) <= r) {
-            int dx = (int)nearbyint(c * sqrt(((double)r * r - (double)dy * dy) * inv_r2));   // cvRound
-            j1 = c - dx < 0 ? 0 : c - dx;
-            j2 = c + dx + 1 > k ? k : c + dx + 1;
-        }
-        int w = j2 - j1;
-        if (w <= 0) { se->lvl[i] = 255; se->j1[i] = 0; se->j2m[i] = 0; continue; }
-        int l = 0;
-        while ((2 << l) <= w) ++l;               // 2^l <= w < 2^(l+1)
-        se->lvl[i] = (unsigned char)l;
-        se->j1[i] = (unsigned char)j1;
-        se->j2m[i] = (unsigned char)(j2 - (1 << l));
-        if (w > maxw) maxw = w;
+        const int dy = i - r;
+        const int dx = (int)nearbyint(c * sqrt(((double)r * r - (double)dy * dy) * inv_r2));   // cvRound
+        const int j1 = c - dx < 0 ? 0 : c - dx;
+        const int j2 = c + dx + 1 > k ? k : c + dx + 1;
+        if (j2 - j1 <= 0) return -1;
+        lo[i] = j1 - c;                   // columns [lo, hi] relative to the output pixel
+        hi[i] = j2 - 1 - c;
     }
-    int nl = 1;
-    while ((1 << nl) <= maxw) ++nl;
-    se->nlevels = nl;
-    return nl <= MAX_LEVELS ? 0 : -1;
+    se->k = k;
+    se->an = c;
+    se->pad = (4 - (c & 3)) & 3;          // extra columns on the left: the region starts on a 4-pixel boundary
+    se->th = th;
+    se->RH = th + k - 1;
+    const int RW = TW + k - 1 + se->pad;
+    se->pitch = ((RW - 1) >> 2) + 2;      // words per region row (+1 so that the two-word window fetch stays in-row)
+    if ((se->pitch & 1) == 0) ++se->pitch;   // odd: rows 16 apart fall on disjoint banks
+    se->level_words = se->pitch * se->RH;
+
+    // distinct chords, narrowest first; they must be nested
+    bool used[MAX_ROWS] = {false};
+    int nrows = 0, maxtab = 0;
+    int plo = 0, phi = -1;                // previous chord (empty)
+    for (int m = 0;; ++m) {
+        int best = -1;
+        for (int i = 0; i < k; ++i)
+            if (!used[i] && (best < 0 || hi[i] - lo[i] < hi[best] - lo[best])) best = i;
+        if (best < 0) break;
+        if (m >= MAX_CHORDS) return -1;
+        const int clo = lo[best], chi = hi[best];
+        if (m > 0 && (clo > plo || chi < phi)) return -1;          // not nested: cannot happen for cv2's ellipse
+        Chord& ch = se->chord[m];
+        ch.nf = 0;
+        auto window = [&](int a, int b) {          // min over columns [a, b]: one or two power-of-two tables
+            const int w = b - a + 1;
+            if (w <= 0) return;
+            int l = 0;
+            while ((2 << l) <= w) ++l;             // 2^l <= w < 2^(l+1)
+            if (l > maxtab) maxtab = l;
+            const int starts[2] = {a, b - (1 << l) + 1};
+            for (int q = 0; q < ((1 << l) == w ? 1 : 2); ++q) {
+                const int bx = starts[q] + c + se->pad;            // byte column inside the region row
+                Fetch f;
+                f.woff = l * se->level_words + (bx >> 2);
+                f.shift = (bx & 3) * 8;
+                ch.f[ch.nf++] = f;
+            }
+        };
+        if (m == 0) {
+            window(clo, chi);
+        } else {
+            window(clo, plo - 1);
+            const int nleft = ch.nf;
+            window(phi + 1, chi);
+            if (nleft == 1 && ch.nf > 1) {         // keep pairs together: slots (0,1) and (2,3) are consumed as pairs
+                // 1 left + 1 right -> one pair; 1 left + 2 right -> left, left | right, right
+                if (ch.nf == 3) { ch.f[3] = ch.f[2]; ch.f[2] = ch.f[1]; ch.f[1] = ch.f[0]; ch.nf = 4; }
+            }
+        }
+        if (ch.nf == 0) return -1;
+        if (ch.nf == 1) { ch.f[1] = ch.f[0]; }
+        if (ch.nf == 3) { ch.f[3] = ch.f[2]; }
+        if (ch.nf <= 2) { ch.f[2] = ch.f[0]; ch.f[3] = ch.f[0]; }
+        ch.row_begin = nrows;
+        for (int i = 0; i < k; ++i)
+            if (!used[i] && lo[i] == clo && hi[i] == chi) {
+                used[i] = true;
+                se->rowoff[nrows++] = (short)(i * HP);             // (dy + an) * HP with dy = i - an
+            }
+        ch.row_end = nrows;
+        plo = clo; phi = chi;
+        se->nchords = m + 1;
+    }
+    se->ntables = maxtab + 1;
+    if (se->ntables > MAX_TABLES) return -1;
+    // the window fetches address the tables relative to a lane's own word: woff is used as p[woff], p = table 0 + row + xw
+    return 0;
 }
+
+size_t plan_smem_bytes(const SEPlan& se) { return ((size_t)se.ntables * se.level_words + 2 * (size_t)se.RH * HP) * 4; }
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -237,37 +392,91 @@ size_t rolling_ball_workspace_bytes(int planes, int H, int W) {
     return 2 * align256((size_t)planes * H * W) + align256(sizeof(int) * 2 * (size_t)planes);
 }
 
+// Largest radius this build can run: the haloed region of the smallest tile must fit in shared memory and the
+// per-thread row state covers 256 region rows.
+int rolling_ball_max_radius() {
+    static int cached = 0;
+    if (!cached) {
+        int best = 1;
+        for (int k = 1; k <= MAX_ROWS; ++k) {
+            SEPlan se;
+            if (32 + k - 1 <= 32 * A_ITS && build_plan(k, 32, &se) == 0 && plan_smem_bytes(se) <= 226 * 1024) best = k;
+            else break;
+        }
+        cached = best;
+    }
+    return cached;
+}
+
+// Host-only dump of the chord plan (tests pin the plan builder on the CPU with a numpy model of the kernel):
+// [k, an, pad, pitch, RH, level_words, ntables, nchords, th, HP], then per chord {nf, woff0, shift0, .., woff3, shift3,
+// row_begin, row_end}, then rowoff[row_end of the last chord].
+int rolling_ball_plan_dump(int radius, int th, int* out, int cap) {
+    SEPlan se;
+    DC_REQUIRE(out && radius >= 1 && th >= 1 && th <= TH_MAX, DC_EINVAL, "dc_debug_rolling_ball_plan: bad argument");
+    DC_REQUIRE(build_plan(radius, th, &se) == 0, DC_EINVAL, "dc_debug_rolling_ball_plan: no plan for radius %d", radius);
+    const int nrows = se.chord[se.nchords - 1].row_end;
+    const int need = 10 + 11 * se.nchords + nrows;
+    DC_REQUIRE(cap >= need, DC_EINVAL, "dc_debug_rolling_ball_plan: need %d ints", need);
+    int n = 0;
+    const int head[10] = {se.k, se.an, se.pad, se.pitch, se.RH, se.level_words, se.ntables, se.nchords, se.th, HP};
+    for (int v : head) out[n++] = v;
+    for (int m = 0; m < se.nchords; ++m) {
+        const Chord& ch = se.chord[m];
+        out[n++] = ch.nf;
+        for (int q = 0; q < 4; ++q) { out[n++] = ch.f[q].woff; out[n++] = ch.f[q].shift; }
+        out[n++] = ch.row_begin;
+        out[n++] = ch.row_end;
+    }
+    for (int j = 0; j < nrows; ++j) out[n++] = se.rowoff[j];
+    return n;
+}
+
 int launch_rolling_ball(const dc_rolling_ball_args_t* a, cudaStream_t stream) {
     DC_REQUIRE(a && a->in && a->out, DC_EINVAL, "dc_rolling_ball: null pointer argument");
     DC_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0 && a->C > 0, DC_EINVAL, "dc_rolling_ball: bad shape");
-    DC_REQUIRE(a->radius >= 1 && a->radius <= MAX_RADIUS, DC_EINVAL, "dc_rolling_ball: radius %d outside [1,%d]",
-               a->radius, MAX_RADIUS);
+    DC_REQUIRE(a->radius >= 1 && a->radius <= rolling_ball_max_radius(), DC_EINVAL,
+               "dc_rolling_ball: radius %d outside [1,%d] (the haloed tile of a larger element does not fit in shared memory)",
+               a->radius, rolling_ball_max_radius());
     const int planes = a->B * a->C, H = a->H, W = a->W;
     DC_REQUIRE(planes <= 65535, DC_EINVAL, "dc_rolling_ball: more than 65535 planes in one call");
     DC_REQUIRE(a->workspace && a->workspace_bytes >= rolling_ball_workspace_bytes(planes, H, W), DC_EWORKSPACE,
                "dc_rolling_ball: workspace too small");
-    SERows se;
-    DC_REQUIRE(build_rows(a->radius, &se) == 0, DC_EINVAL, "dc_rolling_ball: element too wide");
+    // tile height: the tallest whose haloed region fits twice per SM (else once), within the per-thread row state
+    SEPlan se;
+    int th = 0;
+    for (int pass = 0; pass < 2 && !th; ++pass)
+        for (int cand = TH_MAX; cand >= 32 && !th; cand >>= 1) {
+            if (cand + a->radius - 1 > 32 * A_ITS) continue;
+            if (build_plan(a->radius, cand, &se) != 0) continue;
+            if (plan_smem_bytes(se) <= (pass == 0 ? 112 * 1024 : 226 * 1024)) th = cand;
+            if (cand > 32 && cand / 2 >= H) th = 0;            // a shorter tile already covers the whole image
+        }
+    DC_REQUIRE(th > 0 && build_plan(a->radius, th, &se) == 0, DC_EINVAL, "dc_rolling_ball: no tile fits radius %d", a->radius);
+    const size_t smem = plan_smem_bytes(se);
 
     char* p = (char*)a->workspace;
     uint8_t* er = (uint8_t*)p;   p += align256((size_t)planes * H * W);
     uint8_t* corr = (uint8_t*)p; p += align256((size_t)planes * H * W);
     int* minmax = (int*)p;
 
-    const int an = se.k / 2, pad = (4 - (an & 3)) & 3;
-    const int RW = TW + se.k + pad, pitch = ((RW + 3) >> 2) + 1, RH = TH + se.k - 1;
-    const size_t smem = (size_t)se.nlevels * pitch * RH * 4;
-    DC_REQUIRE(smem <= 226 * 1024, DC_EINVAL, "dc_rolling_ball: radius %d needs %zu B of shared memory", a->radius, smem);
-    // function attributes are per device: set on every launch (a host-side call of well under a microsecond)
-    DC_CUDA(cudaFuncSetAttribute(morph_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));   // + 816 B static (rowtab)
-    DC_CUDA(cudaFuncSetAttribute(morph_pass_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));   // + 816 B static (rowtab)
-    dim3 block(TW / 4, TH);
-    dim3 grid(ceil_div(W, TW), ceil_div(H, TH), planes);
-    init_minmax_kernel<<<ceil_div(planes, 256), 256, 0, stream>>>(minmax, planes);
-    morph_pass_kernel<false, false><<<grid, block, smem, stream>>>(a->in, a->C, er, nullptr, 0, H, W, nullptr, se);
-    morph_pass_kernel<true, true><<<grid, block, smem, stream>>>(er, 1, corr, a->in, a->C, H, W, minmax, se);
-    int sblocks = ceil_div(H * W, 256 * 8);
-    if (sblocks > 4096) sblocks = 4096;
+    static unsigned long long attr_done = 0;
+    {
+        int dev = 0;
+        DC_CUDA(cudaGetDevice(&dev));
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (!(__atomic_load_n(&attr_done, __ATOMIC_ACQUIRE) & bit)) {      // per (function, device), once
+            DC_CUDA(cudaFuncSetAttribute(morph_chord_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            DC_CUDA(cudaFuncSetAttribute(morph_chord_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            __atomic_fetch_or(&attr_done, bit, __ATOMIC_RELEASE);
+        }
+    }
+    dim3 grid(ceil_div(W, TW), ceil_div(H, th), planes);
+    morph_chord_kernel<false, false><<<grid, NT, smem, stream>>>(a->in, a->C, er, nullptr, 0, H, W, minmax, se);
+    morph_chord_kernel<true, true><<<grid, NT, smem, stream>>>(er, 1, corr, a->in, a->C, H, W, minmax, se);
+    int sblocks = ceil_div(H * W, 256 * 64);
+    if (sblocks > 1024) sblocks = 1024;
+    if (sblocks < 1) sblocks = 1;
     stretch_kernel<<<dim3(sblocks, planes), 256, 0, stream>>>(corr, a->out, a->C, H, W, minmax);
     DC_CUDA(cudaGetLastError());
     return DC_OK;

@@ -12,7 +12,11 @@ import torch
 
 from . import _lib
 
-MAX_RADIUS = 100
+
+
+def max_radius() -> int:
+    """Largest background radius the GPU kernel accepts (the haloed tile of the element has to fit in shared memory)."""
+    return int(_lib.load().dc_rolling_ball_max_radius())
 
 
 def rolling_ball_workspace_bytes(B: int, H: int, W: int, Cc: int = 1) -> int:
@@ -36,8 +40,9 @@ def rolling_ball_device(images: torch.Tensor, radius: int = 50, out: torch.Tenso
         B, H, W, Cc = images.shape
     else:
         raise ValueError(f"expected u8 [B,H,W] or [B,H,W,C], got {tuple(images.shape)}")
-    if not 1 <= int(radius) <= MAX_RADIUS:
-        raise ValueError(f"radius must be in [1, {MAX_RADIUS}]")
+    if not 1 <= int(radius) <= max_radius():
+        raise ValueError(f"radius must be in [1, {max_radius()}] (larger structuring elements do not fit the kernel's "
+                         "shared-memory tile)")
     images = images.contiguous()
     lib = _lib.load()
     need = rolling_ball_workspace_bytes(B, H, W, Cc)
