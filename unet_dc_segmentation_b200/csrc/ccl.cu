@@ -62,6 +62,34 @@ __device__ __forceinline__ void union_min(int* L, int a, int b) {
     } while (!done);
 }
 
+// Shared-memory variant for the tile kernel.  Ids are raster positions row * 64 + bit (so that the minimum is the
+// first pixel), but a plain array would put the run starts of a column -- e.g. bit 0 of every row of a background
+// tile -- into one bank: slot(id) rotates each row by its row number.
+__device__ __forceinline__ int slot(int id) { return (id & ~63) | ((id + (id >> 6)) & 63); }
+__device__ __forceinline__ int find_root_s(const volatile int* L, int x) {
+    int p = L[slot(x)];
+    while (p != x) { x = p; p = L[slot(x)]; }
+    return x;
+}
+__device__ __forceinline__ void union_min_s(int* L, int a, int b) {
+    bool done;
+    do {
+        a = find_root_s(L, a);
+        b = find_root_s(L, b);
+        if (a < b) {
+            int old = atomicMin(&L[slot(b)], a);
+            done = (old == b);
+            b = old;
+        } else if (b < a) {
+            int old = atomicMin(&L[slot(a)], b);
+            done = (old == a);
+            a = old;
+        } else {
+            done = true;
+        }
+    } while (!done);
+}
+
 __device__ __forceinline__ u64 bits_below(int b) { return b >= 64 ? ~0ull : ((1ull << b) - 1ull); }   // bits [0, b)
 __device__ __forceinline__ u64 bits_upto(int b) { return b >= 63 ? ~0ull : ((2ull << b) - 1ull); }    // bits [0, b]
 
@@ -156,10 +184,10 @@ __global__ void __launch_bounds__(TILE_H) ccl_tile_kernel(const uint8_t* __restr
     const u64 starts = w & ~(w << 1);
     for (u64 s = starts; s; s &= s - 1) {
         const int b = __ffsll((long long)s) - 1;
-        par[t * TILE_W + b] = t * TILE_W + b;
+        par[slot(t * TILE_W + b)] = t * TILE_W + b;
     }
     __syncthreads();
-    merge_rows(w, up, [&](int sd, int su) { union_min(par, t * TILE_W + sd, (t - 1) * TILE_W + su); });
+    merge_rows(w, up, [&](int sd, int su) { union_min_s(par, t * TILE_W + sd, (t - 1) * TILE_W + su); });
     __syncthreads();
 
     // ---- tile-local roots publish their own run; every run start gets its parent in the global plane
@@ -171,7 +199,7 @@ __global__ void __launch_bounds__(TILE_H) ccl_tile_kernel(const uint8_t* __restr
     for (u64 s = starts; s; s &= s - 1) {
         const int b = __ffsll((long long)s) - 1;
         const int self = t * TILE_W + b;
-        const int r = find_root(par, self);
+        const int r = find_root_s(par, self);
         if (r == self) {
             const int e = run_end(w, b);
             const unsigned len = (unsigned)(e - b + 1);
@@ -187,7 +215,7 @@ __global__ void __launch_bounds__(TILE_H) ccl_tile_kernel(const uint8_t* __restr
     __syncthreads();                                       // the roots' records are visible to the whole block
     for (u64 s = starts & ~rootw; s; s &= s - 1) {
         const int b = __ffsll((long long)s) - 1;
-        const int r = find_root(par, t * TILE_W + b);
+        const int r = find_root_s(par, t * TILE_W + b);
         const int e = run_end(w, b);
         const unsigned len = (unsigned)(e - b + 1);
         atomicAdd(&Ai[(ty0 + (r >> 6)) * W + x0 + (r & 63)], pack_acc(len, (unsigned)t * len, (unsigned)(b + e) * len / 2u));

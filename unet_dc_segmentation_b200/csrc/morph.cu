@@ -36,167 +36,200 @@ constexpr int MAX_ROWS = 256;     // element rows
 constexpr int MAX_TABLES = 5;     // range tables of 1, 2, 4, 8, 16 pixels
 constexpr int HP = 17;            // chord-table pitch in words: rows r and r + 16 land 16 banks apart
 constexpr int A_ITS = 8;         // 32-row groups of the haloed region: tile rows + element rows - 1 <= 256
-constexpr int B_ITS = TH_MAX / 32;
 
 struct Fetch {
     int woff;                     // word offset of the window inside the range tables (table base + column)
-    int shift;                    // bit shift of the window inside that word pair (0, 8, 16, 24)
+    unsigned sel_e, sel_o;        // PRMT selectors: shift of the window inside the word pair + split into even / odd pixels
 };
 struct Chord {
-    Fetch f[4];                   // left window (1-2 fetches) then right window (0-2 fetches)
+    Fetch f[4];                   // left window (1-2 fetches) then right window (0-2 fetches); unused slots repeat
     int nf;
     int row_begin, row_end;       // element rows of this width: indices into SEPlan::rowoff
 };
 struct SEPlan {
     int k, an, pad, pitch, RH, level_words, ntables, nchords, th;
     Chord chord[MAX_CHORDS];
-    short rowoff[MAX_ROWS];       // (dy + an) * HP for the rows, grouped by chord
+    int rowoff[MAX_ROWS];         // byte offset (dy + an) * HP * 4 of the rows inside a chord table, grouped by chord
 };
 
 template <bool IS_MAX>
 __device__ __forceinline__ unsigned vop(unsigned a, unsigned b) {
     return IS_MAX ? __vmaxu4(a, b) : __vminu4(a, b);
 }
+// sm_100a has no byte-lane SIMD min/max, but it has the DPX three-operand 16-bit-lane form.  Pixels travel as
+// 16-bit lanes holding the byte TWICE (v * 257: order-preserving), which one PRMT produces from any byte of a word
+// pair -- so the unaligned window fetch (funnel shift) and the split into even / odd pixels are a single instruction.
 template <bool IS_MAX>
-__device__ __forceinline__ unsigned vop3_16(unsigned acc, unsigned a, unsigned b) {       // DPX: 16-bit lanes
+__device__ __forceinline__ unsigned vop3_16(unsigned acc, unsigned a, unsigned b) {
     return IS_MAX ? __vimax3_u16x2(acc, a, b) : __vimin3_u16x2(acc, a, b);
 }
-// u8x4 -> the even pixels / the odd pixels as two 16-bit lanes (sm_100a has no byte-lane SIMD min/max)
-__device__ __forceinline__ unsigned even16(unsigned v) { return __byte_perm(v, 0, 0x4240); }
-__device__ __forceinline__ unsigned odd16(unsigned v) { return __byte_perm(v, 0, 0x4341); }
+__device__ __forceinline__ unsigned pack_lanes(unsigned e, unsigned o) { return __byte_perm(e, o, 0x6240); }   // e0 o1 e2 o3
+// prmt with a selector whose nibbles are all <= 7 (no masking of the selector needed, unlike __byte_perm)
+__device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
+    unsigned d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+// shared-memory accesses by 32-bit address (+ immediate): one address add per window instead of index arithmetic
+template <int IMM>
+__device__ __forceinline__ unsigned lds(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM) : "memory");
+    return v;
+}
+template <int IMM>
+__device__ __forceinline__ void sts(unsigned addr, unsigned v) {
+    asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(addr), "n"(IMM), "r"(v) : "memory");
+}
 
 // One morphology pass over planes addressed as in[((p/C)*H*W + y*W + x)*C + p%C] (in_c = C) and
 // written planar.  SUBTRACT: out = saturate(orig - result), plus a per-plane min/max reduction.
-template <bool IS_MAX, bool SUBTRACT>
+// NB = tile rows / 32.
+template <bool IS_MAX, bool SUBTRACT, int NB>
 __global__ void __launch_bounds__(NT, 2) morph_chord_kernel(const uint8_t* __restrict__ in, int in_c,
                                                             uint8_t* __restrict__ out, const uint8_t* __restrict__ orig,
                                                             int orig_c, int H, int W, int* __restrict__ minmax,
                                                             const __grid_constant__ SEPlan se) {
     extern __shared__ unsigned smem[];
-    const int an = se.an, pad = se.pad, pitch = se.pitch, RH = se.RH, level_words = se.level_words, TH = se.th;
+    constexpr int TH = NB * 32;
+    const int an = se.an, pad = se.pad, pitch = se.pitch, RH = se.RH, level_words = se.level_words;
     const unsigned ident = IS_MAX ? 0u : 0xffffffffu;
-    unsigned* hbuf = smem + se.ntables * level_words;          // two chord tables of RH x HP words
-    const int hwords = RH * HP;
+    const int nA = (RH + 31) >> 5;                             // 32-row groups of the haloed region
+    unsigned* hbuf = smem + se.ntables * level_words;          // two chord tables of (32 nA) x HP words
+    const int hwords = nA * 32 * HP;
 
     const int plane = blockIdx.z;
     const int b = plane / in_c, c = plane % in_c;
     const int x0 = blockIdx.x * TW - an - pad, y0 = blockIdx.y * TH - an;   // region origin in the image (x0 % 4 == 0)
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (!SUBTRACT && minmax && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
         minmax[2 * plane] = 255;                 // the dilate pass (a later launch) reduces into these
         minmax[2 * plane + 1] = 0;
     }
 
-    // ---- stage the tile + halo (range table 0), identity outside the image ----
-    uint8_t* s8 = reinterpret_cast<uint8_t*>(smem);
+    // ---- stage the tile + halo (range table 0), identity outside the image: one warp per region row ----
     const uint8_t* src = in + (size_t)b * H * W * in_c + c;
     if (in_c == 1 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0) {
         // planar input with 4-pixel-aligned rows: one aligned word per 4 region bytes (x0 % 4 == 0 and W % 4 == 0,
         // so a word lies wholly inside or wholly outside the image)
-        for (int i = tid; i < level_words; i += NT) {
-            const int ry = i / pitch, rxw = i - ry * pitch;
-            const int gy = y0 + ry, gx = x0 + 4 * rxw;
-            unsigned v = ident;
-            if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(reinterpret_cast<const unsigned*>(src + (size_t)gy * W + gx));
-            smem[i] = v;
+#pragma unroll 4
+        for (int ry = warp; ry < RH; ry += NT / 32) {
+            const int gy = y0 + ry;
+            const bool rowok = gy >= 0 && gy < H;
+            for (int rxw = lane; rxw < pitch; rxw += 32) {
+                const int gx = x0 + 4 * rxw;
+                unsigned v = ident;
+                if (rowok && gx >= 0 && gx < W) v = __ldg(reinterpret_cast<const unsigned*>(src + (size_t)gy * W + gx));
+                smem[ry * pitch + rxw] = v;
+            }
         }
     } else {
-        for (int i = tid; i < level_words * 4; i += NT) {
-            const int ry = i / (pitch * 4), rx = i - ry * (pitch * 4);
-            const int gy = y0 + ry, gx = x0 + rx;
-            uint8_t v = IS_MAX ? 0 : 255;
-            if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = src[((size_t)gy * W + gx) * in_c];
-            s8[i] = v;
+        uint8_t* s8 = reinterpret_cast<uint8_t*>(smem);
+        for (int ry = warp; ry < RH; ry += NT / 32) {
+            const int gy = y0 + ry;
+            const bool rowok = gy >= 0 && gy < H;
+            for (int rx = lane; rx < pitch * 4; rx += 32) {
+                const int gx = x0 + rx;
+                uint8_t v = IS_MAX ? 0 : 255;
+                if (rowok && gx >= 0 && gx < W) v = src[((size_t)gy * W + gx) * in_c];
+                s8[ry * pitch * 4 + rx] = v;
+            }
         }
     }
     __syncthreads();
-    // ---- range tables: T_l[x] = op(T_{l-1}[x], T_{l-1}[x + 2^(l-1)]) ----
-    for (int l = 1; l < se.ntables; ++l) {
-        const unsigned* prev = smem + (l - 1) * level_words;
-        unsigned* cur = smem + l * level_words;
-        const int step = 1 << (l - 1);           // bytes
-        for (int i = tid; i < level_words; i += NT) {
-            const int rx = i % pitch;
-            const unsigned a = prev[i];
-            unsigned bb;
-            if (step < 4) {
-                const unsigned nxt = (rx + 1 < pitch) ? prev[i + 1] : ident;
-                bb = __funnelshift_r(a, nxt, step * 8);
-            } else {
-                const int ws = step >> 2;
-                bb = (rx + ws < pitch) ? prev[i + ws] : ident;
+    // ---- range tables: T_l[x] = op(T_{l-1}[x], T_{l-1}[x + 2^(l-1)]); a row is built by the warp that owns it ----
+    for (int ry = warp; ry < RH; ry += NT / 32) {
+        unsigned* row = smem + ry * pitch;
+        for (int l = 1; l < se.ntables; ++l) {
+            const unsigned* prev = row + (l - 1) * level_words;
+            unsigned* cur = row + l * level_words;
+            const int step = 1 << (l - 1);           // bytes
+            for (int rxw = lane; rxw < pitch; rxw += 32) {
+                const unsigned a = prev[rxw];
+                unsigned bb;
+                if (step < 4) {
+                    const unsigned nxt = (rxw + 1 < pitch) ? prev[rxw + 1] : ident;
+                    bb = __funnelshift_r(a, nxt, step * 8);
+                } else {
+                    const int ws = step >> 2;
+                    bb = (rxw + ws < pitch) ? prev[rxw + ws] : ident;
+                }
+                cur[rxw] = vop<IS_MAX>(a, bb);
             }
-            cur[i] = vop<IS_MAX>(a, bb);
+            __syncwarp();
         }
-        __syncthreads();
     }
+    __syncthreads();
 
     // ---- chords ----
     // lane -> (row within a 32-row group, word of the row): half-warps work on rows 16 apart, which an odd table
-    // pitch and the chord-table pitch of 17 words put on disjoint banks
-    const int lane = tid & 31, warp = tid >> 5;
+    // pitch and the chord-table pitch of 17 words put on disjoint banks.  Rows >= RH of the last group compute on
+    // whatever follows the tables in shared memory and land in chord-table rows nobody reads.
     const int xw = lane & 15;
     const int row0 = warp + 16 * (lane >> 4);
-    const unsigned id16 = IS_MAX ? 0u : 0x00ff00ffu;
     unsigned he[A_ITS], ho[A_ITS];                // running chord minimum of this thread's region rows (16-bit lanes)
-    unsigned ae[B_ITS], ao[B_ITS];                // result of this thread's output rows
+    unsigned ae[NB], ao[NB];                      // result of this thread's output rows
+    unsigned abase[A_ITS];                        // shared address of this thread's word in row (32 it + row0) of table 0
 #pragma unroll
-    for (int it = 0; it < A_ITS; ++it) he[it] = ho[it] = id16;
+    for (int it = 0; it < A_ITS; ++it) {
+        he[it] = ho[it] = ident;
+        abase[it] = smem_u32(smem) + (unsigned)(((it * 32 + row0) * pitch + xw) * 4);
+    }
 #pragma unroll
-    for (int it = 0; it < B_ITS; ++it) ae[it] = ao[it] = id16;
-    const unsigned* tbase = smem + row0 * pitch + xw;
+    for (int it = 0; it < NB; ++it) ae[it] = ao[it] = ident;
+    const unsigned hbase = smem_u32(hbuf) + (unsigned)((row0 * HP + xw) * 4);
+    constexpr int HSTEP = 32 * HP * 4;            // bytes between a thread's rows in a chord table
     const int nchords = se.nchords;
     for (int m = 0; m < nchords; ++m) {
         const Chord& ch = se.chord[m];
-        unsigned* buf = hbuf + (m & 1) * hwords;
-        const int nf = ch.nf;
-        const int w0 = ch.f[0].woff, s0 = ch.f[0].shift, w1 = ch.f[1].woff, s1 = ch.f[1].shift;
-        const int w2 = ch.f[2].woff, s2 = ch.f[2].shift, w3 = ch.f[3].woff, s3 = ch.f[3].shift;
-#pragma unroll
-        for (int it = 0; it < A_ITS; ++it) {
-            const int r = it * 32 + row0;
-            if (r < RH) {
-                const unsigned* p = tbase + it * 32 * pitch;
-                // (fetch slots beyond nf repeat an earlier window on the host side, so all four are always valid)
-                const unsigned a = __funnelshift_r(p[w0], p[w0 + 1], s0);
-                const unsigned bq = __funnelshift_r(p[w1], p[w1 + 1], s1);
-                he[it] = vop3_16<IS_MAX>(he[it], even16(a), even16(bq));
-                ho[it] = vop3_16<IS_MAX>(ho[it], odd16(a), odd16(bq));
-                if (nf > 2) {
-                    const unsigned cq = __funnelshift_r(p[w2], p[w2 + 1], s2);
-                    const unsigned dq = __funnelshift_r(p[w3], p[w3 + 1], s3);
-                    he[it] = vop3_16<IS_MAX>(he[it], even16(cq), even16(dq));
-                    ho[it] = vop3_16<IS_MAX>(ho[it], odd16(cq), odd16(dq));
-                }
-                buf[r * HP + xw] = __byte_perm(he[it], ho[it], 0x6240);     // bytes: e.lo, o.lo, e.hi, o.hi
-            }
+        const unsigned hb = hbase + (unsigned)((m & 1) * hwords * 4);
+        const bool four = ch.nf > 2;
+        const unsigned w0 = (unsigned)ch.f[0].woff * 4u, w1 = (unsigned)ch.f[1].woff * 4u;
+        const unsigned w2 = (unsigned)ch.f[2].woff * 4u, w3 = (unsigned)ch.f[3].woff * 4u;
+        const unsigned e0 = ch.f[0].sel_e, o0 = ch.f[0].sel_o, e1 = ch.f[1].sel_e, o1 = ch.f[1].sel_o;
+        const unsigned e2 = ch.f[2].sel_e, o2 = ch.f[2].sel_o, e3 = ch.f[3].sel_e, o3 = ch.f[3].sel_o;
+#define DC_CHORD_STEP(it)                                                                                  \
+        if (it < nA) {                                                                                      \
+            const unsigned pa = abase[it] + w0, pb = abase[it] + w1;                                        \
+            const unsigned a0 = lds<0>(pa), a1 = lds<4>(pa), b0 = lds<0>(pb), b1 = lds<4>(pb);              \
+            he[it] = vop3_16<IS_MAX>(he[it], prmt(a0, a1, e0), prmt(b0, b1, e1));                           \
+            ho[it] = vop3_16<IS_MAX>(ho[it], prmt(a0, a1, o0), prmt(b0, b1, o1));                           \
+            if (four) {                                                                                     \
+                const unsigned pc = abase[it] + w2, pd = abase[it] + w3;                                    \
+                const unsigned c0 = lds<0>(pc), c1 = lds<4>(pc), d0 = lds<0>(pd), d1 = lds<4>(pd);          \
+                he[it] = vop3_16<IS_MAX>(he[it], prmt(c0, c1, e2), prmt(d0, d1, e3));                       \
+                ho[it] = vop3_16<IS_MAX>(ho[it], prmt(c0, c1, o2), prmt(d0, d1, o3));                       \
+            }                                                                                               \
+            sts<it * HSTEP>(hb, pack_lanes(he[it], ho[it]));                                                \
         }
+        DC_CHORD_STEP(0) DC_CHORD_STEP(1) DC_CHORD_STEP(2) DC_CHORD_STEP(3)
+        DC_CHORD_STEP(4) DC_CHORD_STEP(5) DC_CHORD_STEP(6) DC_CHORD_STEP(7)
+#undef DC_CHORD_STEP
         __syncthreads();
         // every element row of this width, at the same x: aligned words of the chord table
-        const unsigned* hb = buf + row0 * HP + xw;
         int j = ch.row_begin;
         const int jend = ch.row_end;
         for (; j + 1 < jend; j += 2) {
-            const int o0 = se.rowoff[j], o1 = se.rowoff[j + 1];
-#pragma unroll
-            for (int it = 0; it < B_ITS; ++it) {
-                if (it * 32 + row0 < TH) {
-                    const unsigned v0 = hb[it * 32 * HP + o0], v1 = hb[it * 32 * HP + o1];
-                    ae[it] = vop3_16<IS_MAX>(ae[it], even16(v0), even16(v1));
-                    ao[it] = vop3_16<IS_MAX>(ao[it], odd16(v0), odd16(v1));
-                }
+            const unsigned q0 = hb + (unsigned)se.rowoff[j], q1 = hb + (unsigned)se.rowoff[j + 1];
+#define DC_ROW_PAIR(it)                                                                                    \
+            if (it < NB) {                                                                                  \
+                const unsigned v0 = lds<it * HSTEP>(q0), v1 = lds<it * HSTEP>(q1);                          \
+                ae[it < NB ? it : 0] = vop3_16<IS_MAX>(ae[it < NB ? it : 0], prmt(v0, 0u, 0x2200u), prmt(v1, 0u, 0x2200u)); \
+                ao[it < NB ? it : 0] = vop3_16<IS_MAX>(ao[it < NB ? it : 0], prmt(v0, 0u, 0x3311u), prmt(v1, 0u, 0x3311u)); \
             }
+            DC_ROW_PAIR(0) DC_ROW_PAIR(1) DC_ROW_PAIR(2) DC_ROW_PAIR(3)
+#undef DC_ROW_PAIR
         }
         if (j < jend) {
-            const int o0 = se.rowoff[j];
-#pragma unroll
-            for (int it = 0; it < B_ITS; ++it) {
-                if (it * 32 + row0 < TH) {
-                    const unsigned v0 = hb[it * 32 * HP + o0];
-                    ae[it] = vop3_16<IS_MAX>(ae[it], even16(v0), ae[it]);
-                    ao[it] = vop3_16<IS_MAX>(ao[it], odd16(v0), ao[it]);
-                }
+            const unsigned q0 = hb + (unsigned)se.rowoff[j];
+#define DC_ROW_ONE(it)                                                                                     \
+            if (it < NB) {                                                                                  \
+                const unsigned v0 = lds<it * HSTEP>(q0);                                                    \
+                ae[it < NB ? it : 0] = vop3_16<IS_MAX>(ae[it < NB ? it : 0], prmt(v0, 0u, 0x2200u), ae[it < NB ? it : 0]); \
+                ao[it < NB ? it : 0] = vop3_16<IS_MAX>(ao[it < NB ? it : 0], prmt(v0, 0u, 0x3311u), ao[it < NB ? it : 0]); \
             }
+            DC_ROW_ONE(0) DC_ROW_ONE(1) DC_ROW_ONE(2) DC_ROW_ONE(3)
+#undef DC_ROW_ONE
         }
         // (no second barrier: the next chord writes the other buffer, and the one after that is behind the
         //  next chord's barrier)
@@ -206,11 +239,11 @@ __global__ void __launch_bounds__(NT, 2) morph_chord_kernel(const uint8_t* __res
     int mn = 255, mx = 0;
     const int gx = blockIdx.x * TW + 4 * xw;
 #pragma unroll
-    for (int it = 0; it < B_ITS; ++it) {
+    for (int it = 0; it < NB; ++it) {
         const int ly = it * 32 + row0;
         const int gy = blockIdx.y * TH + ly;
-        if (ly < TH && gy < H && gx < W) {
-            const unsigned acc = __byte_perm(ae[it], ao[it], 0x6240);
+        if (gy < H && gx < W) {
+            const unsigned acc = pack_lanes(ae[it], ao[it]);
             uint8_t* dst = out + ((size_t)plane * H + gy) * W + gx;
             unsigned res = acc;
             if (SUBTRACT) {
@@ -346,8 +379,10 @@ int build_plan(int k, int th, SEPlan* se) {
             for (int q = 0; q < ((1 << l) == w ? 1 : 2); ++q) {
                 const int bx = starts[q] + c + se->pad;            // byte column inside the region row
                 Fetch f;
+                const unsigned sb = (unsigned)(bx & 3);             // first byte of the window inside the word pair
                 f.woff = l * se->level_words + (bx >> 2);
-                f.shift = (bx & 3) * 8;
+                f.sel_e = sb | (sb << 4) | ((sb + 2) << 8) | ((sb + 2) << 12);          // bytes s, s, s+2, s+2
+                f.sel_o = (sb + 1) | ((sb + 1) << 4) | ((sb + 3) << 8) | ((sb + 3) << 12);
                 ch.f[ch.nf++] = f;
             }
         };
@@ -370,7 +405,7 @@ int build_plan(int k, int th, SEPlan* se) {
         for (int i = 0; i < k; ++i)
             if (!used[i] && lo[i] == clo && hi[i] == chi) {
                 used[i] = true;
-                se->rowoff[nrows++] = (short)(i * HP);             // (dy + an) * HP with dy = i - an
+                se->rowoff[nrows++] = i * HP * 4;                  // (dy + an) * HP words, in bytes (dy = i - an)
             }
         ch.row_end = nrows;
         plo = clo; phi = chi;
@@ -382,7 +417,9 @@ int build_plan(int k, int th, SEPlan* se) {
     return 0;
 }
 
-size_t plan_smem_bytes(const SEPlan& se) { return ((size_t)se.ntables * se.level_words + 2 * (size_t)se.RH * HP) * 4; }
+size_t plan_smem_bytes(const SEPlan& se) {
+    return ((size_t)se.ntables * se.level_words + 2 * (size_t)(((se.RH + 31) >> 5) * 32) * HP) * 4;
+}
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -424,11 +461,11 @@ int rolling_ball_plan_dump(int radius, int th, int* out, int cap) {
     for (int m = 0; m < se.nchords; ++m) {
         const Chord& ch = se.chord[m];
         out[n++] = ch.nf;
-        for (int q = 0; q < 4; ++q) { out[n++] = ch.f[q].woff; out[n++] = ch.f[q].shift; }
+        for (int q = 0; q < 4; ++q) { out[n++] = ch.f[q].woff; out[n++] = (int)(ch.f[q].sel_e & 3u) * 8; }
         out[n++] = ch.row_begin;
         out[n++] = ch.row_end;
     }
-    for (int j = 0; j < nrows; ++j) out[n++] = se.rowoff[j];
+    for (int j = 0; j < nrows; ++j) out[n++] = se.rowoff[j] / 4;
     return n;
 }
 
@@ -466,14 +503,22 @@ int launch_rolling_ball(const dc_rolling_ball_args_t* a, cudaStream_t stream) {
         DC_CUDA(cudaGetDevice(&dev));
         const unsigned long long bit = 1ull << (dev & 63);
         if (!(__atomic_load_n(&attr_done, __ATOMIC_ACQUIRE) & bit)) {      // per (function, device), once
-            DC_CUDA(cudaFuncSetAttribute(morph_chord_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-            DC_CUDA(cudaFuncSetAttribute(morph_chord_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+#define DC_MORPH_ATTR(nb)                                                                                                    \
+            DC_CUDA(cudaFuncSetAttribute(morph_chord_kernel<false, false, nb>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
+            DC_CUDA(cudaFuncSetAttribute(morph_chord_kernel<true, true, nb>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            DC_MORPH_ATTR(4) DC_MORPH_ATTR(2) DC_MORPH_ATTR(1)
+#undef DC_MORPH_ATTR
             __atomic_fetch_or(&attr_done, bit, __ATOMIC_RELEASE);
         }
     }
     dim3 grid(ceil_div(W, TW), ceil_div(H, th), planes);
-    morph_chord_kernel<false, false><<<grid, NT, smem, stream>>>(a->in, a->C, er, nullptr, 0, H, W, minmax, se);
-    morph_chord_kernel<true, true><<<grid, NT, smem, stream>>>(er, 1, corr, a->in, a->C, H, W, minmax, se);
+#define DC_MORPH_LAUNCH(nb)                                                                                              \
+    if (th == 32 * nb) {                                                                                                 \
+        morph_chord_kernel<false, false, nb><<<grid, NT, smem, stream>>>(a->in, a->C, er, nullptr, 0, H, W, minmax, se); \
+        morph_chord_kernel<true, true, nb><<<grid, NT, smem, stream>>>(er, 1, corr, a->in, a->C, H, W, minmax, se);      \
+    }
+    DC_MORPH_LAUNCH(4) DC_MORPH_LAUNCH(2) DC_MORPH_LAUNCH(1)
+#undef DC_MORPH_LAUNCH
     int sblocks = ceil_div(H * W, 256 * 64);
     if (sblocks > 1024) sblocks = 1024;
     if (sblocks < 1) sblocks = 1;
