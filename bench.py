@@ -12,8 +12,13 @@ independent batches -- no data-path collective, NCCL only for the
 `value`  : frames already resident in HBM when the timed region starts (device-timed, CUDA events).
 `e2e`    : the same metric through DropletPipeline.run_host with pinned HOST buffers -- the H2D copy of the
            frames and the D2H copy of masks + table rows are inside the timed region.
-`--impl reference` : the reference's CPU path (cv2 rolling ball, torch fp32 UNetDC, threshold, quantify
-           restated in oracle/) on this box's host cores; rank 0 only.
+`--impl reference` : the reference's OWN modules (oracle/_ref: quantify_droplets_batch.py, models/model_2.py,
+           utils/data_loader.py byte-compiled where they lie; rolling_ball_correction_rgb, UNetDC fp32, `> thresh`,
+           quantify with its O(labels x pixels) filter loop) on this box's host cores; rank 0 only.  Falls back to the
+           oracle port (kind "port") when oracle/_ref is absent.
+`parity`  : GPU outputs against the reference's on the cpu_baseline frames: |dp|, mask pixels / droplets differing.
+`config4` : BASELINE configs[3] -- `--frames 4096` frames sharded round-robin over the ranks (strong scaling), tables
+           gathered to rank 0 in frame order inside the timed region, merged-table checksum (equal for every N).
 """
 from __future__ import annotations
 
@@ -127,16 +132,29 @@ def make_frames(n: int, size: int) -> np.ndarray:
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_step(sd, frames_u8, use_threads):
-    """The reference's CPU path on `frames_u8` (u8 [n,H,W]); returns seconds."""
+def cpu_reference_step(sd, frames_u8, use_threads, want_outputs=False):
+    """The reference's CPU path on `frames_u8` (u8 [n,H,W]).  Returns (seconds, droplets, kind[, probs, masks, tables]).
+    kind "reference": the reference's own modules from oracle/_ref; "port": the oracle restatement."""
     import oracle
     import torch
+    from oracle import ref
     torch.set_num_threads(use_threads)
-    t0 = time.perf_counter()
     rgb = [np.repeat(f[:, :, None], 3, 2) for f in frames_u8]          # Image.convert("RGB"), qdb:41
-    probs, masks, tables = oracle.run_path(sd, rgb, radius=RADIUS, prob_thresh=PROB_THRESH, min_area=MIN_AREA,
-                                           px_per_um=PX_PER_UM, use_cv2=True)
-    return time.perf_counter() - t0, sum(len(t) for t in tables)
+    kind = "reference" if ref.available() else "port"
+    t0 = time.perf_counter()
+    if kind == "reference":
+        probs, masks, tables = ref.run_path(sd, rgb, radius=RADIUS, prob_thresh=PROB_THRESH, min_area=MIN_AREA,
+                                            px_per_um=PX_PER_UM)
+    else:
+        probs, masks, tables = oracle.run_path(sd, rgb, radius=RADIUS, prob_thresh=PROB_THRESH, min_area=MIN_AREA,
+                                               px_per_um=PX_PER_UM, use_cv2=True)
+    dt = time.perf_counter() - t0
+    n = sum(len(t) for t in tables)
+    return (dt, n, kind, probs, masks, tables) if want_outputs else (dt, n, kind)
+
+
+CPU_SAMPLE = {"reference": "the reference's own rolling_ball_correction_rgb + UNetDC fp32 + `> thresh` + quantify (oracle/_ref)",
+              "port": "cv2 rolling ball + torch fp32 UNetDC + threshold + oracle quantify (oracle/_ref absent)"}
 
 
 def run_reference(args):
@@ -149,23 +167,23 @@ def run_reference(args):
     sd = calibrated_state_dict(seed=0)
     frames = make_frames(2, args.size)
     per_step = 1
+    kind = "port"
     for w in range(args.warmup):
         cpu_reference_step(sd, frames[:per_step], cores)
     times = []
     for k in range(args.steps):
-        dt, _ = cpu_reference_step(sd, frames[k % 2:k % 2 + per_step], cores)
+        dt, _, kind = cpu_reference_step(sd, frames[k % 2:k % 2 + per_step], cores)
         times.append(dt)
     total = sum(times)
     value = per_step * args.steps / total
-    sample = (f"{per_step} frame of {args.size}x{args.size} per step (of the batch-{args.batch} workload), "
-              f"cv2 rolling ball + torch fp32 UNetDC + threshold + oracle quantify")
+    sample = (f"{per_step} frame of {args.size}x{args.size} per step (of the batch-{args.batch} workload): {CPU_SAMPLE[kind]}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.batch, args.size), "batch": args.batch, "size": args.size,
                    "sample_frames_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                          "torch_threads": torch.get_num_threads()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -173,6 +191,117 @@ def run_reference(args):
     _OUT.write(json.dumps(line) + "\n")
     _OUT.flush()
     return 0
+
+
+# ------------------------------------------------------------------------------------ parity (GPU vs the reference)
+def parity_report(probs, masks, tables, probs_ref, masks_ref, tables_ref, kind):
+    """How far the GPU path is from the reference on the same frames (north_star: probabilities within a stated bf16
+    tolerance, mask disagreements only near prob_thresh, tables bit-exact given the same mask)."""
+    import oracle
+    err = np.abs(probs - probs_ref)
+    diff = masks != masks_ref
+    dist = np.abs(probs_ref - PROB_THRESH)
+    exact = True
+    for i in range(len(masks)):
+        _, cols = oracle.quantify_arrays(masks[i], MIN_AREA, PX_PER_UM)
+        exact = exact and all(np.array_equal(np.asarray(tables[i][c]), v) for c, v in cols.items())
+    n_gpu = [int(len(t["label"])) for t in tables]
+    n_ref = [int(len(t)) for t in tables_ref]
+    a_gpu = [int(np.asarray(t["area"]).sum()) for t in tables]
+    a_ref = [int(t["area"].sum()) if len(t) else 0 for t in tables_ref]
+    return {
+        "against": f"{kind} ({CPU_SAMPLE[kind]})", "frames": int(len(masks)), "pixels": int(masks.size),
+        "prob_max_abs_diff": float(err.max()), "prob_mean_abs_diff": float(err.mean()),
+        "prob_tolerance": {"this_checkpoint": 0.08, "survey_checkpoint": 0.03,
+                           "note": "bench weights have a least-squares out_conv (logits -6..+4); tests/test_gpu_forward.py"},
+        "mask_pixels_differing": int(diff.sum()), "mask_pixels_differing_frac": float(diff.mean()),
+        "of_which_within_0.03_of_thresh": int((diff & (dist <= 0.03)).sum()),
+        "of_which_within_0.08_of_thresh": int((diff & (dist <= 0.08)).sum()),
+        "outside_0.08_band": int((diff & (dist > 0.08)).sum()),
+        "droplets_per_frame_gpu": n_gpu, "droplets_per_frame_reference": n_ref,
+        "droplet_count_delta": [g - r for g, r in zip(n_gpu, n_ref)],
+        "total_area_px_gpu": a_gpu, "total_area_px_reference": a_ref,
+        "total_area_delta_frac": [float((g - r) / max(1, r)) for g, r in zip(a_gpu, a_ref)],
+        "tables_bit_exact_given_gpu_mask": bool(exact),
+    }
+
+
+# ------------------------------------------------------------------------------------ config 4 (strong scaling)
+def frame_content(base, i):
+    """Frame i of the config-4 job: a function of the GLOBAL frame index only, so every sharding sees the same job."""
+    n = len(base)
+    return np.roll(base[i % n], 37 * ((i // n) % 16), axis=1)
+
+
+def run_config4(pipe, dev, rank, world, frames_total, batch, size, barrier, dist):
+    """BASELINE configs[3]: frames_total frames, frame i -> rank i mod world (shard.py), each rank streams its batches
+    through DropletPipeline.run_host_pipelined (pinned host frames -> host masks + tables), then the per-droplet tables
+    are gathered on rank 0 and merged in frame order -- all inside the timed region."""
+    import torch
+    from unet_dc_segmentation_b200 import shard
+    base = make_frames(8, size)
+    mine = shard.shard_indices(frames_total, rank, world)
+    groups = shard.batches(mine, batch)
+    uniq = {}
+    def content(i):
+        key = (i % 8, (i // 8) % 16)
+        if key not in uniq:
+            uniq[key] = frame_content(base, i)
+        return uniq[key]
+    staged = [torch.from_numpy(np.stack([content(i) for i in g])).pin_memory() for g in groups]
+    names = ["area", "equivalent_diameter", "centroid-0", "centroid-1", "area_sqmicron", "eq_diam_micron"]
+    barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    counts, rows, mask_px = [], [], 0
+    for (m_h, tabs) in pipe.run_host_pipelined(iter(staged), dev, copy=False):
+        mask_px += int(m_h.size)                      # masks stay with the rank that computed them (qdb:58 writes them there)
+        for t in tabs:
+            counts.append(len(t["label"]))
+            rows.append(np.stack([np.asarray(t[c]).astype(np.float64) if c != "area" else np.asarray(t[c]).view(np.float64)
+                                  for c in names], axis=1))
+    local = np.concatenate(rows) if rows else np.zeros((0, len(names)))
+    lc = np.asarray(counts, np.int64)
+    if world > 1:
+        n_rows = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+        all_rows = [torch.zeros_like(n_rows) for _ in range(world)]
+        dist.all_gather(all_rows, n_rows)
+        maxr = int(max(int(v.item()) for v in all_rows))
+        nf = (frames_total + world - 1) // world
+        buf = torch.zeros((maxr, len(names)), dtype=torch.float64, device=dev)
+        buf[:local.shape[0]] = torch.from_numpy(local).to(dev)
+        cbuf = torch.zeros(nf, dtype=torch.int64, device=dev)
+        cbuf[:len(lc)] = torch.from_numpy(lc).to(dev)
+        gr = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+        gc = [torch.empty_like(cbuf) for _ in range(world)] if rank == 0 else None
+        dist.gather(buf, gr, dst=0)
+        dist.gather(cbuf, gc, dst=0)
+        merged = None
+        if rank == 0:
+            per_rank_rows = [g.cpu().numpy() for g in gr]
+            per_rank_counts = [g.cpu().numpy() for g in gc]
+            offs = [np.concatenate([[0], np.cumsum(c)]) for c in per_rank_counts]
+            merged = np.concatenate([per_rank_rows[i % world][offs[i % world][i // world]:offs[i % world][i // world + 1]]
+                                     for i in range(frames_total)])
+            merged_counts = np.array([per_rank_counts[i % world][i // world] for i in range(frames_total)], np.int64)
+    else:
+        merged, merged_counts = local, lc
+    torch.cuda.synchronize(); barrier()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    out = {"frames_total": frames_total, "seconds": dt, "value": frames_total / dt, "unit": UNIT, "scaling": "strong",
+           "batches_per_rank": len(groups), "tail_batch": len(groups[-1]) if groups else 0,
+           "sharding": f"frame i -> rank i mod {world}; tables gathered to rank 0 and merged in frame order inside the timed region"}
+    if rank == 0:
+        import hashlib
+        h = hashlib.sha256()
+        h.update(merged_counts.tobytes())
+        h.update(np.ascontiguousarray(merged).tobytes())
+        out.update({"droplets_total": int(merged_counts.sum()), "table_bytes": int(merged.nbytes),
+                    "merged_table_sha256": h.hexdigest()[:16]})
+    return out
 
 
 # ------------------------------------------------------------------------------------ B200 arm
@@ -312,10 +441,16 @@ def run_b200(args):
     rb_gbs = px * wl.ROLLING_BALL_BYTES_PER_PX / (stage_ms[0] * 1e-3) / 1e9
     ccl_bytes = px * (wl.LABEL_BYTES_PER_PX + wl.STATS_BYTES_PER_PX) + int(counts.sum()) * wl.STATS_BYTES_PER_DROPLET
     ccl_gbs = ccl_bytes / (stage_ms[2] * 1e-3) / 1e9
-    launches_per_step = 4 + n_launch + 8
-    # DRAM bytes of the 22 forward launches, from the committed ncu capture of this exact configuration
-    # (profiles/r01e_forward_per_launch.md: sum of dram__bytes_read.sum + dram__bytes_write.sum); null elsewhere
-    traffic = 77.4e9 if (B, S) == (32, 1024) and tuple(model.dilations) == (1, 2, 4, 8, 16) else None
+    launches_per_step = 3 + n_launch + 7          # rolling ball (erode, dilate, stretch) + dc_forward + dc_label_stats
+    # DRAM bytes of the forward launches of THIS configuration, from the newest committed ncu capture
+    # (profiles/forward_traffic.json, written by tools/summarize_profiles.py from the per-launch
+    # dram__bytes_read.sum + dram__bytes_write.sum); null when no capture of this configuration is committed
+    traffic, traffic_src = None, None
+    tj = REPO / "profiles" / "forward_traffic.json"
+    if tj.exists():
+        for rec in json.loads(tj.read_text()):
+            if (rec["batch"], rec["size"]) == (B, S) and tuple(rec["dilations"]) == tuple(model.dilations):
+                traffic, traffic_src = rec["dram_bytes"], rec["source"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -326,7 +461,7 @@ def run_b200(args):
                    "droplets_per_image": float(counts.mean())},
         "roofline": {"kernel": "conv_tc_kernel (21 tcgen05 launches) + stem_kernel = dc_forward", "bound": "tensor",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                     "traffic_note": "DRAM bytes per dc_forward (22 launches), ncu, profiles/r01e_forward_per_launch.md; "
+                     "traffic_note": f"DRAM bytes per dc_forward (22 launches) from the ncu capture {traffic_src}; "
                                      "activations written once + read once would be ~84 GB unfused (SURVEY 8d)",
                      "peak_source": f"{ptype} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
                      "flops_per_launch_group": fwd_flops, "flops_model": "in-bounds taps (conservative), SURVEY.md 8d",
@@ -342,15 +477,23 @@ def run_b200(args):
         "step_ms": [round(x, 2) for x in step_ms],
     }
 
+    if args.frames > 0:
+        line["config4"] = run_config4(pipe, dev, rank, world, args.frames, B, S, barrier, dist)
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         nfr = args.cpu_frames
         frames = batch0[:nfr]
         cpu_reference_step(sd, frames[:1], cores)                           # warm the conv primitives
-        dt, _ = cpu_reference_step(sd, frames, cores)
-        line["cpu_baseline"] = {"value": nfr / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{nfr} of the batch's {S}x{S} frames, once: cv2 rolling ball + torch fp32 "
-                                          f"UNetDC ({torch.get_num_threads()} threads) + threshold + oracle quantify; {dt:.1f} s"}
+        dt, _, kind, probs_ref, masks_ref, tables_ref = cpu_reference_step(sd, frames, cores, want_outputs=True)
+        line["cpu_baseline"] = {"value": nfr / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                                "sample": f"{nfr} of the batch's {S}x{S} frames, once ({torch.get_num_threads()} torch "
+                                          f"threads): {CPU_SAMPLE[kind]}; {dt:.1f} s"}
+        # the same frames through the GPU path: how far is it from the reference?
+        res = pipe.run_device(torch.from_numpy(np.ascontiguousarray(frames)).to(dev), return_prob=True)
+        torch.cuda.synchronize()
+        line["parity"] = parity_report(res.probs[:, 0].cpu().numpy(), res.masks.cpu().numpy(), res.tables.to_host(),
+                                       probs_ref, masks_ref, tables_ref, kind)
     if rank == 0:
         _OUT.write(json.dumps(line) + "\n")
         _OUT.flush()
@@ -378,7 +521,9 @@ def main():
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--capacity", type=int, default=16384)
     ap.add_argument("--unique-frames", type=int, default=8)
-    ap.add_argument("--cpu-frames", type=int, default=4)
+    ap.add_argument("--cpu-frames", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=4096,
+                    help="BASELINE configs[3]: total frames of the strong-scaling job reported under `config4` (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -34,74 +34,8 @@ REF = Path("/root/reference")
 
 
 # ----------------------------------------------------------------------------- shims
-def install_shims():
-    import scipy.ndimage as ndi
-
-    mpl = types.ModuleType("matplotlib")
-    mpl.use = lambda *a, **k: None
-    plt = types.ModuleType("matplotlib.pyplot")
-    mpl.pyplot = plt
-    sys.modules.setdefault("matplotlib", mpl)
-    sys.modules.setdefault("matplotlib.pyplot", plt)
-
-    alb = types.ModuleType("albumentations")
-    albt = types.ModuleType("albumentations.pytorch")
-    albt.ToTensorV2 = object
-    alb.pytorch = albt
-    sys.modules.setdefault("albumentations", alb)
-    sys.modules.setdefault("albumentations.pytorch", albt)
-
-    cross = ndi.generate_binary_structure(2, 1)
-
-    def label(img, connectivity=1, **_):
-        assert connectivity == 1
-        img = np.asarray(img)
-        comp = np.zeros(img.shape, np.int64)
-        total = 0
-        for v in np.unique(img):              # only equal-valued 4-neighbours connect
-            if v == 0:
-                continue
-            lab, n = ndi.label(img == v, structure=cross)
-            comp[lab > 0] = lab[lab > 0] + total
-            total += n
-        # number the components in raster order of their first pixel (skimage's order)
-        flat = comp.ravel()
-        first = np.full(total + 1, flat.size, np.int64)
-        idx = np.flatnonzero(flat)
-        np.minimum.at(first, flat[idx], idx)
-        order = np.argsort(first[1:], kind="stable")
-        remap = np.zeros(total + 1, np.int64)
-        remap[order + 1] = np.arange(1, total + 1)
-        return remap[comp]
-
-    def regionprops_table(lbl, properties=()):
-        lbl = np.asarray(lbl)
-        ids = np.unique(lbl)
-        ids = ids[ids != 0]
-        res = {}
-        area = ndi.sum_labels(np.ones(lbl.shape, np.float64), lbl, ids).astype(np.int64)
-        com = np.array(ndi.center_of_mass(np.ones(lbl.shape, np.float64), lbl, ids), dtype=np.float64).reshape(-1, 2)
-        for p in properties:
-            if p == "label":
-                res["label"] = ids.astype(np.int64)
-            elif p == "area":
-                res["area"] = area
-            elif p == "equivalent_diameter":
-                res["equivalent_diameter"] = np.sqrt(4.0 * area / np.pi)
-            elif p == "centroid":
-                res["centroid-0"] = com[:, 0]
-                res["centroid-1"] = com[:, 1]
-            else:
-                raise KeyError(p)
-        return res
-
-    sk = types.ModuleType("skimage")
-    skm = types.ModuleType("skimage.measure")
-    skm.label = label
-    skm.regionprops_table = regionprops_table
-    sk.measure = skm
-    sys.modules.setdefault("skimage", sk)
-    sys.modules.setdefault("skimage.measure", skm)
+sys.path.insert(0, str(REPO))
+from oracle.shims import install_shims   # noqa: E402  (matplotlib / albumentations / skimage.measure stand-ins)
 
 
 def import_reference():

@@ -85,3 +85,28 @@ def test_cli_default_img_size_resizes_like_the_reference(cuda_device, workdir):
     assert mask.shape == (80, 112)
     assert not (out / "all_droplets.xlsx").exists() and not (out / "all_droplets_noexcel.csv").exists()
     assert not (out / "overlays").exists()
+
+
+def test_cli_reference_loop_still_works(cuda_device, workdir):
+    """--reference_loop keeps the reference-shaped per-image functions (preprocess / run_batch) on the CLI: same files,
+    every table equal to the oracle's quantify() of the mask that loop wrote."""
+    import cv2
+    import pandas as pd
+    from unet_dc_segmentation_b200 import cli
+    out = workdir / "out_loop"
+    assert cli.main(["--img_dir", str(workdir / "in"), "--ckpt_path", str(workdir / "ckpt.pth"), "--out_dir", str(out),
+                     "--batch", "3", "--skip_excel", "--skip_histogram", "--img_size", "96", "--reference_loop",
+                     "--save_overlays"]) == 0
+    fast = workdir / "out_native"
+    for n in ["frame0", "frame1", "frame2", "wide"]:
+        mask = cv2.imread(str(out / "predicted_masks" / f"{n}_pred.png"), cv2.IMREAD_GRAYSCALE)
+        df = pd.read_csv(out / f"{n}_droplets.csv", float_precision="round_trip")
+        want = oracle.quantify(mask // 255, 1, None)
+        assert len(df) == len(want)
+        for c in want.columns:
+            np.testing.assert_array_equal(df[c].to_numpy(), want[c].to_numpy(), err_msg=f"{n}.{c}")
+        assert (out / "overlays" / f"{n}_overlay.png").exists()
+        if (fast / "predicted_masks" / f"{n}_pred.png").exists():
+            # the two loops feed the stem differently (f32 RGB vs folded u8 grey): a few threshold-edge pixels may differ
+            other = cv2.imread(str(fast / "predicted_masks" / f"{n}_pred.png"), cv2.IMREAD_GRAYSCALE)
+            assert (other != mask).mean() < 0.01

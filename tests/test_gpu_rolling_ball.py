@@ -85,13 +85,15 @@ def test_config3_size_2048_properties(cuda_device):
     assert all(lut[a] <= lut[b] for a, b in zip(keys, keys[1:]))
 
 
-@pytest.mark.parametrize("shape,radius", [((1, 200, 260), 128), ((2, 150, 90), 150), ((1, 300, 300), 177), ((1, 64, 64), 120)])
+@pytest.mark.parametrize("shape,radius", [((1, 200, 260), 128), ((2, 150, 90), 150), ((1, 300, 300), None), ((1, 64, 64), 120)])
 def test_large_radii_vs_cv2(cuda_device, shape, radius):
     """Radii beyond 100 (the reference CLI takes any --background_radius): shorter tiles, more chord levels;
     against OpenCV itself with the reference's four calls (utils/data_loader.py:17-21)."""
     import cv2
     import torch
     from unet_dc_segmentation_b200 import rolling_ball_device
+    from unet_dc_segmentation_b200.morphology import max_radius
+    radius = radius or max_radius()              # None: the largest element the kernel takes
     rs = np.random.RandomState(radius)
     B, H, W = shape
     imgs = rs.randint(0, 256, (B, H, W)).astype(np.uint8)

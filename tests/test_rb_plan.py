@@ -10,7 +10,7 @@ from rb_model import load_plan, morph_pass
 
 @pytest.mark.parametrize("radius,th", [(1, 128), (2, 128), (3, 64), (4, 128), (5, 32), (7, 128), (8, 128), (15, 128),
                                        (20, 64), (33, 128), (50, 128), (50, 64), (51, 128), (64, 128), (77, 128),
-                                       (100, 128), (128, 128), (150, 64), (200, 32)])
+                                       (100, 128), (128, 128), (150, 64), (174, 32)])
 def test_chord_plan_matches_cv2(radius, th):
     import cv2
     rs = np.random.RandomState(radius)

@@ -14,6 +14,12 @@ bit-exact against OpenCV's findContours + drawContours).  On the host, exactly a
 PNG / CSV / XLSX writing.  Added flags: `--img_size` (default 512 = the reference's
 IMG_SIZE constant) and `--density_maps` (the per-image maps of the reference's second front end, quantify_pipline.py:131-141).  Under torchrun (one rank per GPU) frames are sharded i -> rank i mod N, every
 rank writes the per-image files of its own frames, and the tables are gathered on rank 0, which writes the reports.
+
+``main`` runs the FAST path (``run_fast``): frames are decoded by a thread pool, batched, and streamed through
+``DropletPipeline.run_host_pipelined`` -- u8 frames up, u8 masks (+ overlay stencils) and table rows down, nothing
+else crosses PCIe -- while another pool writes the PNG / CSV files.  ``preprocess`` / ``run_batch`` keep the
+reference's function-by-function shape (per-image round trips) for callers that use them as a library;
+``--reference_loop`` makes ``main`` use them.
 """
 from __future__ import annotations
 
@@ -164,6 +170,98 @@ def write_reports(out_dir: Path, per_image_rows, all_props, skip_excel: bool, sk
             plt.close()
 
 
+def _decode(path):
+    """qdb:41: decode to RGB.  A frame whose three channels are identical (every grayscale file) is returned as one
+    [H,W] plane: the rolling ball then corrects it once and the network folds the three identical input channels."""
+    from PIL import Image
+    im = np.array(Image.open(path).convert("RGB"))
+    if np.array_equal(im[..., 0], im[..., 1]) and np.array_equal(im[..., 1], im[..., 2]):
+        return np.ascontiguousarray(im[..., 0])
+    return im
+
+
+def _table_frame(cols: dict, px_per_um):
+    """Per-image DataFrame with the reference's column contract (qdb:87-94): empty and column-less without droplets."""
+    import pandas as pd
+    from .quantify import COLUMNS, MICRON_COLUMNS
+    if len(cols["label"]) == 0:
+        return pd.DataFrame()
+    return pd.DataFrame({k: cols[k] for k in COLUMNS + (MICRON_COLUMNS if px_per_um else [])})
+
+
+def run_fast(images, mine, model, args, out_dir, mask_dir, overlay_dir):
+    """The batched path behind ``main``: the per-image work of qdb:146-160 (preprocess + run_batch) for the frames
+    ``mine`` (indices into ``images``), with every device stage batched and the host stages (decode, PNG / CSV
+    writing) in thread pools around it.  Returns (indices, per_image_rows, all_props) in frame order."""
+    import collections
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    import cv2
+    from .pipeline import DropletPipeline
+    dev = next(model.parameters()).device
+    pipe = DropletPipeline(model, args.background_radius, args.prob_thresh, args.min_area, args.px_per_micron,
+                           img_size=args.img_size)
+    nthreads = max(2, min(16, (os.cpu_count() or 4)))
+    metas = collections.deque()                      # one entry per batch handed to the pipeline, in order
+    idx, per_image_rows, all_props = [], [], []
+
+    with ThreadPoolExecutor(nthreads) as decoders, ThreadPoolExecutor(nthreads) as writers:
+        def batches():
+            window = 4 * args.batch                  # decoded frames in flight (bounded host memory)
+            pending = collections.deque()
+            it = iter(mine)
+            def refill():
+                while len(pending) < window:
+                    i = next(it, None)
+                    if i is None:
+                        return
+                    pending.append((i, decoders.submit(_decode, images[i])))
+            refill()
+            cur, cur_meta = [], []
+            while pending:
+                i, fut = pending.popleft()
+                refill()
+                fr = fut.result()
+                if cur and (fr.shape != cur[0].shape or len(cur) == args.batch):
+                    metas.append(cur_meta)
+                    yield np.stack(cur)
+                    cur, cur_meta = [], []
+                cur.append(fr)
+                cur_meta.append(i)
+            if cur:
+                metas.append(cur_meta)
+                yield np.stack(cur)
+
+        def write_image(i, mask, stencil):
+            name = images[i].stem
+            cv2.imwrite(str(Path(mask_dir) / f"{name}_pred.png"), mask * 255)                 # qdb:58
+            if overlay_dir is not None:
+                img = cv2.imread(str(images[i]))                                              # qdb:75
+                if img is not None:
+                    draw_overlay(img, stencil)                                                # qdb:76-77, from the GPU
+                    cv2.imwrite(str(Path(overlay_dir) / f"{name}_overlay.png"), img)          # qdb:78
+
+        jobs = []
+        want_ov = overlay_dir is not None
+        for res in pipe.run_host_pipelined(batches(), dev, copy=True, want_overlay=want_ov):
+            masks, tables = res[0], res[1]
+            stencils = res[2] if want_ov else None
+            for b, i in enumerate(metas.popleft()):
+                jobs.append(writers.submit(write_image, i, masks[b], stencils[b] if want_ov else None))
+                df = _table_frame(tables[b], args.px_per_micron)
+                df.insert(0, "filename", images[i].name)                                      # qdb:62
+                df.to_csv(Path(mask_dir).parent / f"{images[i].stem}_droplets.csv", index=False)   # qdb:63
+                idx.append(i)
+                all_props.append(df)
+                per_image_rows.append({"filename": images[i].name, "droplet_count": len(df),
+                                       "total_area_px": df["area"].sum() if not df.empty else 0})   # qdb:67-72
+                if args.density_maps:
+                    save_density_maps(str(images[i]), images[i].stem, torch.from_numpy(masks[b]).to(dev)[None], out_dir)
+        for j in jobs:
+            j.result()
+    return idx, per_image_rows, all_props
+
+
 def build_parser() -> argparse.ArgumentParser:
     p = argparse.ArgumentParser("Segment lipid droplets and build a report")
     p.add_argument("--img_dir", required=True)
@@ -174,11 +272,14 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--min_area", type=int, default=1, help="ignore objects smaller than this (pixels²)")
     p.add_argument("--px_per_micron", type=float, help="pixels per micron for physical-unit columns")
     p.add_argument("--save_overlays", action="store_true")
-    p.add_argument("--background_radius", type=int, default=50, help="radius for rolling ball background correction")
+    p.add_argument("--background_radius", type=int, default=50,
+                   help="radius for rolling ball background correction (the GPU kernel takes 1..174)")
     p.add_argument("--skip_excel", action="store_true", help="skip generation of the Excel workbook")
     p.add_argument("--skip_histogram", action="store_true", help="skip histogram plot generation")
     p.add_argument("--density_maps", action="store_true",
                    help="also write the radial / spatial droplet-density maps of the reference's quantify_pipline.py")
+    p.add_argument("--reference_loop", action="store_true",
+                   help="run the reference-shaped per-image loop (preprocess / run_batch) instead of the batched pipeline")
     p.add_argument("--img_size", type=int, default=IMG_SIZE,
                    help="network input size (reference constant IMG_SIZE = 512); use the frame size for native-resolution inference")
     return p
@@ -217,15 +318,18 @@ def main(argv=None) -> int:
         tensors.clear()
         meta.clear()
 
-    for i in mine:
-        t, osize = preprocess(images[i], args.background_radius, args.img_size)
-        tensors.append(t)
-        meta.append((str(images[i]), osize))
-        idx.append(i)
-        if len(tensors) == args.batch:
+    if args.reference_loop:
+        for i in mine:
+            t, osize = preprocess(images[i], args.background_radius, args.img_size)
+            tensors.append(t)
+            meta.append((str(images[i]), osize))
+            idx.append(i)
+            if len(tensors) == args.batch:
+                flush()
+        if tensors:
             flush()
-    if tensors:
-        flush()
+    else:
+        idx, per_image_rows, all_props = run_fast(images, mine, model, args, out_dir, mask_dir, overlay_dir)
 
     local = [(i, (row, df)) for i, row, df in zip(idx, per_image_rows, all_props)]
     merged = shard.gather_results(local, len(images), dst=0)

@@ -22,6 +22,7 @@ import torch
 from . import _lib
 from .model import UNetDC
 from .morphology import resize_linear_u8_device, rolling_ball_device, rolling_ball_workspace_bytes
+from .overlay import overlay_stencil_device, overlay_workspace_bytes
 from .quantify import DEFAULT_CAPACITY, DropletTables, alloc_tables, label_stats_device, label_workspace_bytes
 
 
@@ -30,6 +31,7 @@ class BatchResult:
     masks: torch.Tensor            # u8 [B,H,W] {0,1} (device)
     tables: DropletTables          # device-resident table
     probs: torch.Tensor | None     # f32 [B,1,H,W] when requested
+    stencil: torch.Tensor | None = None   # u8 [B,H,W] overlay stencil (qdb:76-77) when requested
 
 
 class DropletPipeline:
@@ -50,14 +52,17 @@ class DropletPipeline:
         self._rb_ws = None
         self._rb_out = None
         self._ccl_ws = None
+        self._ovl_ws = None
         self._staging = None
         self._slots = [None, None]       # run_host_pipelined's device / pinned buffers, kept across calls
         self._streams = None
 
     # ------------------------------------------------------------------ device-resident entry
     def run_device(self, images: torch.Tensor, return_prob: bool = False, want_labels: bool = False,
-                   mask_out: torch.Tensor | None = None, tables_out: DropletTables | None = None) -> BatchResult:
-        """images: CUDA u8 [B,H,W] grayscale or [B,H,W,3].  mask_out / tables_out: preallocated outputs."""
+                   mask_out: torch.Tensor | None = None, tables_out: DropletTables | None = None,
+                   want_overlay: bool = False, stencil_out: torch.Tensor | None = None) -> BatchResult:
+        """images: CUDA u8 [B,H,W] grayscale or [B,H,W,3].  mask_out / tables_out / stencil_out: preallocated outputs.
+        want_overlay: also compute the pixels the reference's findContours + drawContours paint (qdb:76-77)."""
         _lib.require_cuda(images, "images")
         x = images
         if self.background_radius:
@@ -81,7 +86,13 @@ class DropletPipeline:
             self._ccl_ws = torch.empty(need, dtype=torch.uint8, device=masks.device)
         tables = label_stats_device(masks, self.min_area, self.px_per_micron, self.capacity,
                                     want_labels=want_labels, workspace=self._ccl_ws, out=tables_out)
-        return BatchResult(masks, tables, probs)
+        stencil = None
+        if want_overlay:
+            need = overlay_workspace_bytes(*masks.shape)
+            if self._ovl_ws is None or self._ovl_ws.device != masks.device or self._ovl_ws.numel() < need:
+                self._ovl_ws = torch.empty(need, dtype=torch.uint8, device=masks.device)
+            stencil = overlay_stencil_device(masks, out=stencil_out, workspace=self._ovl_ws)
+        return BatchResult(masks, tables, probs, stencil)
 
     # ------------------------------------------------------------------ host entry (what a user calls)
     def run_host(self, images: torch.Tensor | np.ndarray, device: torch.device | str = "cuda"):
@@ -106,7 +117,8 @@ class DropletPipeline:
         return masks.numpy(), tables.to_host()
 
     # ------------------------------------------------------------------ pipelined host entry
-    def run_host_pipelined(self, batches, device: torch.device | str = "cuda", copy: bool = True):
+    def run_host_pipelined(self, batches, device: torch.device | str = "cuda", copy: bool = True,
+                           want_overlay: bool = False):
         """Generator over host batches (each u8 [B,H,W] or [B,H,W,3], ideally pinned; all the same shape):
         yields (masks u8 numpy [B,H,W], list of per-image column dicts) per batch, in order.
 
@@ -117,7 +129,8 @@ class DropletPipeline:
         Everything yielded is owned by the caller (``list(pipe.run_host_pipelined(...))`` is safe).  ``copy=False``
         yields the masks as a VIEW of the pipeline's two-slot pinned read-back buffer instead: that view is valid
         only until the generator is advanced again (the next batch's read-back is queued into the other slot and the
-        one after that into this one)."""
+        one after that into this one).  ``want_overlay``: yields (masks, tables, stencils) with the overlay stencil
+        of every mask (u8 [B,H,W], qdb:76-77)."""
         dev = torch.device(device)
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
@@ -136,6 +149,8 @@ class DropletPipeline:
             B = shape[0]
             d = {"dev_in": torch.empty(shape, dtype=torch.uint8, device=dev),
                  "masks": torch.empty(tuple(shape[:3]), dtype=torch.uint8, device=dev),
+                 "stencil": torch.empty(tuple(shape[:3]), dtype=torch.uint8, device=dev) if want_overlay else None,
+                 "h_stencil": torch.empty(tuple(shape[:3]), dtype=torch.uint8).pin_memory() if want_overlay else None,
                  "tables": alloc_tables(B, self.capacity, micron, dev),
                  "h_masks": torch.empty(tuple(shape[:3]), dtype=torch.uint8).pin_memory(),
                  "h_counts": torch.empty(B, dtype=torch.int32).pin_memory(),
@@ -149,7 +164,7 @@ class DropletPipeline:
             host = torch.from_numpy(np.ascontiguousarray(host)) if isinstance(host, np.ndarray) else host
             sl = slots[k % 2]
             if (sl is None or sl["dev_in"].shape != host.shape or sl["tables"].capacity != self.capacity
-                    or (sl["tables"].area_um2 is not None) != micron):
+                    or (sl["tables"].area_um2 is not None) != micron or (sl["stencil"] is not None) != want_overlay):
                 sl = slots[k % 2] = make_slot(tuple(host.shape))
             with torch.cuda.stream(s_in):
                 s_in.wait_event(sl["ev_free"])            # the slot's previous batch has been computed and read back
@@ -161,13 +176,16 @@ class DropletPipeline:
             s_out = s_outs[k % 2]
             with torch.cuda.stream(s_run):
                 s_run.wait_event(sl["ev_in"])
-                self.run_device(sl["dev_in"], mask_out=sl["masks"], tables_out=sl["tables"])
+                self.run_device(sl["dev_in"], mask_out=sl["masks"], tables_out=sl["tables"], want_overlay=want_overlay,
+                                stencil_out=sl["stencil"])
                 sl["ev_run"].record(s_run)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(sl["ev_run"])
                 sl["h_counts"].copy_(sl["tables"].counts, non_blocking=True)
                 sl["ev_counts"].record(s_out)
                 sl["h_masks"].copy_(sl["masks"], non_blocking=True)
+                if want_overlay:
+                    sl["h_stencil"].copy_(sl["stencil"], non_blocking=True)
 
         def finish(k):
             sl = slots[k % 2]
@@ -204,6 +222,9 @@ class DropletPipeline:
                     col = sl["h_cols"][j, b, :n].numpy()
                     d[name] = col.view(np.int64).copy() if name == "area" else col.copy()
                 out.append(d)
+            if want_overlay:
+                st = sl["h_stencil"].numpy()
+                return masks, out, (st.copy() if copy else st)
             return masks, out
 
         k = 0
