@@ -333,7 +333,8 @@ def run_b200(args):
     model = UNetDC(3, 1)
     model.load_state_dict(sd)
     model = model.to(dev).eval()
-    pipe = DropletPipeline(model, RADIUS, PROB_THRESH, MIN_AREA, PX_PER_UM, capacity=args.capacity)
+    pipe = DropletPipeline(model, RADIUS, PROB_THRESH, MIN_AREA, PX_PER_UM, capacity=args.capacity,
+                           use_graphs=args.graphs)
 
     # distinct frames per rank; NVAR variants of the batch so consecutive steps never see the same input
     base = make_frames(min(B, args.unique_frames), S)
@@ -471,7 +472,8 @@ def run_b200(args):
                    "label_stats": {"ms": stage_ms[2], "GBps_algorithmic": ccl_gbs, "frac_hbm": ccl_gbs / pk["hbm_gbs"]}},
         "layers": layers,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * S * S, "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": ms_e2e / K, "api": "DropletPipeline.run_host_pipelined (pinned host frames -> host masks + tables)"},
+                "ms_per_step": ms_e2e / K, "api": "DropletPipeline.run_host_pipelined (pinned host frames -> host masks + tables)"
+                       + (", CUDA-graph replay per batch" if args.graphs else "")},
         "gpu_launches": launches_per_step * K,
         "clocks": clocks,
         "step_ms": [round(x, 2) for x in step_ms],
@@ -525,6 +527,8 @@ def main():
     ap.add_argument("--frames", type=int, default=4096,
                     help="BASELINE configs[3]: total frames of the strong-scaling job reported under `config4` (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graphs", action="store_true",
+                    help="e2e arm: replay each batch's launches as one CUDA graph (DropletPipeline(use_graphs=True))")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     global _OUT

@@ -2,7 +2,7 @@
 
 The reference (malani86/unet-DC-segmentation) is pure Python, so "compiling it where it lies" means
 ``py_compile``: ``build_ref()`` (run by ``__graft_entry__.build()`` in the build container, where /root/reference
-exists) byte-compiles the five modules behind quantify_droplets_batch.py into ``oracle/_ref/*.pyc``.  No reference
+exists) byte-compiles the five modules behind quantify_droplets_batch.py into ``oracle/_ref/*.refc`` (ordinary .pyc content; the extension differs because snapshot tools drop ``*.pyc``).  No reference
 SOURCE is copied: the directory is git-ignored, holds compiled code objects only, and travels to the GPU box with the
 snapshot like our own built ``.so`` files.  ``load()`` imports those code objects (under the sys.modules shims of
 oracle/shims.py for the three third-party packages this image lacks) and returns the reference's functions, which
@@ -24,6 +24,7 @@ _HERE = Path(__file__).resolve().parent
 REF_SRC = Path("/root/reference")
 REF_OUT = _HERE / "_ref"
 # module name -> file relative to the reference root
+EXT = ".refc"              # byte-compiled module (the .pyc format under a name snapshot tools do not filter out)
 MODULES = {
     "quantify_droplets_batch": "quantify_droplets_batch.py",
     "models": "models/__init__.py",
@@ -43,11 +44,11 @@ def build_ref(force: bool = False) -> bool:
     manifest = {"python": sys.version.split()[0], "magic": importlib.util.MAGIC_NUMBER.hex(), "modules": {}}
     for name, rel in MODULES.items():
         src = REF_SRC / rel
-        dst = REF_OUT / (rel[:-3] + ".pyc")
+        dst = REF_OUT / (rel[:-3] + EXT)
         dst.parent.mkdir(parents=True, exist_ok=True)
         if force or not dst.exists() or dst.stat().st_mtime < src.stat().st_mtime:
             py_compile.compile(str(src), cfile=str(dst), dfile=f"<reference>/{rel}", doraise=True, optimize=0)
-        manifest["modules"][name] = {"file": rel[:-3] + ".pyc", "source_sha256": hashlib.sha256(src.read_bytes()).hexdigest()}
+        manifest["modules"][name] = {"file": rel[:-3] + EXT, "source_sha256": hashlib.sha256(src.read_bytes()).hexdigest()}
     (REF_OUT / "MANIFEST.json").write_text(json.dumps(manifest, indent=1))
     return True
 
@@ -71,7 +72,7 @@ class _RefFinder(importlib.abc.MetaPathFinder):
         rel = MODULES.get(fullname)
         if rel is None:
             return None
-        pyc = REF_OUT / (rel[:-3] + ".pyc")
+        pyc = REF_OUT / (rel[:-3] + EXT)
         if not pyc.exists():
             return None
         loader = importlib.machinery.SourcelessFileLoader(fullname, str(pyc))

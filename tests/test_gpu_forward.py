@@ -164,6 +164,15 @@ def test_whole_path_vs_reference_golden(cuda_device):
     for k, (mk, tb) in enumerate(held):
         np.testing.assert_array_equal(mk, masks if k % 2 == 0 else want_f_masks, err_msg=f"held batch {k}")
     assert not np.shares_memory(held[0][0], held[2][0])
+    # CUDA-graph replay of the per-batch launches (one graph per buffer slot, captured on the slot's second use)
+    gpipe = DropletPipeline(m, background_radius=50, prob_thresh=0.3, min_area=1, px_per_micron=3.45, use_graphs=True)
+    for k, (mk, tb) in enumerate(gpipe.run_host_pipelined(seq[k % 2] for k in range(7))):
+        wm, wt = (masks, tables) if k % 2 == 0 else (want_f_masks, want_f_tables)
+        np.testing.assert_array_equal(mk, wm, err_msg=f"graph batch {k}")
+        for i in range(2):
+            for c in wt[i]:
+                np.testing.assert_array_equal(tb[i][c], wt[i][c], err_msg=f"graph batch {k} image {i} column {c}")
+    assert all(sl["graph"] is not None for sl in gpipe._slots)
 
 
 def test_config1_eight_256_images(cuda_device):

@@ -37,11 +37,14 @@ class BatchResult:
 class DropletPipeline:
     def __init__(self, model: UNetDC, background_radius: int | None = 50, prob_thresh: float = 0.3,
                  min_area: int = 1, px_per_micron: float | None = None, capacity: int = DEFAULT_CAPACITY,
-                 img_size: int | None = None):
+                 img_size: int | None = None, use_graphs: bool = False):
         """img_size: network input size.  None = native resolution (frames must be multiples of 16; both resizes of
         the reference are then the identity).  An integer reproduces the as-shipped flow (IMG_SIZE = 512, qdb:30):
         corrected frames are resized to img_size x img_size (qdb:44) and the mask is resized back to the frame size
-        (qdb:57), both with cv2's effective INTER_LINEAR, on the device."""
+        (qdb:57), both with cv2's effective INTER_LINEAR, on the device.
+        use_graphs: ``run_host_pipelined`` captures the ~35 kernel launches of a batch into one CUDA graph per buffer
+        slot (after one eager pass) and replays it: the launch-bound small-batch configurations (8 x 256^2 is 0.3 ms of
+        GPU work behind 35 launches) then cost one launch per batch."""
         self.model = model
         self.img_size = img_size
         self.background_radius = background_radius
@@ -56,6 +59,7 @@ class DropletPipeline:
         self._staging = None
         self._slots = [None, None]       # run_host_pipelined's device / pinned buffers, kept across calls
         self._streams = None
+        self.use_graphs = bool(use_graphs)
 
     # ------------------------------------------------------------------ device-resident entry
     def run_device(self, images: torch.Tensor, return_prob: bool = False, want_labels: bool = False,
@@ -156,7 +160,7 @@ class DropletPipeline:
                  "h_counts": torch.empty(B, dtype=torch.int32).pin_memory(),
                  "h_cols": torch.empty((7 if micron else 5, B, self.capacity), dtype=torch.float64).pin_memory(),
                  "ev_in": torch.cuda.Event(), "ev_run": torch.cuda.Event(), "ev_counts": torch.cuda.Event(),
-                 "ev_free": torch.cuda.Event()}
+                 "ev_free": torch.cuda.Event(), "graph": None, "uses": 0}
             d["ev_free"].record(s_run)
             return d
 
@@ -174,10 +178,22 @@ class DropletPipeline:
         def compute(k):
             sl = slots[k % 2]
             s_out = s_outs[k % 2]
-            with torch.cuda.stream(s_run):
-                s_run.wait_event(sl["ev_in"])
+            def work():
                 self.run_device(sl["dev_in"], mask_out=sl["masks"], tables_out=sl["tables"], want_overlay=want_overlay,
                                 stencil_out=sl["stencil"])
+            if self.use_graphs and sl["graph"] is None and sl["uses"] >= 1:
+                # second use of the slot: every buffer the batch touches exists and is static -> capture once
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    work()
+                sl["graph"] = g
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(sl["ev_in"])
+                if sl["graph"] is not None:
+                    sl["graph"].replay()
+                else:
+                    work()
+                sl["uses"] += 1
                 sl["ev_run"].record(s_run)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(sl["ev_run"])
