@@ -296,6 +296,13 @@ def run_config4(pipe, dev, rank, world, frames_total, batch, size, barrier, dist
            "sharding": f"frame i -> rank i mod {world}; tables gathered to rank 0 and merged in frame order inside the timed region"}
     if rank == 0:
         import hashlib
+        # frames repeat with period 128 (frame_content): every repeat must give the same table rows
+        offs = np.concatenate([[0], np.cumsum(merged_counts)])
+        mism = 0
+        for i in range(128, frames_total):
+            a, b = merged[offs[i - 128]:offs[i - 128 + 1]], merged[offs[i]:offs[i + 1]]
+            mism += int(a.shape != b.shape or not np.array_equal(a.view(np.int64), b.view(np.int64)))
+        out["repeat_mismatches"] = mism
         h = hashlib.sha256()
         h.update(merged_counts.tobytes())
         h.update(np.ascontiguousarray(merged).tobytes())

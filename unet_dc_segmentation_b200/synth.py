@@ -97,6 +97,17 @@ def calibrated_state_dict(seed: int = 0, calib_size: int = 512, n_calib: int = 1
     import torch
     import torch.nn.functional as F
 
+    # The statistics and the least-squares fit are CPU reductions whose summation order follows the thread count:
+    # pin it, so that every process (any rank count, any box) manufactures bit-identical weights.
+    prev_threads = torch.get_num_threads()
+    torch.set_num_threads(4)
+    try:
+        return _calibrated_state_dict(torch, F, seed, calib_size, n_calib, prob_thresh, dilations, fit_head)
+    finally:
+        torch.set_num_threads(prev_threads)
+
+
+def _calibrated_state_dict(torch, F, seed, calib_size, n_calib, prob_thresh, dilations, fit_head):
     sd = default_init_state_dict(seed)
     frames, truth = [], []
     for i in range(n_calib):
