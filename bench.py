@@ -234,11 +234,14 @@ def frame_content(base, i):
 
 
 def run_config4(pipe, dev, rank, world, frames_total, batch, size, barrier, dist):
-    """BASELINE configs[3]: frames_total frames, frame i -> rank i mod world (shard.py), each rank streams its batches
-    through DropletPipeline.run_host_pipelined (pinned host frames -> host masks + tables), then the per-droplet tables
-    are gathered on rank 0 and merged in frame order -- all inside the timed region."""
+    """BASELINE configs[3]: frames_total frames, frame i -> rank i mod world (shard.py).  Each rank streams its batches
+    through DropletPipeline.run_host_pipelined (pinned host frames up, host masks down; the masks stay with the rank that
+    computed them, as qdb:58 writes them there) with the tables archived on the device; at the end the per-droplet
+    tables are compacted, gathered on rank 0 over NCCL, put into frame order and read back to the host once -- all
+    inside the timed region."""
     import torch
     from unet_dc_segmentation_b200 import shard
+    from unet_dc_segmentation_b200.quantify import alloc_tables
     base = make_frames(8, size)
     mine = shard.shard_indices(frames_total, rank, world)
     groups = shard.batches(mine, batch)
@@ -249,42 +252,52 @@ def run_config4(pipe, dev, rank, world, frames_total, batch, size, barrier, dist
             uniq[key] = frame_content(base, i)
         return uniq[key]
     staged = [torch.from_numpy(np.stack([content(i) for i in g])).pin_memory() for g in groups]
-    names = ["area", "equivalent_diameter", "centroid-0", "centroid-1", "area_sqmicron", "eq_diam_micron"]
+    ncol = 6
+    archive = alloc_tables(len(mine), pipe.capacity, True, dev)
+    nf = (frames_total + world - 1) // world
+    host_rows = torch.empty((frames_total * 4096, ncol), dtype=torch.float64).pin_memory() if rank == 0 else None
     barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
-    counts, rows, mask_px = [], [], 0
-    for (m_h, tabs) in pipe.run_host_pipelined(iter(staged), dev, copy=False):
-        mask_px += int(m_h.size)                      # masks stay with the rank that computed them (qdb:58 writes them there)
-        for t in tabs:
-            counts.append(len(t["label"]))
-            rows.append(np.stack([np.asarray(t[c]).astype(np.float64) if c != "area" else np.asarray(t[c]).view(np.float64)
-                                  for c in names], axis=1))
-    local = np.concatenate(rows) if rows else np.zeros((0, len(names)))
-    lc = np.asarray(counts, np.int64)
+    mask_px = 0
+    for (m_h, _) in pipe.run_host_pipelined(iter(staged), dev, copy=False, tables_archive=archive):
+        mask_px += int(m_h.size)
+    counts, rows = archive.compact_rows()                      # device: int64 [len(mine)], f64 [R, 6]
     if world > 1:
-        n_rows = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+        n_rows = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
         all_rows = [torch.zeros_like(n_rows) for _ in range(world)]
         dist.all_gather(all_rows, n_rows)
         maxr = int(max(int(v.item()) for v in all_rows))
-        nf = (frames_total + world - 1) // world
-        buf = torch.zeros((maxr, len(names)), dtype=torch.float64, device=dev)
-        buf[:local.shape[0]] = torch.from_numpy(local).to(dev)
+        buf = torch.zeros((maxr, ncol), dtype=torch.float64, device=dev)
+        buf[:rows.shape[0]] = rows
         cbuf = torch.zeros(nf, dtype=torch.int64, device=dev)
-        cbuf[:len(lc)] = torch.from_numpy(lc).to(dev)
+        cbuf[:counts.shape[0]] = counts
         gr = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
         gc = [torch.empty_like(cbuf) for _ in range(world)] if rank == 0 else None
         dist.gather(buf, gr, dst=0)
         dist.gather(cbuf, gc, dst=0)
-        merged = None
-        if rank == 0:
-            per_rank_rows = [g.cpu().numpy() for g in gr]
-            per_rank_counts = [g.cpu().numpy() for g in gc]
-            offs = [np.concatenate([[0], np.cumsum(c)]) for c in per_rank_counts]
-            merged = np.concatenate([per_rank_rows[i % world][offs[i % world][i // world]:offs[i % world][i // world + 1]]
-                                     for i in range(frames_total)])
-            merged_counts = np.array([per_rank_counts[i % world][i // world] for i in range(frames_total)], np.int64)
     else:
-        merged, merged_counts = local, lc
+        gr, gc, maxr = [rows], [counts], rows.shape[0]
+    merged = merged_counts = None
+    if rank == 0:
+        # frame order on the device: frame i is image i // world of rank i % world
+        cnt = torch.stack([torch.nn.functional.pad(c, (0, nf - c.shape[0])) for c in gc])          # [world, nf]
+        off = torch.cumsum(cnt, 1) - cnt                                                           # row offset inside a rank
+        fi = torch.arange(frames_total, device=dev)
+        r_of, j_of = fi % world, fi // world
+        f_cnt = cnt[r_of, j_of]
+        f_start = r_of * maxr + off[r_of, j_of]                                                    # row in the stacked gather
+        out_start = torch.cumsum(f_cnt, 0) - f_cnt
+        total = int(f_cnt.sum().item())
+        idx = torch.repeat_interleave(f_start - out_start, f_cnt) + torch.arange(total, device=dev)
+        stacked = torch.cat([g[:maxr] for g in gr]) if world > 1 else gr[0]
+        merged_dev = stacked[idx]
+        if total <= host_rows.shape[0]:
+            host_rows[:total].copy_(merged_dev, non_blocking=True)
+            torch.cuda.synchronize()
+            merged = host_rows[:total].numpy()
+        else:
+            merged = merged_dev.cpu().numpy()
+        merged_counts = f_cnt.cpu().numpy()
     torch.cuda.synchronize(); barrier()
     dt = time.perf_counter() - t0
     if world > 1:

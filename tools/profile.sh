@@ -4,7 +4,7 @@
 # and tools/metrics_table.py (see profiles/README.md).
 # usage (under gpurun, repo root): bash tools/profile.sh <tag>
 TAG=${1:-r01}
-ARGS="--steps 2 --warmup 3 --no-cpu-baseline"
+ARGS="--steps 2 --warmup 3 --no-cpu-baseline --frames 0"
 M="gpu__time_duration.sum,launch__grid_size,launch__block_size,launch__registers_per_thread,launch__shared_mem_per_block_dynamic,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__throughput.avg.pct_of_peak_sustained_elapsed,l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed,l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum,l1tex__m_xbar2l1tex_read_bytes.sum,lts__t_sector_hit_rate.pct,sm__cycles_elapsed.avg,smsp__inst_executed.sum"
 mkdir -p gpurun_out
 python bench.py $ARGS > gpurun_out/plain_$TAG.json 2> gpurun_out/plain_$TAG.err || { echo "plain run failed"; tail gpurun_out/plain_$TAG.err; exit 1; }
@@ -13,6 +13,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-fil
 # one warm forward = 22 launches (stem + 21 conv); 3 warm-up steps precede it
 ncu --metrics $M --clock-control none -k regex:'conv_|stem_' -s 66 -c 22 --csv --log-file gpurun_out/fwd_metrics_$TAG.csv \
     python bench.py $ARGS > /dev/null 2>&1; echo "forward metrics rc=$?"
-ncu --metrics $M --clock-control none -k regex:'morph_|stretch_|ccl_|init_minmax' -s 36 -c 12 --csv --log-file gpurun_out/aux_metrics_$TAG.csv \
+ncu --metrics $M --clock-control none -k regex:'morph_|stretch_|ccl_' -s 30 -c 10 --csv --log-file gpurun_out/aux_metrics_$TAG.csv \
     python bench.py $ARGS > /dev/null 2>&1; echo "aux metrics rc=$?"
 du -sh gpurun_out

@@ -68,7 +68,9 @@ class DropletPipeline:
         """images: CUDA u8 [B,H,W] grayscale or [B,H,W,3].  mask_out / tables_out / stencil_out: preallocated outputs.
         want_overlay: also compute the pixels the reference's findContours + drawContours paint (qdb:76-77)."""
         _lib.require_cuda(images, "images")
+        nvtx = torch.cuda.nvtx                    # ranges per stage (visible to nsys / ncu --nvtx; free otherwise)
         x = images
+        nvtx.range_push("dc:rolling_ball")
         if self.background_radius:
             if self._rb_out is None or self._rb_out.shape != x.shape or self._rb_out.device != x.device:
                 self._rb_out = torch.empty_like(x)
@@ -77,6 +79,8 @@ class DropletPipeline:
                 need = rolling_ball_workspace_bytes(x.shape[0], x.shape[1], x.shape[2], 1 if x.dim() == 3 else x.shape[3])
                 self._rb_ws = torch.empty(need, dtype=torch.uint8, device=x.device)
             x = rolling_ball_device(x, self.background_radius, out=self._rb_out, workspace=self._rb_ws)
+        nvtx.range_pop()
+        nvtx.range_push("dc:forward")
         oh, ow = int(images.shape[1]), int(images.shape[2])
         resized = self.img_size is not None and (oh, ow) != (self.img_size, self.img_size)
         if resized:
@@ -85,11 +89,14 @@ class DropletPipeline:
             masks = resize_linear_u8_device(masks, (ow, oh), out=mask_out)                     # qdb:57
         else:
             masks, probs = self.model.predict_u8(x, self.prob_thresh, return_prob=return_prob, mask_out=mask_out)
+        nvtx.range_pop()
+        nvtx.range_push("dc:label_stats")
         need = label_workspace_bytes(*masks.shape)
         if self._ccl_ws is None or self._ccl_ws.device != masks.device or self._ccl_ws.numel() < need:
             self._ccl_ws = torch.empty(need, dtype=torch.uint8, device=masks.device)
         tables = label_stats_device(masks, self.min_area, self.px_per_micron, self.capacity,
                                     want_labels=want_labels, workspace=self._ccl_ws, out=tables_out)
+        nvtx.range_pop()
         stencil = None
         if want_overlay:
             need = overlay_workspace_bytes(*masks.shape)
@@ -122,7 +129,7 @@ class DropletPipeline:
 
     # ------------------------------------------------------------------ pipelined host entry
     def run_host_pipelined(self, batches, device: torch.device | str = "cuda", copy: bool = True,
-                           want_overlay: bool = False):
+                           want_overlay: bool = False, tables_archive: DropletTables | None = None):
         """Generator over host batches (each u8 [B,H,W] or [B,H,W,3], ideally pinned; all the same shape):
         yields (masks u8 numpy [B,H,W], list of per-image column dicts) per batch, in order.
 
@@ -134,7 +141,10 @@ class DropletPipeline:
         yields the masks as a VIEW of the pipeline's two-slot pinned read-back buffer instead: that view is valid
         only until the generator is advanced again (the next batch's read-back is queued into the other slot and the
         one after that into this one).  ``want_overlay``: yields (masks, tables, stencils) with the overlay stencil
-        of every mask (u8 [B,H,W], qdb:76-77)."""
+        of every mask (u8 [B,H,W], qdb:76-77).  ``tables_archive`` (from ``alloc_tables(total_frames, ...)``): the
+        tables stay on the DEVICE, batch after batch in consecutive rows of the archive, and ``None`` is yielded in
+        their place -- for jobs whose tables are merged elsewhere (sharded runs gather them to one rank) instead of being
+        read back batch by batch; the archive's capacity applies and is not grown."""
         dev = torch.device(device)
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
@@ -175,13 +185,22 @@ class DropletPipeline:
                 sl["dev_in"].copy_(host, non_blocking=True)
                 sl["ev_in"].record(s_in)
 
+        archive_pos = [0]
+
         def compute(k):
             sl = slots[k % 2]
             s_out = s_outs[k % 2]
+            tables_out = sl["tables"]
+            if tables_archive is not None:
+                nb = sl["dev_in"].shape[0]
+                tables_out = tables_archive.rows(archive_pos[0], archive_pos[0] + nb)
+                if tables_out.counts.shape[0] != nb:
+                    raise ValueError("tables_archive is too small for the frames streamed through it")
+                archive_pos[0] += nb
             def work():
-                self.run_device(sl["dev_in"], mask_out=sl["masks"], tables_out=sl["tables"], want_overlay=want_overlay,
+                self.run_device(sl["dev_in"], mask_out=sl["masks"], tables_out=tables_out, want_overlay=want_overlay,
                                 stencil_out=sl["stencil"])
-            if self.use_graphs and sl["graph"] is None and sl["uses"] >= 1:
+            if self.use_graphs and tables_archive is None and sl["graph"] is None and sl["uses"] >= 1:
                 # second use of the slot: every buffer the batch touches exists and is static -> capture once
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
@@ -207,6 +226,12 @@ class DropletPipeline:
             sl = slots[k % 2]
             s_out = s_outs[k % 2]
             t = sl["tables"]
+            if tables_archive is not None:
+                with torch.cuda.stream(s_out):
+                    sl["ev_free"].record(s_out)
+                s_out.synchronize()
+                masks = sl["h_masks"].numpy()
+                return (masks.copy() if copy else masks), None
             sl["ev_counts"].synchronize()
             counts = sl["h_counts"].numpy().copy()
             nmax = int(counts.max()) if counts.size else 0

@@ -33,6 +33,23 @@ class DropletTables:
     labels: torch.Tensor | None   # int32 [B,H,W]
     capacity: int
 
+    def rows(self, a: int, b: int) -> "DropletTables":
+        """Views of images [a, b) of this table (same memory): lets a caller archive many batches in one allocation."""
+        cut = lambda t: None if t is None else t[a:b]           # noqa: E731
+        return DropletTables(self.counts[a:b], self.area[a:b], self.centroid0[a:b], self.centroid1[a:b], self.eq_diam[a:b],
+                             cut(self.area_um2), cut(self.diam_um), cut(self.labels), self.capacity)
+
+    def compact_rows(self):
+        """Device-side compaction: (counts int64 [B], rows f64 [sum(min(counts, capacity)), C]) with the columns area (bit
+        pattern of the int64), equivalent_diameter, centroid-0, centroid-1 [, area_sqmicron, eq_diam_micron], image by
+        image.  One boolean-mask gather per column; synchronises (the row count is data dependent)."""
+        n = torch.clamp(self.counts.to(torch.int64), max=self.capacity)
+        valid = torch.arange(self.capacity, device=self.counts.device)[None, :] < n[:, None]
+        cols = [self.area.view(torch.float64), self.eq_diam, self.centroid0, self.centroid1]
+        if self.area_um2 is not None:
+            cols += [self.area_um2, self.diam_um]
+        return n, torch.stack([c[valid] for c in cols], dim=1)
+
     def to_host(self):
         """One D2H per column; returns a list (per image) of dicts of numpy columns."""
         counts = self.counts.cpu().numpy()
