@@ -256,11 +256,17 @@ def run_config4(pipe, dev, rank, world, frames_total, batch, size, barrier, dist
     archive = alloc_tables(len(mine), pipe.capacity, True, dev)
     nf = (frames_total + world - 1) // world
     host_rows = torch.empty((frames_total * 4096, ncol), dtype=torch.float64).pin_memory() if rank == 0 else None
+    if world > 1:                                              # first use of a collective sets up its connections
+        w = torch.zeros(8, dtype=torch.float64, device=dev)
+        dist.all_gather([torch.zeros_like(w) for _ in range(world)], w)
+        dist.gather(w, [torch.zeros_like(w) for _ in range(world)] if rank == 0 else None, dst=0)
     barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     mask_px = 0
     for (m_h, _) in pipe.run_host_pipelined(iter(staged), dev, copy=False, tables_archive=archive):
         mask_px += int(m_h.size)
+    torch.cuda.synchronize()
+    t_stream = time.perf_counter() - t0
     counts, rows = archive.compact_rows()                      # device: int64 [len(mine)], f64 [R, 6]
     if world > 1:
         n_rows = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
@@ -305,6 +311,7 @@ def run_config4(pipe, dev, rank, world, frames_total, batch, size, barrier, dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     out = {"frames_total": frames_total, "seconds": dt, "value": frames_total / dt, "unit": UNIT, "scaling": "strong",
+           "seconds_streaming_rank0": t_stream, "seconds_gather_merge_readback": dt - t_stream,
            "batches_per_rank": len(groups), "tail_batch": len(groups[-1]) if groups else 0,
            "sharding": f"frame i -> rank i mod {world}; tables gathered to rank 0 and merged in frame order inside the timed region"}
     if rank == 0:

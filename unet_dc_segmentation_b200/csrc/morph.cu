@@ -77,6 +77,14 @@ __device__ __forceinline__ unsigned lds(unsigned addr) {
     asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned lds_dyn(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_dyn(unsigned addr, unsigned v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 template <int IMM>
 __device__ __forceinline__ void sts(unsigned addr, unsigned v) {
     asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(addr), "n"(IMM), "r"(v) : "memory");
@@ -84,8 +92,8 @@ __device__ __forceinline__ void sts(unsigned addr, unsigned v) {
 
 // One morphology pass over planes addressed as in[((p/C)*H*W + y*W + x)*C + p%C] (in_c = C) and
 // written planar.  SUBTRACT: out = saturate(orig - result), plus a per-plane min/max reduction.
-// NB = tile rows / 32.
-template <bool IS_MAX, bool SUBTRACT, int NB>
+// NB = tile rows / 32; NA = 32-row groups of the haloed region this instantiation covers (RH <= 32 NA).
+template <bool IS_MAX, bool SUBTRACT, int NB, int NA>
 __global__ void __launch_bounds__(NT, 2) morph_chord_kernel(const uint8_t* __restrict__ in, int in_c,
                                                             uint8_t* __restrict__ out, const uint8_t* __restrict__ orig,
                                                             int orig_c, int H, int W, int* __restrict__ minmax,
@@ -94,9 +102,8 @@ __global__ void __launch_bounds__(NT, 2) morph_chord_kernel(const uint8_t* __res
     constexpr int TH = NB * 32;
     const int an = se.an, pad = se.pad, pitch = se.pitch, RH = se.RH, level_words = se.level_words;
     const unsigned ident = IS_MAX ? 0u : 0xffffffffu;
-    const int nA = (RH + 31) >> 5;                             // 32-row groups of the haloed region
-    unsigned* hbuf = smem + se.ntables * level_words;          // two chord tables of (32 nA) x HP words
-    const int hwords = nA * 32 * HP;
+    unsigned* hbuf = smem + se.ntables * level_words;          // two chord tables of (32 NA) x HP words
+    constexpr int hwords = NA * 32 * HP;
 
     const int plane = blockIdx.z;
     const int b = plane / in_c, c = plane % in_c;
@@ -107,56 +114,82 @@ __global__ void __launch_bounds__(NT, 2) morph_chord_kernel(const uint8_t* __res
         minmax[2 * plane + 1] = 0;
     }
 
-    // ---- stage the tile + halo (range table 0), identity outside the image: one warp per region row ----
+    // ---- stage the tile + halo (range table 0) and build the range tables, one warp per region row ----
+    // T_l[x] = op(T_{l-1}[x], T_{l-1}[x + 2^(l-1)]), identity outside the image / beyond the row.
     const uint8_t* src = in + (size_t)b * H * W * in_c + c;
-    if (in_c == 1 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0) {
-        // planar input with 4-pixel-aligned rows: one aligned word per 4 region bytes (x0 % 4 == 0 and W % 4 == 0,
-        // so a word lies wholly inside or wholly outside the image)
+    const int ntables = se.ntables;
+    if (in_c == 1 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0 && pitch <= 32) {
+        // planar input with 4-pixel-aligned rows and a region row of at most 32 words: a lane holds one word of the
+        // row (x0 % 4 == 0 and W % 4 == 0, so a word lies wholly inside or wholly outside the image) and the tables
+        // are built in registers -- the neighbour words come from shuffles, nothing is read back from shared memory
+        const int gx = x0 + 4 * lane;
+        const bool colok = lane < pitch && gx >= 0 && gx < W;
 #pragma unroll 4
         for (int ry = warp; ry < RH; ry += NT / 32) {
             const int gy = y0 + ry;
-            const bool rowok = gy >= 0 && gy < H;
-            for (int rxw = lane; rxw < pitch; rxw += 32) {
-                const int gx = x0 + 4 * rxw;
-                unsigned v = ident;
-                if (rowok && gx >= 0 && gx < W) v = __ldg(reinterpret_cast<const unsigned*>(src + (size_t)gy * W + gx));
-                smem[ry * pitch + rxw] = v;
+            unsigned v = ident;
+            if (colok && gy >= 0 && gy < H) v = __ldg(reinterpret_cast<const unsigned*>(src + (size_t)gy * W + gx));
+            unsigned* row = smem + ry * pitch + lane;
+            if (lane < pitch) row[0] = v;
+            for (int l = 1; l < ntables; ++l) {
+                const int step = 1 << (l - 1);                         // bytes
+                const int ws = step < 4 ? 1 : (step >> 2);             // words to the partner
+                unsigned nxt = __shfl_down_sync(0xffffffffu, v, ws);
+                if (lane + ws >= pitch) nxt = ident;
+                const unsigned bb = step < 4 ? __funnelshift_r(v, nxt, step * 8) : nxt;
+                // op on the four bytes through the 16-bit lanes of the DPX instruction
+                const unsigned e = vop3_16<IS_MAX>(prmt(v, 0u, 0x2200u), prmt(bb, 0u, 0x2200u), prmt(bb, 0u, 0x2200u));
+                const unsigned o = vop3_16<IS_MAX>(prmt(v, 0u, 0x3311u), prmt(bb, 0u, 0x3311u), prmt(bb, 0u, 0x3311u));
+                v = pack_lanes(e, o);
+                if (lane < pitch) row[l * level_words] = v;
             }
         }
     } else {
-        uint8_t* s8 = reinterpret_cast<uint8_t*>(smem);
-        for (int ry = warp; ry < RH; ry += NT / 32) {
-            const int gy = y0 + ry;
-            const bool rowok = gy >= 0 && gy < H;
-            for (int rx = lane; rx < pitch * 4; rx += 32) {
-                const int gx = x0 + rx;
-                uint8_t v = IS_MAX ? 0 : 255;
-                if (rowok && gx >= 0 && gx < W) v = src[((size_t)gy * W + gx) * in_c];
-                s8[ry * pitch * 4 + rx] = v;
+        if (in_c == 1 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0) {
+            for (int ry = warp; ry < RH; ry += NT / 32) {
+                const int gy = y0 + ry;
+                const bool rowok = gy >= 0 && gy < H;
+                for (int rxw = lane; rxw < pitch; rxw += 32) {
+                    const int gx = x0 + 4 * rxw;
+                    unsigned v = ident;
+                    if (rowok && gx >= 0 && gx < W) v = __ldg(reinterpret_cast<const unsigned*>(src + (size_t)gy * W + gx));
+                    smem[ry * pitch + rxw] = v;
+                }
+            }
+        } else {
+            uint8_t* s8 = reinterpret_cast<uint8_t*>(smem);
+            for (int ry = warp; ry < RH; ry += NT / 32) {
+                const int gy = y0 + ry;
+                const bool rowok = gy >= 0 && gy < H;
+                for (int rx = lane; rx < pitch * 4; rx += 32) {
+                    const int gx = x0 + rx;
+                    uint8_t v = IS_MAX ? 0 : 255;
+                    if (rowok && gx >= 0 && gx < W) v = src[((size_t)gy * W + gx) * in_c];
+                    s8[ry * pitch * 4 + rx] = v;
+                }
             }
         }
-    }
-    __syncthreads();
-    // ---- range tables: T_l[x] = op(T_{l-1}[x], T_{l-1}[x + 2^(l-1)]); a row is built by the warp that owns it ----
-    for (int ry = warp; ry < RH; ry += NT / 32) {
-        unsigned* row = smem + ry * pitch;
-        for (int l = 1; l < se.ntables; ++l) {
-            const unsigned* prev = row + (l - 1) * level_words;
-            unsigned* cur = row + l * level_words;
-            const int step = 1 << (l - 1);           // bytes
-            for (int rxw = lane; rxw < pitch; rxw += 32) {
-                const unsigned a = prev[rxw];
-                unsigned bb;
-                if (step < 4) {
-                    const unsigned nxt = (rxw + 1 < pitch) ? prev[rxw + 1] : ident;
-                    bb = __funnelshift_r(a, nxt, step * 8);
-                } else {
-                    const int ws = step >> 2;
-                    bb = (rxw + ws < pitch) ? prev[rxw + ws] : ident;
+        __syncthreads();
+        for (int ry = warp; ry < RH; ry += NT / 32) {          // a row is built by the warp that owns it
+            unsigned* row = smem + ry * pitch;
+            for (int l = 1; l < ntables; ++l) {
+                const unsigned* prev = row + (l - 1) * level_words;
+                unsigned* cur = row + l * level_words;
+                const int step = 1 << (l - 1);           // bytes
+                for (int rxw = lane; rxw < pitch; rxw += 32) {
+                    const unsigned a = prev[rxw];
+                    unsigned bb;
+                    if (step < 4) {
+                        const unsigned nxt = (rxw + 1 < pitch) ? prev[rxw + 1] : ident;
+                        bb = __funnelshift_r(a, nxt, step * 8);
+                    } else {
+                        const int ws = step >> 2;
+                        bb = (rxw + ws < pitch) ? prev[rxw + ws] : ident;
+                    }
+                    cur[rxw] = vop<IS_MAX>(a, bb);
                 }
-                cur[rxw] = vop<IS_MAX>(a, bb);
+                __syncwarp();
             }
-            __syncwarp();
         }
     }
     __syncthreads();
@@ -167,69 +200,59 @@ __global__ void __launch_bounds__(NT, 2) morph_chord_kernel(const uint8_t* __res
     // whatever follows the tables in shared memory and land in chord-table rows nobody reads.
     const int xw = lane & 15;
     const int row0 = warp + 16 * (lane >> 4);
-    unsigned he[A_ITS], ho[A_ITS];                // running chord minimum of this thread's region rows (16-bit lanes)
+    unsigned he[NA], ho[NA];                      // running chord minimum of this thread's region rows (16-bit lanes)
     unsigned ae[NB], ao[NB];                      // result of this thread's output rows
-    unsigned abase[A_ITS];                        // shared address of this thread's word in row (32 it + row0) of table 0
 #pragma unroll
-    for (int it = 0; it < A_ITS; ++it) {
-        he[it] = ho[it] = ident;
-        abase[it] = smem_u32(smem) + (unsigned)(((it * 32 + row0) * pitch + xw) * 4);
-    }
+    for (int it = 0; it < NA; ++it) he[it] = ho[it] = ident;
 #pragma unroll
     for (int it = 0; it < NB; ++it) ae[it] = ao[it] = ident;
+    const unsigned abase = smem_u32(smem) + (unsigned)((row0 * pitch + xw) * 4);
+    const unsigned astep = (unsigned)(32 * pitch * 4);          // bytes between a thread's rows in a range table
     const unsigned hbase = smem_u32(hbuf) + (unsigned)((row0 * HP + xw) * 4);
     constexpr int HSTEP = 32 * HP * 4;            // bytes between a thread's rows in a chord table
     const int nchords = se.nchords;
     for (int m = 0; m < nchords; ++m) {
         const Chord& ch = se.chord[m];
         const unsigned hb = hbase + (unsigned)((m & 1) * hwords * 4);
-        const bool four = ch.nf > 2;
-        const unsigned w0 = (unsigned)ch.f[0].woff * 4u, w1 = (unsigned)ch.f[1].woff * 4u;
-        const unsigned w2 = (unsigned)ch.f[2].woff * 4u, w3 = (unsigned)ch.f[3].woff * 4u;
+        const unsigned w0 = abase + (unsigned)ch.f[0].woff * 4u, w1 = abase + (unsigned)ch.f[1].woff * 4u;
         const unsigned e0 = ch.f[0].sel_e, o0 = ch.f[0].sel_o, e1 = ch.f[1].sel_e, o1 = ch.f[1].sel_o;
-        const unsigned e2 = ch.f[2].sel_e, o2 = ch.f[2].sel_o, e3 = ch.f[3].sel_e, o3 = ch.f[3].sel_o;
-#define DC_CHORD_STEP(it)                                                                                  \
-        if (it < nA) {                                                                                      \
-            const unsigned pa = abase[it] + w0, pb = abase[it] + w1;                                        \
-            const unsigned a0 = lds<0>(pa), a1 = lds<4>(pa), b0 = lds<0>(pb), b1 = lds<4>(pb);              \
-            he[it] = vop3_16<IS_MAX>(he[it], prmt(a0, a1, e0), prmt(b0, b1, e1));                           \
-            ho[it] = vop3_16<IS_MAX>(ho[it], prmt(a0, a1, o0), prmt(b0, b1, o1));                           \
-            if (four) {                                                                                     \
-                const unsigned pc = abase[it] + w2, pd = abase[it] + w3;                                    \
-                const unsigned c0 = lds<0>(pc), c1 = lds<4>(pc), d0 = lds<0>(pd), d1 = lds<4>(pd);          \
-                he[it] = vop3_16<IS_MAX>(he[it], prmt(c0, c1, e2), prmt(d0, d1, e3));                       \
-                ho[it] = vop3_16<IS_MAX>(ho[it], prmt(c0, c1, o2), prmt(d0, d1, o3));                       \
-            }                                                                                               \
-            sts<it * HSTEP>(hb, pack_lanes(he[it], ho[it]));                                                \
+        if (ch.nf <= 2) {
+#pragma unroll
+            for (int it = 0; it < NA; ++it) {
+                const unsigned pa = w0 + it * astep, pb = w1 + it * astep;
+                const unsigned a0 = lds<0>(pa), a1 = lds<4>(pa), b0 = lds<0>(pb), b1 = lds<4>(pb);
+                he[it] = vop3_16<IS_MAX>(he[it], prmt(a0, a1, e0), prmt(b0, b1, e1));
+                ho[it] = vop3_16<IS_MAX>(ho[it], prmt(a0, a1, o0), prmt(b0, b1, o1));
+                sts_dyn(hb + it * HSTEP, pack_lanes(he[it], ho[it]));
+            }
+        } else {
+            const unsigned w2 = abase + (unsigned)ch.f[2].woff * 4u, w3 = abase + (unsigned)ch.f[3].woff * 4u;
+            const unsigned e2 = ch.f[2].sel_e, o2 = ch.f[2].sel_o, e3 = ch.f[3].sel_e, o3 = ch.f[3].sel_o;
+#pragma unroll
+            for (int it = 0; it < NA; ++it) {
+                const unsigned pa = w0 + it * astep, pb = w1 + it * astep, pc = w2 + it * astep, pd = w3 + it * astep;
+                const unsigned a0 = lds<0>(pa), a1 = lds<4>(pa), b0 = lds<0>(pb), b1 = lds<4>(pb);
+                const unsigned c0 = lds<0>(pc), c1 = lds<4>(pc), d0 = lds<0>(pd), d1 = lds<4>(pd);
+                he[it] = vop3_16<IS_MAX>(he[it], prmt(a0, a1, e0), prmt(b0, b1, e1));
+                ho[it] = vop3_16<IS_MAX>(ho[it], prmt(a0, a1, o0), prmt(b0, b1, o1));
+                he[it] = vop3_16<IS_MAX>(he[it], prmt(c0, c1, e2), prmt(d0, d1, e3));
+                ho[it] = vop3_16<IS_MAX>(ho[it], prmt(c0, c1, o2), prmt(d0, d1, o3));
+                sts_dyn(hb + it * HSTEP, pack_lanes(he[it], ho[it]));
+            }
         }
-        DC_CHORD_STEP(0) DC_CHORD_STEP(1) DC_CHORD_STEP(2) DC_CHORD_STEP(3)
-        DC_CHORD_STEP(4) DC_CHORD_STEP(5) DC_CHORD_STEP(6) DC_CHORD_STEP(7)
-#undef DC_CHORD_STEP
         __syncthreads();
-        // every element row of this width, at the same x: aligned words of the chord table
-        int j = ch.row_begin;
+        // every element row of this width, at the same x: aligned words of the chord table, two rows per step (an
+        // odd count repeats its last row: min / max do not care)
         const int jend = ch.row_end;
-        for (; j + 1 < jend; j += 2) {
-            const unsigned q0 = hb + (unsigned)se.rowoff[j], q1 = hb + (unsigned)se.rowoff[j + 1];
-#define DC_ROW_PAIR(it)                                                                                    \
-            if (it < NB) {                                                                                  \
-                const unsigned v0 = lds<it * HSTEP>(q0), v1 = lds<it * HSTEP>(q1);                          \
-                ae[it < NB ? it : 0] = vop3_16<IS_MAX>(ae[it < NB ? it : 0], prmt(v0, 0u, 0x2200u), prmt(v1, 0u, 0x2200u)); \
-                ao[it < NB ? it : 0] = vop3_16<IS_MAX>(ao[it < NB ? it : 0], prmt(v0, 0u, 0x3311u), prmt(v1, 0u, 0x3311u)); \
-            }
-            DC_ROW_PAIR(0) DC_ROW_PAIR(1) DC_ROW_PAIR(2) DC_ROW_PAIR(3)
-#undef DC_ROW_PAIR
-        }
-        if (j < jend) {
+        for (int j = ch.row_begin; j < jend; j += 2) {
             const unsigned q0 = hb + (unsigned)se.rowoff[j];
-#define DC_ROW_ONE(it)                                                                                     \
-            if (it < NB) {                                                                                  \
-                const unsigned v0 = lds<it * HSTEP>(q0);                                                    \
-                ae[it < NB ? it : 0] = vop3_16<IS_MAX>(ae[it < NB ? it : 0], prmt(v0, 0u, 0x2200u), ae[it < NB ? it : 0]); \
-                ao[it < NB ? it : 0] = vop3_16<IS_MAX>(ao[it < NB ? it : 0], prmt(v0, 0u, 0x3311u), ao[it < NB ? it : 0]); \
+            const unsigned q1 = hb + (unsigned)se.rowoff[j + 1 < jend ? j + 1 : j];
+#pragma unroll
+            for (int it = 0; it < NB; ++it) {
+                const unsigned v0 = lds_dyn(q0 + it * HSTEP), v1 = lds_dyn(q1 + it * HSTEP);
+                ae[it] = vop3_16<IS_MAX>(ae[it], prmt(v0, 0u, 0x2200u), prmt(v1, 0u, 0x2200u));
+                ao[it] = vop3_16<IS_MAX>(ao[it], prmt(v0, 0u, 0x3311u), prmt(v1, 0u, 0x3311u));
             }
-            DC_ROW_ONE(0) DC_ROW_ONE(1) DC_ROW_ONE(2) DC_ROW_ONE(3)
-#undef DC_ROW_ONE
         }
         // (no second barrier: the next chord writes the other buffer, and the one after that is behind the
         //  next chord's barrier)
@@ -417,8 +440,9 @@ int build_plan(int k, int th, SEPlan* se) {
     return 0;
 }
 
+int plan_groups(const SEPlan& se) { return (se.th == 128 && se.RH <= 192) ? 6 : 8; }     // NA of the instantiation used
 size_t plan_smem_bytes(const SEPlan& se) {
-    return ((size_t)se.ntables * se.level_words + 2 * (size_t)(((se.RH + 31) >> 5) * 32) * HP) * 4;
+    return ((size_t)se.ntables * se.level_words + 2 * (size_t)(plan_groups(se) * 32) * HP) * 4;
 }
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -503,21 +527,22 @@ int launch_rolling_ball(const dc_rolling_ball_args_t* a, cudaStream_t stream) {
         DC_CUDA(cudaGetDevice(&dev));
         const unsigned long long bit = 1ull << (dev & 63);
         if (!(__atomic_load_n(&attr_done, __ATOMIC_ACQUIRE) & bit)) {      // per (function, device), once
-#define DC_MORPH_ATTR(nb)                                                                                                    \
-            DC_CUDA(cudaFuncSetAttribute(morph_chord_kernel<false, false, nb>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
-            DC_CUDA(cudaFuncSetAttribute(morph_chord_kernel<true, true, nb>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-            DC_MORPH_ATTR(4) DC_MORPH_ATTR(2) DC_MORPH_ATTR(1)
+#define DC_MORPH_ATTR(nb, na)                                                                                                    \
+            DC_CUDA(cudaFuncSetAttribute(morph_chord_kernel<false, false, nb, na>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
+            DC_CUDA(cudaFuncSetAttribute(morph_chord_kernel<true, true, nb, na>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            DC_MORPH_ATTR(4, 6) DC_MORPH_ATTR(4, 8) DC_MORPH_ATTR(2, 8) DC_MORPH_ATTR(1, 8)
 #undef DC_MORPH_ATTR
             __atomic_fetch_or(&attr_done, bit, __ATOMIC_RELEASE);
         }
     }
     dim3 grid(ceil_div(W, TW), ceil_div(H, th), planes);
-#define DC_MORPH_LAUNCH(nb)                                                                                              \
-    if (th == 32 * nb) {                                                                                                 \
-        morph_chord_kernel<false, false, nb><<<grid, NT, smem, stream>>>(a->in, a->C, er, nullptr, 0, H, W, minmax, se); \
-        morph_chord_kernel<true, true, nb><<<grid, NT, smem, stream>>>(er, 1, corr, a->in, a->C, H, W, minmax, se);      \
+    const int na = (th == 128 && se.RH <= 192) ? 6 : 8;        // 32-row groups the instantiation covers
+#define DC_MORPH_LAUNCH(nb, nax)                                                                                              \
+    if (th == 32 * nb && na == nax) {                                                                                         \
+        morph_chord_kernel<false, false, nb, nax><<<grid, NT, smem, stream>>>(a->in, a->C, er, nullptr, 0, H, W, minmax, se); \
+        morph_chord_kernel<true, true, nb, nax><<<grid, NT, smem, stream>>>(er, 1, corr, a->in, a->C, H, W, minmax, se);      \
     }
-    DC_MORPH_LAUNCH(4) DC_MORPH_LAUNCH(2) DC_MORPH_LAUNCH(1)
+    DC_MORPH_LAUNCH(4, 6) DC_MORPH_LAUNCH(4, 8) DC_MORPH_LAUNCH(2, 8) DC_MORPH_LAUNCH(1, 8)
 #undef DC_MORPH_LAUNCH
     int sblocks = ceil_div(H * W, 256 * 64);
     if (sblocks > 1024) sblocks = 1024;
