@@ -49,7 +49,8 @@ struct Chord {
 struct SEPlan {
     int k, an, pad, pitch, RH, level_words, ntables, nchords, th;
     Chord chord[MAX_CHORDS];
-    int rowoff[MAX_ROWS];         // byte offset (dy + an) * HP * 4 of the rows inside a chord table, grouped by chord
+    int rowoff[MAX_ROWS + MAX_CHORDS];   // byte offset (dy + an) * HP * 4 of the rows inside a chord table, grouped by
+                                         // chord, each chord's list padded to an even length (last row repeated)
 };
 
 template <bool IS_MAX>
@@ -93,14 +94,16 @@ __device__ __forceinline__ void sts(unsigned addr, unsigned v) {
 // One morphology pass over planes addressed as in[((p/C)*H*W + y*W + x)*C + p%C] (in_c = C) and
 // written planar.  SUBTRACT: out = saturate(orig - result), plus a per-plane min/max reduction.
 // NB = tile rows / 32; NA = 32-row groups of the haloed region this instantiation covers (RH <= 32 NA).
-template <bool IS_MAX, bool SUBTRACT, int NB, int NA>
+// PITCH / NTAB > 0: the region pitch and the number of range tables are compile-time (the instantiation for the
+// reference's default radius 50: every shared-memory offset of the chord loop becomes an immediate).
+template <bool IS_MAX, bool SUBTRACT, int NB, int NA, int PITCH, int NTAB>
 __global__ void __launch_bounds__(NT, 2) morph_chord_kernel(const uint8_t* __restrict__ in, int in_c,
                                                             uint8_t* __restrict__ out, const uint8_t* __restrict__ orig,
                                                             int orig_c, int H, int W, int* __restrict__ minmax,
                                                             const __grid_constant__ SEPlan se) {
     extern __shared__ unsigned smem[];
     constexpr int TH = NB * 32;
-    const int an = se.an, pad = se.pad, pitch = se.pitch, RH = se.RH, level_words = se.level_words;
+    const int an = se.an, pad = se.pad, pitch = PITCH ? PITCH : se.pitch, RH = se.RH, level_words = pitch * RH;
     const unsigned ident = IS_MAX ? 0u : 0xffffffffu;
     unsigned* hbuf = smem + se.ntables * level_words;          // two chord tables of (32 NA) x HP words
     constexpr int hwords = NA * 32 * HP;
@@ -117,31 +120,38 @@ __global__ void __launch_bounds__(NT, 2) morph_chord_kernel(const uint8_t* __res
     // ---- stage the tile + halo (range table 0) and build the range tables, one warp per region row ----
     // T_l[x] = op(T_{l-1}[x], T_{l-1}[x + 2^(l-1)]), identity outside the image / beyond the row.
     const uint8_t* src = in + (size_t)b * H * W * in_c + c;
-    const int ntables = se.ntables;
+    const int ntables = NTAB ? NTAB : se.ntables;
     if (in_c == 1 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0 && pitch <= 32) {
         // planar input with 4-pixel-aligned rows and a region row of at most 32 words: a lane holds one word of the
         // row (x0 % 4 == 0 and W % 4 == 0, so a word lies wholly inside or wholly outside the image) and the tables
         // are built in registers -- the neighbour words come from shuffles, nothing is read back from shared memory
         const int gx = x0 + 4 * lane;
         const bool colok = lane < pitch && gx >= 0 && gx < W;
+        const uint8_t* colp = src + gx;                                // this lane's column (dereferenced only when colok)
+        const unsigned sbase = smem_u32(smem) + (unsigned)(lane * 4);
+        const unsigned lw4 = (unsigned)level_words * 4u;
 #pragma unroll 4
         for (int ry = warp; ry < RH; ry += NT / 32) {
             const int gy = y0 + ry;
             unsigned v = ident;
-            if (colok && gy >= 0 && gy < H) v = __ldg(reinterpret_cast<const unsigned*>(src + (size_t)gy * W + gx));
-            unsigned* row = smem + ry * pitch + lane;
-            if (lane < pitch) row[0] = v;
-            for (int l = 1; l < ntables; ++l) {
-                const int step = 1 << (l - 1);                         // bytes
-                const int ws = step < 4 ? 1 : (step >> 2);             // words to the partner
-                unsigned nxt = __shfl_down_sync(0xffffffffu, v, ws);
-                if (lane + ws >= pitch) nxt = ident;
-                const unsigned bb = step < 4 ? __funnelshift_r(v, nxt, step * 8) : nxt;
-                // op on the four bytes through the 16-bit lanes of the DPX instruction
-                const unsigned e = vop3_16<IS_MAX>(prmt(v, 0u, 0x2200u), prmt(bb, 0u, 0x2200u), prmt(bb, 0u, 0x2200u));
-                const unsigned o = vop3_16<IS_MAX>(prmt(v, 0u, 0x3311u), prmt(bb, 0u, 0x3311u), prmt(bb, 0u, 0x3311u));
-                v = pack_lanes(e, o);
-                if (lane < pitch) row[l * level_words] = v;
+            if (colok && (unsigned)gy < (unsigned)H) v = __ldg(reinterpret_cast<const unsigned*>(colp + (size_t)gy * W));
+            const unsigned row = sbase + (unsigned)(ry * pitch * 4);
+            if (lane < pitch) sts_dyn(row, v);
+#pragma unroll
+            for (int l = 1; l < MAX_TABLES; ++l) {
+                if (l < ntables) {
+                    const int step = 1 << (l - 1);                         // bytes (compile time)
+                    const int ws = step < 4 ? 1 : (step >> 2);             // words to the partner
+                    unsigned nxt = __shfl_down_sync(0xffffffffu, v, ws);
+                    if (lane + ws >= pitch) nxt = ident;
+                    const unsigned bb = step < 4 ? __funnelshift_r(v, nxt, step * 8) : nxt;
+                    // op on the four bytes through the 16-bit lanes of the DPX instruction
+                    const unsigned be = prmt(bb, 0u, 0x2200u), bo = prmt(bb, 0u, 0x3311u);
+                    const unsigned e = vop3_16<IS_MAX>(prmt(v, 0u, 0x2200u), be, be);
+                    const unsigned o = vop3_16<IS_MAX>(prmt(v, 0u, 0x3311u), bo, bo);
+                    v = pack_lanes(e, o);
+                    if (lane < pitch) sts_dyn(row + l * lw4, v);
+                }
             }
         }
     } else {
@@ -207,7 +217,8 @@ __global__ void __launch_bounds__(NT, 2) morph_chord_kernel(const uint8_t* __res
 #pragma unroll
     for (int it = 0; it < NB; ++it) ae[it] = ao[it] = ident;
     const unsigned abase = smem_u32(smem) + (unsigned)((row0 * pitch + xw) * 4);
-    const unsigned astep = (unsigned)(32 * pitch * 4);          // bytes between a thread's rows in a range table
+    const unsigned astep = (unsigned)(32 * pitch * 4);          // bytes between a thread's rows in a range table (an
+                                                                // immediate when PITCH is a template constant)
     const unsigned hbase = smem_u32(hbuf) + (unsigned)((row0 * HP + xw) * 4);
     constexpr int HSTEP = 32 * HP * 4;            // bytes between a thread's rows in a chord table
     const int nchords = se.nchords;
@@ -241,12 +252,12 @@ __global__ void __launch_bounds__(NT, 2) morph_chord_kernel(const uint8_t* __res
             }
         }
         __syncthreads();
-        // every element row of this width, at the same x: aligned words of the chord table, two rows per step (an
-        // odd count repeats its last row: min / max do not care)
+        // every element row of this width, at the same x: aligned words of the chord table, two rows per step (the
+        // plan pads an odd count by repeating its last row: min / max do not care)
         const int jend = ch.row_end;
         for (int j = ch.row_begin; j < jend; j += 2) {
             const unsigned q0 = hb + (unsigned)se.rowoff[j];
-            const unsigned q1 = hb + (unsigned)se.rowoff[j + 1 < jend ? j + 1 : j];
+            const unsigned q1 = hb + (unsigned)se.rowoff[j + 1];
 #pragma unroll
             for (int it = 0; it < NB; ++it) {
                 const unsigned v0 = lds_dyn(q0 + it * HSTEP), v1 = lds_dyn(q1 + it * HSTEP);
@@ -430,6 +441,7 @@ int build_plan(int k, int th, SEPlan* se) {
                 used[i] = true;
                 se->rowoff[nrows++] = i * HP * 4;                  // (dy + an) * HP words, in bytes (dy = i - an)
             }
+        if ((nrows - ch.row_begin) & 1) { se->rowoff[nrows] = se->rowoff[nrows - 1]; ++nrows; }
         ch.row_end = nrows;
         plo = clo; phi = chi;
         se->nchords = m + 1;
@@ -476,7 +488,7 @@ int rolling_ball_plan_dump(int radius, int th, int* out, int cap) {
     SEPlan se;
     DC_REQUIRE(out && radius >= 1 && th >= 1 && th <= TH_MAX, DC_EINVAL, "dc_debug_rolling_ball_plan: bad argument");
     DC_REQUIRE(build_plan(radius, th, &se) == 0, DC_EINVAL, "dc_debug_rolling_ball_plan: no plan for radius %d", radius);
-    const int nrows = se.chord[se.nchords - 1].row_end;
+    const int nrows = se.chord[se.nchords - 1].row_end;          // (includes the pair padding)
     const int need = 10 + 11 * se.nchords + nrows;
     DC_REQUIRE(cap >= need, DC_EINVAL, "dc_debug_rolling_ball_plan: need %d ints", need);
     int n = 0;
@@ -527,22 +539,26 @@ int launch_rolling_ball(const dc_rolling_ball_args_t* a, cudaStream_t stream) {
         DC_CUDA(cudaGetDevice(&dev));
         const unsigned long long bit = 1ull << (dev & 63);
         if (!(__atomic_load_n(&attr_done, __ATOMIC_ACQUIRE) & bit)) {      // per (function, device), once
-#define DC_MORPH_ATTR(nb, na)                                                                                                    \
-            DC_CUDA(cudaFuncSetAttribute(morph_chord_kernel<false, false, nb, na>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
-            DC_CUDA(cudaFuncSetAttribute(morph_chord_kernel<true, true, nb, na>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-            DC_MORPH_ATTR(4, 6) DC_MORPH_ATTR(4, 8) DC_MORPH_ATTR(2, 8) DC_MORPH_ATTR(1, 8)
+#define DC_MORPH_ATTR(nb, na, pi, nt)                                                                                           \
+            DC_CUDA(cudaFuncSetAttribute(morph_chord_kernel<false, false, nb, na, pi, nt>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
+            DC_CUDA(cudaFuncSetAttribute(morph_chord_kernel<true, true, nb, na, pi, nt>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            DC_MORPH_ATTR(4, 6, 31, 3) DC_MORPH_ATTR(4, 6, 0, 0) DC_MORPH_ATTR(4, 8, 0, 0) DC_MORPH_ATTR(2, 8, 0, 0) DC_MORPH_ATTR(1, 8, 0, 0)
 #undef DC_MORPH_ATTR
             __atomic_fetch_or(&attr_done, bit, __ATOMIC_RELEASE);
         }
     }
     dim3 grid(ceil_div(W, TW), ceil_div(H, th), planes);
-    const int na = (th == 128 && se.RH <= 192) ? 6 : 8;        // 32-row groups the instantiation covers
-#define DC_MORPH_LAUNCH(nb, nax)                                                                                              \
-    if (th == 32 * nb && na == nax) {                                                                                         \
-        morph_chord_kernel<false, false, nb, nax><<<grid, NT, smem, stream>>>(a->in, a->C, er, nullptr, 0, H, W, minmax, se); \
-        morph_chord_kernel<true, true, nb, nax><<<grid, NT, smem, stream>>>(er, 1, corr, a->in, a->C, H, W, minmax, se);      \
+    const int na = plan_groups(se);                            // 32-row groups the instantiation covers
+    // the reference's default radius (50; also its neighbours with the same region pitch and table count) runs the
+    // instantiation with compile-time shared-memory offsets
+    const bool special = th == 128 && na == 6 && se.pitch == 31 && se.ntables == 3;
+#define DC_MORPH_LAUNCH(nb, nax, pi, nt, cond)                                                                                    \
+    if (th == 32 * nb && na == nax && (cond)) {                                                                                   \
+        morph_chord_kernel<false, false, nb, nax, pi, nt><<<grid, NT, smem, stream>>>(a->in, a->C, er, nullptr, 0, H, W, minmax, se); \
+        morph_chord_kernel<true, true, nb, nax, pi, nt><<<grid, NT, smem, stream>>>(er, 1, corr, a->in, a->C, H, W, minmax, se);      \
     }
-    DC_MORPH_LAUNCH(4, 6) DC_MORPH_LAUNCH(4, 8) DC_MORPH_LAUNCH(2, 8) DC_MORPH_LAUNCH(1, 8)
+    DC_MORPH_LAUNCH(4, 6, 31, 3, special) DC_MORPH_LAUNCH(4, 6, 0, 0, !special) DC_MORPH_LAUNCH(4, 8, 0, 0, true)
+    DC_MORPH_LAUNCH(2, 8, 0, 0, true) DC_MORPH_LAUNCH(1, 8, 0, 0, true)
 #undef DC_MORPH_LAUNCH
     int sblocks = ceil_div(H * W, 256 * 64);
     if (sblocks > 1024) sblocks = 1024;
