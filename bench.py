@@ -266,6 +266,8 @@ def run_config4(pipe, dev, rank, world, frames_total, batch, size, barrier, dist
     for (m_h, _) in pipe.run_host_pipelined(iter(staged), dev, copy=False, tables_archive=archive):
         mask_px += int(m_h.size)
     torch.cuda.synchronize()
+    t_stream_own = time.perf_counter() - t0
+    barrier()                                                  # (the gather below would wait for the slowest rank anyway)
     t_stream = time.perf_counter() - t0
     counts, rows = archive.compact_rows()                      # device: int64 [len(mine)], f64 [R, 6]
     if world > 1:
@@ -311,7 +313,8 @@ def run_config4(pipe, dev, rank, world, frames_total, batch, size, barrier, dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     out = {"frames_total": frames_total, "seconds": dt, "value": frames_total / dt, "unit": UNIT, "scaling": "strong",
-           "seconds_streaming_rank0": t_stream, "seconds_gather_merge_readback": dt - t_stream,
+           "seconds_streaming_rank0": t_stream_own, "seconds_streaming_slowest_rank": t_stream,
+           "seconds_gather_merge_readback": dt - t_stream,
            "batches_per_rank": len(groups), "tail_batch": len(groups[-1]) if groups else 0,
            "sharding": f"frame i -> rank i mod {world}; tables gathered to rank 0 and merged in frame order inside the timed region"}
     if rank == 0:

@@ -115,3 +115,27 @@ def test_shard_helpers():
     with pytest.raises(ValueError):
         shard.merge_in_frame_order(per_rank + [[(0, "dup")]], 7)
     assert shard.gather_results([(0, "a"), (1, "b")], 2) == ["a", "b"]       # no process group: identity
+
+
+def test_combined_csv_text_equals_pandas_concat():
+    """cli.combined_csv_text (all_droplets.csv from the per-image CSV bodies) is byte-identical to what the reference
+    writes (pd.concat(all_props).to_csv, qdb:165-166), and declines whenever a frame has no droplets."""
+    import numpy as np
+    import pandas as pd
+    from unet_dc_segmentation_b200 import cli
+    rs = np.random.RandomState(0)
+    frames = []
+    for k in range(4):
+        n = int(rs.randint(1, 40))
+        a = rs.randint(1, 500, n).astype(np.int64)
+        df = pd.DataFrame({"label": np.arange(1, n + 1), "area": a, "equivalent_diameter": np.sqrt(4 * a / np.pi),
+                           "centroid-0": rs.rand(n) * 1024, "centroid-1": rs.rand(n) * 1e-7,
+                           "area_sqmicron": a / (3.45 ** 2), "eq_diam_micron": np.sqrt(4 * a / np.pi) / 3.45})
+        df.insert(0, "filename", f"f{k}.png")
+        frames.append(df)
+    texts = [df.to_csv(index=False) for df in frames]
+    assert cli.combined_csv_text(frames, texts) == pd.concat(frames, ignore_index=True).to_csv(index=False)
+    empty = pd.DataFrame()
+    empty.insert(0, "filename", "none.png")
+    assert cli.combined_csv_text(frames + [empty], texts + [empty.to_csv(index=False)]) is None
+    assert cli.combined_csv_text(frames, None) is None

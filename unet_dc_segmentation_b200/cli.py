@@ -50,8 +50,9 @@ def _device() -> torch.device:
 def load_model(ckpt) -> UNetDC:
     """qdb:34-37: build UNetDC(3, 1), load the checkpoint's state_dict, eval mode on the GPU."""
     dev = _device()
-    m = UNetDC(in_channels=3, out_channels=1)
-    m.load_state_dict(torch.load(ckpt, map_location=dev))
+    with torch.device("meta"):                     # no random initialisation of 31 M parameters that are about to be replaced
+        m = UNetDC(in_channels=3, out_channels=1)
+    m.load_state_dict(torch.load(ckpt, map_location=dev), assign=True)
     return m.to(dev).eval()
 
 
@@ -130,7 +131,20 @@ def save_density_maps(fpath, name, mask_dev, density_dir) -> None:
     plt.imsave(Path(density_dir) / f"{name}_spatial_density.png", normalize(spatial), cmap="hot")    # qpl:141
 
 
-def write_reports(out_dir: Path, per_image_rows, all_props, skip_excel: bool, skip_histogram: bool) -> None:
+def combined_csv_text(all_props, csv_texts):
+    """all_droplets.csv without formatting every number a second time: when every frame has droplets (so that every
+    per-image table has the same columns and dtypes) the text of ``pd.concat(all_props).to_csv(index=False)`` is the
+    header plus the bodies of the per-image CSVs.  Returns None when that does not hold (pandas does it then)."""
+    if not csv_texts or len(csv_texts) != len(all_props) or any(t is None for t in csv_texts):
+        return None
+    cols = list(all_props[0].columns)
+    if any(df.empty or list(df.columns) != cols for df in all_props):
+        return None
+    header = csv_texts[0].split("\n", 1)[0] + "\n"
+    return header + "".join(t.split("\n", 1)[1] for t in csv_texts)
+
+
+def write_reports(out_dir: Path, per_image_rows, all_props, skip_excel: bool, skip_histogram: bool, csv_texts=None) -> None:
     """qdb:163-199: summary_per_image.csv, all_droplets.csv (+xlsx or the noexcel copy), stats, histogram."""
     import pandas as pd
     summary_df = pd.DataFrame(per_image_rows)
@@ -138,7 +152,11 @@ def write_reports(out_dir: Path, per_image_rows, all_props, skip_excel: bool, sk
     if not all_props:
         return
     combined = pd.concat(all_props, ignore_index=True)
-    combined.to_csv(out_dir / "all_droplets.csv", index=False)
+    text = combined_csv_text(all_props, csv_texts)
+    if text is not None:
+        (out_dir / "all_droplets.csv").write_text(text)
+    else:
+        combined.to_csv(out_dir / "all_droplets.csv", index=False)
     if not skip_excel:
         try:
             import xlsxwriter  # noqa: F401
@@ -232,9 +250,12 @@ def run_fast(images, mine, model, args, out_dir, mask_dir, overlay_dir):
                 metas.append(cur_meta)
                 yield np.stack(cur)
 
-        def write_image(i, mask, stencil):
+        def write_image(i, mask, stencil, df):
             name = images[i].stem
             cv2.imwrite(str(Path(mask_dir) / f"{name}_pred.png"), mask * 255)                 # qdb:58
+            text = df.to_csv(index=False)                                                     # qdb:63
+            (Path(mask_dir).parent / f"{name}_droplets.csv").write_text(text)
+            return text
             if overlay_dir is not None:
                 img = cv2.imread(str(images[i]))                                              # qdb:75
                 if img is not None:
@@ -247,19 +268,17 @@ def run_fast(images, mine, model, args, out_dir, mask_dir, overlay_dir):
             masks, tables = res[0], res[1]
             stencils = res[2] if want_ov else None
             for b, i in enumerate(metas.popleft()):
-                jobs.append(writers.submit(write_image, i, masks[b], stencils[b] if want_ov else None))
                 df = _table_frame(tables[b], args.px_per_micron)
                 df.insert(0, "filename", images[i].name)                                      # qdb:62
-                df.to_csv(Path(mask_dir).parent / f"{images[i].stem}_droplets.csv", index=False)   # qdb:63
+                jobs.append(writers.submit(write_image, i, masks[b], stencils[b] if want_ov else None, df))
                 idx.append(i)
                 all_props.append(df)
                 per_image_rows.append({"filename": images[i].name, "droplet_count": len(df),
                                        "total_area_px": df["area"].sum() if not df.empty else 0})   # qdb:67-72
                 if args.density_maps:
                     save_density_maps(str(images[i]), images[i].stem, torch.from_numpy(masks[b]).to(dev)[None], out_dir)
-        for j in jobs:
-            j.result()
-    return idx, per_image_rows, all_props
+        csv_texts = [j.result() for j in jobs]
+    return idx, per_image_rows, all_props, csv_texts
 
 
 def build_parser() -> argparse.ArgumentParser:
@@ -311,6 +330,7 @@ def main(argv=None) -> int:
 
     tensors, meta, idx = [], [], []
     per_image_rows, all_props = [], []
+    csv_texts = None
 
     def flush():
         run_batch(tensors, meta, model, mask_dir, overlay_dir, args.prob_thresh, args.min_area, args.px_per_micron,
@@ -329,12 +349,14 @@ def main(argv=None) -> int:
         if tensors:
             flush()
     else:
-        idx, per_image_rows, all_props = run_fast(images, mine, model, args, out_dir, mask_dir, overlay_dir)
+        idx, per_image_rows, all_props, csv_texts = run_fast(images, mine, model, args, out_dir, mask_dir, overlay_dir)
 
-    local = [(i, (row, df)) for i, row, df in zip(idx, per_image_rows, all_props)]
+    texts = csv_texts if csv_texts is not None else [None] * len(idx)
+    local = [(i, (row, df, t)) for i, row, df, t in zip(idx, per_image_rows, all_props, texts)]
     merged = shard.gather_results(local, len(images), dst=0)
     if rank == 0:
-        write_reports(out_dir, [m[0] for m in merged], [m[1] for m in merged], args.skip_excel, args.skip_histogram)
+        write_reports(out_dir, [m[0] for m in merged], [m[1] for m in merged], args.skip_excel, args.skip_histogram,
+                      csv_texts=[m[2] for m in merged])
         print("\n All done. Outputs are in ", out_dir)
     if world > 1:
         import torch.distributed as dist
