@@ -270,6 +270,8 @@ def run_config4(pipe, dev, rank, world, frames_total, batch, size, barrier, dist
     barrier()                                                  # (the gather below would wait for the slowest rank anyway)
     t_stream = time.perf_counter() - t0
     counts, rows = archive.compact_rows()                      # device: int64 [len(mine)], f64 [R, 6]
+    torch.cuda.synchronize()
+    t_compact = time.perf_counter() - t0
     if world > 1:
         n_rows = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
         all_rows = [torch.zeros_like(n_rows) for _ in range(world)]
@@ -285,6 +287,8 @@ def run_config4(pipe, dev, rank, world, frames_total, batch, size, barrier, dist
         dist.gather(cbuf, gc, dst=0)
     else:
         gr, gc, maxr = [rows], [counts], rows.shape[0]
+    torch.cuda.synchronize()
+    t_gather = time.perf_counter() - t0
     merged = merged_counts = None
     if rank == 0:
         # frame order on the device: frame i is image i // world of rank i % world
@@ -315,6 +319,8 @@ def run_config4(pipe, dev, rank, world, frames_total, batch, size, barrier, dist
     out = {"frames_total": frames_total, "seconds": dt, "value": frames_total / dt, "unit": UNIT, "scaling": "strong",
            "seconds_streaming_rank0": t_stream_own, "seconds_streaming_slowest_rank": t_stream,
            "seconds_gather_merge_readback": dt - t_stream,
+           "seconds_tail_rank0": {"compact": t_compact - t_stream, "nccl_gather": t_gather - t_compact,
+                                  "order_and_readback": dt - t_gather},
            "batches_per_rank": len(groups), "tail_batch": len(groups[-1]) if groups else 0,
            "sharding": f"frame i -> rank i mod {world}; tables gathered to rank 0 and merged in frame order inside the timed region"}
     if rank == 0:
@@ -437,7 +443,7 @@ def run_b200(args):
     t_e2e0 = time.perf_counter()
     d2h = 0
     n_out = 0
-    for m_h, tabs in pipe.run_host_pipelined(host_batches_iter(K), dev):
+    for m_h, tabs in pipe.run_host_pipelined(host_batches_iter(K), dev, copy=False):      # consumed before advancing
         d2h = m_h.nbytes + sum(sum(v.nbytes for c, v in t.items() if c != "label") for t in tabs) + 4 * B
         n_out += len(tabs)
     torch.cuda.synchronize()
@@ -502,7 +508,8 @@ def run_b200(args):
                    "label_stats": {"ms": stage_ms[2], "GBps_algorithmic": ccl_gbs, "frac_hbm": ccl_gbs / pk["hbm_gbs"]}},
         "layers": layers,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * S * S, "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": ms_e2e / K, "api": "DropletPipeline.run_host_pipelined (pinned host frames -> host masks + tables)"
+                "ms_per_step": ms_e2e / K, "api": "DropletPipeline.run_host_pipelined(copy=False) (pinned host frames -> host masks + tables, each batch "
+                              "consumed before the generator is advanced)"
                        + (", CUDA-graph replay per batch" if args.graphs else "")},
         "gpu_launches": launches_per_step * K,
         "clocks": clocks,

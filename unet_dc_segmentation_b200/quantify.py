@@ -44,11 +44,19 @@ class DropletTables:
         pattern of the int64), equivalent_diameter, centroid-0, centroid-1 [, area_sqmicron, eq_diam_micron], image by
         image.  One boolean-mask gather per column; synchronises (the row count is data dependent)."""
         n = torch.clamp(self.counts.to(torch.int64), max=self.capacity)
-        valid = torch.arange(self.capacity, device=self.counts.device)[None, :] < n[:, None]
+        # flat positions of the rows in use: image b, row r -> b * capacity + r, image by image (one data-dependent
+        # size, one synchronisation; every column is then a plain gather)
+        start = torch.cumsum(n, 0) - n
+        total = int(n.sum().item())
+        img = torch.repeat_interleave(torch.arange(n.shape[0], device=n.device), n, output_size=total)
+        flat = img * self.capacity + (torch.arange(total, device=n.device) - start[img])
         cols = [self.area.view(torch.float64), self.eq_diam, self.centroid0, self.centroid1]
         if self.area_um2 is not None:
             cols += [self.area_um2, self.diam_um]
-        return n, torch.stack([c[valid] for c in cols], dim=1)
+        out = torch.empty((total, len(cols)), dtype=torch.float64, device=n.device)
+        for j, c in enumerate(cols):
+            out[:, j] = c.reshape(-1).index_select(0, flat)
+        return n, out
 
     def to_host(self):
         """One D2H per column; returns a list (per image) of dicts of numpy columns."""
