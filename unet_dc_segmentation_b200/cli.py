@@ -255,12 +255,12 @@ def run_fast(images, mine, model, args, out_dir, mask_dir, overlay_dir):
             cv2.imwrite(str(Path(mask_dir) / f"{name}_pred.png"), mask * 255)                 # qdb:58
             text = df.to_csv(index=False)                                                     # qdb:63
             (Path(mask_dir).parent / f"{name}_droplets.csv").write_text(text)
-            return text
             if overlay_dir is not None:
                 img = cv2.imread(str(images[i]))                                              # qdb:75
                 if img is not None:
                     draw_overlay(img, stencil)                                                # qdb:76-77, from the GPU
                     cv2.imwrite(str(Path(overlay_dir) / f"{name}_overlay.png"), img)          # qdb:78
+            return text
 
         jobs = []
         want_ov = overlay_dir is not None
