@@ -49,7 +49,7 @@ extern "C" {
 
 /* Bumped whenever a struct or signature in this header changes; dc_version() returns the value the library was
  * built with and the Python binding refuses to load a library that disagrees. */
-#define DC_ABI_VERSION 200
+#define DC_ABI_VERSION 201
 
 const char* dc_last_error(void);
 int dc_version(void);
@@ -144,13 +144,22 @@ typedef struct dc_model_desc {
     const float* bias[DC_NUM_LAYERS];
     int dilations[5]; /* enc1..enc4, bottleneck: (1,2,4,8,16) for UNetDC, all 1 for plain UNet */
     int base_channels; /* 64 */
+    /* UNetDC(in_channels, out_channels), models/model_2.py:6.  (3, 1) -- what quantify_droplets_batch.py:35 builds -- is
+     * the fused fast path.  Other counts run the same tensor-core layers around two plain kernels: in_channels != 3
+     * (1..64): the fp32 NCHW input is converted to bf16 NHWC zero-padded to 64 channels and enc1.0 runs as an ordinary
+     * 3x3 layer, so weight[0] is then bf16 [64][9*64] in the DC_KIND_CONV3X3 layout (input channels padded with zeros)
+     * and only in_kind 0 is accepted; out_channels != 1 (1..64): dec1.3 stores its bf16 feature map and a 1x1 kernel
+     * applies out_conv (weight[22] fp32 [out][64], bias[22] fp32 [out]) + sigmoid.  0 means the default. */
+    int in_channels;
+    int out_channels;
 } dc_model_desc_t;
 
 int dc_model_create(dc_model_t** out, int device, const dc_model_desc_t* desc);
 int dc_model_destroy(dc_model_t* m);
 int dc_forward_workspace_bytes(const dc_model_t* m, int B, int H, int W, size_t* bytes);
-/* in_kind as dc_stem_args.  prob_out fp32 [B,H,W] and/or mask_out u8 [B,H,W] may be NULL.
- * mask = prob > thresh (fp32 compare, quantify_droplets_batch.py:56). H, W multiples of 16. */
+/* in_kind as dc_stem_args (in_kind 0: fp32 [B,in_channels,H,W]).  prob_out fp32 [B,out_channels,H,W] and/or mask_out
+ * u8 [B,H,W] may be NULL.  mask = prob[:, 0] > thresh (fp32 compare, quantify_droplets_batch.py:56). H, W multiples
+ * of 16. */
 int dc_forward(dc_model_t* m, int in_kind, const void* in, int B, int H, int W, float thresh, float* prob_out,
                uint8_t* mask_out, void* workspace, size_t workspace_bytes, void* stream);
 /* number of kernels one dc_forward launches (for bench accounting) */

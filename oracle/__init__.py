@@ -163,7 +163,7 @@ def quantify(bin_mask: np.ndarray, min_area: int = 1, px_per_um: float | None = 
 _BLOCKS = [("enc1", 1), ("enc2", 2), ("enc3", 4), ("enc4", 8), ("bottleneck", 16)]
 
 
-def unetdc_forward(state_dict, x, dilations=(1, 2, 4, 8, 16), emulate_bf16=False, gray_input=False):
+def unetdc_forward(state_dict, x, dilations=(1, 2, 4, 8, 16), emulate_bf16=False, gray_input=False, round_last=False):
     """Plain PyTorch fp32 restatement of reference models/model_2.py:56-80 in eval mode.
 
     state_dict uses the reference's 136 keys; x: f32 [B,3,H,W]; returns f32 [B,1,H,W] probs.
@@ -174,7 +174,8 @@ def unetdc_forward(state_dict, x, dilations=(1, 2, 4, 8, 16), emulate_bf16=False
     activation -> bf16, fp32 accumulation, the last feature map and the 1x1 head kept in fp32).  It separates
     "the kernels compute what they claim" (GPU vs this, tight) from "bf16 storage vs the fp32 reference"
     (this vs fp32, inherent to the precision choice).  ``gray_input``: x holds u8 grey levels / 255 replicated
-    to 3 channels; the CUDA stem then feeds the exact integers and folds 1/255 and the 3 channels into the weights."""
+    to 3 channels; the CUDA stem then feeds the exact integers and folds 1/255 and the 3 channels into the weights.
+    ``round_last``: models with out_channels != 1 store the last feature map in bf16 before the 1x1 head kernel."""
     import torch
     import torch.nn.functional as F
 
@@ -215,7 +216,7 @@ def unetdc_forward(state_dict, x, dilations=(1, 2, 4, 8, 16), emulate_bf16=False
         for lvl in (4, 3, 2, 1):                            # model_2.py:67-77
             t = r(F.conv_transpose2d(t, r(sd[f"upconv{lvl}.weight"]), sd[f"upconv{lvl}.bias"], stride=2))
             t = torch.cat([t, skips[lvl - 1]], dim=1)
-            t = block(t, f"dec{lvl}", 1, round_out=(lvl > 1))
+            t = block(t, f"dec{lvl}", 1, round_out=(lvl > 1 or round_last))
         t = F.conv2d(t, sd["out_conv.weight"], sd["out_conv.bias"])   # model_2.py:79
         return torch.sigmoid(t)                                        # model_2.py:80
 

@@ -244,3 +244,32 @@ def test_survey_checkpoint_stated_tolerance(cuda_device):
         _, cols = oracle.quantify_arrays(masks[i], 1, None)
         cols["n"] = len(cols["label"])
         assert_table_equal(tables[i], cols, f"image {i}")
+
+
+@pytest.mark.parametrize("cin,cout", [(1, 1), (4, 2), (3, 3), (7, 1)])
+def test_other_channel_counts(cuda_device, cin, cout):
+    """UNetDC(in_channels, out_channels) (models/model_2.py:6,10,32) beyond the (3, 1) the inference script builds:
+    enc1.0 then runs as an ordinary 3x3 layer on the zero-padded input and out_conv as a 1x1 kernel (csrc/generic.cu)."""
+    import torch
+    import unet_dc_segmentation_b200 as pkg
+    torch.manual_seed(cin * 10 + cout)
+    m = pkg.UNetDC(cin, cout)
+    for name, mod in m.named_modules():                      # non-trivial BatchNorm statistics, as a trained net has
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.uniform_(-0.2, 0.2)
+            mod.running_var.uniform_(0.5, 1.5)
+            mod.weight.data.uniform_(0.8, 1.6)
+            mod.bias.data.uniform_(-0.1, 0.1)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    assert sd["enc1.0.weight"].shape == (64, cin, 3, 3) and sd["out_conv.weight"].shape == (cout, 64, 1, 1)
+    m = m.to(cuda_device).eval()
+    x = torch.rand(2, cin, 48, 64)
+    y = m(x.to(cuda_device))
+    assert tuple(y.shape) == (2, cout, 48, 64)
+    want = oracle.unetdc_forward(sd, x).numpy()
+    emu = oracle.unetdc_forward(sd, x, emulate_bf16=True, round_last=(cout != 1)).numpy()
+    _check_probs(y.cpu().numpy(), want, emu if (cin, cout) != (3, 1) else None, f"UNetDC({cin},{cout})")
+    assert m.num_launches() == 22 + (cin != 3) + (cout != 1)
+    if cin != 3:
+        with pytest.raises(ValueError):
+            m.predict_u8(torch.zeros(1, 48, 64, dtype=torch.uint8, device=cuda_device), 0.3)

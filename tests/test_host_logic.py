@@ -32,8 +32,11 @@ def test_load_state_dict_roundtrip_and_constructor_contract():
     assert not missing.missing_keys and not missing.unexpected_keys
     for k, v in m.state_dict().items():
         assert torch.equal(v, sd[k]), k
+    assert UNetDC(1, 2).state_dict()["enc1.0.weight"].shape == (64, 1, 3, 3)          # any channel counts, as the reference
     with pytest.raises(ValueError):
-        UNetDC(1, 1)
+        UNetDC(0, 1)
+    with pytest.raises(ValueError):
+        UNetDC(3, 65)
 
 
 def test_bn_fold_equals_conv_then_bn():

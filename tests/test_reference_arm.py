@@ -42,3 +42,14 @@ def test_reference_quantify_empty_and_filtered(reference):
     assert reference.quantify(np.zeros((16, 16), np.uint8), 1, None).equals(pd.DataFrame())
     cb = (np.add.outer(np.arange(16), np.arange(16)) % 2).astype(np.uint8)
     assert reference.quantify(cb, 2, 3.0).empty and oracle.quantify(cb, 2, 3.0).empty
+
+
+@pytest.mark.parametrize("cin,cout", [(3, 1), (1, 1), (5, 2)])
+def test_module_contract_matches_the_reference_for_any_channel_count(reference, cin, cout):
+    """Same constructor, same state_dict keys / shapes / dtypes as the reference class it replaces (model_2.py:6-32)."""
+    from unet_dc_segmentation_b200.model import UNetDC
+    ours = UNetDC(cin, cout).state_dict()
+    theirs = reference.UNetDC(cin, cout).state_dict()
+    assert list(ours.keys()) == list(theirs.keys())
+    for k in ours:
+        assert ours[k].shape == theirs[k].shape and ours[k].dtype == theirs[k].dtype, k

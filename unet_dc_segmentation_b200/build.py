@@ -15,7 +15,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB_PATH = LIB_DIR / "libunetdc_b200.so"
-SOURCES = ["api.cu", "conv_tc.cu", "morph.cu", "ccl.cu", "resize.cu", "density.cu"]
+SOURCES = ["api.cu", "conv_tc.cu", "morph.cu", "ccl.cu", "resize.cu", "density.cu", "generic.cu"]
 HEADERS = [CSRC / "common.cuh", PKG.parent / "include" / "unetdc_b200.h"]
 
 NVCC_FLAGS = [

@@ -58,6 +58,7 @@ using namespace dc;
 struct dc_model {
     int device;
     dc_model_desc_t desc;
+    int cin, cout;           // UNetDC(in_channels, out_channels); (3, 1) is the fused path
     float head_b;
     // host copies of the biases of the 64-channel layers (enc1.0, enc1.3, upconv1, dec1.0): their kernels take the
     // bias as kernel parameters (constant-bank operands) instead of staging it in shared memory
@@ -75,6 +76,8 @@ struct ForwardBuffers {
     char* pool[4];   // 2x2 max-pooled encoder output
     char* bott;      // bottleneck.3 output
     char* db[4];     // dec{l}.3 output for l = 1..3 (index l); dec1.3 goes straight to the head
+    char* xin;       // in_channels != 3: the input as bf16 NHWC padded to 64 channels
+    char* feat;      // out_channels != 1: dec1.3 output for the 1x1 head kernel
     size_t total;
 };
 
@@ -82,7 +85,7 @@ struct ForwardBuffers {
 // forward_impl below); two buffers may share memory when their lifetimes do not intersect.  Largest first, each at
 // the lowest offset that is free for its whole lifetime.  At 32 x 1024^2 this is 15.6 GB (the skip halves of cat[0..3]
 // have to survive the whole bottom of the U) instead of the 30.5 GB of one private buffer per tensor.
-ForwardBuffers carve(char* base, int B, int H, int W) {
+ForwardBuffers carve(char* base, int B, int H, int W, bool generic_in = false, bool generic_out = false) {
     ForwardBuffers f;
     memset(&f, 0, sizeof(f));
     struct Item { size_t bytes; int t0, t1; char** slot; size_t off; };
@@ -92,6 +95,8 @@ ForwardBuffers carve(char* base, int B, int H, int W) {
         Item it = {align256(elems * 2), t0, t1, slot, 0};
         items[n++] = it;
     };
+    if (generic_in) add(&f.xin, (size_t)B * H * W * 64, -1, 0);
+    if (generic_out) add(&f.feat, (size_t)B * H * W * 64, 21, 22);
     for (int l = 0; l < 5; ++l) {
         const size_t px = (size_t)B * (H >> l) * (W >> l);
         const size_t C = (size_t)64 << l;
@@ -259,10 +264,14 @@ int dc_model_create(dc_model_t** out, int device, const dc_model_desc_t* desc) {
     for (int i = 0; i < 5; ++i)
         DC_REQUIRE(desc->dilations[i] >= 1 && desc->dilations[i] <= 64, DC_EINVAL, "dc_model_create: dilation[%d] = %d", i,
                    desc->dilations[i]);
+    const int cin = desc->in_channels > 0 ? desc->in_channels : 3, cout = desc->out_channels > 0 ? desc->out_channels : 1;
+    DC_REQUIRE(cin <= 64 && cout <= 64, DC_EINVAL, "dc_model_create: in_channels %d / out_channels %d (at most 64)", cin, cout);
     dc_model* m = new (std::nothrow) dc_model;
     DC_REQUIRE(m, DC_EINVAL, "dc_model_create: out of host memory");
     m->device = device;
     m->desc = *desc;
+    m->cin = cin;
+    m->cout = cout;
     cudaError_t e = cudaMemcpy(&m->head_b, desc->bias[22], sizeof(float), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) {
         delete m;
@@ -270,6 +279,7 @@ int dc_model_create(dc_model_t** out, int device, const dc_model_desc_t* desc) {
     }
     memset(m->has_bias64, 0, sizeof(m->has_bias64));
     for (int layer : {0, 1, 19, 20}) {
+        if (layer == 0 && cin != 3) continue;          // enc1.0 then runs as an ordinary conv layer
         e = cudaMemcpy(m->bias64[layer], desc->bias[layer], 64 * sizeof(float), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) {
             delete m;
@@ -290,13 +300,13 @@ int dc_forward_workspace_bytes(const dc_model_t* m, int B, int H, int W, size_t*
     DC_REQUIRE(m && bytes, DC_EINVAL, "dc_forward_workspace_bytes: null argument");
     DC_REQUIRE(B > 0 && H > 0 && W > 0 && H % 16 == 0 && W % 16 == 0, DC_EINVAL,
                "dc_forward: H and W must be positive multiples of 16 (got %d x %d x %d)", B, H, W);
-    *bytes = carve(nullptr, B, H, W).total;
+    *bytes = carve(nullptr, B, H, W, m->cin != 3, m->cout != 1).total;
     return DC_OK;
 }
 
 int dc_forward_num_launches(const dc_model_t* m) {
-    (void)m;
-    return 22;   // stem + 17 conv3x3 + 4 upconv
+    // stem + 17 conv3x3 + 4 upconv (+ the input conversion / the 1x1 head kernel for other channel counts)
+    return 22 + (m && m->cin != 3 ? 1 : 0) + (m && m->cout != 1 ? 1 : 0);
 }
 
 }  // extern "C"
@@ -313,7 +323,9 @@ static int forward_impl(dc_model_t* m, int in_kind, const void* in, int B, int H
     int dev = -1;
     DC_CUDA(cudaGetDevice(&dev));
     DC_REQUIRE(dev == m->device, DC_EINVAL, "dc_forward: model lives on device %d, current device is %d", m->device, dev);
-    ForwardBuffers f = carve((char*)workspace, B, H, W);
+    const bool gen_in = m->cin != 3, gen_out = m->cout != 1;
+    DC_REQUIRE(!gen_in || in_kind == 0, DC_EINVAL, "dc_forward: u8 inputs need in_channels == 3 (model has %d)", m->cin);
+    ForwardBuffers f = carve((char*)workspace, B, H, W, gen_in, gen_out);
     DC_REQUIRE(workspace_bytes >= f.total, DC_EWORKSPACE, "dc_forward: workspace too small (%zu < %zu)", workspace_bytes,
                f.total);
     DC_REQUIRE(((uintptr_t)workspace & 255) == 0, DC_EINVAL, "dc_forward: workspace must be 256-byte aligned");
@@ -350,7 +362,10 @@ static int forward_impl(dc_model_t* m, int in_kind, const void* in, int B, int H
     } while (0)
 
     // encoder (model_2.py:58-61) -- layer ids per include/unetdc_b200.h
-    {
+    if (gen_in) {
+        DC_TRY(launch_pad_input((const float*)in, f.xin, B, m->cin, H, W, stream));
+        DC_TRY(conv(0, DC_KIND_CONV3X3, DC_EPI_STORE, 1, H, W, 64, 64, d.dilations[0], f.xin, 64, f.a[0], 64, 0, nullptr));
+    } else {
         dc_stem_args_t s;
         memset(&s, 0, sizeof(s));
         s.in_kind = in_kind; s.B = B; s.H = H; s.W = W; s.Cout = 64; s.dilation = d.dilations[0];
@@ -383,9 +398,13 @@ static int forward_impl(dc_model_t* m, int in_kind, const void* in, int B, int H
         if (l > 0) {
             DC_TRY(conv(base + 2, DC_KIND_CONV3X3, DC_EPI_STORE, 1, h, w, c, c, 1, f.ad[l], c, f.db[l], c, 0, nullptr));
             src = f.db[l];
-        } else {
+        } else if (!gen_out) {
             // dec1.3 + out_conv + sigmoid + threshold (model_2.py:79-80, qdb:56)
             DC_TRY(conv(base + 2, DC_KIND_CONV3X3, DC_EPI_HEAD, 1, h, w, c, c, 1, f.ad[l], c, nullptr, 0, 0, nullptr));
+        } else {
+            DC_TRY(conv(base + 2, DC_KIND_CONV3X3, DC_EPI_STORE, 1, h, w, c, c, 1, f.ad[l], c, f.feat, c, 0, nullptr));
+            DC_TRY(launch_head1x1(f.feat, (const float*)d.weight[22], d.bias[22], prob_out, mask_out, thresh, B, m->cout, H, W,
+                                  stream));
         }
     }
 #undef DC_TRY

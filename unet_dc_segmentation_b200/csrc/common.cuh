@@ -48,6 +48,9 @@ size_t rolling_ball_workspace_bytes(int planes, int H, int W);
 int rolling_ball_max_radius();
 int rolling_ball_plan_dump(int radius, int th, int* out, int cap);
 int num_sms();
+int launch_pad_input(const float* in, void* out_nhwc64, int B, int C, int H, int W, cudaStream_t stream);
+int launch_head1x1(const void* feat_nhwc64, const float* w, const float* b, float* prob, uint8_t* mask, float thresh, int B,
+                   int OC, int H, int W, cudaStream_t stream);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- PTX wrappers (sm_100a)

@@ -73,7 +73,15 @@ class _Packed:
                                      sd[f"{name}.{idx + 1}.weight"], sd[f"{name}.{idx + 1}.bias"],
                                      sd[f"{name}.{idx + 1}.running_mean"], sd[f"{name}.{idx + 1}.running_var"],
                                      module._bn_eps(name, idx + 1))
-                w = wf.reshape(wf.shape[0], -1).contiguous() if i == 0 else pack_conv3x3(wf)
+                if i == 0 and module.in_channels == 3:
+                    w = wf.reshape(wf.shape[0], -1).contiguous()          # stem: fp32 [64][27]
+                elif i == 0:
+                    # other input channel counts: enc1.0 runs as an ordinary 3x3 layer on the input padded to 64 channels
+                    wp = torch.zeros((wf.shape[0], 64, 3, 3), dtype=wf.dtype, device=wf.device)
+                    wp[:, :module.in_channels] = wf
+                    w = pack_conv3x3(wp)
+                else:
+                    w = pack_conv3x3(wf)
                 b = b.contiguous()
             self.blobs += [w, b]
             desc.weight[i] = w.data_ptr()
@@ -86,6 +94,8 @@ class _Packed:
         for i, d in enumerate(module.dilations):
             desc.dilations[i] = int(d)
         desc.base_channels = 64
+        desc.in_channels = module.in_channels
+        desc.out_channels = module.out_channels
         self.device = device
         self.handle = C.c_void_p()
         with torch.cuda.device(device):
@@ -116,9 +126,11 @@ class UNetDC(nn.Module):
 
     def __init__(self, in_channels: int = 3, out_channels: int = 1):
         super().__init__()
-        if in_channels != 3 or out_channels != 1:
-            raise ValueError("the sm_100a kernels implement UNetDC(in_channels=3, out_channels=1), the only "
-                             "configuration the reference's inference path builds (quantify_droplets_batch.py:35)")
+        if not (1 <= in_channels <= 64 and 1 <= out_channels <= 64):
+            raise ValueError("UNetDC (sm_100a): in_channels and out_channels must be in [1, 64]")
+        # (3, 1) -- what quantify_droplets_batch.py:35 builds -- is the fused fast path (tcgen05 stem, out_conv + sigmoid
+        # + threshold in dec1.3's epilogue); other counts wrap the same layers in two plain kernels (csrc/generic.cu)
+        self.in_channels, self.out_channels = int(in_channels), int(out_channels)
         cin = in_channels
         for (name, width), d in zip(_ENCODER, self.dilations):
             setattr(self, name, _conv_pair(cin, width, d))
@@ -164,7 +176,7 @@ class UNetDC(nn.Module):
         dev = pk.device
         with torch.cuda.device(dev):
             ws = pk.workspace_for(B, H, W)
-            prob = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev) if want_prob else None
+            prob = torch.empty((B, self.out_channels, H, W), dtype=torch.float32, device=dev) if want_prob else None
             mask = None
             if want_mask:
                 if mask_out is not None:
@@ -181,10 +193,10 @@ class UNetDC(nn.Module):
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """f32 [B,3,H,W] -> f32 [B,1,H,W] probabilities (sigmoid applied, model_2.py:80)."""
+        """f32 [B,in_channels,H,W] -> f32 [B,out_channels,H,W] probabilities (sigmoid applied, model_2.py:80)."""
         _lib.require_cuda(x, "UNetDC input")
-        if x.dim() != 4 or x.shape[1] != 3:
-            raise ValueError(f"expected [B,3,H,W], got {tuple(x.shape)}")
+        if x.dim() != 4 or x.shape[1] != self.in_channels:
+            raise ValueError(f"expected [B,{self.in_channels},H,W], got {tuple(x.shape)}")
         x = x.to(torch.float32).contiguous()
         B, _, H, W = x.shape
         prob, _ = self._run(0, x, B, H, W, 0.5, True, False)
@@ -199,6 +211,8 @@ class UNetDC(nn.Module):
                 or u8 [B,H,W,3]; the /255 is done in the first kernel.
         Returns (mask u8 [B,H,W] {0,1}, probs f32 [B,1,H,W] or None)."""
         _lib.require_cuda(images, "images")
+        if self.in_channels != 3:
+            raise ValueError("predict_u8 feeds u8 frames as RGB (qdb:41): it needs a model with in_channels == 3")
         if images.dtype != torch.uint8:
             raise TypeError("predict_u8 takes uint8 images")
         images = images.contiguous()
