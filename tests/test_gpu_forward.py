@@ -260,6 +260,7 @@ def test_other_channel_counts(cuda_device, cin, cout):
             mod.running_var.uniform_(0.5, 1.5)
             mod.weight.data.uniform_(0.8, 1.6)
             mod.bias.data.uniform_(-0.1, 0.1)
+    m.out_conv.weight.data.mul_(25.0)                        # logits of a few units: a wrong channel would show
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     assert sd["enc1.0.weight"].shape == (64, cin, 3, 3) and sd["out_conv.weight"].shape == (cout, 64, 1, 1)
     m = m.to(cuda_device).eval()
@@ -269,6 +270,7 @@ def test_other_channel_counts(cuda_device, cin, cout):
     want = oracle.unetdc_forward(sd, x).numpy()
     emu = oracle.unetdc_forward(sd, x, emulate_bf16=True, round_last=(cout != 1)).numpy()
     _check_probs(y.cpu().numpy(), want, emu if (cin, cout) != (3, 1) else None, f"UNetDC({cin},{cout})")
+    assert float(want.std()) > 0.05, "degenerate test: the reference output is flat"
     assert m.num_launches() == 22 + (cin != 3) + (cout != 1)
     if cin != 3:
         with pytest.raises(ValueError):
