@@ -173,6 +173,24 @@ def test_whole_path_vs_reference_golden(cuda_device):
             for c in wt[i]:
                 np.testing.assert_array_equal(tb[i][c], wt[i][c], err_msg=f"graph batch {k} image {i} column {c}")
     assert all(sl["graph"] is not None for sl in gpipe._slots)
+    # tables archived on the device (sharded jobs gather them elsewhere): same rows, batch after batch
+    from unet_dc_segmentation_b200.quantify import alloc_tables
+    archive = alloc_tables(10, pipe.capacity, True, cuda_device)
+    got_masks = [mk for mk, tb in pipe.run_host_pipelined((seq[k % 2] for k in range(5)), tables_archive=archive) if tb is None]
+    assert len(got_masks) == 5
+    counts, rows = archive.compact_rows()
+    rows = rows.cpu().numpy()
+    pos = 0
+    for k in range(5):
+        wt = tables if k % 2 == 0 else want_f_tables
+        for i in range(2):
+            n = len(wt[i]["label"])
+            assert int(counts[2 * k + i]) == n
+            np.testing.assert_array_equal(rows[pos:pos + n, 0].view(np.int64), wt[i]["area"])
+            for j, c in enumerate(["equivalent_diameter", "centroid-0", "centroid-1", "area_sqmicron", "eq_diam_micron"]):
+                np.testing.assert_array_equal(rows[pos:pos + n, j + 1], wt[i][c], err_msg=f"archive batch {k} image {i} {c}")
+            pos += n
+    assert pos == rows.shape[0]
 
 
 def test_config1_eight_256_images(cuda_device):

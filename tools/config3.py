@@ -73,9 +73,9 @@ def main():
     ccl_bytes = px * (wl.LABEL_BYTES_PER_PX + wl.STATS_BYTES_PER_PX) + int(n.sum()) * wl.STATS_BYTES_PER_DROPLET
     rows = [f"config 3 on B200: batch {B} of {S}x{S}, droplets per mask {n.mean():.0f} (min {n.min()}, max {n.max()}); HBM peak {hbm} GB/s (measured copy)",
             "", "| stage | ms / batch | frames/s | algorithmic GB/s | of HBM peak | bound |", "|---|---|---|---|---|---|",
-            f"| rolling ball radius 50 (dc_rolling_ball, 4 launches) | {ms_rb:.2f} | {B / ms_rb * 1e3:.0f} | {rb_bytes / ms_rb / 1e6:.0f} | {rb_bytes / ms_rb / 1e6 / hbm:.4f} | instructions (1995-tap exact ellipse) |",
-            f"| labelling + droplet table (dc_label_stats, 8 launches) | {ms_ccl:.2f} | {B / ms_ccl * 1e3:.0f} | {ccl_bytes / ms_ccl / 1e6:.0f} | {ccl_bytes / ms_ccl / 1e6 / hbm:.4f} | latency / atomics |",
-            f"| overlay stencil (dc_overlay_stencil, 6 launches) | {ms_ov:.2f} | {B / ms_ov * 1e3:.0f} | {ov_bytes / ms_ov / 1e6:.0f} | {ov_bytes / ms_ov / 1e6 / hbm:.4f} | background labelling (same union-find) |",
+            f"| rolling ball radius 50 (dc_rolling_ball, 3 launches) | {ms_rb:.2f} | {B / ms_rb * 1e3:.0f} | {rb_bytes / ms_rb / 1e6:.0f} | {rb_bytes / ms_rb / 1e6 / hbm:.4f} | INT/ALU pipe (1995-tap exact ellipse as 16 nested chord tables) |",
+            f"| labelling + droplet table (dc_label_stats, 7 launches) | {ms_ccl:.2f} | {B / ms_ccl * 1e3:.0f} | {ccl_bytes / ms_ccl / 1e6:.0f} | {ccl_bytes / ms_ccl / 1e6 / hbm:.4f} | run-based on a bit-packed mask: DRAM traffic ~ the mask itself; latency of the tile kernel |",
+            f"| overlay stencil (dc_overlay_stencil, 5 launches) | {ms_ov:.2f} | {B / ms_ov * 1e3:.0f} | {ov_bytes / ms_ov / 1e6:.0f} | {ov_bytes / ms_ov / 1e6 / hbm:.4f} | run-based background labelling + 64-px-per-thread bit stencil |",
             f"| ROI mask (dc_roi_mask, 11 launches; batch {Bd}) | {ms_roi:.2f} | {Bd / ms_roi * 1e3:.0f} | {pxd * 4 / ms_roi / 1e6:.0f} | {pxd * 4 / ms_roi / 1e6 / hbm:.4f} | tiled gray + 15x15 blur, then bit-packed morphology (3 B/px in, 1 B/px out algorithmic) |",
             f"| radial ring counts (dc_radial_density, 3 launches; batch {Bd}) | {ms_rad:.2f} | {Bd / ms_rad * 1e3:.0f} | {pxd * 6 / ms_rad / 1e6:.0f} | {pxd * 6 / ms_rad / 1e6 / hbm:.4f} | f64 sqrt per pixel (2 x 1 B in, 4 B out) |",
             f"| spatial density (dc_spatial_density, 2 launches; batch {Bd}) | {ms_spa:.2f} | {Bd / ms_spa * 1e3:.0f} | {pxd * 6 / ms_spa / 1e6:.0f} | {pxd * 6 / ms_spa / 1e6 / hbm:.4f} | f64 accumulation, 29 taps x 2 planes x 2 axes (2 B in, 4 B out) |"]
