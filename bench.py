@@ -233,55 +233,6 @@ def frame_content(base, i):
     return np.roll(base[i % n], 37 * ((i // n) % 16), axis=1)
 
 
-def _gather_merge(archive, world, rank, nf, frames_total, dev, dist, host_rows, timing, t0):
-    """Tail of the config-4 job: compact this rank's archived tables, gather them on rank 0 (NCCL), permute into frame
-    order on the device, read back once.  Returns (merged rows f64 [R, 6] numpy, counts per frame) on rank 0."""
-    import torch
-    ncol = 6
-    counts, rows = archive.compact_rows()                      # device: int64 [frames of this rank], f64 [R, 6]
-    torch.cuda.synchronize()
-    timing["compact"] = time.perf_counter() - t0
-    if world > 1:
-        n_rows = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
-        all_rows = [torch.zeros_like(n_rows) for _ in range(world)]
-        dist.all_gather(all_rows, n_rows)
-        maxr = int(max(int(v.item()) for v in all_rows))
-        buf = torch.zeros((maxr, ncol), dtype=torch.float64, device=dev)
-        buf[:rows.shape[0]] = rows
-        cbuf = torch.zeros(nf, dtype=torch.int64, device=dev)
-        cbuf[:counts.shape[0]] = counts
-        gr = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
-        gc = [torch.empty_like(cbuf) for _ in range(world)] if rank == 0 else None
-        dist.gather(buf, gr, dst=0)
-        dist.gather(cbuf, gc, dst=0)
-    else:
-        gr, gc, maxr = [rows], [counts], rows.shape[0]
-    torch.cuda.synchronize()
-    timing["gather"] = time.perf_counter() - t0
-    merged = merged_counts = None
-    if rank == 0:
-        # frame order on the device: frame i is image i // world of rank i % world
-        cnt = torch.stack([torch.nn.functional.pad(c, (0, nf - c.shape[0])) for c in gc])          # [world, nf]
-        off = torch.cumsum(cnt, 1) - cnt                                                           # row offset inside a rank
-        fi = torch.arange(frames_total, device=dev)
-        r_of, j_of = fi % world, fi // world
-        f_cnt = cnt[r_of, j_of]
-        f_start = r_of * maxr + off[r_of, j_of]                                                    # row in the stacked gather
-        out_start = torch.cumsum(f_cnt, 0) - f_cnt
-        total = int(f_cnt.sum().item())
-        idx = torch.repeat_interleave(f_start - out_start, f_cnt, output_size=total) + torch.arange(total, device=dev)
-        stacked = torch.cat([g[:maxr] for g in gr]) if world > 1 else gr[0]
-        merged_dev = stacked[idx]
-        if total <= host_rows.shape[0]:
-            host_rows[:total].copy_(merged_dev, non_blocking=True)
-            torch.cuda.synchronize()
-            merged = host_rows[:total].numpy()
-        else:
-            merged = merged_dev.cpu().numpy()
-        merged_counts = f_cnt.cpu().numpy()
-    return merged, merged_counts
-
-
 def run_config4(pipe, dev, rank, world, frames_total, batch, size, barrier, dist):
     """BASELINE configs[3]: frames_total frames, frame i -> rank i mod world (shard.py).  Each rank streams its batches
     through DropletPipeline.run_host_pipelined (pinned host frames up, host masks down; the masks stay with the rank that
@@ -303,7 +254,6 @@ def run_config4(pipe, dev, rank, world, frames_total, batch, size, barrier, dist
     staged = [torch.from_numpy(np.stack([content(i) for i in g])).pin_memory() for g in groups]
     ncol = 6
     archive = alloc_tables(len(mine), pipe.capacity, True, dev)
-    nf = (frames_total + world - 1) // world
     host_rows = torch.empty((frames_total * 4096, ncol), dtype=torch.float64).pin_memory() if rank == 0 else None
     # first use of a collective sets up its connections and first use of a torch op loads its kernels: run the tail
     # once on a dummy archive (two droplets per frame) before the clock starts
@@ -311,7 +261,7 @@ def run_config4(pipe, dev, rank, world, frames_total, batch, size, barrier, dist
     dummy.counts.fill_(2)
     for t in (dummy.area, dummy.centroid0, dummy.centroid1, dummy.eq_diam, dummy.area_um2, dummy.diam_um):
         t.zero_()
-    _gather_merge(dummy, world, rank, nf, frames_total, dev, dist, host_rows, {}, time.perf_counter())
+    shard.gather_tables_in_frame_order(dummy, frames_total, host_rows)
     barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     mask_px = 0
@@ -322,7 +272,8 @@ def run_config4(pipe, dev, rank, world, frames_total, batch, size, barrier, dist
     barrier()                                                  # (the gather below would wait for the slowest rank anyway)
     t_stream = time.perf_counter() - t0
     timing = {}
-    merged, merged_counts = _gather_merge(archive, world, rank, nf, frames_total, dev, dist, host_rows, timing, t0)
+    merged, merged_counts = shard.gather_tables_in_frame_order(archive, frames_total, host_rows, timing)
+    timing = {k: v + t_stream for k, v in timing.items()}      # (relative to the start of the job)
     torch.cuda.synchronize(); barrier()
     dt = time.perf_counter() - t0
     if world > 1:

@@ -50,3 +50,74 @@ def gather_results(local: list[tuple[int, object]], n_items: int, dst: int = 0):
     if rank != dst:
         return None
     return merge_in_frame_order(buf, n_items)
+
+
+def gather_tables_in_frame_order(archive, n_frames_total: int, host_out=None, timing: dict | None = None):
+    """Sharded runs (frame i -> rank i mod G): gather every rank's archived droplet tables on rank 0 and return them
+    there in FRAME order as (rows, counts) -- rows f64 [sum(counts), C] (columns as DropletTables.compact_rows: area's
+    int64 bit pattern, equivalent_diameter, centroid-0, centroid-1 [, area_sqmicron, eq_diam_micron]), counts int64
+    [n_frames_total] -- both numpy on the host; (None, None) on the other ranks.
+
+    `archive`: this rank's DropletTables holding its frames in order (image j of rank r is frame r + j*G), as filled
+    by DropletPipeline.run_host_pipelined(tables_archive=...).  The tables never pass through the ranks' hosts: they are
+    compacted on the device, gathered with ONE collective (NCCL on GPUs; gloo in the CPU tests), permuted into frame
+    order on rank 0's device and read back once (into `host_out`, a pinned f64 [>= rows, C] tensor, when given).
+    Labels are per image (row r of an image = label r + 1), so no renumbering is needed."""
+    import time
+    import torch
+    import torch.distributed as dist
+    t0 = time.perf_counter()
+    dev = archive.counts.device
+
+    def sync():
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    world = dist.get_world_size() if multi else 1
+    rank = dist.get_rank() if multi else 0
+    nf = (n_frames_total + world - 1) // world
+    counts, rows = archive.compact_rows()                      # int64 [frames of this rank], f64 [R, C]
+    ncol = rows.shape[1]
+    sync()
+    if timing is not None:
+        timing["compact"] = time.perf_counter() - t0
+    if multi:
+        n_rows = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
+        all_rows = [torch.zeros_like(n_rows) for _ in range(world)]
+        dist.all_gather(all_rows, n_rows)
+        maxr = int(max(int(v.item()) for v in all_rows))
+        buf = torch.zeros((maxr, ncol), dtype=torch.float64, device=dev)
+        buf[:rows.shape[0]] = rows
+        cbuf = torch.zeros(nf, dtype=torch.int64, device=dev)
+        cbuf[:counts.shape[0]] = counts
+        gr = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+        gc = [torch.empty_like(cbuf) for _ in range(world)] if rank == 0 else None
+        dist.gather(buf, gr, dst=0)
+        dist.gather(cbuf, gc, dst=0)
+    else:
+        gr, gc, maxr = [rows], [counts], rows.shape[0]
+    sync()
+    if timing is not None:
+        timing["gather"] = time.perf_counter() - t0
+    if rank != 0:
+        return None, None
+    # frame order on the device: frame i is image i // world of rank i % world
+    cnt = torch.stack([torch.nn.functional.pad(c, (0, nf - c.shape[0])) for c in gc])          # [world, nf]
+    off = torch.cumsum(cnt, 1) - cnt                                                           # row offset inside a rank
+    fi = torch.arange(n_frames_total, device=dev)
+    r_of, j_of = fi % world, fi // world
+    f_cnt = cnt[r_of, j_of]
+    f_start = r_of * maxr + off[r_of, j_of]                                                    # row in the stacked gather
+    out_start = torch.cumsum(f_cnt, 0) - f_cnt
+    total = int(f_cnt.sum().item())
+    idx = torch.repeat_interleave(f_start - out_start, f_cnt, output_size=total) + torch.arange(total, device=dev)
+    stacked = torch.cat([g[:maxr] for g in gr]) if multi else gr[0]
+    merged_dev = stacked[idx]
+    if host_out is not None and total <= host_out.shape[0]:
+        host_out[:total].copy_(merged_dev, non_blocking=True)
+        sync()
+        merged = host_out[:total].numpy()
+    else:
+        merged = merged_dev.cpu().numpy()
+    return merged, f_cnt.cpu().numpy()
