@@ -86,10 +86,6 @@ __device__ __forceinline__ unsigned lds_dyn(unsigned addr) {
 __device__ __forceinline__ void sts_dyn(unsigned addr, unsigned v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-template <int IMM>
-__device__ __forceinline__ void sts(unsigned addr, unsigned v) {
-    asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(addr), "n"(IMM), "r"(v) : "memory");
-}
 
 // One morphology pass over planes addressed as in[((p/C)*H*W + y*W + x)*C + p%C] (in_c = C) and
 // written planar.  SUBTRACT: out = saturate(orig - result), plus a per-plane min/max reduction.
