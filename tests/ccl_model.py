@@ -8,16 +8,17 @@ from __future__ import annotations
 
 import numpy as np
 
-TILE_W, TILE_H = 64, 128
-M64 = (1 << 64) - 1
+TILE_H = 128
+BITS = 64                      # word width of the model (set by label_stats: 32 = droplet path, 64 = overlay path)
+M64 = (1 << 64) - 1            # mask of one word (kept under its old name)
 
 
 def bits_below(b):
-    return M64 if b >= 64 else (1 << b) - 1
+    return M64 if b >= BITS else (1 << b) - 1
 
 
 def bits_upto(b):
-    return M64 if b >= 63 else (2 << b) - 1
+    return M64 if b >= BITS - 1 else (2 << b) - 1
 
 
 def ffs(w):            # 0-based index of the lowest set bit
@@ -26,12 +27,12 @@ def ffs(w):            # 0-based index of the lowest set bit
 
 def run_start(w, b):
     z = ~w & M64 & bits_below(b)
-    return z.bit_length() if z else 0          # 64 - clz(z)
+    return z.bit_length() if z else 0          # BITS - clz(z)
 
 
 def run_end(w, b):
     z = ~w & M64 & ~bits_upto(b) & M64
-    return ffs(z) - 1 if z else 63
+    return ffs(z) - 1 if z else BITS - 1
 
 
 def merge_rows(dn, up, unite):
@@ -61,15 +62,18 @@ def union_min(P, a, b):
         P[a] = b
 
 
-def label_stats(mask: np.ndarray, min_area: int = 1, invert: bool = False):
-    """Returns (labels int32 [H,W], area, sum_row, sum_col) following csrc/ccl.cu."""
+def label_stats(mask: np.ndarray, min_area: int = 1, invert: bool = False, word_bits: int = 32):
+    """Returns (labels int32 [H,W], area, sum_row, sum_col) following csrc/ccl.cu with `word_bits`-pixel words."""
+    global BITS, M64
+    BITS, M64 = word_bits, (1 << word_bits) - 1
+    TW = word_bits
     H, W = mask.shape
-    WW = (W + 63) // 64
+    WW = (W + TW - 1) // TW
     fgm = (mask != 0) != invert
     bits = [[0] * WW for _ in range(H)]
     for y in range(H):
         for wx in range(WW):
-            seg = fgm[y, wx * 64:min(W, wx * 64 + 64)]
+            seg = fgm[y, wx * TW:min(W, wx * TW + TW)]
             w = 0
             for k, v in enumerate(seg):
                 if v:
@@ -80,17 +84,17 @@ def label_stats(mask: np.ndarray, min_area: int = 1, invert: bool = False):
     # K1: tiles
     for ty0 in range(0, H, TILE_H):
         for wx in range(WW):
-            x0 = wx * 64
+            x0 = wx * TW
             par = {}
             rows = [bits[ty0 + t][wx] if ty0 + t < H else 0 for t in range(TILE_H)]
             for t, w in enumerate(rows):
                 s = w & ~(w << 1) & M64
                 while s:
                     b = ffs(s)
-                    par[t * 64 + b] = t * 64 + b
+                    par[t * TW + b] = t * TW + b
                     s &= s - 1
             for t in range(1, TILE_H):
-                merge_rows(rows[t], rows[t - 1], lambda sd, su, t=t: union_min(par, t * 64 + sd, (t - 1) * 64 + su))
+                merge_rows(rows[t], rows[t - 1], lambda sd, su, t=t: union_min(par, t * TW + sd, (t - 1) * TW + su))
             for t, w in enumerate(rows):
                 s = w & ~(w << 1) & M64
                 gbase = (ty0 + t) * W + x0
@@ -99,9 +103,9 @@ def label_stats(mask: np.ndarray, min_area: int = 1, invert: bool = False):
                     e = run_end(w, b)
                     ln = e - b + 1
                     pk = ln | (((b + e) * ln // 2) << 16) | ((t * ln) << 36)
-                    r = find(par, t * 64 + b)
-                    groot = (ty0 + (r >> 6)) * W + x0 + (r & 63)
-                    if r == t * 64 + b:
+                    r = find(par, t * TW + b)
+                    groot = (ty0 + r // TW) * W + x0 + (r % TW)
+                    if r == t * TW + b:
                         ACC[gbase + b] = ACC.get(gbase + b, 0) + pk
                         P[gbase + b] = gbase + b
                         AUX[gbase + b] = 0
@@ -115,21 +119,21 @@ def label_stats(mask: np.ndarray, min_area: int = 1, invert: bool = False):
     # K2: borders
     for y in range(TILE_H, H, TILE_H):
         for wx in range(WW):
-            g = y * W + wx * 64
+            g = y * W + wx * TW
             merge_rows(bits[y][wx], bits[y - 1][wx], lambda sd, su, g=g: union_min(P, g + sd, g - W + su))
     for y in range(H):
         for wx in range(1, WW):
             a, b = bits[y][wx - 1], bits[y][wx]
-            if (a >> 63) & b & 1:
-                g = y * W + wx * 64
-                union_min(P, g, g - 64 + run_start(a, 63))
+            if (a >> (TW - 1)) & b & 1:
+                g = y * W + wx * TW
+                union_min(P, g, g - TW + run_start(a, TW - 1))
     # K2b: areas
     roots = [(y, wx) for y in range(H) for wx in range(WW) if rootbits[y][wx]]
     if min_area > 1:
         for y, wx in roots:
             s = rootbits[y][wx]
             while s:
-                gi = y * W + wx * 64 + ffs(s)
+                gi = y * W + wx * TW + ffs(s)
                 AUX[find(P, gi)] += ACC[gi] & 0xFFFF
                 s &= s - 1
     # K3-K5: kept roots, ids in raster order
@@ -137,7 +141,7 @@ def label_stats(mask: np.ndarray, min_area: int = 1, invert: bool = False):
     for y, wx in roots:
         s = rootbits[y][wx]
         while s:
-            gi = y * W + wx * 64 + ffs(s)
+            gi = y * W + wx * TW + ffs(s)
             if P[gi] == gi:
                 if min_area <= 1 or AUX[gi] >= min_area:
                     n += 1
@@ -152,14 +156,14 @@ def label_stats(mask: np.ndarray, min_area: int = 1, invert: bool = False):
     for y, wx in roots:
         s = rootbits[y][wx]
         while s:
-            gi = y * W + wx * 64 + ffs(s)
+            gi = y * W + wx * TW + ffs(s)
             i = AUX[find(P, gi)]
             if i:
                 pk = ACC[gi]
                 a, sc, sr = pk & 0xFFFF, (pk >> 16) & 0xFFFFF, pk >> 36
                 area[i - 1] += a
                 s0[i - 1] += sr + a * ((y // TILE_H) * TILE_H)
-                s1[i - 1] += sc + a * (wx * 64)
+                s1[i - 1] += sc + a * (wx * TW)
             s &= s - 1
     # K8
     labels = np.zeros((H, W), np.int32)
@@ -170,6 +174,6 @@ def label_stats(mask: np.ndarray, min_area: int = 1, invert: bool = False):
             while s:
                 b = ffs(s)
                 e = run_end(w, b)
-                labels[y, wx * 64 + b:wx * 64 + e + 1] = AUX[find(P, y * W + wx * 64 + b)]
+                labels[y, wx * TW + b:wx * TW + e + 1] = AUX[find(P, y * W + wx * TW + b)]
                 s &= s - 1
     return labels, area, s0, s1

@@ -42,11 +42,12 @@ def test_byte_to_bit_packing_trick():
 
 
 @pytest.mark.parametrize("name", list(_cases()))
-@pytest.mark.parametrize("min_area", [1, 5])
-def test_run_based_scheme_matches_oracle(name, min_area):
+@pytest.mark.parametrize("min_area,word_bits", [(1, 32), (5, 32), (1, 64)])
+def test_run_based_scheme_matches_oracle(name, min_area, word_bits):
+    """word_bits 32: the droplet path (dc_label_stats); 64: the background labelling of dc_overlay_stencil."""
     m = _cases()[name]
     want_l, cols = oracle.quantify_arrays(m, min_area, None)
-    labels, area, s0, s1 = label_stats(m, min_area)
+    labels, area, s0, s1 = label_stats(m, min_area, word_bits=word_bits)
     np.testing.assert_array_equal(labels, want_l)
     np.testing.assert_array_equal(area, cols["area"])
     if len(area):

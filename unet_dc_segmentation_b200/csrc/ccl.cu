@@ -32,8 +32,7 @@ namespace {
 
 typedef unsigned long long u64;
 
-constexpr int TILE_W = 64;        // one 64-bit word
-constexpr int TILE_H = 128;       // rows per tile = threads per block (one thread per word-row)
+constexpr int TILE_H = 128;       // rows per tile = threads per block (one thread per word-row); tile width = one word
 constexpr int WORDS_PER_BLOCK = 256;   // compaction granularity of the kept-root scan
 
 __device__ __forceinline__ int find_root(const volatile int* L, int x) {
@@ -62,58 +61,75 @@ __device__ __forceinline__ void union_min(int* L, int a, int b) {
     } while (!done);
 }
 
-// Shared-memory variant for the tile kernel.  Ids are raster positions row * 64 + bit (so that the minimum is the
+// Word type of the bit planes.  The droplet path packs 32 pixels per word (one 32 x 128 tile per 128-thread block:
+// 16 KB of shared parent array, 13 blocks per SM, single-instruction bit scans); the overlay's background labelling
+// packs 64 (few, long runs: fewer clipped runs and half as many words for the bit stencil).
+template <class T> struct WT;
+template <> struct WT<u64> {
+    static constexpr int BITS = 64;
+    static __device__ __forceinline__ int ffs(u64 w) { return __ffsll((long long)w) - 1; }              // lowest set bit
+    static __device__ __forceinline__ int top(u64 z) { return 64 - __clzll((long long)z); }            // 1 + highest set bit
+};
+template <> struct WT<unsigned> {
+    static constexpr int BITS = 32;
+    static __device__ __forceinline__ int ffs(unsigned w) { return __ffs((int)w) - 1; }
+    static __device__ __forceinline__ int top(unsigned z) { return 32 - __clz((int)z); }
+};
+
+template <class T> __device__ __forceinline__ T bits_below(int b) { return b >= WT<T>::BITS ? (T)~(T)0 : (T)(((T)1 << b) - (T)1); }       // bits [0, b)
+template <class T> __device__ __forceinline__ T bits_upto(int b) { return b >= WT<T>::BITS - 1 ? (T)~(T)0 : (T)(((T)2 << b) - (T)1); }     // bits [0, b]
+
+// first / last bit of the run of ones of `w` that contains bit b (bit b is set)
+template <class T> __device__ __forceinline__ int run_start(T w, int b) {
+    const T z = (T)~w & bits_below<T>(b);
+    return z ? WT<T>::top(z) : 0;
+}
+template <class T> __device__ __forceinline__ int run_end(T w, int b) {
+    const T z = (T)~w & (T)~bits_upto<T>(b);
+    return z ? WT<T>::ffs(z) - 1 : WT<T>::BITS - 1;
+}
+
+// For every pair (run of `dn`, run of `up`) that overlaps in x: unite(start of the dn run, start of the up run).
+// A maximal stretch of dn & up lies inside exactly one run of each word, and two stretches never share both runs,
+// so every overlapping pair is visited exactly once.
+template <class T, class U>
+__device__ __forceinline__ void merge_rows(T dn, T up, U&& unite) {
+    T ov = dn & up;
+    while (ov) {
+        const int b = WT<T>::ffs(ov);
+        unite(run_start<T>(dn, b), run_start<T>(up, b));
+        ov &= (T)~bits_upto<T>(min(run_end<T>(dn, b), run_end<T>(up, b)));
+    }
+}
+
+// Shared-memory union-find of the tile kernel.  Ids are raster positions row * BITS + bit (so that the minimum is the
 // first pixel), but a plain array would put the run starts of a column -- e.g. bit 0 of every row of a background
 // tile -- into one bank: slot(id) rotates each row by its row number.
-__device__ __forceinline__ int slot(int id) { return (id & ~63) | ((id + (id >> 6)) & 63); }
-__device__ __forceinline__ int find_root_s(const volatile int* L, int x) {
-    int p = L[slot(x)];
-    while (p != x) { x = p; p = L[slot(x)]; }
+template <int BITS> __device__ __forceinline__ int slot(int id) {
+    return (id & ~(BITS - 1)) | ((id + (id / BITS)) & (BITS - 1));
+}
+template <int BITS> __device__ __forceinline__ int find_root_s(const volatile int* L, int x) {
+    int p = L[slot<BITS>(x)];
+    while (p != x) { x = p; p = L[slot<BITS>(x)]; }
     return x;
 }
-__device__ __forceinline__ void union_min_s(int* L, int a, int b) {
+template <int BITS> __device__ __forceinline__ void union_min_s(int* L, int a, int b) {
     bool done;
     do {
-        a = find_root_s(L, a);
-        b = find_root_s(L, b);
+        a = find_root_s<BITS>(L, a);
+        b = find_root_s<BITS>(L, b);
         if (a < b) {
-            int old = atomicMin(&L[slot(b)], a);
+            int old = atomicMin(&L[slot<BITS>(b)], a);
             done = (old == b);
             b = old;
         } else if (b < a) {
-            int old = atomicMin(&L[slot(a)], b);
+            int old = atomicMin(&L[slot<BITS>(a)], b);
             done = (old == a);
             a = old;
         } else {
             done = true;
         }
     } while (!done);
-}
-
-__device__ __forceinline__ u64 bits_below(int b) { return b >= 64 ? ~0ull : ((1ull << b) - 1ull); }   // bits [0, b)
-__device__ __forceinline__ u64 bits_upto(int b) { return b >= 63 ? ~0ull : ((2ull << b) - 1ull); }    // bits [0, b]
-
-// first / last bit of the run of ones of `w` that contains bit b (bit b is set)
-__device__ __forceinline__ int run_start(u64 w, int b) {
-    const u64 z = ~w & bits_below(b);
-    return z ? 64 - __clzll((long long)z) : 0;
-}
-__device__ __forceinline__ int run_end(u64 w, int b) {
-    const u64 z = ~w & ~bits_upto(b);
-    return z ? __ffsll((long long)z) - 2 : 63;
-}
-
-// For every pair (run of `dn`, run of `up`) that overlaps in x: unite(start of the dn run, start of the up run).
-// A maximal stretch of dn & up lies inside exactly one run of each word, and two stretches never share both runs,
-// so every overlapping pair is visited exactly once.
-template <class U>
-__device__ __forceinline__ void merge_rows(u64 dn, u64 up, U&& unite) {
-    u64 ov = dn & up;
-    while (ov) {
-        const int b = __ffsll((long long)ov) - 1;
-        unite(run_start(dn, b), run_start(up, b));
-        ov &= ~bits_upto(min(run_end(dn, b), run_end(up, b)));
-    }
 }
 
 // bit k = (byte k of v != 0)
@@ -126,27 +142,30 @@ __device__ __forceinline__ u64 pack_acc(unsigned len, unsigned srow, unsigned sc
     return (u64)len | ((u64)scol << 16) | ((u64)srow << 36);
 }
 
-// ---- K1: one 64 x 128 tile per block: pack the mask to bits, union-find over the tile's runs in shared memory,
+// ---- K1: one BITS x 128 tile per block: pack the mask to bits, union-find over the tile's runs in shared memory,
 //          per-run moments summed into the tile-local roots.  invert != 0 labels the ZERO pixels instead (the
 //          background components the overlay stencil needs).
-__global__ void __launch_bounds__(TILE_H) ccl_tile_kernel(const uint8_t* __restrict__ mask, u64* __restrict__ bits,
-                                                          u64* __restrict__ rootbits, int* __restrict__ P,
+template <class T>
+__global__ void __launch_bounds__(TILE_H) ccl_tile_kernel(const uint8_t* __restrict__ mask, T* __restrict__ bits,
+                                                          T* __restrict__ rootbits, int* __restrict__ P,
                                                           u64* __restrict__ ACC, unsigned* __restrict__ AUX, int H, int W,
                                                           int WW, int invert, int zero_aux) {
-    __shared__ int par[TILE_W * TILE_H];
-    __shared__ u64 rowbits[TILE_H];
+    constexpr int BITS = WT<T>::BITS;
+    constexpr int LPR = BITS / 16;                         // lanes (16-pixel loads) per tile row
+    __shared__ int par[BITS * TILE_H];
+    __shared__ T rowbits[TILE_H];
     const int t = threadIdx.x;
     const int wx = blockIdx.x, ty0 = blockIdx.y * TILE_H, img = blockIdx.z;
     const size_t HW = (size_t)H * W;
     const uint8_t* m = mask + (size_t)img * HW;
-    const int x0 = wx * TILE_W;
+    const int x0 = wx * BITS;
 
-    // ---- pack: 4 lanes per row, 16 pixels (one 16-byte load) per lane
+    // ---- pack: LPR lanes per row, 16 pixels (one 16-byte load) per lane
     if (((W & 15) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15) == 0)) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < LPR; ++j) {
             const int c = t + j * TILE_H;
-            const int row = c >> 2, q = c & 3;
+            const int row = c / LPR, q = c % LPR;
             const int y = ty0 + row, x = x0 + q * 16;
             unsigned b16 = 0;
             if (y < H && x < W) {
@@ -154,18 +173,18 @@ __global__ void __launch_bounds__(TILE_H) ccl_tile_kernel(const uint8_t* __restr
                 b16 = nz4(v.x) | (nz4(v.y) << 4) | (nz4(v.z) << 8) | (nz4(v.w) << 12);
                 if (invert) b16 ^= 0xFFFFu;
             }
-            u64 part = (u64)b16 << (16 * q);
-            part |= __shfl_xor_sync(0xffffffffu, part, 1);
-            part |= __shfl_xor_sync(0xffffffffu, part, 2);
+            T part = (T)b16 << (16 * q);
+#pragma unroll
+            for (int d = 1; d < LPR; d <<= 1) part |= __shfl_xor_sync(0xffffffffu, part, d);
             if (q == 0) rowbits[row] = part;
         }
     } else {
         const int y = ty0 + t;
-        u64 w = 0;
+        T w = 0;
         if (y < H) {
-            const int n = min(TILE_W, W - x0);
+            const int n = min(BITS, W - x0);
             const uint8_t* r = m + (size_t)y * W + x0;
-            for (int k = 0; k < n; ++k) w |= (u64)((r[k] != 0) != (invert != 0)) << k;
+            for (int k = 0; k < n; ++k) w |= (T)((r[k] != 0) != (invert != 0)) << k;
         }
         rowbits[t] = w;
     }
@@ -173,21 +192,21 @@ __global__ void __launch_bounds__(TILE_H) ccl_tile_kernel(const uint8_t* __restr
 
     const int y = ty0 + t;
     const bool inb = y < H;
-    const u64 w = rowbits[t];                              // 0 for rows below the image
-    const u64 up = t > 0 ? rowbits[t - 1] : 0ull;
+    const T w = rowbits[t];                                // 0 for rows below the image
+    const T up = t > 0 ? rowbits[t - 1] : (T)0;
     const size_t word_idx = ((size_t)img * H + (inb ? y : 0)) * WW + wx;
-    if (__syncthreads_or(w != 0ull) == 0) {                // empty tile: nothing to label
-        if (inb) { bits[word_idx] = 0ull; rootbits[word_idx] = 0ull; }
+    if (__syncthreads_or(w != (T)0) == 0) {                // empty tile: nothing to label
+        if (inb) { bits[word_idx] = (T)0; rootbits[word_idx] = (T)0; }
         return;
     }
     if (inb) bits[word_idx] = w;
-    const u64 starts = w & ~(w << 1);
-    for (u64 s = starts; s; s &= s - 1) {
-        const int b = __ffsll((long long)s) - 1;
-        par[slot(t * TILE_W + b)] = t * TILE_W + b;
+    const T starts = w & (T)~(w << 1);
+    for (T s = starts; s; s &= s - 1) {
+        const int b = WT<T>::ffs(s);
+        par[slot<BITS>(t * BITS + b)] = t * BITS + b;
     }
     __syncthreads();
-    merge_rows(w, up, [&](int sd, int su) { union_min_s(par, t * TILE_W + sd, (t - 1) * TILE_W + su); });
+    merge_rows<T>(w, up, [&](int sd, int su) { union_min_s<BITS>(par, t * BITS + sd, (t - 1) * BITS + su); });
     __syncthreads();
 
     // ---- tile-local roots publish their own run; every run start gets its parent in the global plane
@@ -195,94 +214,98 @@ __global__ void __launch_bounds__(TILE_H) ccl_tile_kernel(const uint8_t* __restr
     u64* Ai = ACC + (size_t)img * HW;
     unsigned* Xi = AUX + (size_t)img * HW;
     const int gbase = y * W + x0;                          // pixel index of bit 0 of this word (H*W < 2^31)
-    u64 rootw = 0;
-    for (u64 s = starts; s; s &= s - 1) {
-        const int b = __ffsll((long long)s) - 1;
-        const int self = t * TILE_W + b;
-        const int r = find_root_s(par, self);
+    T rootw = 0;
+    for (T s = starts; s; s &= s - 1) {
+        const int b = WT<T>::ffs(s);
+        const int self = t * BITS + b;
+        const int r = find_root_s<BITS>(par, self);
         if (r == self) {
-            const int e = run_end(w, b);
+            const int e = run_end<T>(w, b);
             const unsigned len = (unsigned)(e - b + 1);
             Ai[gbase + b] = pack_acc(len, (unsigned)t * len, (unsigned)(b + e) * len / 2u);
             Pi[gbase + b] = gbase + b;
             if (zero_aux) Xi[gbase + b] = 0u;
-            rootw |= 1ull << b;
+            rootw |= (T)1 << b;
         } else {
-            Pi[gbase + b] = (ty0 + (r >> 6)) * W + x0 + (r & 63);
+            Pi[gbase + b] = (ty0 + r / BITS) * W + x0 + (r & (BITS - 1));
         }
     }
     if (inb) rootbits[word_idx] = rootw;
     __syncthreads();                                       // the roots' records are visible to the whole block
-    for (u64 s = starts & ~rootw; s; s &= s - 1) {
-        const int b = __ffsll((long long)s) - 1;
-        const int r = find_root_s(par, t * TILE_W + b);
-        const int e = run_end(w, b);
+    for (T s = starts & (T)~rootw; s; s &= s - 1) {
+        const int b = WT<T>::ffs(s);
+        const int r = find_root_s<BITS>(par, t * BITS + b);
+        const int e = run_end<T>(w, b);
         const unsigned len = (unsigned)(e - b + 1);
-        atomicAdd(&Ai[(ty0 + (r >> 6)) * W + x0 + (r & 63)], pack_acc(len, (unsigned)t * len, (unsigned)(b + e) * len / 2u));
+        atomicAdd(&Ai[(ty0 + r / BITS) * W + x0 + (r & (BITS - 1))], pack_acc(len, (unsigned)t * len, (unsigned)(b + e) * len / 2u));
     }
 }
 
 // ---- K2: merge across tile borders (runs are clipped at tile borders, so every start has a P entry)
-__global__ void ccl_border_kernel(const u64* __restrict__ bits, int* P, int H, int W, int WW) {
+template <class T>
+__global__ void ccl_border_kernel(const T* __restrict__ bits, int* P, int H, int W, int WW) {
+    constexpr int BITS = WT<T>::BITS;
     const int nbr = (H - 1) / TILE_H;                      // horizontal borders: rows y = TILE_H * k, k = 1..nbr
     const long long nh = (long long)nbr * WW, nv = (long long)H * (WW - 1);
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const u64* Bi = bits + (size_t)blockIdx.y * H * WW;
+    const T* Bi = bits + (size_t)blockIdx.y * H * WW;
     int* Pi = P + (size_t)blockIdx.y * H * W;
     if (i < nh) {
         const int k = (int)(i / WW) + 1, wx = (int)(i % WW);
         const int y = k * TILE_H;
-        const u64 dn = Bi[(size_t)y * WW + wx], up = Bi[(size_t)(y - 1) * WW + wx];
-        const int g = y * W + wx * TILE_W;
-        merge_rows(dn, up, [&](int sd, int su) { union_min(Pi, g + sd, g - W + su); });
+        const T dn = Bi[(size_t)y * WW + wx], up = Bi[(size_t)(y - 1) * WW + wx];
+        const int g = y * W + wx * BITS;
+        merge_rows<T>(dn, up, [&](int sd, int su) { union_min(Pi, g + sd, g - W + su); });
     } else if (i < nh + nv) {
         i -= nh;
         const int y = (int)(i / (WW - 1)), wx = (int)(i % (WW - 1)) + 1;
-        const u64 a = Bi[(size_t)y * WW + wx - 1], b = Bi[(size_t)y * WW + wx];
-        if ((a >> 63) & b & 1ull) {
-            const int g = y * W + wx * TILE_W;
-            union_min(Pi, g, g - TILE_W + run_start(a, 63));
+        const T a = Bi[(size_t)y * WW + wx - 1], b = Bi[(size_t)y * WW + wx];
+        if ((a >> (BITS - 1)) & b & (T)1) {
+            const int g = y * W + wx * BITS;
+            union_min(Pi, g, g - BITS + run_start<T>(a, BITS - 1));
         }
     }
 }
 
 // ---- K2b (only when min_area > 1): total pixel count per final root
-__global__ void ccl_area_kernel(const u64* __restrict__ rootbits, const int* __restrict__ P, const u64* __restrict__ ACC,
+template <class T>
+__global__ void ccl_area_kernel(const T* __restrict__ rootbits, const int* __restrict__ P, const u64* __restrict__ ACC,
                                 unsigned* __restrict__ AUX, int H, int W, int WW) {
     const long long NW = (long long)H * WW;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NW) return;
-    const u64 rw = rootbits[(size_t)blockIdx.y * NW + i];
+    const T rw = rootbits[(size_t)blockIdx.y * NW + i];
     if (!rw) return;
     const size_t HW = (size_t)H * W;
     const int* Pi = P + blockIdx.y * HW;
-    const int gbase = (int)(i / WW) * W + (int)(i % WW) * TILE_W;
-    for (u64 s = rw; s; s &= s - 1) {
-        const int gi = gbase + __ffsll((long long)s) - 1;
+    const int gbase = (int)(i / WW) * W + (int)(i % WW) * WT<T>::BITS;
+    for (T s = rw; s; s &= s - 1) {
+        const int gi = gbase + WT<T>::ffs(s);
         atomicAdd(&AUX[blockIdx.y * HW + find_root(Pi, gi)], (unsigned)(ACC[blockIdx.y * HW + gi] & 0xFFFFull));
     }
 }
 
 // ---- K3: final roots that survive the min_area filter -> keptbits, and their count per WORDS_PER_BLOCK words
-__global__ void __launch_bounds__(WORDS_PER_BLOCK) ccl_mark_kernel(const u64* __restrict__ rootbits, const int* __restrict__ P,
-                                                                   unsigned* __restrict__ AUX, u64* __restrict__ keptbits,
+template <class T>
+__global__ void __launch_bounds__(WORDS_PER_BLOCK) ccl_mark_kernel(const T* __restrict__ rootbits, const int* __restrict__ P,
+                                                                   unsigned* __restrict__ AUX, T* __restrict__ keptbits,
                                                                    int* __restrict__ blockcnt, int H, int W, int WW, int nblk,
                                                                    long long min_area) {
     const long long NW = (long long)H * WW;
     const long long i = (long long)blockIdx.x * WORDS_PER_BLOCK + threadIdx.x;
     const size_t HW = (size_t)H * W;
-    u64 kept = 0;
+    T kept = 0;
     if (i < NW) {
-        const u64 rw = rootbits[(size_t)blockIdx.y * NW + i];
+        const T rw = rootbits[(size_t)blockIdx.y * NW + i];
         if (rw) {
             const int* Pi = P + blockIdx.y * HW;
             unsigned* Xi = AUX + blockIdx.y * HW;
-            const int gbase = (int)(i / WW) * W + (int)(i % WW) * TILE_W;
-            for (u64 s = rw; s; s &= s - 1) {
-                const int b = __ffsll((long long)s) - 1;
+            const int gbase = (int)(i / WW) * W + (int)(i % WW) * WT<T>::BITS;
+            for (T s = rw; s; s &= s - 1) {
+                const int b = WT<T>::ffs(s);
                 const int gi = gbase + b;
                 if (Pi[gi] != gi) continue;                           // merged into a component with an earlier first pixel
-                if (min_area <= 1 || (long long)Xi[gi] >= min_area) kept |= 1ull << b;
+                if (min_area <= 1 || (long long)Xi[gi] >= min_area) kept |= (T)1 << b;
                 else Xi[gi] = 0u;                                     // label 0: filtered out (qdb:83-85)
             }
         }
@@ -290,7 +313,7 @@ __global__ void __launch_bounds__(WORDS_PER_BLOCK) ccl_mark_kernel(const u64* __
     }
     // block sum of the popcounts
     __shared__ int warp_sum[WORDS_PER_BLOCK / 32];
-    int v = __popcll(kept);
+    int v = __popcll((u64)kept);
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
     if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = v;
     __syncthreads();
@@ -347,14 +370,15 @@ __global__ void __launch_bounds__(1024) ccl_scan_kernel(const int* __restrict__ 
 }
 
 // ---- K5: consecutive ids (1..n, raster order of first pixel) written at the kept roots
-__global__ void __launch_bounds__(WORDS_PER_BLOCK) ccl_ids_kernel(const u64* __restrict__ keptbits, const int* __restrict__ blockoff,
+template <class T>
+__global__ void __launch_bounds__(WORDS_PER_BLOCK) ccl_ids_kernel(const T* __restrict__ keptbits, const int* __restrict__ blockoff,
                                                                   unsigned* __restrict__ AUX, int H, int W, int WW, int nblk) {
     __shared__ int warp_cnt[WORDS_PER_BLOCK / 32];
     const long long NW = (long long)H * WW;
     const long long i = (long long)blockIdx.x * WORDS_PER_BLOCK + threadIdx.x;
-    const u64 kw = i < NW ? keptbits[(size_t)blockIdx.y * NW + i] : 0ull;
+    const T kw = i < NW ? keptbits[(size_t)blockIdx.y * NW + i] : (T)0;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int c = __popcll(kw);
+    const int c = __popcll((u64)kw);
     int incl = c;
     for (int d = 1; d < 32; d <<= 1) {
         int n = __shfl_up_sync(0xffffffffu, incl, d);
@@ -367,26 +391,27 @@ __global__ void __launch_bounds__(WORDS_PER_BLOCK) ccl_ids_kernel(const u64* __r
     if (!kw) return;
     unsigned id = (unsigned)(blockoff[(size_t)blockIdx.y * nblk + blockIdx.x] + before + incl - c);
     unsigned* Xi = AUX + (size_t)blockIdx.y * H * W;
-    const int gbase = (int)(i / WW) * W + (int)(i % WW) * TILE_W;
-    for (u64 s = kw; s; s &= s - 1) Xi[gbase + __ffsll((long long)s) - 1] = ++id;
+    const int gbase = (int)(i / WW) * W + (int)(i % WW) * WT<T>::BITS;
+    for (T s = kw; s; s &= s - 1) Xi[gbase + WT<T>::ffs(s)] = ++id;
 }
 
 // ---- K6: every tile-local component adds its moments to the table row of its final root
-__global__ void ccl_accumulate_kernel(const u64* __restrict__ rootbits, const int* __restrict__ P, const u64* __restrict__ ACC,
+template <class T>
+__global__ void ccl_accumulate_kernel(const T* __restrict__ rootbits, const int* __restrict__ P, const u64* __restrict__ ACC,
                                       const unsigned* __restrict__ AUX, int H, int W, int WW, int capacity,
                                       u64* __restrict__ area, u64* __restrict__ s0, u64* __restrict__ s1) {
     const long long NW = (long long)H * WW;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NW) return;
-    const u64 rw = rootbits[(size_t)blockIdx.y * NW + i];
+    const T rw = rootbits[(size_t)blockIdx.y * NW + i];
     if (!rw) return;
     const size_t HW = (size_t)H * W;
     const int* Pi = P + blockIdx.y * HW;
-    const int y = (int)(i / WW), x0 = (int)(i % WW) * TILE_W;
+    const int y = (int)(i / WW), x0 = (int)(i % WW) * WT<T>::BITS;
     const u64 ty0 = (u64)((y / TILE_H) * TILE_H);
     const int gbase = y * W + x0;
-    for (u64 s = rw; s; s &= s - 1) {
-        const int gi = gbase + __ffsll((long long)s) - 1;
+    for (T s = rw; s; s &= s - 1) {
+        const int gi = gbase + WT<T>::ffs(s);
         const unsigned id = AUX[blockIdx.y * HW + find_root(Pi, gi)];
         if (id == 0u || id > (unsigned)capacity) continue;
         const u64 pk = ACC[blockIdx.y * HW + gi];
@@ -422,25 +447,27 @@ __global__ void ccl_finalize_kernel(const int* __restrict__ counts, int capacity
 }
 
 // ---- K8 (only when the caller wants the label image): 4 pixels per thread, straight from the runs
-__global__ void ccl_labels_kernel(const u64* __restrict__ bits, const int* __restrict__ P, const unsigned* __restrict__ AUX,
+template <class T>
+__global__ void ccl_labels_kernel(const T* __restrict__ bits, const int* __restrict__ P, const unsigned* __restrict__ AUX,
                                   int* __restrict__ labels_out, int H, int W, int WW) {
+    constexpr int BITS = WT<T>::BITS;
     const int W4 = (W + 3) >> 2;
     const long long n = (long long)H * W4;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int y = (int)(i / W4), x = (int)(i % W4) * 4;
     const size_t HW = (size_t)H * W;
-    const u64 w = bits[((size_t)blockIdx.y * H + y) * WW + (x >> 6)];
-    const int sh = x & 63;
+    const T w = bits[((size_t)blockIdx.y * H + y) * WW + x / BITS];
+    const int sh = x & (BITS - 1);
     int out[4] = {0, 0, 0, 0};
-    if ((w >> sh) & 0xFull) {
+    if ((w >> sh) & (T)0xF) {
         const int* Pi = P + blockIdx.y * HW;
-        const int gbase = y * W + (x & ~63);
+        const int gbase = y * W + (x & ~(BITS - 1));
         int prev_start = -1, prev_id = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (!((w >> (sh + k)) & 1ull)) continue;
-            const int st = run_start(w, sh + k);
+            if (!((w >> (sh + k)) & (T)1)) continue;
+            const int st = run_start<T>(w, sh + k);
             if (st != prev_start) {
                 prev_start = st;
                 prev_id = (int)AUX[blockIdx.y * HW + find_root(Pi, gbase + st)];
@@ -461,7 +488,7 @@ __global__ void ccl_labels_kernel(const u64* __restrict__ bits, const int* __res
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Workspace {
-    u64 *bits, *rootbits, *keptbits;
+    void *bits, *rootbits, *keptbits;      // bit planes of u32 (droplet path) or u64 (overlay) words
     int* P;
     u64* ACC;
     unsigned* AUX;
@@ -469,20 +496,20 @@ struct Workspace {
     size_t total;
 };
 
-Workspace carve_ws(char* base, int B, int H, int W) {
+Workspace carve_ws(char* base, int B, int H, int W, int word_bits) {
     Workspace ws;
     const size_t hw = (size_t)H * W * B;
-    const size_t nw = (size_t)H * ceil_div(W, TILE_W) * B;
-    const size_t nblk = (size_t)ceil_div(H * ceil_div(W, TILE_W), WORDS_PER_BLOCK) * B;
+    const size_t nw = (size_t)H * ceil_div(W, word_bits) * B;
+    const size_t nblk = (size_t)ceil_div(H * ceil_div(W, word_bits), WORDS_PER_BLOCK) * B;
     size_t off = 0;
     auto take = [&](size_t bytes) {
         char* p = base ? base + off : nullptr;
         off += align256(bytes);
         return p;
     };
-    ws.bits = (u64*)take(nw * 8);
-    ws.rootbits = (u64*)take(nw * 8);
-    ws.keptbits = (u64*)take(nw * 8);
+    ws.bits = take(nw * (word_bits / 8));
+    ws.rootbits = take(nw * (word_bits / 8));
+    ws.keptbits = take(nw * (word_bits / 8));
     ws.P = (int*)take(hw * 4);
     ws.ACC = (u64*)take(hw * 8);
     ws.AUX = (unsigned*)take(hw * 4);
@@ -521,7 +548,7 @@ __global__ void ovl_mark_kernel(const u64* __restrict__ bits, const int* __restr
     const size_t HW = (size_t)H * W;
     const u64 w = bits[((size_t)blockIdx.y * H + y) * WW + (x >> 6)];
     if (!((w >> (x & 63)) & 1ull)) return;
-    const int g = y * W + (x & ~63) + run_start(w, x & 63);
+    const int g = y * W + (x & ~63) + run_start<u64>(w, x & 63);
     AUX[blockIdx.y * HW + find_root(P + blockIdx.y * HW, g)] = 1u;
 }
 
@@ -536,10 +563,10 @@ __global__ void ovl_outer_kernel(const u64* __restrict__ bits, const int* __rest
     u64 o = 0;
     if (w) {
         const int* Pi = P + blockIdx.y * HW;
-        const int gbase = (int)(i / WW) * W + (int)(i % WW) * TILE_W;
+        const int gbase = (int)(i / WW) * W + (int)(i % WW) * 64;
         for (u64 s = w & ~(w << 1); s; s &= s - 1) {
             const int b = __ffsll((long long)s) - 1;
-            if (AUX[blockIdx.y * HW + find_root(Pi, gbase + b)]) o |= bits_upto(run_end(w, b)) & ~bits_below(b);
+            if (AUX[blockIdx.y * HW + find_root(Pi, gbase + b)]) o |= bits_upto<u64>(run_end<u64>(w, b)) & ~bits_below<u64>(b);
         }
     }
     outer[(size_t)blockIdx.y * NW + i] = o;
@@ -579,7 +606,7 @@ __global__ void ovl_stencil_kernel(const u64* __restrict__ bg, const u64* __rest
     const int y = (int)(i / WW), wx = (int)(i % WW);
     const u64* bgi = bg + (size_t)blockIdx.y * NW;
     const u64* oui = outer + (size_t)blockIdx.y * NW;
-    const u64 tailmask = (W & 63) ? bits_below(W & 63) : ~0ull;
+    const u64 tailmask = (W & 63) ? bits_below<u64>(W & 63) : ~0ull;
     // FG(r): foreground = not background, 0 outside the image.  OUT(r): outer background, 1 outside the image.
     auto BG = [&](int r) { return PlaneRow{(r >= 0 && r < H) ? bgi + (size_t)r * WW : nullptr, WW, ~0ull, tailmask}; };
     auto OUT = [&](int r) { return PlaneRow{(r >= 0 && r < H) ? oui + (size_t)r * WW : nullptr, WW, ~0ull, tailmask}; };
@@ -599,9 +626,9 @@ __global__ void ovl_stencil_kernel(const u64* __restrict__ bg, const u64* __rest
     v |= step_dr(y + 1, -1) | step_dr(y - 1, 1) | step_dr(y, -2) | step_dr(y - 2, 0);
     v |= step_dl(y - 1, -1) | step_dl(y + 1, 1) | step_dl(y - 2, 0) | step_dl(y, 2);
     v &= (wx == WW - 1) ? tailmask : ~0ull;
-    uint8_t* dst = stencil + (size_t)blockIdx.y * H * W + (size_t)y * W + (size_t)wx * TILE_W;
-    const int n = min(TILE_W, W - wx * TILE_W);
-    if (n == TILE_W && (W & 15) == 0 && (reinterpret_cast<uintptr_t>(stencil) & 15) == 0) {
+    uint8_t* dst = stencil + (size_t)blockIdx.y * H * W + (size_t)y * W + (size_t)wx * 64;
+    const int n = min(64, W - wx * 64);
+    if (n == 64 && (W & 15) == 0 && (reinterpret_cast<uintptr_t>(stencil) & 15) == 0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const unsigned h = (unsigned)(v >> (16 * k)) & 0xFFFFu;
@@ -616,7 +643,11 @@ __global__ void ovl_stencil_kernel(const u64* __restrict__ bg, const u64* __rest
 
 }  // namespace
 
-size_t label_workspace_bytes(int B, int H, int W) { return carve_ws(nullptr, B, H, W).total; }
+constexpr int LABEL_WORD_BITS = 32;       // droplet labelling: 32-pixel words (one 32 x 128 tile per block)
+typedef unsigned LabelWord;
+constexpr int OVERLAY_WORD_BITS = 64;     // background labelling of the overlay stencil: 64-pixel words
+
+size_t label_workspace_bytes(int B, int H, int W) { return carve_ws(nullptr, B, H, W, LABEL_WORD_BITS).total; }
 
 int launch_label_stats(const dc_label_args_t* a, cudaStream_t stream) {
     DC_REQUIRE(a && a->mask && a->counts && a->area && a->centroid0 && a->centroid1 && a->eq_diam, DC_EINVAL,
@@ -631,29 +662,33 @@ int launch_label_stats(const dc_label_args_t* a, cudaStream_t stream) {
                "dc_label_stats: workspace too small (%zu < %zu)", a->workspace_bytes, label_workspace_bytes(B, H, W));
     DC_REQUIRE(((uintptr_t)a->workspace & 7) == 0, DC_EINVAL, "dc_label_stats: workspace must be 8-byte aligned");
     DC_REQUIRE(B <= 65535, DC_EINVAL, "dc_label_stats: batch > 65535");
-    const int WW = ceil_div(W, TILE_W);
+    typedef LabelWord T;
+    const int WW = ceil_div(W, LABEL_WORD_BITS);
     const long long NW = (long long)H * WW;
     const int nblk = (int)((NW + WORDS_PER_BLOCK - 1) / WORDS_PER_BLOCK);
     DC_REQUIRE(ceil_div(H, TILE_H) <= 65535, DC_EINVAL, "dc_label_stats: image too tall");
-    const Workspace ws = carve_ws((char*)a->workspace, B, H, W);
+    const Workspace ws = carve_ws((char*)a->workspace, B, H, W, LABEL_WORD_BITS);
+    T* bits = (T*)ws.bits;
+    T* rootbits = (T*)ws.rootbits;
+    T* keptbits = (T*)ws.keptbits;
     const int filter = a->min_area > 1;
 
-    ccl_tile_kernel<<<dim3(WW, ceil_div(H, TILE_H), B), TILE_H, 0, stream>>>(a->mask, ws.bits, ws.rootbits, ws.P, ws.ACC,
-                                                                            ws.AUX, H, W, WW, 0, filter);
+    ccl_tile_kernel<T><<<dim3(WW, ceil_div(H, TILE_H), B), TILE_H, 0, stream>>>(a->mask, bits, rootbits, ws.P, ws.ACC, ws.AUX, H,
+                                                                               W, WW, 0, filter);
     const long long nborder = (long long)((H - 1) / TILE_H) * WW + (long long)H * (WW - 1);
     if (nborder > 0)
-        ccl_border_kernel<<<dim3((unsigned)((nborder + 255) / 256), B), 256, 0, stream>>>(ws.bits, ws.P, H, W, WW);
+        ccl_border_kernel<T><<<dim3((unsigned)((nborder + 255) / 256), B), 256, 0, stream>>>(bits, ws.P, H, W, WW);
     const dim3 wg((unsigned)((NW + 255) / 256), B);
-    if (filter) ccl_area_kernel<<<wg, 256, 0, stream>>>(ws.rootbits, ws.P, ws.ACC, ws.AUX, H, W, WW);
-    ccl_mark_kernel<<<dim3(nblk, B), WORDS_PER_BLOCK, 0, stream>>>(ws.rootbits, ws.P, ws.AUX, ws.keptbits, ws.blockcnt, H, W,
-                                                                  WW, nblk, a->min_area);
+    if (filter) ccl_area_kernel<T><<<wg, 256, 0, stream>>>(rootbits, ws.P, ws.ACC, ws.AUX, H, W, WW);
+    ccl_mark_kernel<T><<<dim3(nblk, B), WORDS_PER_BLOCK, 0, stream>>>(rootbits, ws.P, ws.AUX, keptbits, ws.blockcnt, H, W, WW, nblk,
+                                                                     a->min_area);
     // accumulators live in the caller's table: area (i64) and, until finalize, centroid0/1 reused as i64 sums
     long long* s0 = reinterpret_cast<long long*>(a->centroid0);
     long long* s1 = reinterpret_cast<long long*>(a->centroid1);
     ccl_scan_kernel<<<B, 1024, 0, stream>>>(ws.blockcnt, ws.blockoff, a->counts, nblk, a->capacity, (long long*)a->area, s0, s1);
-    ccl_ids_kernel<<<dim3(nblk, B), WORDS_PER_BLOCK, 0, stream>>>(ws.keptbits, ws.blockoff, ws.AUX, H, W, WW, nblk);
-    ccl_accumulate_kernel<<<wg, 256, 0, stream>>>(ws.rootbits, ws.P, ws.ACC, ws.AUX, H, W, WW, a->capacity, (u64*)a->area,
-                                                  (u64*)s0, (u64*)s1);
+    ccl_ids_kernel<T><<<dim3(nblk, B), WORDS_PER_BLOCK, 0, stream>>>(keptbits, ws.blockoff, ws.AUX, H, W, WW, nblk);
+    ccl_accumulate_kernel<T><<<wg, 256, 0, stream>>>(rootbits, ws.P, ws.ACC, ws.AUX, H, W, WW, a->capacity, (u64*)a->area,
+                                                     (u64*)s0, (u64*)s1);
     const long long hw = (long long)H * W;
     const int maxrows = (int)(a->capacity < (hw + 1) / 2 ? a->capacity : (hw + 1) / 2);
     ccl_finalize_kernel<<<dim3(ceil_div(maxrows, 256), B), 256, 0, stream>>>(a->counts, a->capacity, (const long long*)a->area,
@@ -661,14 +696,13 @@ int launch_label_stats(const dc_label_args_t* a, cudaStream_t stream) {
                                                                             a->area_um2, a->diam_um, a->px_per_um);
     if (a->labels_out) {
         const long long n4 = (long long)H * ((W + 3) >> 2);
-        ccl_labels_kernel<<<dim3((unsigned)((n4 + 255) / 256), B), 256, 0, stream>>>(ws.bits, ws.P, ws.AUX, a->labels_out, H, W,
-                                                                                    WW);
+        ccl_labels_kernel<T><<<dim3((unsigned)((n4 + 255) / 256), B), 256, 0, stream>>>(bits, ws.P, ws.AUX, a->labels_out, H, W, WW);
     }
     DC_CUDA(cudaGetLastError());
     return DC_OK;
 }
 
-size_t overlay_workspace_bytes(int B, int H, int W) { return carve_ws(nullptr, B, H, W).total; }
+size_t overlay_workspace_bytes(int B, int H, int W) { return carve_ws(nullptr, B, H, W, OVERLAY_WORD_BITS).total; }
 
 int launch_overlay_stencil(const dc_overlay_args_t* a, cudaStream_t stream) {
     DC_REQUIRE(a && a->mask && a->stencil, DC_EINVAL, "dc_overlay_stencil: null pointer argument");
@@ -680,20 +714,23 @@ int launch_overlay_stencil(const dc_overlay_args_t* a, cudaStream_t stream) {
                "dc_overlay_stencil: workspace too small (%zu < %zu)", a->workspace_bytes, overlay_workspace_bytes(B, H, W));
     DC_REQUIRE(((uintptr_t)a->workspace & 7) == 0, DC_EINVAL, "dc_overlay_stencil: workspace must be 8-byte aligned");
     DC_REQUIRE(ceil_div(H, TILE_H) <= 65535, DC_EINVAL, "dc_overlay_stencil: image too tall");
-    const int WW = ceil_div(W, TILE_W);
+    const int WW = ceil_div(W, OVERLAY_WORD_BITS);
     const long long NW = (long long)H * WW;
-    const Workspace ws = carve_ws((char*)a->workspace, B, H, W);
+    const Workspace ws = carve_ws((char*)a->workspace, B, H, W, OVERLAY_WORD_BITS);
+    u64* bits = (u64*)ws.bits;
+    u64* rootbits = (u64*)ws.rootbits;
+    u64* outer = (u64*)ws.keptbits;
 
     // label the background (runs of zero pixels); AUX is zeroed at every tile-local root
-    ccl_tile_kernel<<<dim3(WW, ceil_div(H, TILE_H), B), TILE_H, 0, stream>>>(a->mask, ws.bits, ws.rootbits, ws.P, ws.ACC,
-                                                                            ws.AUX, H, W, WW, 1, 1);
+    ccl_tile_kernel<u64><<<dim3(WW, ceil_div(H, TILE_H), B), TILE_H, 0, stream>>>(a->mask, bits, rootbits, ws.P, ws.ACC, ws.AUX, H,
+                                                                                 W, WW, 1, 1);
     const long long nborder = (long long)((H - 1) / TILE_H) * WW + (long long)H * (WW - 1);
     if (nborder > 0)
-        ccl_border_kernel<<<dim3((unsigned)((nborder + 255) / 256), B), 256, 0, stream>>>(ws.bits, ws.P, H, W, WW);
-    ovl_mark_kernel<<<dim3(ceil_div(2 * W + 2 * H, 256), B), 256, 0, stream>>>(ws.bits, ws.P, ws.AUX, H, W, WW);
+        ccl_border_kernel<u64><<<dim3((unsigned)((nborder + 255) / 256), B), 256, 0, stream>>>(bits, ws.P, H, W, WW);
+    ovl_mark_kernel<<<dim3(ceil_div(2 * W + 2 * H, 256), B), 256, 0, stream>>>(bits, ws.P, ws.AUX, H, W, WW);
     const dim3 wg((unsigned)((NW + 255) / 256), B);
-    ovl_outer_kernel<<<wg, 256, 0, stream>>>(ws.bits, ws.P, ws.AUX, ws.keptbits, H, W, WW);
-    ovl_stencil_kernel<<<wg, 256, 0, stream>>>(ws.bits, ws.keptbits, a->stencil, H, W, WW);
+    ovl_outer_kernel<<<wg, 256, 0, stream>>>(bits, ws.P, ws.AUX, outer, H, W, WW);
+    ovl_stencil_kernel<<<wg, 256, 0, stream>>>(bits, outer, a->stencil, H, W, WW);
     DC_CUDA(cudaGetLastError());
     return DC_OK;
 }
