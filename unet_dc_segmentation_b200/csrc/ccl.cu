@@ -145,7 +145,10 @@ __device__ __forceinline__ u64 pack_acc(unsigned len, unsigned srow, unsigned sc
 // ---- K1: one BITS x 128 tile per block: pack the mask to bits, union-find over the tile's runs in shared memory,
 //          per-run moments summed into the tile-local roots.  invert != 0 labels the ZERO pixels instead (the
 //          background components the overlay stencil needs).
-template <class T>
+// SINGLE_PASS: every run start zeroes its record, then every run adds its moments to its root atomically (one pass
+// over the runs; wins when a tile has few, long runs -- the overlay's background).  Otherwise the roots store their
+// own run and only the other runs add (two passes, but half the global writes: wins on droplet masks, measured).
+template <class T, bool SINGLE_PASS>
 __global__ void __launch_bounds__(TILE_H) ccl_tile_kernel(const uint8_t* __restrict__ mask, T* __restrict__ bits,
                                                           T* __restrict__ rootbits, int* __restrict__ P,
                                                           u64* __restrict__ ACC, unsigned* __restrict__ AUX, int H, int W,
@@ -199,45 +202,80 @@ __global__ void __launch_bounds__(TILE_H) ccl_tile_kernel(const uint8_t* __restr
         if (inb) { bits[word_idx] = (T)0; rootbits[word_idx] = (T)0; }
         return;
     }
-    if (inb) bits[word_idx] = w;
-    const T starts = w & (T)~(w << 1);
-    for (T s = starts; s; s &= s - 1) {
-        const int b = WT<T>::ffs(s);
-        par[slot<BITS>(t * BITS + b)] = t * BITS + b;
-    }
-    __syncthreads();
-    merge_rows<T>(w, up, [&](int sd, int su) { union_min_s<BITS>(par, t * BITS + sd, (t - 1) * BITS + su); });
-    __syncthreads();
+    if constexpr (SINGLE_PASS) {
+        if (inb) bits[word_idx] = w;
+        int* Pi = P + (size_t)img * HW;
+        u64* Ai = ACC + (size_t)img * HW;
+        unsigned* Xi = AUX + (size_t)img * HW;
+        const int gbase = y * W + x0;                          // pixel index of bit 0 of this word (H*W < 2^31)
+        const T starts = w & (T)~(w << 1);
+        for (T s = starts; s; s &= s - 1) {
+            const int b = WT<T>::ffs(s);
+            par[slot<BITS>(t * BITS + b)] = t * BITS + b;
+            Ai[gbase + b] = 0ull;                              // any run start may turn out to be its component's root
+        }
+        __syncthreads();
+        merge_rows<T>(w, up, [&](int sd, int su) { union_min_s<BITS>(par, t * BITS + sd, (t - 1) * BITS + su); });
+        __syncthreads();                                       // (also: the zeroed records are visible to the whole block)
 
-    // ---- tile-local roots publish their own run; every run start gets its parent in the global plane
-    int* Pi = P + (size_t)img * HW;
-    u64* Ai = ACC + (size_t)img * HW;
-    unsigned* Xi = AUX + (size_t)img * HW;
-    const int gbase = y * W + x0;                          // pixel index of bit 0 of this word (H*W < 2^31)
-    T rootw = 0;
-    for (T s = starts; s; s &= s - 1) {
-        const int b = WT<T>::ffs(s);
-        const int self = t * BITS + b;
-        const int r = find_root_s<BITS>(par, self);
-        if (r == self) {
+        // ---- every run start gets its parent in the global plane and adds its moments to its tile-local root
+        T rootw = 0;
+        for (T s = starts; s; s &= s - 1) {
+            const int b = WT<T>::ffs(s);
+            const int self = t * BITS + b;
+            const int r = find_root_s<BITS>(par, self);
             const int e = run_end<T>(w, b);
             const unsigned len = (unsigned)(e - b + 1);
-            Ai[gbase + b] = pack_acc(len, (unsigned)t * len, (unsigned)(b + e) * len / 2u);
-            Pi[gbase + b] = gbase + b;
-            if (zero_aux) Xi[gbase + b] = 0u;
-            rootw |= (T)1 << b;
-        } else {
-            Pi[gbase + b] = (ty0 + r / BITS) * W + x0 + (r & (BITS - 1));
+            const int groot = (ty0 + r / BITS) * W + x0 + (r & (BITS - 1));
+            Pi[gbase + b] = groot;
+            atomicAdd(&Ai[groot], pack_acc(len, (unsigned)t * len, (unsigned)(b + e) * len / 2u));
+            if (r == self) {
+                if (zero_aux) Xi[groot] = 0u;
+                rootw |= (T)1 << b;
+            }
         }
-    }
-    if (inb) rootbits[word_idx] = rootw;
-    __syncthreads();                                       // the roots' records are visible to the whole block
-    for (T s = starts & (T)~rootw; s; s &= s - 1) {
-        const int b = WT<T>::ffs(s);
-        const int r = find_root_s<BITS>(par, t * BITS + b);
-        const int e = run_end<T>(w, b);
-        const unsigned len = (unsigned)(e - b + 1);
-        atomicAdd(&Ai[(ty0 + r / BITS) * W + x0 + (r & (BITS - 1))], pack_acc(len, (unsigned)t * len, (unsigned)(b + e) * len / 2u));
+        if (inb) rootbits[word_idx] = rootw;
+    } else {
+        if (inb) bits[word_idx] = w;
+        const T starts = w & (T)~(w << 1);
+        for (T s = starts; s; s &= s - 1) {
+            const int b = WT<T>::ffs(s);
+            par[slot<BITS>(t * BITS + b)] = t * BITS + b;
+        }
+        __syncthreads();
+        merge_rows<T>(w, up, [&](int sd, int su) { union_min_s<BITS>(par, t * BITS + sd, (t - 1) * BITS + su); });
+        __syncthreads();
+
+        // ---- tile-local roots publish their own run; every run start gets its parent in the global plane
+        int* Pi = P + (size_t)img * HW;
+        u64* Ai = ACC + (size_t)img * HW;
+        unsigned* Xi = AUX + (size_t)img * HW;
+        const int gbase = y * W + x0;                          // pixel index of bit 0 of this word (H*W < 2^31)
+        T rootw = 0;
+        for (T s = starts; s; s &= s - 1) {
+            const int b = WT<T>::ffs(s);
+            const int self = t * BITS + b;
+            const int r = find_root_s<BITS>(par, self);
+            if (r == self) {
+                const int e = run_end<T>(w, b);
+                const unsigned len = (unsigned)(e - b + 1);
+                Ai[gbase + b] = pack_acc(len, (unsigned)t * len, (unsigned)(b + e) * len / 2u);
+                Pi[gbase + b] = gbase + b;
+                if (zero_aux) Xi[gbase + b] = 0u;
+                rootw |= (T)1 << b;
+            } else {
+                Pi[gbase + b] = (ty0 + r / BITS) * W + x0 + (r & (BITS - 1));
+            }
+        }
+        if (inb) rootbits[word_idx] = rootw;
+        __syncthreads();                                       // the roots' records are visible to the whole block
+        for (T s = starts & (T)~rootw; s; s &= s - 1) {
+            const int b = WT<T>::ffs(s);
+            const int r = find_root_s<BITS>(par, t * BITS + b);
+            const int e = run_end<T>(w, b);
+            const unsigned len = (unsigned)(e - b + 1);
+            atomicAdd(&Ai[(ty0 + r / BITS) * W + x0 + (r & (BITS - 1))], pack_acc(len, (unsigned)t * len, (unsigned)(b + e) * len / 2u));
+        }
     }
 }
 
@@ -673,7 +711,7 @@ int launch_label_stats(const dc_label_args_t* a, cudaStream_t stream) {
     T* keptbits = (T*)ws.keptbits;
     const int filter = a->min_area > 1;
 
-    ccl_tile_kernel<T><<<dim3(WW, ceil_div(H, TILE_H), B), TILE_H, 0, stream>>>(a->mask, bits, rootbits, ws.P, ws.ACC, ws.AUX, H,
+    ccl_tile_kernel<T, false><<<dim3(WW, ceil_div(H, TILE_H), B), TILE_H, 0, stream>>>(a->mask, bits, rootbits, ws.P, ws.ACC, ws.AUX, H,
                                                                                W, WW, 0, filter);
     const long long nborder = (long long)((H - 1) / TILE_H) * WW + (long long)H * (WW - 1);
     if (nborder > 0)
@@ -722,7 +760,7 @@ int launch_overlay_stencil(const dc_overlay_args_t* a, cudaStream_t stream) {
     u64* outer = (u64*)ws.keptbits;
 
     // label the background (runs of zero pixels); AUX is zeroed at every tile-local root
-    ccl_tile_kernel<u64><<<dim3(WW, ceil_div(H, TILE_H), B), TILE_H, 0, stream>>>(a->mask, bits, rootbits, ws.P, ws.ACC, ws.AUX, H,
+    ccl_tile_kernel<u64, true><<<dim3(WW, ceil_div(H, TILE_H), B), TILE_H, 0, stream>>>(a->mask, bits, rootbits, ws.P, ws.ACC, ws.AUX, H,
                                                                                  W, WW, 1, 1);
     const long long nborder = (long long)((H - 1) / TILE_H) * WW + (long long)H * (WW - 1);
     if (nborder > 0)
