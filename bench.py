@@ -141,6 +141,12 @@ def cpu_reference_step(sd, frames_u8, use_threads, want_outputs=False):
     torch.set_num_threads(use_threads)
     rgb = [np.repeat(f[:, :, None], 3, 2) for f in frames_u8]          # Image.convert("RGB"), qdb:41
     kind = "reference" if ref.available() else "port"
+    if kind == "reference":
+        try:
+            ref.load()
+        except Exception as exc:  # noqa: BLE001  (compiled by another Python, a clashing `utils` package, ...)
+            print(f"bench.py: oracle/_ref cannot be loaded ({exc}); timing the port instead", file=sys.stderr)
+            kind = "port"
     t0 = time.perf_counter()
     if kind == "reference":
         probs, masks, tables = ref.run_path(sd, rgb, radius=RADIUS, prob_thresh=PROB_THRESH, min_area=MIN_AREA,
