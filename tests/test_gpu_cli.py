@@ -110,3 +110,47 @@ def test_cli_reference_loop_still_works(cuda_device, workdir):
             # the two loops feed the stem differently (f32 RGB vs folded u8 grey): a few threshold-edge pixels may differ
             other = cv2.imread(str(fast / "predicted_masks" / f"{n}_pred.png"), cv2.IMREAD_GRAYSCALE)
             assert (other != mask).mean() < 0.01
+
+
+def test_cli_true_colour_frames(cuda_device, tmp_path):
+    """A frame whose channels differ takes the [B,H,W,3] path (rolling ball per channel, qdb:41-43; u8 HWC stem), next
+    to a grayscale frame of the same size: both end as masks + tables consistent with the oracle, and the colour
+    frame's network input equals the reference's per-channel rolling ball (checked through the mask the f32 module
+    path gives for the same preprocessed frame)."""
+    import cv2
+    import pandas as pd
+    import torch
+    from PIL import Image
+    from unet_dc_segmentation_b200 import cli
+    from unet_dc_segmentation_b200.synth import calibrated_state_dict, synthetic_image
+    (tmp_path / "in").mkdir()
+    g = synthetic_image(96, 420, n_droplets=10)
+    rgb = np.stack([g, (g.astype(np.int32) * 3 // 4).astype(np.uint8), np.roll(g, 5, axis=1)], axis=-1)
+    Image.fromarray(rgb).save(tmp_path / "in" / "colour.png")
+    Image.fromarray(g).save(tmp_path / "in" / "grey.png")
+    sd = calibrated_state_dict(seed=0, calib_size=64, n_calib=2)
+    torch.save(sd, tmp_path / "ckpt.pth")
+    out = tmp_path / "out"
+    assert cli.main(["--img_dir", str(tmp_path / "in"), "--ckpt_path", str(tmp_path / "ckpt.pth"), "--out_dir", str(out),
+                     "--batch", "4", "--skip_excel", "--skip_histogram", "--img_size", "96", "--save_overlays"]) == 0
+    for n in ("colour", "grey"):
+        mask = cv2.imread(str(out / "predicted_masks" / f"{n}_pred.png"), cv2.IMREAD_GRAYSCALE)
+        assert mask.shape == (96, 96)
+        df = pd.read_csv(out / f"{n}_droplets.csv", float_precision="round_trip")
+        want = oracle.quantify(mask // 255, 1, None)
+        assert len(df) == len(want)
+        for c in want.columns:
+            np.testing.assert_array_equal(df[c].to_numpy(), want[c].to_numpy(), err_msg=f"{n}.{c}")
+        assert (out / "overlays" / f"{n}_overlay.png").exists()
+    # the colour frame against the reference-shaped per-image functions (same kernels, f32 NCHW entry): masks agree up
+    # to threshold-edge pixels
+    m = cli.load_model(tmp_path / "ckpt.pth")
+    t, _ = cli.preprocess(tmp_path / "in" / "colour.png", 50, 96)
+    want_pre = oracle.rolling_ball_correction_rgb(rgb, 50)
+    np.testing.assert_array_equal((t.permute(1, 2, 0) * 255.0).round().to(torch.uint8).cpu().numpy(), want_pre)
+    probs = m(t[None])
+    ref_mask = (probs[0, 0] > 0.3).to(torch.uint8).cpu().numpy()
+    got = cv2.imread(str(out / "predicted_masks" / "colour_pred.png"), cv2.IMREAD_GRAYSCALE) // 255
+    assert (got != ref_mask).mean() < 0.01
+    summary = pd.read_csv(out / "summary_per_image.csv")
+    assert list(summary["filename"]) == ["colour.png", "grey.png"]

@@ -14,6 +14,7 @@ Stages, all on the current CUDA stream (no host synchronisation until the tables
 """
 from __future__ import annotations
 
+from contextlib import contextmanager
 from dataclasses import dataclass
 
 import numpy as np
@@ -24,6 +25,16 @@ from .model import UNetDC
 from .morphology import resize_linear_u8_device, rolling_ball_device, rolling_ball_workspace_bytes
 from .overlay import overlay_stencil_device, overlay_workspace_bytes
 from .quantify import DEFAULT_CAPACITY, DropletTables, alloc_tables, label_stats_device, label_workspace_bytes
+
+
+@contextmanager
+def _nvtx(name: str):
+    """NVTX range per stage (visible to nsys / ncu --nvtx; free otherwise), closed even when the stage raises."""
+    torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()
 
 
 @dataclass
@@ -68,35 +79,31 @@ class DropletPipeline:
         """images: CUDA u8 [B,H,W] grayscale or [B,H,W,3].  mask_out / tables_out / stencil_out: preallocated outputs.
         want_overlay: also compute the pixels the reference's findContours + drawContours paint (qdb:76-77)."""
         _lib.require_cuda(images, "images")
-        nvtx = torch.cuda.nvtx                    # ranges per stage (visible to nsys / ncu --nvtx; free otherwise)
         x = images
-        nvtx.range_push("dc:rolling_ball")
-        if self.background_radius:
-            if self._rb_out is None or self._rb_out.shape != x.shape or self._rb_out.device != x.device:
-                self._rb_out = torch.empty_like(x)
-                self._rb_ws = None
-            if self._rb_ws is None:
-                need = rolling_ball_workspace_bytes(x.shape[0], x.shape[1], x.shape[2], 1 if x.dim() == 3 else x.shape[3])
-                self._rb_ws = torch.empty(need, dtype=torch.uint8, device=x.device)
-            x = rolling_ball_device(x, self.background_radius, out=self._rb_out, workspace=self._rb_ws)
-        nvtx.range_pop()
-        nvtx.range_push("dc:forward")
-        oh, ow = int(images.shape[1]), int(images.shape[2])
-        resized = self.img_size is not None and (oh, ow) != (self.img_size, self.img_size)
-        if resized:
-            x = resize_linear_u8_device(x, (self.img_size, self.img_size))                     # qdb:44
-            masks, probs = self.model.predict_u8(x, self.prob_thresh, return_prob=return_prob)
-            masks = resize_linear_u8_device(masks, (ow, oh), out=mask_out)                     # qdb:57
-        else:
-            masks, probs = self.model.predict_u8(x, self.prob_thresh, return_prob=return_prob, mask_out=mask_out)
-        nvtx.range_pop()
-        nvtx.range_push("dc:label_stats")
-        need = label_workspace_bytes(*masks.shape)
-        if self._ccl_ws is None or self._ccl_ws.device != masks.device or self._ccl_ws.numel() < need:
-            self._ccl_ws = torch.empty(need, dtype=torch.uint8, device=masks.device)
-        tables = label_stats_device(masks, self.min_area, self.px_per_micron, self.capacity,
-                                    want_labels=want_labels, workspace=self._ccl_ws, out=tables_out)
-        nvtx.range_pop()
+        with _nvtx("dc:rolling_ball"):
+            if self.background_radius:
+                if self._rb_out is None or self._rb_out.shape != x.shape or self._rb_out.device != x.device:
+                    self._rb_out = torch.empty_like(x)
+                    self._rb_ws = None
+                if self._rb_ws is None:
+                    need = rolling_ball_workspace_bytes(x.shape[0], x.shape[1], x.shape[2], 1 if x.dim() == 3 else x.shape[3])
+                    self._rb_ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+                x = rolling_ball_device(x, self.background_radius, out=self._rb_out, workspace=self._rb_ws)
+        with _nvtx("dc:forward"):
+            oh, ow = int(images.shape[1]), int(images.shape[2])
+            resized = self.img_size is not None and (oh, ow) != (self.img_size, self.img_size)
+            if resized:
+                x = resize_linear_u8_device(x, (self.img_size, self.img_size))                     # qdb:44
+                masks, probs = self.model.predict_u8(x, self.prob_thresh, return_prob=return_prob)
+                masks = resize_linear_u8_device(masks, (ow, oh), out=mask_out)                     # qdb:57
+            else:
+                masks, probs = self.model.predict_u8(x, self.prob_thresh, return_prob=return_prob, mask_out=mask_out)
+        with _nvtx("dc:label_stats"):
+            need = label_workspace_bytes(*masks.shape)
+            if self._ccl_ws is None or self._ccl_ws.device != masks.device or self._ccl_ws.numel() < need:
+                self._ccl_ws = torch.empty(need, dtype=torch.uint8, device=masks.device)
+            tables = label_stats_device(masks, self.min_area, self.px_per_micron, self.capacity,
+                                        want_labels=want_labels, workspace=self._ccl_ws, out=tables_out)
         stencil = None
         if want_overlay:
             need = overlay_workspace_bytes(*masks.shape)
