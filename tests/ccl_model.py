@@ -1,6 +1,7 @@
 """Pure-Python model of the run-based labelling scheme of csrc/ccl.cu (test infrastructure, CPU only).
 
-It mirrors the kernels phase by phase -- 64 x 128 tiles, runs clipped at 64-pixel words, union-find over run starts
+It mirrors the kernels phase by phase -- 32 x 128 tiles (64 x 128 for the overlay's background), runs clipped at the
+word width, union-find over run starts
 with min-index roots, the packed per-tile accumulators, border merges, kept-root numbering by popcount prefix -- so
 that the DESIGN of the GPU algorithm (bit tricks, field widths, offsets) is checked against the oracle on the CPU,
 where there is no GPU to run the kernels themselves.  Sequential: no atomics, no barriers."""

@@ -10,14 +10,15 @@
 //                                             tile-local component, ccl_accumulate_kernel (one 64-bit atomic triple
 //                                             per tile-local component) + ccl_finalize_kernel (IEEE f64 divide/sqrt)
 //
-// Data layout.  The u8 mask is read ONCE (1 B/px) and packed to 1 bit/px (`bits`, 64-px words, row pitch
-// WW = ceil(W/64) words).  Everything after that works on runs (maximal horizontal stretches of set bits inside one
-// 64-px word): a 1024^2 frame with ~3 k droplets has ~30 k runs, so the int32 label plane of a per-pixel algorithm
+// Data layout.  The u8 mask is read ONCE (1 B/px) and packed to 1 bit/px (`bits`: 32-px words on the droplet path,
+// 64-px words for the overlay's background; row pitch WW = ceil(W / word) words).  Everything after that works on
+// runs (maximal horizontal stretches of set bits inside one word): a 1024^2 frame with ~3 k droplets has ~30 k runs,
+// so the int32 label plane of a per-pixel algorithm
 // (4 B/px written, then re-read by every later pass) never exists.  Union-find state lives in planes indexed by the
 // pixel index of a run's FIRST pixel and is touched only there (sparse: a few sectors per droplet):
 //   P   int32  parent (pixel index of another run start of the same component, smaller or equal)
 //   ACC u64    per tile-local root: area | sum(col - tile_x0) << 16 | sum(row - tile_y0) << 36 of its tile-local
-//              component (field maxima for a 64 x 128 tile: 8192, 258 048, 520 192: no carries between fields)
+//              component (field maxima for the widest, 64 x 128, tile: 8192, 258 048, 520 192: no carries between fields)
 //   AUX u32    per final root: total area (min_area > 1), then the final label id (0 = filtered out)
 // `rootbits` marks the run starts that are tile-local roots, `keptbits` the final roots that survive min_area.
 // The int32 label image is written only when the caller asks for it (labels_out), straight from the runs.
