@@ -238,6 +238,9 @@ class DropletPipeline:
                     sl["ev_free"].record(s_out)
                 s_out.synchronize()
                 masks = sl["h_masks"].numpy()
+                if want_overlay:
+                    st = sl["h_stencil"].numpy()
+                    return (masks.copy() if copy else masks), None, (st.copy() if copy else st)
                 return (masks.copy() if copy else masks), None
             sl["ev_counts"].synchronize()
             counts = sl["h_counts"].numpy().copy()
