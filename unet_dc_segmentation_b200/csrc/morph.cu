@@ -224,13 +224,27 @@ __global__ void __launch_bounds__(NT, 2) morph_chord_kernel(const uint8_t* __res
         const unsigned w0 = abase + (unsigned)ch.f[0].woff * 4u, w1 = abase + (unsigned)ch.f[1].woff * 4u;
         const unsigned e0 = ch.f[0].sel_e, o0 = ch.f[0].sel_o, e1 = ch.f[1].sel_e, o1 = ch.f[1].sel_o;
         if (ch.nf <= 2) {
+            // loads of a group of rows first, arithmetic after: one shared-memory latency per group, not per row
+            constexpr int G = 3;
 #pragma unroll
-            for (int it = 0; it < NA; ++it) {
-                const unsigned pa = w0 + it * astep, pb = w1 + it * astep;
-                const unsigned a0 = lds<0>(pa), a1 = lds<4>(pa), b0 = lds<0>(pb), b1 = lds<4>(pb);
-                he[it] = vop3_16<IS_MAX>(he[it], prmt(a0, a1, e0), prmt(b0, b1, e1));
-                ho[it] = vop3_16<IS_MAX>(ho[it], prmt(a0, a1, o0), prmt(b0, b1, o1));
-                sts_dyn(hb + it * HSTEP, pack_lanes(he[it], ho[it]));
+            for (int g0 = 0; g0 < NA; g0 += G) {
+                unsigned a0[G], a1[G], b0[G], b1[G];
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                    if (g0 + u < NA) {
+                        const unsigned pa = w0 + (g0 + u) * astep, pb = w1 + (g0 + u) * astep;
+                        a0[u] = lds<0>(pa); a1[u] = lds<4>(pa); b0[u] = lds<0>(pb); b1[u] = lds<4>(pb);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                    if (g0 + u < NA) {
+                        const int it = g0 + u;
+                        he[it] = vop3_16<IS_MAX>(he[it], prmt(a0[u], a1[u], e0), prmt(b0[u], b1[u], e1));
+                        ho[it] = vop3_16<IS_MAX>(ho[it], prmt(a0[u], a1[u], o0), prmt(b0[u], b1[u], o1));
+                        sts_dyn(hb + it * HSTEP, pack_lanes(he[it], ho[it]));
+                    }
+                }
             }
         } else {
             const unsigned w2 = abase + (unsigned)ch.f[2].woff * 4u, w3 = abase + (unsigned)ch.f[3].woff * 4u;
@@ -254,11 +268,13 @@ __global__ void __launch_bounds__(NT, 2) morph_chord_kernel(const uint8_t* __res
         for (int j = ch.row_begin; j < jend; j += 2) {
             const unsigned q0 = hb + (unsigned)se.rowoff[j];
             const unsigned q1 = hb + (unsigned)se.rowoff[j + 1];
+            unsigned v0[NB], v1[NB];
+#pragma unroll
+            for (int it = 0; it < NB; ++it) { v0[it] = lds_dyn(q0 + it * HSTEP); v1[it] = lds_dyn(q1 + it * HSTEP); }
 #pragma unroll
             for (int it = 0; it < NB; ++it) {
-                const unsigned v0 = lds_dyn(q0 + it * HSTEP), v1 = lds_dyn(q1 + it * HSTEP);
-                ae[it] = vop3_16<IS_MAX>(ae[it], prmt(v0, 0u, 0x2200u), prmt(v1, 0u, 0x2200u));
-                ao[it] = vop3_16<IS_MAX>(ao[it], prmt(v0, 0u, 0x3311u), prmt(v1, 0u, 0x3311u));
+                ae[it] = vop3_16<IS_MAX>(ae[it], prmt(v0[it], 0u, 0x2200u), prmt(v1[it], 0u, 0x2200u));
+                ao[it] = vop3_16<IS_MAX>(ao[it], prmt(v0[it], 0u, 0x3311u), prmt(v1[it], 0u, 0x3311u));
             }
         }
         // (no second barrier: the next chord writes the other buffer, and the one after that is behind the
