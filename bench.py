@@ -425,7 +425,7 @@ def run_b200(args):
 
     # ---- per-launch profile of the forward (one extra, untimed pass) for the roofline table
     pk, ptype = peaks()
-    names, fl = wl.launch_flops(S, S, model.dilations, in_bounds=True)
+    names, fl = wl.launch_flops(S, S, model.dilations, in_bounds=True, fused_level1=model.fuse_level1)
     import ctypes as C
     n_launch = model.num_launches()
     ms_arr = (C.c_float * n_launch)()
@@ -468,7 +468,7 @@ def run_b200(args):
                    "droplets_per_image": float(counts.mean())},
         "roofline": {"kernel": "conv_tc_kernel (21 tcgen05 launches) + stem_kernel = dc_forward", "bound": "tensor",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                     "traffic_note": f"DRAM bytes per dc_forward (22 launches) from the ncu capture {traffic_src}; "
+                     "traffic_note": f"DRAM bytes per dc_forward ({n_launch} launches) from the ncu capture {traffic_src}; "
                                      "activations written once + read once would be ~84 GB unfused (SURVEY 8d)",
                      "peak_source": f"{ptype} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
                      "flops_per_launch_group": fwd_flops, "flops_model": "in-bounds taps (conservative), SURVEY.md 8d",

@@ -49,7 +49,7 @@ extern "C" {
 
 /* Bumped whenever a struct or signature in this header changes; dc_version() returns the value the library was
  * built with and the Python binding refuses to load a library that disagrees. */
-#define DC_ABI_VERSION 201
+#define DC_ABI_VERSION 202
 
 const char* dc_last_error(void);
 int dc_version(void);
@@ -100,6 +100,34 @@ typedef struct dc_conv_args {
 } dc_conv_args_t;
 
 int dc_conv_tc(const dc_conv_args_t* args, void* stream);
+
+/* ConvTranspose2d(128, 64, 2, stride 2) -> cat([up, skip]) -> Conv2d(128, 64, 3, padding 1) + BatchNorm + ReLU
+ * (upconv1 + dec1.0, models/model_2.py:29, :76-77) as one layer that never writes `up`: per output parity class
+ * (y & 1, x & 1) the two convolutions compose into a 2x2-tap convolution over the transposed conv's INPUT x, with
+ * weights the host composes in fp32 and rounds to bf16 once, plus the 3x3 over the skip half.
+ *   x     bf16 [B,H,W,x_stride], channels [0,128)
+ *   skip  bf16 [B,2H,2W,skip_stride], channels [0,64) from the pointer (it may point into a channel slice)
+ *   weight bf16 [64][41*64]: row co; 64-wide column slices ((chunk*4 + tap)*4 + cls) for chunk = x channels
+ *         [64 chunk, 64 chunk + 64), tap = a*2 + b (x pixel (i - 1 + py + a, j - 1 + px + b) for output
+ *         (2i + py, 2j + px)), cls = py*2 + px; then slices 32 + ky*3 + kx = the skip half of the 3x3 weights
+ *   bias9 fp32 [9][64]: row (row class * 3 + col class), class 0 / 1 / 2 = first / interior / last output row
+ *         (column): the conv bias plus the transposed conv's bias through the taps that lie inside the image
+ *   out   bf16 [B,2H,2W,out_stride] at channel out_offset. */
+typedef struct dc_upfuse_args {
+    int B, H, W;
+    const void* x;
+    int x_stride;
+    const void* skip;
+    int skip_stride;
+    const void* weight;
+    const float* bias9;
+    int relu;
+    void* out;
+    int out_stride;
+    int out_offset;
+} dc_upfuse_args_t;
+
+int dc_conv_upfused(const dc_upfuse_args_t* args, void* stream);
 
 /* TEST AID, never called on the product path: pins which kernel family dc_conv_tc picks for layers that have a
  * choice, so that the fallback kernels stay under test.  AUTO (the default): CTA-pair halo kernel where it fits,
@@ -152,6 +180,10 @@ typedef struct dc_model_desc {
      * applies out_conv (weight[22] fp32 [out][64], bias[22] fp32 [out]) + sigmoid.  0 means the default. */
     int in_channels;
     int out_channels;
+    /* Optional: upconv1 + dec1.0 as one launch (dc_conv_upfused).  fused_weight1 / fused_bias1 in the layouts of
+     * dc_upfuse_args.weight / .bias9; NULL = run the two layers separately from weight[19], weight[20]. */
+    const void* fused_weight1;
+    const float* fused_bias1;
 } dc_model_desc_t;
 
 int dc_model_create(dc_model_t** out, int device, const dc_model_desc_t* desc);

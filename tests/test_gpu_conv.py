@@ -160,6 +160,48 @@ def test_upconv2x2(cuda_device, B, H, W, cin, cout):
     assert bool((cat[..., cout:] == 0).all())
 
 
+UPFUSED_CASES = [
+    # B, H, W of the transposed conv's input (the output is twice that)
+    (1, 16, 8),       # exactly one tile: its pair partner redoes it
+    (2, 16, 8),       # one pair
+    (1, 40, 24),      # ragged rows, three tile columns, odd tile count
+    (3, 24, 20),      # ragged in both directions
+    (2, 64, 64),      # several waves of pairs on a small grid
+    (1, 8, 8),        # smaller than a tile
+]
+
+
+@pytest.mark.parametrize("B,H,W", UPFUSED_CASES)
+def test_upconv_conv3x3_fused(cuda_device, B, H, W):
+    """dc_conv_upfused (upconv1 + dec1.0 as one launch) against the CPU evaluation of the same composed blobs, and
+    loosely against the unfused fp32 chain conv_transpose2d -> cat -> conv2d it stands for."""
+    import torch
+    import torch.nn.functional as F
+    import oracle
+    from unet_dc_segmentation_b200 import layers
+    from unet_dc_segmentation_b200.model import compose_upconv
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + W)
+    wu = torch.randn(128, 64, 2, 2, generator=g) / 128 ** 0.5
+    bu = torch.randn(64, generator=g) * 0.3
+    wd = torch.randn(64, 128, 3, 3, generator=g) / (3.0 * 128 ** 0.5)
+    bd = torch.randn(64, generator=g) * 0.1
+    weight, bias9 = compose_upconv(wu, bu, wd, bd)
+    x = _rand_act(B, H, W, 128, 5)
+    cat = _rand_act(B, 2 * H, 2 * W, 128, 6)              # skip = channels [64,128) of a 128-channel buffer
+    xs, ss = x.float().permute(0, 3, 1, 2), cat[..., 64:].float().permute(0, 3, 1, 2)
+    for relu in (True, False):
+        want = oracle.composed_upconv_conv3x3(xs, ss, weight, bias9, relu=relu).permute(0, 2, 3, 1)
+        out = torch.full((B, 2 * H, 2 * W, 96), 7.0, dtype=torch.bfloat16).cuda()
+        layers.upconv_conv3x3(x.cuda(), cat.cuda(), weight.cuda(), bias9.cuda(), relu=relu, skip_offset=64, out=out,
+                              out_offset=16)
+        torch.cuda.synchronize()
+        _close(out[..., 16:80], want, f"fused upconv+conv {B}x{H}x{W} relu={relu}")
+        assert bool((out[..., :16] == 7).all()) and bool((out[..., 80:] == 7).all())
+    chain = F.relu(F.conv2d(torch.cat([F.conv_transpose2d(xs, wu, bu, stride=2), ss], 1), wd, bd, padding=1)).permute(0, 2, 3, 1)
+    err = (out[..., 16:80].float().cpu().clamp(min=0) - chain).abs().max()
+    assert float(err) < 0.05, f"fused layer vs unfused fp32 chain: max err {float(err):.4f}"
+
+
 def test_head_epilogue(cuda_device):
     import torch
     import torch.nn.functional as F

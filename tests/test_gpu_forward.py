@@ -30,6 +30,14 @@ import oracle
 from conftest import assert_table_equal, load_golden
 
 pytestmark = pytest.mark.gpu
+
+
+def _fused(sd):
+    """Blobs of the composed upconv1 + dec1.0 layer the CUDA forward runs by default (UNetDC.fuse_level1)."""
+    from unet_dc_segmentation_b200.model import fused_level1_blobs
+    return fused_level1_blobs({k: v.detach().float().cpu() for k, v in sd.items() if k.startswith(("dec1.", "upconv1."))})
+
+
 PROB_TOL = 0.08
 MEAN_TOL = 0.004
 EMU_MEAN_TOL = 0.001
@@ -70,7 +78,7 @@ def test_forward_vs_reference_golden(cuda_device, tag, cls):
     x = torch.from_numpy(np.repeat(g[f"{tag}/images"][:, None], 3, 1).astype(np.float32) / 255.0)
     y = m(x.to(cuda_device))
     assert y.shape == (2, 1, 64, 64) and y.dtype == torch.float32
-    emu = oracle.unetdc_forward(sd, x, dil, emulate_bf16=True).numpy()
+    emu = oracle.unetdc_forward(sd, x, dil, emulate_bf16=True, fused_level1=_fused(sd)).numpy()
     _check_probs(y.cpu().numpy(), g[f"{tag}/probs"], emu, tag)
 
 
@@ -83,8 +91,8 @@ def test_forward_vs_oracle_sizes(cuda_device, B, H, W):
     imgs = np.stack([synthetic_image(max(H, W), 300 + b)[:H, :W] for b in range(B)])
     x = torch.from_numpy(np.repeat(imgs[:, None], 3, 1).astype(np.float32) / 255.0)
     want = oracle.unetdc_forward(sd, x).numpy()
-    emu = oracle.unetdc_forward(sd, x, emulate_bf16=True).numpy()
-    emu_gray = oracle.unetdc_forward(sd, x, emulate_bf16=True, gray_input=True).numpy()
+    emu = oracle.unetdc_forward(sd, x, emulate_bf16=True, fused_level1=_fused(sd)).numpy()
+    emu_gray = oracle.unetdc_forward(sd, x, emulate_bf16=True, fused_level1=_fused(sd), gray_input=True).numpy()
     _check_probs(m(x.to(cuda_device)).cpu().numpy(), want, emu, f"f32 NCHW {B}x{H}x{W}")
     # u8 entry points (the /255 happens in the first kernel)
     mask_g, prob_g = m.predict_u8(torch.from_numpy(imgs).to(cuda_device), 0.3, return_prob=True)
@@ -95,6 +103,25 @@ def test_forward_vs_oracle_sizes(cuda_device, B, H, W):
     # rounding of the weights; the RGB entry rounds 27 weights separately: two bf16 roundings of one fp32 layer
     _check_probs(prob_c.cpu().numpy(), want, None, f"u8 HWC {B}x{H}x{W}")
     assert torch.equal(mask_g.cpu(), (prob_g[:, 0].cpu() > 0.3).to(torch.uint8))
+
+
+def test_forward_with_level1_unfused(cuda_device):
+    """UNetDC.fuse_level1 = False: upconv1 and dec1.0 as two launches (`up` stored in bf16), held to the emulation of
+    THAT schedule; the two schedules agree with each other within the bf16 noise of one stored tensor."""
+    import torch
+    from unet_dc_segmentation_b200.synth import calibrated_state_dict, synthetic_image
+    sd = calibrated_state_dict(seed=0, calib_size=64, n_calib=2)
+    imgs = np.stack([synthetic_image(96, 410 + b)[:80, :96] for b in range(2)])
+    x = torch.from_numpy(np.repeat(imgs[:, None], 3, 1).astype(np.float32) / 255.0)
+    want = oracle.unetdc_forward(sd, x).numpy()
+    m = _model("UNetDC", sd, cuda_device)
+    y_fused = m(x.to(cuda_device)).cpu().numpy()
+    m.fuse_level1 = False
+    m.invalidate()
+    assert m.num_launches() == 22
+    y = m(x.to(cuda_device)).cpu().numpy()
+    _check_probs(y, want, oracle.unetdc_forward(sd, x, emulate_bf16=True).numpy(), "level 1 unfused")
+    assert np.abs(y - y_fused).max() <= PROB_TOL
 
 
 def test_module_contract(cuda_device):
@@ -108,7 +135,7 @@ def test_module_contract(cuda_device):
         m.train()(torch.zeros(1, 3, 16, 16, device=cuda_device))   # eval-mode only
     with pytest.raises(ValueError):
         m.eval()(torch.zeros(1, 3, 24, 16, device=cuda_device))    # H, W multiples of 16
-    assert m.num_launches() == 22
+    assert m.num_launches() == 21          # stem + 17 conv3x3 + 3 upconv (upconv1 rides in dec1.0)
 
 
 def test_whole_path_vs_reference_golden(cuda_device):
@@ -232,7 +259,7 @@ def test_forward_other_dilation_sets(cuda_device, dil):
     imgs = np.stack([synthetic_image(128, 700 + b) for b in range(2)])
     x = torch.from_numpy(np.repeat(imgs[:, None], 3, 1).astype(np.float32) / 255.0)
     want = oracle.unetdc_forward(sd, x, dil).numpy()
-    emu = oracle.unetdc_forward(sd, x, dil, emulate_bf16=True).numpy()
+    emu = oracle.unetdc_forward(sd, x, dil, emulate_bf16=True, fused_level1=_fused(sd)).numpy()
     _check_probs(m(x.to(cuda_device)).cpu().numpy(), want, emu, f"dilations {dil}")
 
 
@@ -286,10 +313,10 @@ def test_other_channel_counts(cuda_device, cin, cout):
     y = m(x.to(cuda_device))
     assert tuple(y.shape) == (2, cout, 48, 64)
     want = oracle.unetdc_forward(sd, x).numpy()
-    emu = oracle.unetdc_forward(sd, x, emulate_bf16=True, round_last=(cout != 1)).numpy()
+    emu = oracle.unetdc_forward(sd, x, emulate_bf16=True, fused_level1=_fused(sd), round_last=(cout != 1)).numpy()
     _check_probs(y.cpu().numpy(), want, emu if (cin, cout) != (3, 1) else None, f"UNetDC({cin},{cout})")
     assert float(want.std()) > 0.05, "degenerate test: the reference output is flat"
-    assert m.num_launches() == 22 + (cin != 3) + (cout != 1)
+    assert m.num_launches() == 21 + (cin != 3) + (cout != 1)
     if cin != 3:
         with pytest.raises(ValueError):
             m.predict_u8(torch.zeros(1, 48, 64, dtype=torch.uint8, device=cuda_device), 0.3)

@@ -142,3 +142,35 @@ def test_combined_csv_text_equals_pandas_concat():
     empty.insert(0, "filename", "none.png")
     assert cli.combined_csv_text(frames + [empty], texts + [empty.to_csv(index=False)]) is None
     assert cli.combined_csv_text(frames, None) is None
+
+
+def test_compose_upconv_equals_the_two_layers():
+    """model.compose_upconv: the composed 2x2-over-x + 3x3-over-skip layer (evaluated on the CPU from the blobs the
+    kernel consumes) is conv_transpose2d -> cat -> conv2d(padding=1) of models/model_2.py:76-77, border bias included."""
+    import torch
+    import torch.nn.functional as F
+    import oracle
+    from unet_dc_segmentation_b200 import model as M
+    g = torch.Generator().manual_seed(3)
+    wu = torch.randn(128, 64, 2, 2, generator=g) * 0.1
+    bu = torch.randn(64, generator=g)
+    wd = torch.randn(64, 128, 3, 3, generator=g) * 0.05
+    bd = torch.randn(64, generator=g)
+    x = torch.randn(2, 128, 5, 7, generator=g)
+    skip = torch.randn(2, 64, 10, 14, generator=g)
+    want = F.conv2d(torch.cat([F.conv_transpose2d(x, wu, bu, stride=2), skip], 1), wd, bd, padding=1)
+    w, b9 = M.compose_upconv(wu, bu, wd, bd)
+    assert w.dtype == torch.bfloat16 and tuple(w.shape) == (64, 41 * 64) and tuple(b9.shape) == (9, 64)
+    got = oracle.composed_upconv_conv3x3(x, skip, w, b9, relu=False)
+    assert float((got - want).abs().max()) < 0.05                  # bf16 rounding of the composed weights only
+    # without that rounding the two are the same linear map
+    class _NoRound:
+        def __getattr__(self, k):
+            return torch.float32 if k == "bfloat16" else getattr(torch, k)
+    real, M.torch = M.torch, _NoRound()
+    try:
+        w32, b932 = M.compose_upconv(wu, bu, wd, bd)
+    finally:
+        M.torch = real
+    got32 = oracle.composed_upconv_conv3x3(x, skip, w32, b932, relu=False)
+    assert float((got32 - want).abs().max()) < 1e-4

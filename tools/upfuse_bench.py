@@ -1,0 +1,49 @@
+"""Level 1 of the decoder at the benchmark shape (32 x 512 x 512 x 128 -> 32 x 1024 x 1024 x 64): upconv1 + dec1.0 as two
+launches against dc_conv_upfused, CUDA events, median of N."""
+import statistics
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from unet_dc_segmentation_b200 import layers                                    # noqa: E402
+from unet_dc_segmentation_b200.model import compose_upconv, pack_conv3x3, pack_upconv   # noqa: E402
+
+B, H, W = (int(v) for v in sys.argv[1:4]) if len(sys.argv) > 3 else (32, 512, 512)
+dev = torch.device("cuda:0")
+g = torch.Generator().manual_seed(0)
+wu = torch.randn(128, 64, 2, 2, generator=g) / 128 ** 0.5
+bu = torch.randn(64, generator=g) * 0.3
+wd = torch.randn(64, 128, 3, 3, generator=g) / (3.0 * 128 ** 0.5)
+bd = torch.randn(64, generator=g) * 0.1
+fw, fb = (t.to(dev) for t in compose_upconv(wu, bu, wd, bd))
+pu, pd = pack_upconv(wu).to(dev), pack_conv3x3(wd).to(dev)
+bu_d, bd_d = bu.to(dev), bd.to(dev)
+x = torch.randn((B, H, W, 128), device=dev).bfloat16()
+cat = torch.randn((B, 2 * H, 2 * W, 128), device=dev).bfloat16()
+out = torch.empty((B, 2 * H, 2 * W, 64), dtype=torch.bfloat16, device=dev)
+out2 = torch.empty_like(out)
+
+
+def two():
+    layers.upconv2x2(x, pu, bu_d, out=cat, out_offset=0)
+    layers.conv3x3(cat, pd, bd_d, out=out)
+
+
+def fused():
+    layers.upconv_conv3x3(x, cat, fw, fb, skip_offset=64, out=out2)
+
+
+def timed(fn, n=7):
+    ts = []
+    for _ in range(n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts[2:])
+
+
+t2, tf = timed(two), timed(fused)
+d = (out.float() - out2.float()).abs()
+print(f"B {B} H {H} W {W}: upconv1 + dec1.0 {t2:.3f} ms, fused {tf:.3f} ms, max |diff| {float(d.max()):.4f} mean {float(d.mean()):.5f}")

@@ -16,10 +16,10 @@ DC_KIND_CONV3X3, DC_KIND_UPCONV2 = 0, 1
 DC_EPI_STORE, DC_EPI_STORE_POOL, DC_EPI_HEAD, DC_EPI_UPSCATTER = 0, 1, 2, 3
 DC_NUM_LAYERS = 23
 DC_CONV_FAMILY_AUTO, DC_CONV_FAMILY_NO_PAIR, DC_CONV_FAMILY_GENERIC = 0, 1, 2
-ABI_VERSION = 201          # DC_ABI_VERSION of include/unetdc_b200.h these ctypes structures mirror
+ABI_VERSION = 202          # DC_ABI_VERSION of include/unetdc_b200.h these ctypes structures mirror
 
 EXPORTS = [
-    "dc_last_error", "dc_version", "dc_device_check", "dc_conv_tc", "dc_debug_set_conv_family", "dc_stem", "dc_model_create",
+    "dc_last_error", "dc_version", "dc_device_check", "dc_conv_tc", "dc_conv_upfused", "dc_debug_set_conv_family", "dc_stem", "dc_model_create",
     "dc_model_destroy", "dc_forward_workspace_bytes", "dc_forward", "dc_forward_num_launches", "dc_forward_profile",
     "dc_rolling_ball_workspace_bytes", "dc_rolling_ball", "dc_rolling_ball_max_radius", "dc_debug_rolling_ball_plan", "dc_label_workspace_bytes", "dc_label_stats",
     "dc_resize_linear_u8", "dc_overlay_workspace_bytes", "dc_overlay_stencil",
@@ -60,6 +60,17 @@ class ModelDesc(Structure):
     _fields_ = [
         ("weight", c_void_p * DC_NUM_LAYERS), ("bias", c_void_p * DC_NUM_LAYERS),
         ("dilations", c_int * 5), ("base_channels", c_int), ("in_channels", c_int), ("out_channels", c_int),
+        ("fused_weight1", c_void_p), ("fused_bias1", c_void_p),
+    ]
+
+
+class UpfuseArgs(Structure):
+    _fields_ = [
+        ("B", c_int), ("H", c_int), ("W", c_int),
+        ("x", c_void_p), ("x_stride", c_int),
+        ("skip", c_void_p), ("skip_stride", c_int),
+        ("weight", c_void_p), ("bias9", c_void_p), ("relu", c_int),
+        ("out", c_void_p), ("out_stride", c_int), ("out_offset", c_int),
     ]
 
 
@@ -148,6 +159,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
                            "rebuild with `python -m unet_dc_segmentation_b200.build --force`")
     lib.dc_device_check.argtypes = [c_int, POINTER(c_int)]
     lib.dc_conv_tc.argtypes = [POINTER(ConvArgs), c_void_p]
+    lib.dc_conv_upfused.argtypes = [POINTER(UpfuseArgs), c_void_p]
     lib.dc_debug_set_conv_family.argtypes = [c_int]
     lib.dc_stem.argtypes = [POINTER(StemArgs), c_void_p]
     lib.dc_model_create.argtypes = [POINTER(c_void_p), c_int, POINTER(ModelDesc)]

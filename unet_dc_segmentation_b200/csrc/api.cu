@@ -64,6 +64,8 @@ struct dc_model {
     // bias as kernel parameters (constant-bank operands) instead of staging it in shared memory
     float bias64[DC_NUM_LAYERS][64];
     bool has_bias64[DC_NUM_LAYERS];
+    bool fused1;             // upconv1 + dec1.0 as one launch (desc.fused_weight1)
+    float fused_bias9[9 * 64];
 };
 
 namespace {
@@ -160,6 +162,15 @@ int dc_conv_tc(const dc_conv_args_t* args, void* stream) {
     int rc = check_current_device(nullptr);
     if (rc != DC_OK) return rc;
     return launch_conv_tc(args, (cudaStream_t)stream);
+}
+
+int dc_conv_upfused(const dc_upfuse_args_t* args, void* stream) {
+    int rc = check_current_device(nullptr);
+    if (rc != DC_OK) return rc;
+    DC_REQUIRE(args && args->bias9, DC_EINVAL, "dc_conv_upfused: null argument");
+    float bias9[9 * 64];        // single-layer entry (tests): the interior row travels as kernel parameters
+    DC_CUDA(cudaMemcpy(bias9, args->bias9, sizeof(bias9), cudaMemcpyDeviceToHost));
+    return launch_conv_upfused(args, (cudaStream_t)stream, bias9);
 }
 
 int dc_stem(const dc_stem_args_t* args, void* stream) {
@@ -287,6 +298,15 @@ int dc_model_create(dc_model_t** out, int device, const dc_model_desc_t* desc) {
         }
         m->has_bias64[layer] = true;
     }
+    m->fused1 = desc->fused_weight1 != nullptr;
+    if (m->fused1) {
+        e = desc->fused_bias1 ? cudaMemcpy(m->fused_bias9, desc->fused_bias1, sizeof(m->fused_bias9), cudaMemcpyDeviceToHost)
+                              : cudaErrorInvalidValue;
+        if (e != cudaSuccess) {
+            delete m;
+            return cuda_fail(e, "cudaMemcpy(fused_bias1)");
+        }
+    }
     *out = m;
     return DC_OK;
 }
@@ -306,7 +326,7 @@ int dc_forward_workspace_bytes(const dc_model_t* m, int B, int H, int W, size_t*
 
 int dc_forward_num_launches(const dc_model_t* m) {
     // stem + 17 conv3x3 + 4 upconv (+ the input conversion / the 1x1 head kernel for other channel counts)
-    return 22 + (m && m->cin != 3 ? 1 : 0) + (m && m->cout != 1 ? 1 : 0);
+    return 22 + (m && m->cin != 3 ? 1 : 0) + (m && m->cout != 1 ? 1 : 0) - (m && m->fused1 ? 1 : 0);
 }
 
 }  // extern "C"
@@ -392,9 +412,21 @@ static int forward_impl(dc_model_t* m, int in_kind, const void* in, int B, int H
     for (int l = 3; l >= 0; --l) {
         const int h = H >> l, w = W >> l, c = 64 << l;
         const int base = 10 + 3 * (3 - l);
+        if (l == 0 && m->fused1) {
+            // upconv1 + dec1.0 in one launch: `up` (channels [0,64) of cat[0]) is never written
+            dc_upfuse_args_t u;
+            memset(&u, 0, sizeof(u));
+            u.B = B; u.H = h / 2; u.W = w / 2;
+            u.x = src; u.x_stride = 2 * c;
+            u.skip = f.cat[0] + (size_t)c * 2; u.skip_stride = 2 * c;
+            u.weight = d.fused_weight1; u.bias9 = d.fused_bias1; u.relu = 1;
+            u.out = f.ad[0]; u.out_stride = c; u.out_offset = 0;
+            DC_TRY(launch_conv_upfused(&u, stream, m->fused_bias9));
+        } else {
         DC_TRY(conv(base, DC_KIND_UPCONV2, DC_EPI_UPSCATTER, 0, h / 2, w / 2, 2 * c, c, 1, src, 2 * c, f.cat[l], 2 * c, 0,
                     nullptr));
         DC_TRY(conv(base + 1, DC_KIND_CONV3X3, DC_EPI_STORE, 1, h, w, 2 * c, c, 1, f.cat[l], 2 * c, f.ad[l], c, 0, nullptr));
+        }
         if (l > 0) {
             DC_TRY(conv(base + 2, DC_KIND_CONV3X3, DC_EPI_STORE, 1, h, w, c, c, 1, f.ad[l], c, f.db[l], c, 0, nullptr));
             src = f.db[l];

@@ -31,6 +31,8 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // from the kernel parameters (constant-bank operands) instead of shared memory.
 int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream, const float* bias_host = nullptr);
 int launch_stem(const dc_stem_args_t* a, cudaStream_t stream, const float* bias_host = nullptr);
+// bias9_host: HOST copy of a->bias9 (the interior class becomes kernel parameters); required.
+int launch_conv_upfused(const dc_upfuse_args_t* a, cudaStream_t stream, const float* bias9_host);
 int set_conv_family(int family);
 int launch_label_stats(const dc_label_args_t* a, cudaStream_t stream);
 int launch_rolling_ball(const dc_rolling_ball_args_t* a, cudaStream_t stream);
@@ -213,6 +215,14 @@ __device__ __forceinline__ void tma_load_4d_2sm(void* dst, const void* tmap, uin
         "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1),
         "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2,
+                                                int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
 // arrive on the leader CTA's copy of `bar` (from either CTA of the pair).  Relaxed: what it orders is TMEM reads

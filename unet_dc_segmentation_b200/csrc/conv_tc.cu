@@ -86,6 +86,7 @@ __device__ __forceinline__ int fast_div(int n, const FastDiv& f) {
 struct alignas(64) ConvParams {
     CUtensorMap tmA;
     CUtensorMap tmB;
+    CUtensorMap tmS;                // conv_upfused2_kernel only: the skip tensor as two column-parity planes
     int B, H, W, Cin, Cout;
     int dil, ntaps, kchunks;
     int tiles_w, tiles_h, n_tiles, total_tiles, m_tiles;      // m_tiles = pixel tiles = total_tiles / n_tiles
@@ -208,7 +209,10 @@ __device__ __forceinline__ void release_accumulator(uint64_t* bar, int lane) {
     }
 }
 
-template <int BN, int TH, int TW, int NHALF = 1, bool PAIR = false, bool COOP = true>
+// UPF (conv_upfused2_kernel): the tile is TH x TW pixels of the HALF-resolution grid and the NHALF = 4 accumulators are
+// the four output parities (py, px) = (half / 2, half % 2): pixel (h, w) of accumulator `half` is output pixel
+// (2h + py, 2w + px); p.H, p.W are the half-resolution shape and the bias depends on the border class of the pixel.
+template <int BN, int TH, int TW, int NHALF = 1, bool PAIR = false, bool COOP = true, bool UPF = false>
 __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, const int lane, const int group,
                                              const uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                              const float* bias_s, uint8_t* stg_all) {
@@ -228,11 +232,12 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
     // Output addressing, split into a per-lane part fixed for the whole kernel and warp-uniform parts per tile /
     // half / chunk (the address arithmetic used to cost more instructions than the arithmetic on the data).
     // After the transpose this lane stores chunk sq of pixels pL0 + 8 r (r = 0..3) of its warp's 32.
-    const bool up = p.epilogue == DC_EPI_UPSCATTER;
+    const bool up = !UPF && p.epilogue == DC_EPI_UPSCATTER;
+    const bool up_geo = UPF || up;                             // output pixels are 2 apart in a [B,2H,2W,*] tensor
     const int pL0 = e * 32 + (lane >> 2);
     const int row0 = pL0 / TW, col0 = pL0 % TW;
-    const long long cs = (long long)p.out_stride * (up ? 2 : 1);                 // elements per tile column
-    const long long rs = (long long)p.out_stride * (up ? 4 : 1) * p.W;           // elements per tile row
+    const long long cs = (long long)p.out_stride * (up_geo ? 2 : 1);             // elements per tile column
+    const long long rs = (long long)p.out_stride * (up_geo ? 4 : 1) * p.W;       // elements per tile row
     __nv_bfloat16* const lane_ptr = p.out + (row0 * rs + col0 * cs + p.out_offset + sq * 8);
     // pooled pixel of this lane: lane / 4 of the 8 the warp's 32 pixels pool into
     const int prow = (TW == 16) ? e : 2 * e + (lane >> 4);
@@ -248,7 +253,7 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
             tile = blockIdx.x + it * gridDim.x;
             if (tile >= p.total_tiles) break;
         }
-        const TileCoord t = decode_tile<TH, TW * NHALF>(p, tile, BN);
+        const TileCoord t = decode_tile<TH, UPF ? TW : TW * NHALF>(p, tile, BN);
         const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(&tfull_bar[as], aphase);
@@ -298,8 +303,8 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
         uint32_t vbuf[2][32];
         tmem_ld32(tbase, vbuf[0]);
         // warp-uniform offsets of this tile
-        const long long tile_off = up ? (((long long)t.img * (2 * p.H) + 2 * t.h0) * (2 * p.W) + 2 * t.w0) * p.out_stride
-                                      : (((long long)t.img * p.H + t.h0) * p.W + t.w0) * p.out_stride + t.n0;
+        const long long tile_off = up_geo ? (((long long)t.img * (2 * p.H) + 2 * t.h0) * (2 * p.W) + 2 * t.w0) * p.out_stride
+                                          : (((long long)t.img * p.H + t.h0) * p.W + t.w0) * p.out_stride + t.n0;
         const long long ptile_off = (((long long)t.img * (p.H >> 1) + (t.h0 >> 1)) * (p.W >> 1) + (t.w0 >> 1)) * p.pool_stride + t.n0;
         const int hmax = p.H - t.h0;
         int q0 = 0, rem0 = 0;                                  // UPSCATTER: n0 = q0 * Cout + rem0
@@ -316,7 +321,7 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
             if (j + 1 < NI) tmem_ld32(tbase + (uint32_t)(((j + 1) / CPG) * BN + ((j + 1) % CPG) * CSTEP), vbuf[(j + 1) & 1]);
             else release_accumulator<PAIR>(&tempty_bar[as], lane);            // this warp has read all it will
             if (cc == 0) {
-                const int wmax = p.W - t.w0 - half * TW;
+                const int wmax = p.W - t.w0 - (UPF ? 0 : half * TW);
                 vmask = 0;
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
@@ -324,7 +329,7 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                     vmask |= (uint32_t)((row < hmax) && (col < wmax)) << r;
                 }
                 pval = (2 * prow < hmax) && (2 * pcol < wmax);
-                half_off = half * TW * cs;
+                half_off = UPF ? ((long long)(half >> 1) * (2 * p.W) + (half & 1)) * p.out_stride : half * TW * cs;
                 phalf_off = (long long)(half * (TW / 2)) * p.pool_stride;
             }
             int bias_at = t.n0 + c0;
@@ -358,6 +363,19 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                     x[4 * k + 1] = __uint_as_float(v[4 * k + 1]) + b.y;
                     x[4 * k + 2] = __uint_as_float(v[4 * k + 2]) + b.z;
                     x[4 * k + 3] = __uint_as_float(v[4 * k + 3]) + b.w;
+                }
+            }
+            if (UPF) {
+                // taps of the 3x3 that fall outside the (upsampled) image carry no transposed-conv bias: only the
+                // pixels of the first / last output row and column differ from the interior constant
+                const int hh = t.h0 + lh, ww = t.w0 + lw;
+                const int rc = ((half >> 1) == 0 && hh == 0) ? 0 : (((half >> 1) == 1 && hh == p.H - 1) ? 2 : 1);
+                const int cc9 = ((half & 1) == 0 && ww == 0) ? 0 : (((half & 1) == 1 && ww == p.W - 1) ? 2 : 1);
+                if (rc * 3 + cc9 != 4) {               // p.bias = the interior row (4) of the fp32 [9][64] class table
+                    const float* b4 = p.bias + c0;
+                    const float* bc = b4 + (rc * 3 + cc9 - 4) * 64;
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) x[k] += __ldg(bc + k) - __ldg(b4 + k);
                 }
             }
             uint32_t pk[16];
@@ -932,6 +950,223 @@ conv_halo2_kernel(const __grid_constant__ ConvParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------- upconv1 folded into dec1.0
+// ConvTranspose2d(128, 64, 2, stride 2) -> cat([up, skip]) -> Conv2d(128, 64, 3, padding 1) + BN + ReLU
+// (reference models/model_2.py:29, :76-77) as ONE kernel that never materialises `up`.  A 2x2/stride-2 transposed
+// conv followed by a 3x3 conv is, for the output pixels of one parity class (py, px) = (y & 1, x & 1), a 2x2-tap conv
+// over the HALF-resolution tensor x with composed weights (the host folds Wu into Wd in fp32: model.py compose_upconv)
+// -- K = 4 x 128 instead of 9 x 64 -- plus the ordinary 3x3 over the skip half sampled at stride 2.  Taps of the 3x3
+// that fall outside the upsampled image contribute nothing, bias of the transposed conv included: TMA's zero fill does
+// that for the data, the border-class bias of the epilogue for the bias.
+//
+// Tile = 16 x 8 pixels of the half-resolution grid per CTA = a 32 x 16 output patch; its four parity classes are the
+// four accumulators (4 x 64 TMEM columns, double buffered = 512), i.e. the four independent MMA chains an N = 64
+// layer needs.  K is walked as three "chunks", each with its own region and barrier pair (stage == chunk):
+//   chunk 0, 1: x channels [0,64) / [64,128): region (16+2) x (8+2) half-res pixels; class (py, px), tap (a, b) is
+//               the window starting at row py + a, column px + b.  Composed weights (4 KB per CTA and (chunk, tap,
+//               class)) stream through a ring of (chunk, tap) groups of four class slices.
+//   chunk 2   : the skip tensor's 34 x 18 full-resolution pixels around the patch, loaded as two column-parity planes
+//               (a 5-D tensor map splits W into (W/2, 2)) of 34 x 9 pixels: the window of class (py, px), tap (ky, kx)
+//               starts at row py + ky with 8-row groups TWO region rows apart (SBO) in plane (px + kx) & 1, column
+//               (px + kx) >> 1.  Its nine 4 KB weight slices are resident.
+// Roles as conv_halo2_kernel plus warp 3 = producer of the composed-weight ring (so that the region loads of the
+// next tile are never queued behind weight slices).
+constexpr int UPF_U_W = HT_W + 2, UPF_U_H = HT_H + 2;
+constexpr int UPF_U_BYTES = UPF_U_W * UPF_U_H * 128;                 // 23,040
+constexpr int UPF_S_W = HT_W + 1, UPF_S_H = 2 * HT_H + 2;
+constexpr int UPF_PLANE_BYTES = UPF_S_W * UPF_S_H * 128;             // 39,168
+constexpr int UPF_WT_BYTES = 32 * KCHUNK * 2;                        // this CTA's 32 rows of one 64 x 64 weight slice
+constexpr int UPF_GROUPS = 3;                                        // ring depth in (chunk, tap) groups of 4 slices
+constexpr int UPF_BIAS_BYTES = 256;
+constexpr int UPF_SLICES = 2 * 4 * 4 + 9;                            // composed (chunk, tap, class) + skip taps
+constexpr size_t UPF_SMEM = 9 * UPF_WT_BYTES + UPF_GROUPS * 4 * UPF_WT_BYTES + 2 * UPF_U_BYTES + 2 * UPF_PLANE_BYTES +
+                            1024 + HALO_BAR_BYTES + UPF_BIAS_BYTES + EPI_STAGE_TOTAL;
+static_assert(UPF_SMEM <= 227 * 1024, "conv_upfused2_kernel: shared memory");
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv_upfused2_kernel(const __grid_constant__ ConvParams p) {
+    constexpr int BN = 64;
+    constexpr int TMEM_COLS = 512;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* w_skip = smem;                                          // 9 resident slices
+    uint8_t* w_ring = w_skip + 9 * UPF_WT_BYTES;                     // UPF_GROUPS x 4 slices
+    uint8_t* u_reg = w_ring + UPF_GROUPS * 4 * UPF_WT_BYTES;         // x regions of chunk 0, 1
+    uint8_t* s_reg = u_reg + 2 * UPF_U_BYTES;                        // skip planes: [0] odd columns (from 2 w0 - 1), [1] even
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_reg + 2 * UPF_PLANE_BYTES);
+    uint64_t* empty_bar = full_bar + HALO_MAX_STAGES;
+    uint64_t* bfull_bar = empty_bar + HALO_MAX_STAGES;
+    uint64_t* bempty_bar = bfull_bar + HALO_MAX_STAGES;
+    uint64_t* tfull_bar = bempty_bar + HALO_MAX_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint64_t* w_bar = tempty_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+    float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + HALO_BAR_BYTES);
+    uint8_t* stg_s = reinterpret_cast<uint8_t*>(full_bar) + HALO_BAR_BYTES + UPF_BIAS_BYTES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int n_pairs = pair_count(p);
+
+    stage_bias(p, bias_s);
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmB);
+        tma_prefetch_desc(&p.tmS);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < HALO_MAX_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1);
+            mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8 * EPI_GROUPS); }
+        mbar_init(w_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ region producer (one per CTA)
+        if (elect_one()) {
+            if (leader) mbar_expect_tx(w_bar, 2u * 9u * UPF_WT_BYTES);
+            for (int tap = 0; tap < 9; ++tap)
+                tma_load_2d_2sm(w_skip + tap * UPF_WT_BYTES, &p.tmB, w_bar, (32 + tap) * KCHUNK, (int)rank * 32);
+        }
+        __syncwarp();
+        int it = 0;
+        for (int pair = cluster_id; pair < n_pairs; pair += n_clusters, ++it) {
+            const TileCoord t = decode_tile<HT_H, HT_W>(p, pair_to_tile(p, pair, (int)rank), BN);
+            const uint32_t ph = (uint32_t)it & 1u;
+            for (int kc = 0; kc < 2; ++kc) {
+                mbar_wait(&empty_bar[kc], ph ^ 1u);
+                if (elect_one()) {
+                    if (leader) mbar_expect_tx(&full_bar[kc], 2u * UPF_U_BYTES);
+                    tma_load_4d_2sm(u_reg + kc * UPF_U_BYTES, &p.tmA, &full_bar[kc], kc * KCHUNK, t.w0 - 1, t.h0 - 1, t.img);
+                }
+                __syncwarp();
+            }
+            mbar_wait(&empty_bar[2], ph ^ 1u);
+            if (elect_one()) {
+                if (leader) mbar_expect_tx(&full_bar[2], 4u * UPF_PLANE_BYTES);
+                // W is split into (W/2, parity): odd columns 2 w0 - 1, 2 w0 + 1, ... = (parity 1, from w0 - 1)
+                tma_load_5d_2sm(s_reg, &p.tmS, &full_bar[2], 0, 1, t.w0 - 1, 2 * t.h0 - 1, t.img);
+                tma_load_5d_2sm(s_reg + UPF_PLANE_BYTES, &p.tmS, &full_bar[2], 0, 0, t.w0, 2 * t.h0 - 1, t.img);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------------ composed-weight producer (one per CTA)
+        int bg = 0;
+        uint32_t bphase = 0;
+        for (int pair = cluster_id; pair < n_pairs; pair += n_clusters) {
+            for (int g = 0; g < 8; ++g) {                        // g = chunk * 4 + tap
+                mbar_wait(&bempty_bar[bg], bphase ^ 1u);
+                if (elect_one()) {
+                    if (leader) mbar_expect_tx(&bfull_bar[bg], 2u * 4u * UPF_WT_BYTES);
+#pragma unroll
+                    for (int cls = 0; cls < 4; ++cls)
+                        tma_load_2d_2sm(w_ring + (bg * 4 + cls) * UPF_WT_BYTES, &p.tmB, &bfull_bar[bg], (g * 4 + cls) * KCHUNK,
+                                        (int)rank * 32);
+                }
+                __syncwarp();
+                if (++bg == UPF_GROUPS) { bg = 0; bphase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (leader) {
+            const uint32_t idesc = umma_idesc_bf16(2 * TILE_M, BN);
+            const uint32_t u_addr = smem_u32(u_reg), s_addr = smem_u32(s_reg);
+            const uint32_t ring_addr = smem_u32(w_ring), wskip_addr = smem_u32(w_skip);
+            int bg = 0;
+            uint32_t bphase = 0;
+            int it = 0;
+            mbar_wait(w_bar, 0);
+            for (int pair = cluster_id; pair < n_pairs; pair += n_clusters, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+                const uint32_t ph = (uint32_t)it & 1u;
+                mbar_wait(&tempty_bar[as], aphase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * 4 * BN);
+#pragma unroll 1
+                for (int kc = 0; kc < 2; ++kc) {
+                    mbar_wait(&full_bar[kc], ph);
+                    tc_fence_after();
+                    const uint32_t region = u_addr + (uint32_t)(kc * UPF_U_BYTES);
+#pragma unroll
+                    for (int tap = 0; tap < 4; ++tap) {
+                        mbar_wait(&bfull_bar[bg], bphase);
+                        tc_fence_after();
+                        const uint32_t wg = ring_addr + (uint32_t)(bg * 4 * UPF_WT_BYTES);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < KCHUNK / 16; ++k) {
+#pragma unroll
+                                for (int cls = 0; cls < 4; ++cls) {
+                                    const uint32_t a_addr = region + (uint32_t)((((cls >> 1) + (tap >> 1)) * UPF_U_W + (cls & 1) + (tap & 1)) * 128);
+                                    const uint64_t adesc = umma_desc_sw128_strided(a_addr, UPF_U_W * 128u);
+                                    const uint64_t bdesc = umma_desc_sw128(wg + (uint32_t)(cls * UPF_WT_BYTES));
+                                    umma_bf16_2sm(d_tmem + (uint32_t)(cls * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                                  (kc | tap | k) ? 1u : 0u);
+                                }
+                            }
+                            umma_commit_2sm(&bempty_bar[bg]);
+                        }
+                        __syncwarp();
+                        if (++bg == UPF_GROUPS) { bg = 0; bphase ^= 1u; }
+                    }
+                    if (elect_one()) umma_commit_2sm(&empty_bar[kc]);
+                    __syncwarp();
+                }
+                mbar_wait(&full_bar[2], ph);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint64_t bdesc = umma_desc_sw128(wskip_addr + (uint32_t)(tap * UPF_WT_BYTES));
+#pragma unroll
+                        for (int k = 0; k < KCHUNK / 16; ++k) {
+#pragma unroll
+                            for (int cls = 0; cls < 4; ++cls) {
+                                const int ry = (cls >> 1) + tap / 3, cx = (cls & 1) + tap % 3;
+                                const uint32_t a_addr = s_addr + (uint32_t)((cx & 1) * UPF_PLANE_BYTES + (ry * UPF_S_W + (cx >> 1)) * 128);
+                                const uint64_t adesc = umma_desc_sw128_strided(a_addr, 2u * UPF_S_W * 128u);
+                                umma_bf16_2sm(d_tmem + (uint32_t)(cls * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                            }
+                        }
+                    }
+                    umma_commit_2sm(&empty_bar[2]);
+                    umma_commit_2sm(&tfull_bar[as]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        run_epilogue<BN, HT_H, HT_W, 4, true, true, true>(p, warp & 3, lane, (warp - EPI_WARP0) >> 2, tmem_base, tfull_bar, tempty_bar,
+                                                          bias_s, stg_s);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    }
+}
+
 // ---------------------------------------------------------------------------- stem on tensor cores
 // First layer, Conv2d(3, 64, 3, padding=d, dilation=d) + BN + ReLU (reference models/model_2.py:10, :41-46),
 // fused with the input conversion of quantify_droplets_batch.py:45-46 (u8 -> /255 -> NCHW float).
@@ -1211,7 +1446,7 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dim
                const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_fn();
     DC_REQUIRE(fn, DC_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1438,6 +1673,70 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream, const float* bi
         case 128: return launch_variant<128, 6>(p, stream);
         default:  return launch_variant<64, 8>(p, stream);
     }
+}
+
+int launch_conv_upfused(const dc_upfuse_args_t* a, cudaStream_t stream, const float* bias9_host) {
+    DC_REQUIRE(a && a->x && a->skip && a->weight && a->bias9 && a->out && bias9_host, DC_EINVAL,
+               "dc_conv_upfused: null pointer argument");
+    DC_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0, DC_EINVAL, "dc_conv_upfused: bad shape %d x %d x %d", a->B, a->H, a->W);
+    DC_REQUIRE(a->x_stride >= 128 && a->x_stride % 8 == 0 && a->skip_stride >= 64 && a->skip_stride % 8 == 0, DC_EINVAL,
+               "dc_conv_upfused: x_stride %d / skip_stride %d", a->x_stride, a->skip_stride);
+    DC_REQUIRE(((uintptr_t)a->x & 15) == 0 && ((uintptr_t)a->skip & 15) == 0 && ((uintptr_t)a->weight & 15) == 0 &&
+                   ((uintptr_t)a->out & 15) == 0,
+               DC_EINVAL, "dc_conv_upfused: x / skip / weight / out must be 16-byte aligned");
+    DC_REQUIRE(a->out_stride % 8 == 0 && a->out_offset % 8 == 0 && a->out_offset >= 0 && a->out_stride >= a->out_offset + 64,
+               DC_EINVAL, "dc_conv_upfused: out_stride %d / out_offset %d", a->out_stride, a->out_offset);
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    {   // x: [B, H, W, 128 of x_stride], one haloed region per 64-channel chunk
+        cuuint64_t dims[4] = {128, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B};
+        cuuint64_t str[3] = {(cuuint64_t)a->x_stride * 2, (cuuint64_t)a->W * a->x_stride * 2,
+                             (cuuint64_t)a->H * a->W * a->x_stride * 2};
+        cuuint32_t box[4] = {KCHUNK, UPF_U_W, UPF_U_H, 1};
+        int rc = encode_map(&p.tmA, a->x, 4, dims, str, box);
+        if (rc != DC_OK) return rc;
+    }
+    {   // skip: [B, 2H, 2W, 64 of skip_stride] seen as [B, 2H, W, parity, 64]: a box is one column-parity plane
+        const cuuint64_t ps = (cuuint64_t)a->skip_stride * 2;
+        cuuint64_t dims[5] = {64, 2, (cuuint64_t)a->W, (cuuint64_t)(2 * a->H), (cuuint64_t)a->B};
+        cuuint64_t str[4] = {ps, 2 * ps, 2 * (cuuint64_t)a->W * ps, 4 * (cuuint64_t)a->H * a->W * ps};
+        cuuint32_t box[5] = {KCHUNK, 1, UPF_S_W, UPF_S_H, 1};
+        int rc = encode_map(&p.tmS, a->skip, 5, dims, str, box);
+        if (rc != DC_OK) return rc;
+    }
+    {   // weights: [64 rows][UPF_SLICES * 64]
+        cuuint64_t dims[2] = {(cuuint64_t)UPF_SLICES * KCHUNK, 64};
+        cuuint64_t str[1] = {(cuuint64_t)UPF_SLICES * KCHUNK * 2};
+        cuuint32_t box[2] = {KCHUNK, 32};
+        int rc = encode_map(&p.tmB, a->weight, 2, dims, str, box);
+        if (rc != DC_OK) return rc;
+    }
+    p.B = a->B; p.H = a->H; p.W = a->W; p.Cin = 192; p.Cout = 64;
+    p.dil = 1; p.ntaps = 9; p.kchunks = 3;
+    p.tiles_w = ceil_div(a->W, HT_W);
+    p.tiles_h = ceil_div(a->H, HT_H);
+    p.n_tiles = 1;
+    const long long total = (long long)a->B * p.tiles_w * p.tiles_h;
+    DC_REQUIRE(total < (1ll << 31), DC_EINVAL, "dc_conv_upfused: too many tiles");
+    p.total_tiles = p.m_tiles = (int)total;
+    p.fd_ntiles = make_fastdiv(1); p.fd_per_img = make_fastdiv(p.tiles_h * p.tiles_w); p.fd_tiles_w = make_fastdiv(p.tiles_w);
+    p.epilogue = DC_EPI_STORE;
+    p.relu = a->relu != 0;
+    p.bias = a->bias9 + 4 * 64;                       // interior class
+    p.bias_const = 1;
+    memcpy(p.bias_c, bias9_host + 4 * 64, sizeof(p.bias_c));
+    p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+    p.out_stride = a->out_stride; p.out_offset = a->out_offset;
+
+    const int n_pairs = (p.m_tiles + 1) / 2;
+    const int max_clusters = num_sms() / 2;
+    const int grid = 2 * (n_pairs < max_clusters ? n_pairs : max_clusters);
+    static unsigned long long attr_done = 0;
+    int rc = set_max_smem_once(conv_upfused2_kernel, (int)UPF_SMEM, &attr_done);
+    if (rc != DC_OK) return rc;
+    conv_upfused2_kernel<<<grid, NUM_THREADS, UPF_SMEM, stream>>>(p);
+    DC_CUDA(cudaGetLastError());
+    return DC_OK;
 }
 
 int set_conv_family(int family) {

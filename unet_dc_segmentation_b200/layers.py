@@ -77,6 +77,26 @@ def upconv2x2(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, out: to
     return out
 
 
+def upconv_conv3x3(x: torch.Tensor, skip: torch.Tensor, weight: torch.Tensor, bias9: torch.Tensor, relu: bool = True,
+                   skip_offset: int = 0, out: torch.Tensor | None = None, out_offset: int = 0) -> torch.Tensor:
+    """ConvTranspose2d(128, 64, 2, 2) -> cat([up, skip]) -> 3x3 conv (+bias, +ReLU) as one launch (dc_conv_upfused).
+    x: bf16 [B,H,W,128]; skip: bf16 [B,2H,2W,S] read at channels [skip_offset, skip_offset + 64); weight / bias9 from
+    model.compose_upconv.  Returns bf16 [B,2H,2W,64] (or `out`, written at channel out_offset)."""
+    _lib.require_cuda(x, "x")
+    B, H, W, S = x.shape
+    if out is None:
+        out = torch.empty((B, 2 * H, 2 * W, 64), dtype=torch.bfloat16, device=x.device)
+    a = _lib.UpfuseArgs()
+    a.B, a.H, a.W = B, H, W
+    a.x, a.x_stride = x.data_ptr(), S
+    a.skip, a.skip_stride = skip.data_ptr() + 2 * int(skip_offset), skip.shape[3]
+    a.weight, a.bias9, a.relu = weight.data_ptr(), bias9.data_ptr(), int(relu)
+    a.out, a.out_stride, a.out_offset = out.data_ptr(), out.shape[3], int(out_offset)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().dc_conv_upfused(C.byref(a), _lib.stream_ptr(x.device)))
+    return out
+
+
 def conv3x3_head(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, head_w: torch.Tensor, head_b: float,
                  thresh: float, dilation: int = 1):
     """Last layer: conv3x3 (64 -> 64) + ReLU, then 1x1 conv + sigmoid + threshold in the epilogue.

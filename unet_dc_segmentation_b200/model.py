@@ -56,6 +56,49 @@ def pack_upconv(w):
     return w.float().permute(2, 3, 1, 0).reshape(4 * co, ci).to(torch.bfloat16).contiguous()
 
 
+def compose_upconv(wu, bu, wd, bd):
+    """ConvTranspose2d(k=2, s=2) followed by cat([up, skip]) and a 3x3 conv, folded into one layer (dc_conv_upfused).
+
+    wu [Cx,C,2,2], bu [C]: the transposed conv (model_2.py:29); wd [Co,2C,3,3], bd [Co]: the 3x3 conv with BatchNorm
+    already folded (model_2.py:40-46), input channels [0,C) = up, [C,2C) = skip (torch.cat order, model_2.py:76).
+    up[Y,X] = bu + x[Y>>1, X>>1] . wu[:, :, Y&1, X&1], so output pixel (2i+py, 2j+px) sees x only at the 2x2
+    neighbourhood (i-1+py+a, j-1+px+b): the weights of that tap are the sum, over the 3x3 taps (ky, kx) that land
+    on it, of wu[..., ry, rx] . wd[..., ky, kx] with (ry, rx) the parity of the upsampled pixel.  Composed in fp64,
+    rounded to bf16 once.  Returns (weight bf16 [Co, 41*64], bias9 f32 [9, Co]) in the layouts of include/unetdc_b200.h."""
+    cx, c = wu.shape[:2]
+    co = wd.shape[0]
+    assert (cx, c, co) == (128, 64, 64) and wd.shape[1] == 2 * c, "level-1 shapes only"
+    wu64, wd64 = wu.double(), wd.double()
+    wd_up, wd_skip = wd64[:, :c], wd64[:, c:]
+    comp = torch.zeros((2, 4, 4, co, 64), dtype=torch.float64, device=wd.device)      # [chunk][tap][cls][co][ci]
+    for py in range(2):
+        for px in range(2):
+            for ky in range(3):
+                for kx in range(3):
+                    ty, tx = py + ky - 1, px + kx - 1                  # offset of the upsampled pixel from (2i, 2j)
+                    a, b = ty // 2 - (py - 1), tx // 2 - (px - 1)      # which of the 2x2 x-taps it reads
+                    w = torch.einsum("oc,ic->oi", wd_up[:, :, ky, kx], wu64[:, :, ty % 2, tx % 2])     # [co, cx]
+                    for chunk in range(2):
+                        comp[chunk, a * 2 + b, py * 2 + px] += w[:, chunk * 64:(chunk + 1) * 64]
+    skip = wd_skip.permute(2, 3, 0, 1).reshape(9, co, 64)                                # [tap][co][c]
+    slices = torch.cat([comp.reshape(32, co, 64), skip], 0)                               # [41][co][64]
+    weight = slices.permute(1, 0, 2).reshape(co, 41 * 64).to(torch.bfloat16).contiguous()
+    tb = torch.einsum("ockl,c->klo", wd_up, bu.double())                                  # bias of `up` through tap (ky, kx)
+    bias9 = torch.zeros((3, 3, co), dtype=torch.float64, device=wd.device)
+    valid = ((1, 2), (0, 1, 2), (0, 1))            # taps inside the image for the first / interior / last row (column)
+    for rc in range(3):
+        for cc in range(3):
+            bias9[rc, cc] = bd.double() + sum(tb[ky, kx] for ky in valid[rc] for kx in valid[cc])
+    return weight, bias9.reshape(9, co).float().contiguous()
+
+
+def fused_level1_blobs(sd, eps: float = 1e-5):
+    """(weight, bias9) of the composed upconv1 + dec1.0 layer from a state_dict (on the tensors' own device)."""
+    wd, bd = fold_conv_bn(sd["dec1.0.weight"], sd["dec1.0.bias"], sd["dec1.1.weight"], sd["dec1.1.bias"],
+                          sd["dec1.1.running_mean"], sd["dec1.1.running_var"], eps)
+    return compose_upconv(sd["upconv1.weight"].float(), sd["upconv1.bias"].float(), wd, bd)
+
+
 class _Packed:
     """Device blobs + the dc_model handle built from one state of the parameters."""
 
@@ -96,6 +139,11 @@ class _Packed:
         desc.base_channels = 64
         desc.in_channels = module.in_channels
         desc.out_channels = module.out_channels
+        if module.fuse_level1:
+            fw, fb = fused_level1_blobs(sd, module._bn_eps("dec1", 1))
+            self.blobs += [fw, fb]
+            desc.fused_weight1 = fw.data_ptr()
+            desc.fused_bias1 = fb.data_ptr()
         self.device = device
         self.handle = C.c_void_p()
         with torch.cuda.device(device):
@@ -123,6 +171,9 @@ class UNetDC(nn.Module):
     """Dilated U-Net of reference models/model_2.py:5-80 (dilations 1/2/4/8/16 in the encoder)."""
 
     dilations = (1, 2, 4, 8, 16)
+    # upconv1 + dec1.0 as one launch with host-composed weights (csrc/conv_tc.cu conv_upfused2_kernel); False runs the
+    # two layers separately (set it before the first forward, or call invalidate())
+    fuse_level1 = True
 
     def __init__(self, in_channels: int = 3, out_channels: int = 1):
         super().__init__()

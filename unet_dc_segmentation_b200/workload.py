@@ -46,12 +46,20 @@ def forward_flops(H: int, W: int, dilations=(1, 2, 4, 8, 16), in_bounds: bool = 
     return sum(layer_flops(l, in_bounds) for l in conv_layers(H, W, dilations))
 
 
-def launch_flops(H: int, W: int, dilations=(1, 2, 4, 8, 16), in_bounds: bool = True):
-    """FLOPs per kernel launch of dc_forward (22 launches: out_conv is fused into the last one)."""
+def launch_flops(H: int, W: int, dilations=(1, 2, 4, 8, 16), in_bounds: bool = True, fused_level1: bool = False):
+    """FLOPs per kernel launch of dc_forward (22 launches: out_conv is fused into the last one; 21 with
+    ``fused_level1``, where upconv1 and dec1.0 are one launch -- counted with the FLOPs of the two layers it replaces,
+    the composed form executes K = 1088 instead of 2 x 128 + 1152 per output pixel)."""
     ls = conv_layers(H, W, dilations)
     fl = [layer_flops(l, in_bounds) for l in ls]
     fl[-2] += fl[-1]
-    return [l[0] for l in ls[:-1]], fl[:-1]
+    names, fl = [l[0] for l in ls[:-1]], fl[:-1]
+    if fused_level1:
+        i = names.index("upconv1")
+        assert names[i + 1] == "dec1.0"
+        names[i:i + 2] = ["upconv1+dec1.0"]
+        fl[i:i + 2] = [fl[i] + fl[i + 1]]
+    return names, fl
 
 
 # bytes per pixel (BASELINE.md section 3)
