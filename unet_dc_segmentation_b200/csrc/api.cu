@@ -87,7 +87,9 @@ struct ForwardBuffers {
 // forward_impl below); two buffers may share memory when their lifetimes do not intersect.  Largest first, each at
 // the lowest offset that is free for its whole lifetime.  At 32 x 1024^2 this is 15.6 GB (the skip halves of cat[0..3]
 // have to survive the whole bottom of the U) instead of the 30.5 GB of one private buffer per tensor.
-ForwardBuffers carve(char* base, int B, int H, int W, bool generic_in = false, bool generic_out = false) {
+// fused1 (upconv1 + dec1.0 as one launch, number 20): cat[0] holds only the skip half (64 channels), and dec2.3's
+// output is read by the launch that writes ad[0], so it has to live one launch longer.
+ForwardBuffers carve(char* base, int B, int H, int W, bool generic_in = false, bool generic_out = false, bool fused1 = false) {
     ForwardBuffers f;
     memset(&f, 0, sizeof(f));
     struct Item { size_t bytes; int t0, t1; char** slot; size_t off; };
@@ -104,10 +106,10 @@ ForwardBuffers carve(char* base, int B, int H, int W, bool generic_in = false, b
         const size_t C = (size_t)64 << l;
         add(&f.a[l], px * C, 2 * l, 2 * l + 1);
         if (l < 4) {
-            add(&f.cat[l], px * 2 * C, 2 * l + 1, 20 - 3 * l);
+            add(&f.cat[l], px * (l == 0 && fused1 ? 1 : 2) * C, 2 * l + 1, 20 - 3 * l);
             add(&f.pool[l], px / 4 * C, 2 * l + 1, 2 * l + 2);
             add(&f.ad[l], px * C, 20 - 3 * l, 21 - 3 * l);
-            if (l > 0) add(&f.db[l], px * C, 21 - 3 * l, 22 - 3 * l);
+            if (l > 0) add(&f.db[l], px * C, 21 - 3 * l, 22 - 3 * l + (l == 1 && fused1 ? 1 : 0));
         } else {
             add(&f.bott, px * C, 9, 10);
         }
@@ -320,7 +322,7 @@ int dc_forward_workspace_bytes(const dc_model_t* m, int B, int H, int W, size_t*
     DC_REQUIRE(m && bytes, DC_EINVAL, "dc_forward_workspace_bytes: null argument");
     DC_REQUIRE(B > 0 && H > 0 && W > 0 && H % 16 == 0 && W % 16 == 0, DC_EINVAL,
                "dc_forward: H and W must be positive multiples of 16 (got %d x %d x %d)", B, H, W);
-    *bytes = carve(nullptr, B, H, W, m->cin != 3, m->cout != 1).total;
+    *bytes = carve(nullptr, B, H, W, m->cin != 3, m->cout != 1, m->fused1).total;
     return DC_OK;
 }
 
@@ -345,7 +347,7 @@ static int forward_impl(dc_model_t* m, int in_kind, const void* in, int B, int H
     DC_REQUIRE(dev == m->device, DC_EINVAL, "dc_forward: model lives on device %d, current device is %d", m->device, dev);
     const bool gen_in = m->cin != 3, gen_out = m->cout != 1;
     DC_REQUIRE(!gen_in || in_kind == 0, DC_EINVAL, "dc_forward: u8 inputs need in_channels == 3 (model has %d)", m->cin);
-    ForwardBuffers f = carve((char*)workspace, B, H, W, gen_in, gen_out);
+    ForwardBuffers f = carve((char*)workspace, B, H, W, gen_in, gen_out, m->fused1);
     DC_REQUIRE(workspace_bytes >= f.total, DC_EWORKSPACE, "dc_forward: workspace too small (%zu < %zu)", workspace_bytes,
                f.total);
     DC_REQUIRE(((uintptr_t)workspace & 255) == 0, DC_EINVAL, "dc_forward: workspace must be 256-byte aligned");
@@ -393,8 +395,8 @@ static int forward_impl(dc_model_t* m, int in_kind, const void* in, int B, int H
         s.out = f.a[0]; s.out_stride = 64; s.out_offset = 0;
         DC_TRY(launch_stem(&s, stream, m->has_bias64[0] ? m->bias64[0] : nullptr));
     }
-    DC_TRY(conv(1, DC_KIND_CONV3X3, DC_EPI_STORE_POOL, 1, H, W, 64, 64, d.dilations[0], f.a[0], 64, f.cat[0], 128, 64,
-                f.pool[0]));
+    DC_TRY(conv(1, DC_KIND_CONV3X3, DC_EPI_STORE_POOL, 1, H, W, 64, 64, d.dilations[0], f.a[0], 64, f.cat[0],
+                m->fused1 ? 64 : 128, m->fused1 ? 0 : 64, f.pool[0]));
     for (int l = 1; l < 4; ++l) {
         const int h = H >> l, w = W >> l, c = 64 << l;
         DC_TRY(conv(2 * l, DC_KIND_CONV3X3, DC_EPI_STORE, 1, h, w, c / 2, c, d.dilations[l], f.pool[l - 1], c / 2, f.a[l], c,
@@ -418,7 +420,7 @@ static int forward_impl(dc_model_t* m, int in_kind, const void* in, int B, int H
             memset(&u, 0, sizeof(u));
             u.B = B; u.H = h / 2; u.W = w / 2;
             u.x = src; u.x_stride = 2 * c;
-            u.skip = f.cat[0] + (size_t)c * 2; u.skip_stride = 2 * c;
+            u.skip = f.cat[0]; u.skip_stride = c;
             u.weight = d.fused_weight1; u.bias9 = d.fused_bias1; u.relu = 1;
             u.out = f.ad[0]; u.out_stride = c; u.out_offset = 0;
             DC_TRY(launch_conv_upfused(&u, stream, m->fused_bias9));
