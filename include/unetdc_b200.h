@@ -107,9 +107,10 @@ int dc_conv_tc(const dc_conv_args_t* args, void* stream);
  * weights the host composes in fp32 and rounds to bf16 once, plus the 3x3 over the skip half.
  *   x     bf16 [B,H,W,x_stride], channels [0,128)
  *   skip  bf16 [B,2H,2W,skip_stride], channels [0,64) from the pointer (it may point into a channel slice)
- *   weight bf16 [64][41*64]: row co; 64-wide column slices ((chunk*4 + tap)*4 + cls) for chunk = x channels
- *         [64 chunk, 64 chunk + 64), tap = a*2 + b (x pixel (i - 1 + py + a, j - 1 + px + b) for output
- *         (2i + py, 2j + px)), cls = py*2 + px; then slices 32 + ky*3 + kx = the skip half of the 3x3 weights
+ *   weight bf16 [2][2176][64]: 64-input-channel rows in the order the kernel's MMA schedule consumes them, one half per
+ *         CTA of a pair (dc_debug_upfuse_schedule below lists the MMAs; unet_dc_segmentation_b200/model.py pack_upfused
+ *         is the packer): the composed 2x2 taps over x per output parity class cls = (y & 1)*2 + (x & 1), then the
+ *         skip half of the 3x3 weights
  *   bias9 fp32 [9][64]: row (row class * 3 + col class), class 0 / 1 / 2 = first / interior / last output row
  *         (column): the conv bias plus the transposed conv's bias through the taps that lie inside the image
  *   out   bf16 [B,2H,2W,out_stride] at channel out_offset. */
@@ -128,6 +129,17 @@ typedef struct dc_upfuse_args {
 } dc_upfuse_args_t;
 
 int dc_conv_upfused(const dc_upfuse_args_t* args, void* stream);
+/* Host only (no GPU needed): the MMA schedule of dc_conv_upfused, 5 ints per MMA in issue order = {chunk (0, 1: x
+ * channels [64 chunk, 64 chunk + 64); 2: skip), window row, window column, first class, classes (1, 2 or 4)}.
+ * Class cls of an MMA on window (r, c) uses tap (r - py, c - px) of its 2x2 (x chunks) or 3x3 (skip) weights; its B
+ * operand is the classes' [64 co][64 ci] tiles stacked, rows [0, N/2) in the first CTA's half of the blob and
+ * [N/2, N) in the second's.  Returns the number of MMAs (42) or a negative DC_E* code. */
+int dc_debug_upfuse_schedule(int* out, int cap);
+/* TEST / MEASUREMENT AID, never called on the product path: which windows dc_conv_upfused shares between classes
+ * (0, the default: N = 256 / 128 / 64 MMAs as the windows allow; 1: no sharing, one N = 64 MMA per class and tap;
+ * 2: sharing in the x chunks only; 3: only the four-class windows).  Weights must be packed for the mode in force
+ * (dc_debug_upfuse_schedule follows it).  Process-wide. */
+int dc_debug_set_upfuse_mode(int mode);
 
 /* TEST AID, never called on the product path: pins which kernel family dc_conv_tc picks for layers that have a
  * choice, so that the fallback kernels stay under test.  AUTO (the default): CTA-pair halo kernel where it fits,

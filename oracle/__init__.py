@@ -163,29 +163,23 @@ def quantify(bin_mask: np.ndarray, min_area: int = 1, px_per_um: float | None = 
 _BLOCKS = [("enc1", 1), ("enc2", 2), ("enc3", 4), ("enc4", 8), ("bottleneck", 16)]
 
 
-def composed_upconv_conv3x3(x, skip, weight, bias9, relu=True):
-    """CPU evaluation of the fused level-1 layer from the blobs the CUDA kernel consumes (include/unetdc_b200.h,
-    dc_upfuse_args): x f32 [B,128,H,W], skip f32 [B,64,2H,2W], weight [64, 41*64], bias9 [9,64] -> f32 [B,64,2H,2W].
-    Equal (up to rounding) to conv_transpose2d -> cat -> conv2d(padding=1) of models/model_2.py:76-77; restated here per
-    output parity class so that the weight layout itself is what the GPU tests check."""
+def composed_upconv_conv3x3(x, skip, comp, skipw, bias9, relu=True):
+    """CPU evaluation of the fused level-1 layer (include/unetdc_b200.h dc_conv_upfused) from the composed weights:
+    x f32 [B,128,H,W], skip f32 [B,64,2H,2W], comp [4 classes][2][2][64][128], skipw [3][3][64][64], bias9 [9,64]
+    -> f32 [B,64,2H,2W].  Equal (up to rounding) to conv_transpose2d -> cat -> conv2d(padding=1) of
+    models/model_2.py:76-77, restated per output parity class: class (py, px) is a 2x2 conv over x zero-padded by one
+    pixel, read from (py, px), plus the 3x3 over skip, plus the bias of the pixel's border class."""
     import torch
     import torch.nn.functional as F
 
     B, _, H, W = x.shape
-    w = weight.to(torch.float32).reshape(64, 41, 64)
     xp = F.pad(x, (1, 1, 1, 1))
     out = torch.zeros((B, 64, 2 * H, 2 * W), dtype=torch.float32)
     for py in range(2):
         for px in range(2):
-            cls = py * 2 + px
-            k = torch.zeros((64, 128, 2, 2), dtype=torch.float32)
-            for chunk in range(2):
-                for a in range(2):
-                    for b in range(2):
-                        k[:, chunk * 64:(chunk + 1) * 64, a, b] = w[:, (chunk * 4 + a * 2 + b) * 4 + cls]
+            k = comp[py * 2 + px].to(torch.float32).permute(2, 3, 0, 1).contiguous()       # [co][cx][a][b]
             out[:, :, py::2, px::2] = F.conv2d(xp[:, :, py:py + H + 1, px:px + W + 1], k)
-    ks = w[:, 32:41].permute(0, 2, 1).reshape(64, 64, 3, 3)
-    out += F.conv2d(skip, ks, padding=1)
+    out += F.conv2d(skip, skipw.to(torch.float32).permute(2, 3, 0, 1).contiguous(), padding=1)
     b9 = bias9.to(torch.float32).reshape(3, 3, 64)
     rows = torch.ones(2 * H, dtype=torch.long); rows[0] = 0; rows[-1] = 2
     cols = torch.ones(2 * W, dtype=torch.long); cols[0] = 0; cols[-1] = 2
@@ -207,7 +201,7 @@ def unetdc_forward(state_dict, x, dilations=(1, 2, 4, 8, 16), emulate_bf16=False
     (this vs fp32, inherent to the precision choice).  ``gray_input``: x holds u8 grey levels / 255 replicated
     to 3 channels; the CUDA stem then feeds the exact integers and folds 1/255 and the 3 channels into the weights.
     ``round_last``: models with out_channels != 1 store the last feature map in bf16 before the 1x1 head kernel.
-    ``fused_level1`` (emulation only): (weight, bias9) of the composed upconv1 + dec1.0 layer the CUDA path runs by
+    ``fused_level1`` (emulation only): (comp, skipw, bias9) of the composed upconv1 + dec1.0 layer the CUDA path runs by
     default (model.compose_upconv; None = the two layers separately, `up` stored in bf16)."""
     import torch
     import torch.nn.functional as F
@@ -248,7 +242,7 @@ def unetdc_forward(state_dict, x, dilations=(1, 2, 4, 8, 16), emulate_bf16=False
         t = block(t, "bottleneck", dilations[4])            # model_2.py:64
         for lvl in (4, 3, 2, 1):                            # model_2.py:67-77
             if lvl == 1 and emulate_bf16 and fused_level1 is not None:
-                t = r(composed_upconv_conv3x3(t, skips[0], fused_level1[0].cpu(), fused_level1[1].cpu()))
+                t = r(composed_upconv_conv3x3(t, skips[0], *(b.cpu() for b in fused_level1)))
                 t = cbr(t, "dec1", 3, 1)
                 t = r(t) if round_last else t
                 continue

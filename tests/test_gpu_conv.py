@@ -179,18 +179,19 @@ def test_upconv_conv3x3_fused(cuda_device, B, H, W):
     import torch.nn.functional as F
     import oracle
     from unet_dc_segmentation_b200 import layers
-    from unet_dc_segmentation_b200.model import compose_upconv
+    from unet_dc_segmentation_b200.model import compose_upconv, pack_upfused
     g = torch.Generator().manual_seed(B * 1000 + H * 10 + W)
     wu = torch.randn(128, 64, 2, 2, generator=g) / 128 ** 0.5
     bu = torch.randn(64, generator=g) * 0.3
     wd = torch.randn(64, 128, 3, 3, generator=g) / (3.0 * 128 ** 0.5)
     bd = torch.randn(64, generator=g) * 0.1
-    weight, bias9 = compose_upconv(wu, bu, wd, bd)
+    comp, skipw, bias9 = compose_upconv(wu, bu, wd, bd)
+    weight = pack_upfused(comp, skipw)
     x = _rand_act(B, H, W, 128, 5)
     cat = _rand_act(B, 2 * H, 2 * W, 128, 6)              # skip = channels [64,128) of a 128-channel buffer
     xs, ss = x.float().permute(0, 3, 1, 2), cat[..., 64:].float().permute(0, 3, 1, 2)
     for relu in (True, False):
-        want = oracle.composed_upconv_conv3x3(xs, ss, weight, bias9, relu=relu).permute(0, 2, 3, 1)
+        want = oracle.composed_upconv_conv3x3(xs, ss, comp, skipw, bias9, relu=relu).permute(0, 2, 3, 1)
         out = torch.full((B, 2 * H, 2 * W, 96), 7.0, dtype=torch.bfloat16).cuda()
         layers.upconv_conv3x3(x.cuda(), cat.cuda(), weight.cuda(), bias9.cuda(), relu=relu, skip_offset=64, out=out,
                               out_offset=16)

@@ -159,9 +159,9 @@ def test_compose_upconv_equals_the_two_layers():
     x = torch.randn(2, 128, 5, 7, generator=g)
     skip = torch.randn(2, 64, 10, 14, generator=g)
     want = F.conv2d(torch.cat([F.conv_transpose2d(x, wu, bu, stride=2), skip], 1), wd, bd, padding=1)
-    w, b9 = M.compose_upconv(wu, bu, wd, bd)
-    assert w.dtype == torch.bfloat16 and tuple(w.shape) == (64, 41 * 64) and tuple(b9.shape) == (9, 64)
-    got = oracle.composed_upconv_conv3x3(x, skip, w, b9, relu=False)
+    comp, skipw, b9 = M.compose_upconv(wu, bu, wd, bd)
+    assert comp.dtype == torch.bfloat16 and tuple(comp.shape) == (4, 2, 2, 64, 128) and tuple(b9.shape) == (9, 64)
+    got = oracle.composed_upconv_conv3x3(x, skip, comp, skipw, b9, relu=False)
     assert float((got - want).abs().max()) < 0.05                  # bf16 rounding of the composed weights only
     # without that rounding the two are the same linear map
     class _NoRound:
@@ -169,8 +169,36 @@ def test_compose_upconv_equals_the_two_layers():
             return torch.float32 if k == "bfloat16" else getattr(torch, k)
     real, M.torch = M.torch, _NoRound()
     try:
-        w32, b932 = M.compose_upconv(wu, bu, wd, bd)
+        c32, s32, b932 = M.compose_upconv(wu, bu, wd, bd)
     finally:
         M.torch = real
-    got32 = oracle.composed_upconv_conv3x3(x, skip, w32, b932, relu=False)
+    got32 = oracle.composed_upconv_conv3x3(x, skip, c32, s32, b932, relu=False)
     assert float((got32 - want).abs().max()) < 1e-4
+
+
+def test_pack_upfused_follows_the_kernel_schedule():
+    """The weight blob of dc_conv_upfused: every MMA of the schedule the library reports (host-only call) gets the
+    tiles of the classes it covers, split between the two CTAs of a pair; 17 groups of 128 rows per CTA; every
+    (class, tap, chunk) of the composed weights and every (class, 3x3 tap) of the skip weights is used exactly once."""
+    import torch
+    from unet_dc_segmentation_b200 import model as M
+    sched = M.upfuse_schedule()
+    assert len(sched) == 42
+    seen = set()
+    rows = 0
+    for chunk, r, c, cls0, ncls in sched:
+        assert ncls in (1, 2, 4) and cls0 % ncls == 0
+        for cls in range(cls0, cls0 + ncls):
+            ky, kx = r - (cls >> 1), c - (cls & 1)
+            assert 0 <= ky < (3 if chunk == 2 else 2) and 0 <= kx < (3 if chunk == 2 else 2)
+            assert (chunk, cls, ky, kx) not in seen
+            seen.add((chunk, cls, ky, kx))
+        rows += 32 * ncls
+    assert len(seen) == 2 * 4 * 4 + 4 * 9 and rows == 2176
+    comp = torch.arange(4 * 2 * 2 * 64 * 128, dtype=torch.float32).reshape(4, 2, 2, 64, 128).bfloat16()
+    skipw = -torch.arange(9 * 64 * 64, dtype=torch.float32).reshape(3, 3, 64, 64).bfloat16()
+    blob = M.pack_upfused(comp, skipw)
+    assert tuple(blob.shape) == (2, 2176, 64)
+    # first MMA: window (1, 1) of x chunk 0, all four classes -> classes 0, 1 in CTA 0, classes 2, 3 in CTA 1
+    assert torch.equal(blob[0, :64], comp[0, 1, 1][:, :64]) and torch.equal(blob[0, 64:128], comp[1, 1, 0][:, :64])
+    assert torch.equal(blob[1, :64], comp[2, 0, 1][:, :64]) and torch.equal(blob[1, 64:128], comp[3, 0, 0][:, :64])

@@ -7,7 +7,7 @@ import torch
 
 sys.path.insert(0, ".")
 from unet_dc_segmentation_b200 import layers                                    # noqa: E402
-from unet_dc_segmentation_b200.model import compose_upconv, pack_conv3x3, pack_upconv   # noqa: E402
+from unet_dc_segmentation_b200.model import compose_upconv, pack_conv3x3, pack_upconv, pack_upfused   # noqa: E402
 
 B, H, W = (int(v) for v in sys.argv[1:4]) if len(sys.argv) > 3 else (32, 512, 512)
 dev = torch.device("cuda:0")
@@ -16,7 +16,8 @@ wu = torch.randn(128, 64, 2, 2, generator=g) / 128 ** 0.5
 bu = torch.randn(64, generator=g) * 0.3
 wd = torch.randn(64, 128, 3, 3, generator=g) / (3.0 * 128 ** 0.5)
 bd = torch.randn(64, generator=g) * 0.1
-fw, fb = (t.to(dev) for t in compose_upconv(wu, bu, wd, bd))
+comp, skipw, fb = compose_upconv(wu, bu, wd, bd)
+fw, fb = pack_upfused(comp, skipw).to(dev), fb.to(dev)
 pu, pd = pack_upconv(wu).to(dev), pack_conv3x3(wd).to(dev)
 bu_d, bd_d = bu.to(dev), bd.to(dev)
 x = torch.randn((B, H, W, 128), device=dev).bfloat16()
@@ -44,6 +45,15 @@ def timed(fn, n=7):
     return statistics.median(ts[2:])
 
 
-t2, tf = timed(two), timed(fused)
-d = (out.float() - out2.float()).abs()
-print(f"B {B} H {H} W {W}: upconv1 + dec1.0 {t2:.3f} ms, fused {tf:.3f} ms, max |diff| {float(d.max()):.4f} mean {float(d.mean()):.5f}")
+from unet_dc_segmentation_b200 import _lib                                      # noqa: E402
+t2 = timed(two)
+print(f"B {B} H {H} W {W}: upconv1 + dec1.0 as two launches {t2:.3f} ms")
+modes = [int(v) for v in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0, 1, 2, 3]
+for mode in modes:
+    _lib.check(_lib.load().dc_debug_set_upfuse_mode(mode))
+    fw = pack_upfused(comp, skipw).to(dev)
+    out2.zero_()
+    tf = timed(fused)
+    d = (out.float() - out2.float()).abs()
+    print(f"  mode {mode}: fused {tf:.3f} ms, max |diff| {float(d.max()):.4f} mean {float(d.mean()):.5f}")
+_lib.check(_lib.load().dc_debug_set_upfuse_mode(0))

@@ -16,7 +16,7 @@ CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB_PATH = LIB_DIR / "libunetdc_b200.so"
 SOURCES = ["api.cu", "conv_tc.cu", "morph.cu", "ccl.cu", "resize.cu", "density.cu", "generic.cu"]
-HEADERS = [CSRC / "common.cuh", PKG.parent / "include" / "unetdc_b200.h"]
+HEADERS = [CSRC / "common.cuh", CSRC / "upf_schedule.inc", PKG.parent / "include" / "unetdc_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -34,6 +34,8 @@ int launch_stem(const dc_stem_args_t* a, cudaStream_t stream, const float* bias_
 // bias9_host: HOST copy of a->bias9 (the interior class becomes kernel parameters); required.
 int launch_conv_upfused(const dc_upfuse_args_t* a, cudaStream_t stream, const float* bias9_host);
 int set_conv_family(int family);
+int upfuse_schedule(int* out, int cap);
+int set_upfuse_mode(int mode);
 int launch_label_stats(const dc_label_args_t* a, cudaStream_t stream);
 int launch_rolling_ball(const dc_rolling_ball_args_t* a, cudaStream_t stream);
 int launch_resize_linear_u8(const dc_resize_args_t* a, cudaStream_t stream);

@@ -52,6 +52,8 @@ constexpr int EPI_WARP0 = 4;
 
 // Kernel-family override for the tests (dc_debug_set_conv_family): the product path never changes it.
 int g_kernel_family = DC_CONV_FAMILY_AUTO;
+// Test / measurement override of the MMA schedule of conv_upfused2_kernel (dc_debug_set_upfuse_mode); 0 on the product path.
+int g_upfuse_mode = 0;
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): set once per device, not per launch.
 template <class K>
@@ -960,29 +962,50 @@ conv_halo2_kernel(const __grid_constant__ ConvParams p) {
 // that for the data, the border-class bias of the epilogue for the bias.
 //
 // Tile = 16 x 8 pixels of the half-resolution grid per CTA = a 32 x 16 output patch; its four parity classes are the
-// four accumulators (4 x 64 TMEM columns, double buffered = 512), i.e. the four independent MMA chains an N = 64
-// layer needs.  K is walked as three "chunks", each with its own region and barrier pair (stage == chunk):
-//   chunk 0, 1: x channels [0,64) / [64,128): region (16+2) x (8+2) half-res pixels; class (py, px), tap (a, b) is
-//               the window starting at row py + a, column px + b.  Composed weights (4 KB per CTA and (chunk, tap,
-//               class)) stream through a ring of (chunk, tap) groups of four class slices.
+// four accumulators (4 x 64 TMEM columns, double buffered = 512).  K is walked as three "chunks", each with its own
+// region and barrier pair (stage == chunk):
+//   chunk 0, 1: x channels [0,64) / [64,128): region (16+2) x (8+2) half-res pixels; class (py, px), tap (a, b) reads
+//               the window starting at row py + a, column px + b.
 //   chunk 2   : the skip tensor's 34 x 18 full-resolution pixels around the patch, loaded as two column-parity planes
-//               (a 5-D tensor map splits W into (W/2, 2)) of 34 x 9 pixels: the window of class (py, px), tap (ky, kx)
-//               starts at row py + ky with 8-row groups TWO region rows apart (SBO) in plane (px + kx) & 1, column
-//               (px + kx) >> 1.  Its nine 4 KB weight slices are resident.
-// Roles as conv_halo2_kernel plus warp 3 = producer of the composed-weight ring (so that the region loads of the
-// next tile are never queued behind weight slices).
+//               (a 5-D tensor map splits W into (W/2, 2)) of 34 x 9 pixels: class (py, px), tap (ky, kx) reads the
+//               window starting at row py + ky with 8-row groups TWO region rows apart (SBO), in plane (px + kx) & 1,
+//               column (px + kx) >> 1.
+// Shared windows.  An N = 64 MMA reads A 4 KB + B 1 KB of shared memory per 32 tensor cycles (160 B/cycle against the
+// 128 the MMA unit gets): that bounds the ordinary N = 64 layers at 74 % tensor.  Here the window only depends on
+// (py + a, px + b) resp. (py + ky, px + kx), so several classes read the SAME window -- with different weights into
+// ADJACENT accumulators -- and run as one MMA of N = 128 (classes 0,1 or 2,3) or N = 256 (all four) whose B operand is
+// the classes' weight tiles stacked: 11 MMAs instead of 16 per K = 16 step of an x chunk, 20 instead of 36 for the
+// skip chunk, same tensor cycles, A reads 44 / 80 KB instead of 64 / 144 KB.  The schedule is the table below; the
+// host packs the weights in exactly this order (dc_debug_upfuse_schedule), per CTA of the pair (a pair MMA takes rows
+// [0, N/2) of B from the leader and [N/2, N) from the peer), and they stream through a ring of 16 KB groups (= 512
+// tensor cycles each; within a group the MMAs go to different accumulators, so no chain waits for itself).
+// Roles as conv_halo2_kernel plus warp 3 = producer of the weight ring (region loads never queue behind weights).
 constexpr int UPF_U_W = HT_W + 2, UPF_U_H = HT_H + 2;
 constexpr int UPF_U_BYTES = UPF_U_W * UPF_U_H * 128;                 // 23,040
 constexpr int UPF_S_W = HT_W + 1, UPF_S_H = 2 * HT_H + 2;
 constexpr int UPF_PLANE_BYTES = UPF_S_W * UPF_S_H * 128;             // 39,168
-constexpr int UPF_WT_BYTES = 32 * KCHUNK * 2;                        // this CTA's 32 rows of one 64 x 64 weight slice
-constexpr int UPF_GROUPS = 3;                                        // ring depth in (chunk, tap) groups of 4 slices
+constexpr int UPF_GROUP_ROWS = 128;                                  // weight rows per CTA and ring slot (16 KB)
+constexpr int UPF_GROUP_BYTES = UPF_GROUP_ROWS * 128;
+constexpr int UPF_RING = 5;
 constexpr int UPF_BIAS_BYTES = 256;
-constexpr int UPF_SLICES = 2 * 4 * 4 + 9;                            // composed (chunk, tap, class) + skip taps
-constexpr size_t UPF_SMEM = 9 * UPF_WT_BYTES + UPF_GROUPS * 4 * UPF_WT_BYTES + 2 * UPF_U_BYTES + 2 * UPF_PLANE_BYTES +
-                            1024 + HALO_BAR_BYTES + UPF_BIAS_BYTES + EPI_STAGE_TOTAL;
+constexpr size_t UPF_SMEM = UPF_RING * UPF_GROUP_BYTES + 2 * UPF_U_BYTES + 2 * UPF_PLANE_BYTES + 1024 + HALO_BAR_BYTES +
+                            UPF_BIAS_BYTES + EPI_STAGE_TOTAL;
 static_assert(UPF_SMEM <= 227 * 1024, "conv_upfused2_kernel: shared memory");
 
+struct UpfOp;
+template <int MODE> inline UpfOp upf_u_op(int i);           // host: MMA i of one K = 16 step of an x chunk / the skip chunk
+template <int MODE> inline UpfOp upf_s_op(int i);
+template <int MODE> inline int upf_u_count();
+template <int MODE> inline int upf_s_count();
+// device: the 4 x (MMAs of group G) of chunk kind KIND (0 = x, 1 = skip); d = accumulator base, a = descriptor of the
+// region's first row, b = descriptor of the group's ring slot; fresh = overwrite at the tile's first K step
+template <int MODE, int KIND, int G>
+__device__ __forceinline__ void upf_issue_group(uint32_t d, uint64_t a, uint64_t b, bool fresh);
+#include "upf_schedule.inc"
+constexpr int UPF_GROUPS_PER_TILE = 2 * 4 + 9;
+constexpr int UPF_ROWS_PER_RANK = UPF_GROUPS_PER_TILE * UPF_GROUP_ROWS;      // 2176 weight rows per CTA of the pair
+
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv_upfused2_kernel(const __grid_constant__ ConvParams p) {
     constexpr int BN = 64;
@@ -990,9 +1013,8 @@ conv_upfused2_kernel(const __grid_constant__ ConvParams p) {
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* w_skip = smem;                                          // 9 resident slices
-    uint8_t* w_ring = w_skip + 9 * UPF_WT_BYTES;                     // UPF_GROUPS x 4 slices
-    uint8_t* u_reg = w_ring + UPF_GROUPS * 4 * UPF_WT_BYTES;         // x regions of chunk 0, 1
+    uint8_t* w_ring = smem;                                          // UPF_RING groups of 128 weight rows
+    uint8_t* u_reg = w_ring + UPF_RING * UPF_GROUP_BYTES;            // x regions of chunk 0, 1
     uint8_t* s_reg = u_reg + 2 * UPF_U_BYTES;                        // skip planes: [0] odd columns (from 2 w0 - 1), [1] even
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_reg + 2 * UPF_PLANE_BYTES);
     uint64_t* empty_bar = full_bar + HALO_MAX_STAGES;
@@ -1000,8 +1022,7 @@ conv_upfused2_kernel(const __grid_constant__ ConvParams p) {
     uint64_t* bempty_bar = bfull_bar + HALO_MAX_STAGES;
     uint64_t* tfull_bar = bempty_bar + HALO_MAX_STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint64_t* w_bar = tempty_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + HALO_BAR_BYTES);
     uint8_t* stg_s = reinterpret_cast<uint8_t*>(full_bar) + HALO_BAR_BYTES + UPF_BIAS_BYTES;
 
@@ -1023,7 +1044,6 @@ conv_upfused2_kernel(const __grid_constant__ ConvParams p) {
             mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8 * EPI_GROUPS); }
-        mbar_init(w_bar, 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -1038,12 +1058,6 @@ conv_upfused2_kernel(const __grid_constant__ ConvParams p) {
 
     if (warp == 0) {
         // ------------------------------------------------------------------ region producer (one per CTA)
-        if (elect_one()) {
-            if (leader) mbar_expect_tx(w_bar, 2u * 9u * UPF_WT_BYTES);
-            for (int tap = 0; tap < 9; ++tap)
-                tma_load_2d_2sm(w_skip + tap * UPF_WT_BYTES, &p.tmB, w_bar, (32 + tap) * KCHUNK, (int)rank * 32);
-        }
-        __syncwarp();
         int it = 0;
         for (int pair = cluster_id; pair < n_pairs; pair += n_clusters, ++it) {
             const TileCoord t = decode_tile<HT_H, HT_W>(p, pair_to_tile(p, pair, (int)rank), BN);
@@ -1066,33 +1080,34 @@ conv_upfused2_kernel(const __grid_constant__ ConvParams p) {
             __syncwarp();
         }
     } else if (warp == 3) {
-        // ------------------------------------------------------------------ composed-weight producer (one per CTA)
+        // ------------------------------------------------------------------ weight producer (one per CTA)
         int bg = 0;
         uint32_t bphase = 0;
         for (int pair = cluster_id; pair < n_pairs; pair += n_clusters) {
-            for (int g = 0; g < 8; ++g) {                        // g = chunk * 4 + tap
+            for (int g = 0; g < UPF_GROUPS_PER_TILE; ++g) {
                 mbar_wait(&bempty_bar[bg], bphase ^ 1u);
                 if (elect_one()) {
-                    if (leader) mbar_expect_tx(&bfull_bar[bg], 2u * 4u * UPF_WT_BYTES);
-#pragma unroll
-                    for (int cls = 0; cls < 4; ++cls)
-                        tma_load_2d_2sm(w_ring + (bg * 4 + cls) * UPF_WT_BYTES, &p.tmB, &bfull_bar[bg], (g * 4 + cls) * KCHUNK,
-                                        (int)rank * 32);
+                    if (leader) mbar_expect_tx(&bfull_bar[bg], 2u * UPF_GROUP_BYTES);
+                    tma_load_2d_2sm(w_ring + bg * UPF_GROUP_BYTES, &p.tmB, &bfull_bar[bg], 0,
+                                    (int)rank * UPF_ROWS_PER_RANK + g * UPF_GROUP_ROWS);
                 }
                 __syncwarp();
-                if (++bg == UPF_GROUPS) { bg = 0; bphase ^= 1u; }
+                if (++bg == UPF_RING) { bg = 0; bphase ^= 1u; }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA only)
         if (leader) {
-            const uint32_t idesc = umma_idesc_bf16(2 * TILE_M, BN);
-            const uint32_t u_addr = smem_u32(u_reg), s_addr = smem_u32(s_reg);
-            const uint32_t ring_addr = smem_u32(w_ring), wskip_addr = smem_u32(w_skip);
+            // Descriptors are base + constant: the address field is (addr & 0x3FFFF) >> 4 and every operand lies below
+            // 256 KB, so desc(addr + off) == desc(addr) + (off >> 4) and each MMA costs two 64-bit adds, not a rebuild
+            // (with the mask in the way the compiler rebuilt every descriptor: 38 uniform-datapath instructions per
+            // MMA, and the issuing warp -- not the tensor pipe -- set the pace).
+            const uint64_t adesc_u = umma_desc_sw128_strided(smem_u32(u_reg), UPF_U_W * 128u);
+            const uint64_t adesc_s = umma_desc_sw128_strided(smem_u32(s_reg), 2u * UPF_S_W * 128u);
+            const uint64_t bdesc_ring = umma_desc_sw128(smem_u32(w_ring));
             int bg = 0;
             uint32_t bphase = 0;
             int it = 0;
-            mbar_wait(w_bar, 0);
             for (int pair = cluster_id; pair < n_pairs; pair += n_clusters, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
@@ -1100,53 +1115,34 @@ conv_upfused2_kernel(const __grid_constant__ ConvParams p) {
                 mbar_wait(&tempty_bar[as], aphase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * 4 * BN);
+#define DC_UPF_GROUP(KIND, G, ADESC, FRESH)                                                                         \
+    {                                                                                                               \
+        mbar_wait(&bfull_bar[bg], bphase);                                                                          \
+        tc_fence_after();                                                                                           \
+        if (elect_one()) {                                                                                          \
+            upf_issue_group<MODE, KIND, G>(d_tmem, ADESC, bdesc_ring + (uint64_t)(bg * (UPF_GROUP_BYTES >> 4)), FRESH); \
+            umma_commit_2sm(&bempty_bar[bg]);                                                                       \
+        }                                                                                                           \
+        __syncwarp();                                                                                               \
+        if (++bg == UPF_RING) { bg = 0; bphase ^= 1u; }                                                             \
+    }
 #pragma unroll 1
                 for (int kc = 0; kc < 2; ++kc) {
                     mbar_wait(&full_bar[kc], ph);
                     tc_fence_after();
-                    const uint32_t region = u_addr + (uint32_t)(kc * UPF_U_BYTES);
-#pragma unroll
-                    for (int tap = 0; tap < 4; ++tap) {
-                        mbar_wait(&bfull_bar[bg], bphase);
-                        tc_fence_after();
-                        const uint32_t wg = ring_addr + (uint32_t)(bg * 4 * UPF_WT_BYTES);
-                        if (elect_one()) {
-#pragma unroll
-                            for (int k = 0; k < KCHUNK / 16; ++k) {
-#pragma unroll
-                                for (int cls = 0; cls < 4; ++cls) {
-                                    const uint32_t a_addr = region + (uint32_t)((((cls >> 1) + (tap >> 1)) * UPF_U_W + (cls & 1) + (tap & 1)) * 128);
-                                    const uint64_t adesc = umma_desc_sw128_strided(a_addr, UPF_U_W * 128u);
-                                    const uint64_t bdesc = umma_desc_sw128(wg + (uint32_t)(cls * UPF_WT_BYTES));
-                                    umma_bf16_2sm(d_tmem + (uint32_t)(cls * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                                  (kc | tap | k) ? 1u : 0u);
-                                }
-                            }
-                            umma_commit_2sm(&bempty_bar[bg]);
-                        }
-                        __syncwarp();
-                        if (++bg == UPF_GROUPS) { bg = 0; bphase ^= 1u; }
-                    }
+                    const uint64_t areg = adesc_u + (uint64_t)(kc * (UPF_U_BYTES >> 4));
+                    DC_UPF_GROUP(0, 0, areg, kc == 0) DC_UPF_GROUP(0, 1, areg, kc == 0)
+                    DC_UPF_GROUP(0, 2, areg, kc == 0) DC_UPF_GROUP(0, 3, areg, kc == 0)
                     if (elect_one()) umma_commit_2sm(&empty_bar[kc]);
                     __syncwarp();
                 }
                 mbar_wait(&full_bar[2], ph);
                 tc_fence_after();
+                DC_UPF_GROUP(1, 0, adesc_s, false) DC_UPF_GROUP(1, 1, adesc_s, false) DC_UPF_GROUP(1, 2, adesc_s, false)
+                DC_UPF_GROUP(1, 3, adesc_s, false) DC_UPF_GROUP(1, 4, adesc_s, false) DC_UPF_GROUP(1, 5, adesc_s, false)
+                DC_UPF_GROUP(1, 6, adesc_s, false) DC_UPF_GROUP(1, 7, adesc_s, false) DC_UPF_GROUP(1, 8, adesc_s, false)
+#undef DC_UPF_GROUP
                 if (elect_one()) {
-#pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const uint64_t bdesc = umma_desc_sw128(wskip_addr + (uint32_t)(tap * UPF_WT_BYTES));
-#pragma unroll
-                        for (int k = 0; k < KCHUNK / 16; ++k) {
-#pragma unroll
-                            for (int cls = 0; cls < 4; ++cls) {
-                                const int ry = (cls >> 1) + tap / 3, cx = (cls & 1) + tap % 3;
-                                const uint32_t a_addr = s_addr + (uint32_t)((cx & 1) * UPF_PLANE_BYTES + (ry * UPF_S_W + (cx >> 1)) * 128);
-                                const uint64_t adesc = umma_desc_sw128_strided(a_addr, 2u * UPF_S_W * 128u);
-                                umma_bf16_2sm(d_tmem + (uint32_t)(cls * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
-                            }
-                        }
-                    }
                     umma_commit_2sm(&empty_bar[2]);
                     umma_commit_2sm(&tfull_bar[as]);
                 }
@@ -1704,10 +1700,10 @@ int launch_conv_upfused(const dc_upfuse_args_t* a, cudaStream_t stream, const fl
         int rc = encode_map(&p.tmS, a->skip, 5, dims, str, box);
         if (rc != DC_OK) return rc;
     }
-    {   // weights: [64 rows][UPF_SLICES * 64]
-        cuuint64_t dims[2] = {(cuuint64_t)UPF_SLICES * KCHUNK, 64};
-        cuuint64_t str[1] = {(cuuint64_t)UPF_SLICES * KCHUNK * 2};
-        cuuint32_t box[2] = {KCHUNK, 32};
+    {   // weights: [2 CTAs of a pair][UPF_ROWS_PER_RANK rows in the order the MMA schedule consumes them][64]
+        cuuint64_t dims[2] = {KCHUNK, (cuuint64_t)2 * UPF_ROWS_PER_RANK};
+        cuuint64_t str[1] = {KCHUNK * 2};
+        cuuint32_t box[2] = {KCHUNK, UPF_GROUP_ROWS};
         int rc = encode_map(&p.tmB, a->weight, 2, dims, str, box);
         if (rc != DC_OK) return rc;
     }
@@ -1731,11 +1727,51 @@ int launch_conv_upfused(const dc_upfuse_args_t* a, cudaStream_t stream, const fl
     const int n_pairs = (p.m_tiles + 1) / 2;
     const int max_clusters = num_sms() / 2;
     const int grid = 2 * (n_pairs < max_clusters ? n_pairs : max_clusters);
-    static unsigned long long attr_done = 0;
-    int rc = set_max_smem_once(conv_upfused2_kernel, (int)UPF_SMEM, &attr_done);
-    if (rc != DC_OK) return rc;
-    conv_upfused2_kernel<<<grid, NUM_THREADS, UPF_SMEM, stream>>>(p);
+#define DC_UPF_CASE(mode)                                                                                    \
+    if (g_upfuse_mode == mode) {                                                                             \
+        static unsigned long long attr_done = 0;                                                             \
+        int rc = set_max_smem_once(conv_upfused2_kernel<mode>, (int)UPF_SMEM, &attr_done);                   \
+        if (rc != DC_OK) return rc;                                                                          \
+        conv_upfused2_kernel<mode><<<grid, NUM_THREADS, UPF_SMEM, stream>>>(p);                              \
+    }
+    DC_UPF_CASE(0) DC_UPF_CASE(1) DC_UPF_CASE(2) DC_UPF_CASE(3)
+#undef DC_UPF_CASE
     DC_CUDA(cudaGetLastError());
+    return DC_OK;
+}
+
+// The MMA schedule of conv_upfused2_kernel for the host-side weight packer: one row {chunk (0, 1 = x channels,
+// 2 = skip), window row, window column, first class, classes} per MMA, in issue order.
+template <int MODE>
+int upfuse_schedule_of(int* out, int cap) {
+    const int nu = upf_u_count<MODE>(), ns = upf_s_count<MODE>();
+    const int n = 2 * nu + ns;
+    DC_REQUIRE(out && cap >= 5 * n, DC_EINVAL, "dc_debug_upfuse_schedule: need room for %d ints", 5 * n);
+    int* o = out;
+    for (int kc = 0; kc < 2; ++kc)
+        for (int i = 0; i < nu; ++i) {
+            const UpfOp op = upf_u_op<MODE>(i);
+            *o++ = kc; *o++ = op.r; *o++ = op.c; *o++ = op.cls0; *o++ = op.ncls;
+        }
+    for (int i = 0; i < ns; ++i) {
+        const UpfOp op = upf_s_op<MODE>(i);
+        *o++ = 2; *o++ = op.r; *o++ = op.c; *o++ = op.cls0; *o++ = op.ncls;
+    }
+    return n;
+}
+
+int upfuse_schedule(int* out, int cap) {
+    switch (g_upfuse_mode) {
+        case 1: return upfuse_schedule_of<1>(out, cap);
+        case 2: return upfuse_schedule_of<2>(out, cap);
+        case 3: return upfuse_schedule_of<3>(out, cap);
+        default: return upfuse_schedule_of<0>(out, cap);
+    }
+}
+
+int set_upfuse_mode(int mode) {
+    DC_REQUIRE(mode >= 0 && mode < UPF_MODES, DC_EINVAL, "dc_debug_set_upfuse_mode: %d", mode);
+    g_upfuse_mode = mode;
     return DC_OK;
 }
 

@@ -64,36 +64,65 @@ def compose_upconv(wu, bu, wd, bd):
     up[Y,X] = bu + x[Y>>1, X>>1] . wu[:, :, Y&1, X&1], so output pixel (2i+py, 2j+px) sees x only at the 2x2
     neighbourhood (i-1+py+a, j-1+px+b): the weights of that tap are the sum, over the 3x3 taps (ky, kx) that land
     on it, of wu[..., ry, rx] . wd[..., ky, kx] with (ry, rx) the parity of the upsampled pixel.  Composed in fp64,
-    rounded to bf16 once.  Returns (weight bf16 [Co, 41*64], bias9 f32 [9, Co]) in the layouts of include/unetdc_b200.h."""
+    rounded to bf16 once.  Returns
+      comp  bf16 [4 classes (py*2+px)][2][2 taps (a, b)][Co][Cx]   composed weights over x
+      skipw bf16 [3][3][Co][C]                                     the skip half of the 3x3 weights
+      bias9 f32  [9][Co]   row (row class * 3 + col class), class 0 / 1 / 2 = first / interior / last output row
+                           (column): bd plus bu through the taps that lie inside the upsampled image."""
     cx, c = wu.shape[:2]
     co = wd.shape[0]
     assert (cx, c, co) == (128, 64, 64) and wd.shape[1] == 2 * c, "level-1 shapes only"
     wu64, wd64 = wu.double(), wd.double()
     wd_up, wd_skip = wd64[:, :c], wd64[:, c:]
-    comp = torch.zeros((2, 4, 4, co, 64), dtype=torch.float64, device=wd.device)      # [chunk][tap][cls][co][ci]
+    comp = torch.zeros((4, 2, 2, co, cx), dtype=torch.float64, device=wd.device)
     for py in range(2):
         for px in range(2):
             for ky in range(3):
                 for kx in range(3):
                     ty, tx = py + ky - 1, px + kx - 1                  # offset of the upsampled pixel from (2i, 2j)
                     a, b = ty // 2 - (py - 1), tx // 2 - (px - 1)      # which of the 2x2 x-taps it reads
-                    w = torch.einsum("oc,ic->oi", wd_up[:, :, ky, kx], wu64[:, :, ty % 2, tx % 2])     # [co, cx]
-                    for chunk in range(2):
-                        comp[chunk, a * 2 + b, py * 2 + px] += w[:, chunk * 64:(chunk + 1) * 64]
-    skip = wd_skip.permute(2, 3, 0, 1).reshape(9, co, 64)                                # [tap][co][c]
-    slices = torch.cat([comp.reshape(32, co, 64), skip], 0)                               # [41][co][64]
-    weight = slices.permute(1, 0, 2).reshape(co, 41 * 64).to(torch.bfloat16).contiguous()
+                    comp[py * 2 + px, a, b] += torch.einsum("oc,ic->oi", wd_up[:, :, ky, kx], wu64[:, :, ty % 2, tx % 2])
+    skipw = wd_skip.permute(2, 3, 0, 1)                                                   # [ky][kx][co][c]
     tb = torch.einsum("ockl,c->klo", wd_up, bu.double())                                  # bias of `up` through tap (ky, kx)
     bias9 = torch.zeros((3, 3, co), dtype=torch.float64, device=wd.device)
     valid = ((1, 2), (0, 1, 2), (0, 1))            # taps inside the image for the first / interior / last row (column)
     for rc in range(3):
         for cc in range(3):
             bias9[rc, cc] = bd.double() + sum(tb[ky, kx] for ky in valid[rc] for kx in valid[cc])
-    return weight, bias9.reshape(9, co).float().contiguous()
+    return (comp.to(torch.bfloat16).contiguous(), skipw.to(torch.bfloat16).contiguous(),
+            bias9.reshape(9, co).float().contiguous())
+
+
+def upfuse_schedule():
+    """The MMA schedule of dc_conv_upfused (host-only library call): rows (chunk, r, c, cls0, ncls)."""
+    buf = (C.c_int * (5 * 128))()
+    n = _lib.load().dc_debug_upfuse_schedule(buf, len(buf))
+    _lib.check(min(n, 0))
+    return [tuple(buf[5 * i:5 * i + 5]) for i in range(n)]
+
+
+def pack_upfused(comp, skipw):
+    """Weights of compose_upconv in the order the kernel's MMAs consume them: bf16 [2 CTAs][2176 rows][64 ci].
+    An MMA on window (r, c) covering classes cls0 .. cls0+ncls-1 takes, for class (py, px), tap (r - py, c - px) of
+    chunk 0 / 1 (x channels [0,64) / [64,128)) or of the skip weights (chunk 2); its B operand is those [64 co][64 ci]
+    tiles stacked, the first half of the rows in CTA 0's blob and the second half in CTA 1's."""
+    halves = ([], [])
+    for chunk, r, c, cls0, ncls in upfuse_schedule():
+        tiles = []
+        for cls in range(cls0, cls0 + ncls):
+            py, px = cls >> 1, cls & 1
+            tiles.append(skipw[r - py, c - px] if chunk == 2 else comp[cls, r - py, c - px][:, chunk * 64:(chunk + 1) * 64])
+        rows = torch.cat(tiles, 0)                                   # [64 * ncls][64]
+        half = rows.shape[0] // 2
+        halves[0].append(rows[:half])
+        halves[1].append(rows[half:])
+    blob = torch.stack([torch.cat(h, 0) for h in halves], 0).contiguous()
+    assert blob.shape == (2, 2176, 64) and blob.dtype == torch.bfloat16
+    return blob
 
 
 def fused_level1_blobs(sd, eps: float = 1e-5):
-    """(weight, bias9) of the composed upconv1 + dec1.0 layer from a state_dict (on the tensors' own device)."""
+    """(comp, skipw, bias9) of the composed upconv1 + dec1.0 layer from a state_dict (on the tensors' own device)."""
     wd, bd = fold_conv_bn(sd["dec1.0.weight"], sd["dec1.0.bias"], sd["dec1.1.weight"], sd["dec1.1.bias"],
                           sd["dec1.1.running_mean"], sd["dec1.1.running_var"], eps)
     return compose_upconv(sd["upconv1.weight"].float(), sd["upconv1.bias"].float(), wd, bd)
@@ -140,7 +169,8 @@ class _Packed:
         desc.in_channels = module.in_channels
         desc.out_channels = module.out_channels
         if module.fuse_level1:
-            fw, fb = fused_level1_blobs(sd, module._bn_eps("dec1", 1))
+            comp, skipw, fb = fused_level1_blobs(sd, module._bn_eps("dec1", 1))
+            fw = pack_upfused(comp, skipw)
             self.blobs += [fw, fb]
             desc.fused_weight1 = fw.data_ptr()
             desc.fused_bias1 = fb.data_ptr()
