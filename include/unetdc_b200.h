@@ -49,7 +49,7 @@ extern "C" {
 
 /* Bumped whenever a struct or signature in this header changes; dc_version() returns the value the library was
  * built with and the Python binding refuses to load a library that disagrees. */
-#define DC_ABI_VERSION 202
+#define DC_ABI_VERSION 203
 
 const char* dc_last_error(void);
 int dc_version(void);
@@ -97,6 +97,11 @@ typedef struct dc_conv_args {
     float thresh;
     float* prob_out;     /* DC_EPI_HEAD: fp32 [B,H,W] or NULL                               */
     uint8_t* mask_out;   /* DC_EPI_HEAD: u8   [B,H,W] {0,1} or NULL                         */
+    /* Optional, DC_KIND_CONV3X3 with Cin == Cout == 64, dilation 1, even H and W: the same weights as bf16
+     * [2][1152][64] in the order of the skip part (chunk 2) of dc_debug_upfuse_schedule.  When given, the layer
+     * runs per output parity class with windows shared between classes (see dc_conv_upfused); NULL = the generic
+     * kernels from `weight`. */
+    const void* weight_par;
 } dc_conv_args_t;
 
 int dc_conv_tc(const dc_conv_args_t* args, void* stream);
@@ -196,6 +201,9 @@ typedef struct dc_model_desc {
      * dc_upfuse_args.weight / .bias9; NULL = run the two layers separately from weight[19], weight[20]. */
     const void* fused_weight1;
     const float* fused_bias1;
+    /* Optional: weights of enc1.3 ([0]) and dec1.3 ([1]) in the dc_conv_args.weight_par layout (used when
+     * dilations[0] == 1); NULL = weight[1] / weight[21] through the generic kernels. */
+    const void* par_weight[2];
 } dc_model_desc_t;
 
 int dc_model_create(dc_model_t** out, int device, const dc_model_desc_t* desc);

@@ -203,6 +203,47 @@ def test_upconv_conv3x3_fused(cuda_device, B, H, W):
     assert float(err) < 0.05, f"fused layer vs unfused fp32 chain: max err {float(err):.4f}"
 
 
+PARITY_CASES = [(1, 32, 16), (2, 32, 16), (1, 80, 48), (3, 48, 40), (2, 128, 128), (1, 16, 16), (1, 2, 2)]
+
+
+@pytest.mark.parametrize("B,H,W", PARITY_CASES)
+def test_conv3x3_parity_class_kernel(cuda_device, B, H, W):
+    """dc_conv_tc with weight_par: a 64 -> 64 channel 3x3 layer computed per output parity class with shared windows
+    (conv_par2_kernel, what enc1.3 / dec1.3 run): plain store (+ channel slices, no ReLU), store + 2x2 max pool, and
+    the out_conv + sigmoid + threshold head, each against the fp32 evaluation and the generic kernel's contract."""
+    import torch
+    import torch.nn.functional as F
+    from unet_dc_segmentation_b200 import layers
+    from unet_dc_segmentation_b200.model import pack_conv3x3, pack_par3x3
+    w, b = _rand_layer(64, 64, 31 + H)
+    wp = pack_par3x3(w).cuda()
+    xin = _rand_act(B, H, W, 128, 9 + W)                      # the layer reads channels [0,64) of a 128-wide buffer
+    xs = xin[..., :64].float().permute(0, 3, 1, 2)
+    lin = F.conv2d(xs, w, b, padding=1)
+    # store, no ReLU, into a channel slice
+    out = torch.full((B, H, W, 160), 7.0, dtype=torch.bfloat16).cuda()
+    layers.conv3x3(xin.cuda(), pack_conv3x3(w).cuda(), b.cuda(), relu=False, cin=64, out=out, out_offset=64, weight_par=wp)
+    torch.cuda.synchronize()
+    _close(out[..., 64:128], lin.permute(0, 2, 3, 1), f"parity store {B}x{H}x{W}")
+    assert bool((out[..., :64] == 7).all()) and bool((out[..., 128:] == 7).all()), "wrote outside its channel slice"
+    # store + pool
+    got, pooled = layers.conv3x3(xin.cuda(), pack_conv3x3(w).cuda(), b.cuda(), cin=64, pool=True, weight_par=wp)
+    torch.cuda.synchronize()
+    _close(got, F.relu(lin).permute(0, 2, 3, 1), "parity pool: full-res output")
+    want_pool = F.max_pool2d(got.float().cpu().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    assert torch.equal(pooled.float().cpu(), want_pool)       # EXACTLY the 2x2 max of the bf16 tensor the kernel wrote
+    # head
+    g = torch.Generator().manual_seed(3)
+    hw, hb = torch.randn(64, generator=g) * 0.2, 0.1
+    want = torch.sigmoid((F.relu(lin) * hw.view(1, -1, 1, 1)).sum(1) + hb)
+    x64 = xin[..., :64].contiguous()
+    prob, mask = layers.conv3x3_head(x64.cuda(), pack_conv3x3(w).cuda(), b.cuda(), hw.cuda(), hb, 0.3, weight_par=wp)
+    torch.cuda.synchronize()
+    err = (prob.cpu() - want).abs().max()
+    assert float(err) < 2e-3, f"parity head prob max err {float(err)}"
+    assert torch.equal(mask.cpu(), (prob.cpu() > 0.3).to(torch.uint8))
+
+
 def test_head_epilogue(cuda_device):
     import torch
     import torch.nn.functional as F

@@ -116,7 +116,7 @@ def test_forward_with_level1_unfused(cuda_device):
     want = oracle.unetdc_forward(sd, x).numpy()
     m = _model("UNetDC", sd, cuda_device)
     y_fused = m(x.to(cuda_device)).cpu().numpy()
-    m.fuse_level1 = False
+    m.fuse_level1 = m.parity_level1 = False          # the generic kernels for enc1.3 / dec1.3 as well
     m.invalidate()
     assert m.num_launches() == 22
     y = m(x.to(cuda_device)).cpu().numpy()

@@ -368,6 +368,8 @@ static int forward_impl(dc_model_t* m, int in_kind, const void* in, int B, int H
         a.weight = d.weight[layer]; a.bias = d.bias[layer];
         a.out = dst; a.out_stride = dst_stride; a.out_offset = dst_off;
         a.pool_out = pool; a.pool_stride = cout;
+        if (layer == 1) a.weight_par = d.par_weight[0];        // launch_conv_tc takes it only when dilation == 1
+        if (layer == 21) a.weight_par = d.par_weight[1];
         if (epi == DC_EPI_HEAD) {
             a.head_w = (const float*)d.weight[22];
             a.head_b = m->head_b;

@@ -107,6 +107,8 @@ struct alignas(64) ConvParams {
     uint8_t* mask_out;
     // conv_halo_kernel only
     int region_w, region_h, region_stride, nstages, nbstages;
+    // parity-class kernels: 1 = p.bias is row 4 of a [9][64] border-class table (conv_upfused2_kernel)
+    int border_bias;
 };
 
 struct TileCoord {
@@ -244,7 +246,10 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
     // pooled pixel of this lane: lane / 4 of the 8 the warp's 32 pixels pool into
     const int prow = (TW == 16) ? e : 2 * e + (lane >> 4);
     const int pcol = (TW == 16) ? (lane >> 2) : ((lane >> 2) & 3);
-    __nv_bfloat16* const pool_lane_ptr = p.pool_out + (((long long)prow * (p.W >> 1) + pcol) * p.pool_stride + sq * 8);
+    // UPF: the pooled tensor has the tile's own (half-resolution) geometry; this lane stores chunk sq of pixels pL0 + 8 r
+    __nv_bfloat16* const pool_lane_ptr =
+        UPF ? p.pool_out + (((long long)row0 * p.W + col0) * p.pool_stride + sq * 8)
+            : p.pool_out + (((long long)prow * (p.W >> 1) + pcol) * p.pool_stride + sq * 8);
     for (int it = COOP ? 0 : group;; it += COOP ? 1 : EPI_GROUPS) {
         int tile;
         if (PAIR) {                     // CTA pair: pair = cluster + it * clusters
@@ -265,7 +270,10 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
         if (p.epilogue == DC_EPI_HEAD) {
 #pragma unroll 1
             for (int half = COOP ? group : 0; half < NHALF; half += COOP ? EPI_GROUPS : 1) {
-                const int h = t.h0 + lh, w = t.w0 + half * TW + lw;
+                // UPF: accumulator `half` = parity class (half / 2, half % 2) of half-resolution pixel (t.h0 + lh, t.w0 + lw)
+                const int h = UPF ? 2 * (t.h0 + lh) + (half >> 1) : t.h0 + lh;
+                const int w = UPF ? 2 * (t.w0 + lw) + (half & 1) : t.w0 + half * TW + lw;
+                const int H_out = UPF ? 2 * p.H : p.H, W_out = UPF ? 2 * p.W : p.W;
                 float head_acc = p.head_b;
                 const uint32_t taddr = tstage + (uint32_t)(half * BN);
                 uint32_t vbuf[2][32];
@@ -290,9 +298,9 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                         head_acc = fmaf(x3, hw.w, head_acc);
                     }
                 }
-                if ((h < p.H) && (w < p.W)) {
+                if ((h < H_out) && (w < W_out)) {
                     const float prob = 1.0f / (1.0f + expf(-head_acc));              // torch.sigmoid, fp32
-                    const size_t opix = ((size_t)t.img * p.H + h) * (size_t)p.W + w;
+                    const size_t opix = ((size_t)t.img * H_out + h) * (size_t)W_out + w;
                     if (p.prob_out) p.prob_out[opix] = prob;
                     if (p.mask_out) p.mask_out[opix] = prob > p.thresh ? 1 : 0;      // qdb:56
                 }
@@ -307,7 +315,9 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
         // warp-uniform offsets of this tile
         const long long tile_off = up_geo ? (((long long)t.img * (2 * p.H) + 2 * t.h0) * (2 * p.W) + 2 * t.w0) * p.out_stride
                                           : (((long long)t.img * p.H + t.h0) * p.W + t.w0) * p.out_stride + t.n0;
-        const long long ptile_off = (((long long)t.img * (p.H >> 1) + (t.h0 >> 1)) * (p.W >> 1) + (t.w0 >> 1)) * p.pool_stride + t.n0;
+        const long long ptile_off = UPF ? (((long long)t.img * p.H + t.h0) * p.W + t.w0) * p.pool_stride + t.n0
+                                        : (((long long)t.img * (p.H >> 1) + (t.h0 >> 1)) * (p.W >> 1) + (t.w0 >> 1)) * p.pool_stride + t.n0;
+        uint32_t pmax[16];                                     // UPF + STORE_POOL: running 2x2 max over the four classes
         const int hmax = p.H - t.h0;
         int q0 = 0, rem0 = 0;                                  // UPSCATTER: n0 = q0 * Cout + rem0
         if (up) { q0 = t.n0 / p.Cout; rem0 = t.n0 - q0 * p.Cout; }
@@ -367,7 +377,7 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                     x[4 * k + 3] = __uint_as_float(v[4 * k + 3]) + b.w;
                 }
             }
-            if (UPF) {
+            if (UPF && p.border_bias) {
                 // taps of the 3x3 that fall outside the (upsampled) image carry no transposed-conv bias: only the
                 // pixels of the first / last output row and column differ from the interior constant
                 const int hh = t.h0 + lh, ww = t.w0 + lw;
@@ -401,7 +411,26 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                 const long long d = (TW == 16) ? (r & 1) * 8 * cs + (r >> 1) * rs : r * rs;      // pixel pL0 + 8 r
                 if (vmask & (1u << r)) *reinterpret_cast<uint4*>(dst + d) = val;
             }
-            if (p.epilogue == DC_EPI_STORE_POOL) {
+            if (UPF && p.epilogue == DC_EPI_STORE_POOL) {
+                // the four classes of this lane's pixel are the 2x2 window (max of bf16-rounded values = bf16 rounding
+                // of the max): keep the running max in registers, store after the fourth class through the same
+                // staging transpose as the full-resolution stores
+#pragma unroll
+                for (int k = 0; k < 16; ++k) pmax[k] = half == 0 ? pk[k] : max_bf16x2(pmax[k], pk[k]);
+                if (half == NHALF - 1) {
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<uint4*>(stg + stg_off(lane, q)) = make_uint4(pmax[4 * q], pmax[4 * q + 1], pmax[4 * q + 2], pmax[4 * q + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const uint4 val = *reinterpret_cast<const uint4*>(stg + stg_off(8 * r + (lane >> 2), sq));
+                        if (vmask & (1u << r))
+                            *reinterpret_cast<uint4*>(pool_lane_ptr + (ptile_off + (long long)r * p.W * p.pool_stride + c0)) = val;
+                    }
+                }
+            } else if (p.epilogue == DC_EPI_STORE_POOL) {
                 // 2x2 max straight from the staged tile: lane (pp, sq) reads chunk sq of the four pixels of pooled
                 // pixel pp (the max of bf16-rounded values = the bf16 rounding of the max)
                 const uint4 a0 = *reinterpret_cast<const uint4*>(stg + stg_off(pool_r0, sq));
@@ -1163,6 +1192,154 @@ conv_upfused2_kernel(const __grid_constant__ ConvParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------- 64 -> 64 channel 3x3 layers by parity class
+// The skip chunk of conv_upfused2_kernel on its own is a plain Conv2d(64, 64, 3, padding 1) computed per output parity
+// class: enc1.3 and dec1.3 (models/model_2.py:10, :30) run through it.  Same windows, same shared-window MMA schedule
+// (chunk kind 2 of upf_schedule.inc), i.e. A reads 80 KB instead of 144 KB per K = 16 step -- these layers sat at
+// 74 % tensor with the MMA unit's shared-memory reads at 90 % in the 4-strip kernel (conv_halo2_kernel<64, 4>).
+// Two region stages (the next tile's planes load during this tile's MMAs), weights through a ring of 3 groups.
+// Epilogues: STORE, STORE_POOL (the four classes of a lane ARE the 2x2 pooling window: the max is taken in registers)
+// and HEAD.
+constexpr int PAR_RING = 3;
+constexpr int PAR_STAGES = 2;
+constexpr int PAR_BIAS_BYTES = 1024;                                  // bias + out_conv weights (HEAD)
+constexpr int PAR_ROWS_PER_RANK = 9 * UPF_GROUP_ROWS;                 // 1152 weight rows per CTA of the pair
+constexpr size_t PAR_SMEM = PAR_RING * UPF_GROUP_BYTES + PAR_STAGES * 2 * UPF_PLANE_BYTES + 1024 + HALO_BAR_BYTES +
+                            PAR_BIAS_BYTES + EPI_STAGE_TOTAL;
+static_assert(PAR_SMEM <= 227 * 1024, "conv_par2_kernel: shared memory");
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv_par2_kernel(const __grid_constant__ ConvParams p) {
+    constexpr int BN = 64;
+    constexpr int TMEM_COLS = 512;
+    constexpr int STAGE_BYTES = 2 * UPF_PLANE_BYTES;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* w_ring = smem;
+    uint8_t* s_reg = w_ring + PAR_RING * UPF_GROUP_BYTES;            // PAR_STAGES x {odd-column plane, even-column plane}
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_reg + PAR_STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + HALO_MAX_STAGES;
+    uint64_t* bfull_bar = empty_bar + HALO_MAX_STAGES;
+    uint64_t* bempty_bar = bfull_bar + HALO_MAX_STAGES;
+    uint64_t* tfull_bar = bempty_bar + HALO_MAX_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + HALO_BAR_BYTES);
+    uint8_t* stg_s = reinterpret_cast<uint8_t*>(full_bar) + HALO_BAR_BYTES + PAR_BIAS_BYTES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int n_pairs = pair_count(p);
+
+    stage_bias(p, bias_s);
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmB);
+        tma_prefetch_desc(&p.tmS);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < HALO_MAX_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1);
+            mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8 * EPI_GROUPS); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ region producer (one per CTA)
+        int it = 0;
+        for (int pair = cluster_id; pair < n_pairs; pair += n_clusters, ++it) {
+            const TileCoord t = decode_tile<HT_H, HT_W>(p, pair_to_tile(p, pair, (int)rank), BN);
+            const int st = it & 1;
+            mbar_wait(&empty_bar[st], (((uint32_t)it >> 1) & 1u) ^ 1u);
+            if (elect_one()) {
+                if (leader) mbar_expect_tx(&full_bar[st], 2u * STAGE_BYTES);
+                tma_load_5d_2sm(s_reg + st * STAGE_BYTES, &p.tmS, &full_bar[st], 0, 1, t.w0 - 1, 2 * t.h0 - 1, t.img);
+                tma_load_5d_2sm(s_reg + st * STAGE_BYTES + UPF_PLANE_BYTES, &p.tmS, &full_bar[st], 0, 0, t.w0, 2 * t.h0 - 1, t.img);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------------ weight producer (one per CTA)
+        int bg = 0;
+        uint32_t bphase = 0;
+        for (int pair = cluster_id; pair < n_pairs; pair += n_clusters) {
+            for (int g = 0; g < 9; ++g) {
+                mbar_wait(&bempty_bar[bg], bphase ^ 1u);
+                if (elect_one()) {
+                    if (leader) mbar_expect_tx(&bfull_bar[bg], 2u * UPF_GROUP_BYTES);
+                    tma_load_2d_2sm(w_ring + bg * UPF_GROUP_BYTES, &p.tmB, &bfull_bar[bg], 0,
+                                    (int)rank * PAR_ROWS_PER_RANK + g * UPF_GROUP_ROWS);
+                }
+                __syncwarp();
+                if (++bg == PAR_RING) { bg = 0; bphase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (leader) {
+            const uint64_t adesc_s = umma_desc_sw128_strided(smem_u32(s_reg), 2u * UPF_S_W * 128u);
+            const uint64_t bdesc_ring = umma_desc_sw128(smem_u32(w_ring));
+            int bg = 0;
+            uint32_t bphase = 0;
+            int it = 0;
+            for (int pair = cluster_id; pair < n_pairs; pair += n_clusters, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(&tempty_bar[as], aphase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * 4 * BN);
+                mbar_wait(&full_bar[as], aphase);                 // region stage == accumulator stage == it & 1
+                tc_fence_after();
+                const uint64_t areg = adesc_s + (uint64_t)(as * (STAGE_BYTES >> 4));
+#define DC_PAR_GROUP(G)                                                                                             \
+    {                                                                                                               \
+        mbar_wait(&bfull_bar[bg], bphase);                                                                          \
+        tc_fence_after();                                                                                           \
+        if (elect_one()) {                                                                                          \
+            upf_issue_group<MODE, 2, G>(d_tmem, areg, bdesc_ring + (uint64_t)(bg * (UPF_GROUP_BYTES >> 4)), true);  \
+            umma_commit_2sm(&bempty_bar[bg]);                                                                       \
+        }                                                                                                           \
+        __syncwarp();                                                                                               \
+        if (++bg == PAR_RING) { bg = 0; bphase ^= 1u; }                                                             \
+    }
+                DC_PAR_GROUP(0) DC_PAR_GROUP(1) DC_PAR_GROUP(2) DC_PAR_GROUP(3) DC_PAR_GROUP(4)
+                DC_PAR_GROUP(5) DC_PAR_GROUP(6) DC_PAR_GROUP(7) DC_PAR_GROUP(8)
+#undef DC_PAR_GROUP
+                if (elect_one()) {
+                    umma_commit_2sm(&empty_bar[as]);
+                    umma_commit_2sm(&tfull_bar[as]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        run_epilogue<BN, HT_H, HT_W, 4, true, true, true>(p, warp & 3, lane, (warp - EPI_WARP0) >> 2, tmem_base, tfull_bar, tempty_bar,
+                                                          bias_s, stg_s);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    }
+}
+
 // ---------------------------------------------------------------------------- stem on tensor cores
 // First layer, Conv2d(3, 64, 3, padding=d, dilation=d) + BN + ReLU (reference models/model_2.py:10, :41-46),
 // fused with the input conversion of quantify_droplets_batch.py:45-46 (u8 -> /255 -> NCHW float).
@@ -1466,6 +1643,67 @@ int launch_variant(const ConvParams& p, cudaStream_t stream) {
 
 }  // namespace
 
+// 64 -> 64 channel 3x3 layer, dilation 1, even H and W, by output parity class (conv_par2_kernel); arguments already
+// validated by launch_conv_tc.
+static int launch_conv_par(const dc_conv_args_t* a, cudaStream_t stream, const float* bias_host) {
+    DC_REQUIRE(((uintptr_t)a->weight_par & 15) == 0, DC_EINVAL, "dc_conv_tc: weight_par must be 16-byte aligned");
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    const int Hh = a->H / 2, Wh = a->W / 2;          // the tile grid is the half-resolution one
+    {   // in: [B, H, W, 64 of in_stride] seen as [B, H, W/2, parity, 64]: a box is one column-parity plane
+        const cuuint64_t ps = (cuuint64_t)a->in_stride * 2;
+        cuuint64_t dims[5] = {64, 2, (cuuint64_t)Wh, (cuuint64_t)a->H, (cuuint64_t)a->B};
+        cuuint64_t str[4] = {ps, 2 * ps, (cuuint64_t)a->W * ps, (cuuint64_t)a->H * a->W * ps};
+        cuuint32_t box[5] = {KCHUNK, 1, UPF_S_W, UPF_S_H, 1};
+        int rc = encode_map(&p.tmS, a->in, 5, dims, str, box);
+        if (rc != DC_OK) return rc;
+    }
+    {   // weights: [2 CTAs of a pair][PAR_ROWS_PER_RANK rows in schedule order][64]
+        cuuint64_t dims[2] = {KCHUNK, (cuuint64_t)2 * PAR_ROWS_PER_RANK};
+        cuuint64_t str[1] = {KCHUNK * 2};
+        cuuint32_t box[2] = {KCHUNK, UPF_GROUP_ROWS};
+        int rc = encode_map(&p.tmB, a->weight_par, 2, dims, str, box);
+        if (rc != DC_OK) return rc;
+    }
+    p.B = a->B; p.H = Hh; p.W = Wh; p.Cin = 64; p.Cout = 64;
+    p.dil = 1; p.ntaps = 9; p.kchunks = 1;
+    p.tiles_w = ceil_div(Wh, HT_W);
+    p.tiles_h = ceil_div(Hh, HT_H);
+    p.n_tiles = 1;
+    const long long total = (long long)a->B * p.tiles_w * p.tiles_h;
+    DC_REQUIRE(total < (1ll << 31), DC_EINVAL, "dc_conv_tc: too many tiles");
+    p.total_tiles = p.m_tiles = (int)total;
+    p.fd_ntiles = make_fastdiv(1); p.fd_per_img = make_fastdiv(p.tiles_h * p.tiles_w); p.fd_tiles_w = make_fastdiv(p.tiles_w);
+    p.epilogue = a->epilogue;
+    p.relu = a->relu != 0;
+    p.bias = a->bias;
+    if (bias_host && a->epilogue != DC_EPI_HEAD) {
+        p.bias_const = 1;
+        memcpy(p.bias_c, bias_host, sizeof(p.bias_c));
+    }
+    p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+    p.out_stride = a->out_stride; p.out_offset = a->out_offset;
+    p.pool_out = reinterpret_cast<__nv_bfloat16*>(a->pool_out);
+    p.pool_stride = a->pool_stride;
+    p.head_w = a->head_w; p.head_b = a->head_b; p.thresh = a->thresh;
+    p.prob_out = a->prob_out; p.mask_out = a->mask_out;
+
+    const int n_pairs = (p.m_tiles + 1) / 2;
+    const int max_clusters = num_sms() / 2;
+    const int grid = 2 * (n_pairs < max_clusters ? n_pairs : max_clusters);
+#define DC_PAR_CASE(mode)                                                                                    \
+    if (g_upfuse_mode == mode) {                                                                             \
+        static unsigned long long attr_done = 0;                                                             \
+        int rc = set_max_smem_once(conv_par2_kernel<mode>, (int)PAR_SMEM, &attr_done);                       \
+        if (rc != DC_OK) return rc;                                                                          \
+        conv_par2_kernel<mode><<<grid, NUM_THREADS, PAR_SMEM, stream>>>(p);                                  \
+    }
+    DC_PAR_CASE(0) DC_PAR_CASE(1) DC_PAR_CASE(2) DC_PAR_CASE(3)
+#undef DC_PAR_CASE
+    DC_CUDA(cudaGetLastError());
+    return DC_OK;
+}
+
 int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream, const float* bias_host) {
     DC_REQUIRE(a && a->in && a->weight && a->bias, DC_EINVAL, "dc_conv_tc: null pointer argument");
     DC_REQUIRE(a->kind == DC_KIND_CONV3X3 || a->kind == DC_KIND_UPCONV2, DC_EINVAL, "dc_conv_tc: kind %d", a->kind);
@@ -1497,6 +1735,9 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream, const float* bi
                    DC_EINVAL, "dc_conv_tc: pool_out / pool_stride");
         DC_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0, DC_EINVAL, "dc_conv_tc: pooled layer needs even H, W");
     }
+    if (!up && a->weight_par && a->Cin == 64 && a->Cout == 64 && a->dilation == 1 && a->H % 2 == 0 && a->W % 2 == 0 &&
+        g_kernel_family == DC_CONV_FAMILY_AUTO)
+        return launch_conv_par(a, stream, bias_host);
     const int gemm_n = up ? 4 * a->Cout : a->Cout;      // upconv: the four output parities are one wide GEMM N
     const int BN = gemm_n % 256 == 0 ? 256 : (gemm_n % 128 == 0 ? 128 : 64);
 
@@ -1719,6 +1960,7 @@ int launch_conv_upfused(const dc_upfuse_args_t* a, cudaStream_t stream, const fl
     p.epilogue = DC_EPI_STORE;
     p.relu = a->relu != 0;
     p.bias = a->bias9 + 4 * 64;                       // interior class
+    p.border_bias = 1;
     p.bias_const = 1;
     memcpy(p.bias_c, bias9_host + 4 * 64, sizeof(p.bias_c));
     p.out = reinterpret_cast<__nv_bfloat16*>(a->out);

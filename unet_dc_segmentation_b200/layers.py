@@ -34,7 +34,8 @@ def stem(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, dilation: in
 
 
 def conv3x3(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, dilation: int = 1, relu: bool = True,
-            cin: int | None = None, out: torch.Tensor | None = None, out_offset: int = 0, pool: bool = False):
+            cin: int | None = None, out: torch.Tensor | None = None, out_offset: int = 0, pool: bool = False,
+            weight_par: torch.Tensor | None = None):
     """3x3 dilated conv (+bias, +ReLU) on tcgen05.  x: bf16 [B,H,W,S] whose channels [0,cin) are read;
     weight: bf16 [Cout, 9*cin]; out (optional): bf16 [B,H,W,S_out], written at channel out_offset.
     Returns out, or (out, pooled bf16 [B,H/2,W/2,Cout]) when pool."""
@@ -51,6 +52,8 @@ def conv3x3(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, dilation:
     a.in_, a.in_stride = x.data_ptr(), S
     a.weight, a.bias = weight.data_ptr(), bias.data_ptr()
     a.out, a.out_stride, a.out_offset = out.data_ptr(), out.shape[3], int(out_offset)
+    if weight_par is not None:
+        a.weight_par = weight_par.data_ptr()
     if pool:
         a.pool_out, a.pool_stride = pooled.data_ptr(), cout
     with torch.cuda.device(x.device):
@@ -98,7 +101,7 @@ def upconv_conv3x3(x: torch.Tensor, skip: torch.Tensor, weight: torch.Tensor, bi
 
 
 def conv3x3_head(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, head_w: torch.Tensor, head_b: float,
-                 thresh: float, dilation: int = 1):
+                 thresh: float, dilation: int = 1, weight_par: torch.Tensor | None = None):
     """Last layer: conv3x3 (64 -> 64) + ReLU, then 1x1 conv + sigmoid + threshold in the epilogue.
     Returns (probs f32 [B,H,W], mask u8 [B,H,W])."""
     _lib.require_cuda(x, "x")
@@ -111,6 +114,8 @@ def conv3x3_head(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, head
     a.in_, a.in_stride = x.data_ptr(), S
     a.weight, a.bias = weight.data_ptr(), bias.data_ptr()
     a.head_w, a.head_b, a.thresh = head_w.data_ptr(), float(head_b), float(thresh)
+    if weight_par is not None:
+        a.weight_par = weight_par.data_ptr()
     a.prob_out, a.mask_out = prob.data_ptr(), mask.data_ptr()
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().dc_conv_tc(C.byref(a), _lib.stream_ptr(x.device)))

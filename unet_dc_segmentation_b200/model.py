@@ -105,9 +105,13 @@ def pack_upfused(comp, skipw):
     """Weights of compose_upconv in the order the kernel's MMAs consume them: bf16 [2 CTAs][2176 rows][64 ci].
     An MMA on window (r, c) covering classes cls0 .. cls0+ncls-1 takes, for class (py, px), tap (r - py, c - px) of
     chunk 0 / 1 (x channels [0,64) / [64,128)) or of the skip weights (chunk 2); its B operand is those [64 co][64 ci]
-    tiles stacked, the first half of the rows in CTA 0's blob and the second half in CTA 1's."""
+    tiles stacked, the first half of the rows in CTA 0's blob and the second half in CTA 1's.
+    comp = None: the skip part alone = a plain 64 -> 64 channel 3x3 layer by parity class, [2][1152][64]
+    (dc_conv_args.weight_par)."""
     halves = ([], [])
     for chunk, r, c, cls0, ncls in upfuse_schedule():
+        if comp is None and chunk != 2:
+            continue
         tiles = []
         for cls in range(cls0, cls0 + ncls):
             py, px = cls >> 1, cls & 1
@@ -117,8 +121,14 @@ def pack_upfused(comp, skipw):
         halves[0].append(rows[:half])
         halves[1].append(rows[half:])
     blob = torch.stack([torch.cat(h, 0) for h in halves], 0).contiguous()
-    assert blob.shape == (2, 2176, 64) and blob.dtype == torch.bfloat16
+    assert blob.shape == (2, 2176 if comp is not None else 1152, 64) and blob.dtype == torch.bfloat16
     return blob
+
+
+def pack_par3x3(w):
+    """[64,64,3,3] (BatchNorm folded) -> the parity-class layout of dc_conv_args.weight_par."""
+    assert tuple(w.shape) == (64, 64, 3, 3)
+    return pack_upfused(None, w.permute(2, 3, 0, 1).to(torch.bfloat16).contiguous())
 
 
 def fused_level1_blobs(sd, eps: float = 1e-5):
@@ -154,6 +164,10 @@ class _Packed:
                     w = pack_conv3x3(wp)
                 else:
                     w = pack_conv3x3(wf)
+                    if module.parity_level1 and (name, idx) in (("enc1", 3), ("dec1", 3)):
+                        wp = pack_par3x3(wf)
+                        self.blobs.append(wp)
+                        desc.par_weight[0 if name == "enc1" else 1] = wp.data_ptr()
                 b = b.contiguous()
             self.blobs += [w, b]
             desc.weight[i] = w.data_ptr()
@@ -204,6 +218,8 @@ class UNetDC(nn.Module):
     # upconv1 + dec1.0 as one launch with host-composed weights (csrc/conv_tc.cu conv_upfused2_kernel); False runs the
     # two layers separately (set it before the first forward, or call invalidate())
     fuse_level1 = True
+    # enc1.3 and dec1.3 per output parity class with shared windows (conv_par2_kernel; taken when dilations[0] == 1)
+    parity_level1 = True
 
     def __init__(self, in_channels: int = 3, out_channels: int = 1):
         super().__init__()
