@@ -425,7 +425,8 @@ def run_b200(args):
 
     # ---- per-launch profile of the forward (one extra, untimed pass) for the roofline table
     pk, ptype = peaks()
-    names, fl = wl.launch_flops(S, S, model.dilations, in_bounds=True, fused_level1=model.fuse_level1)
+    names, fl = wl.launch_flops(S, S, model.dilations, in_bounds=True, fused_level1=model.fuse_level1,
+                                fused_levels=model.fuse_levels)
     import ctypes as C
     n_launch = model.num_launches()
     ms_arr = (C.c_float * n_launch)()

@@ -49,7 +49,7 @@ extern "C" {
 
 /* Bumped whenever a struct or signature in this header changes; dc_version() returns the value the library was
  * built with and the Python binding refuses to load a library that disagrees. */
-#define DC_ABI_VERSION 203
+#define DC_ABI_VERSION 204
 
 const char* dc_last_error(void);
 int dc_version(void);
@@ -131,6 +131,14 @@ typedef struct dc_upfuse_args {
     void* out;
     int out_stride;
     int out_offset;
+    /* C: x has 2C channels, skip and the output C.  0 or 64 = the level-1 layer described above.  128 / 256 / 512
+     * (upconv{2,3,4} + dec{2,3,4}.0): the tile's parity classes are walked in passes of 256 / min(C, 256) classes, and
+     *   weight      bf16 [class group][n-tile][2 CTAs][2C/64 x chunks][4 taps][classes of the group x BN/2 rows][64]
+     *   weight_skip bf16 [n-tile][2 CTAs][C/64 chunks][9 taps][BN/2 rows][64]        (BN = min(C, 256); row = output
+     *               channel n-tile * BN + CTA * BN/2 + r;  model.py pack_upfused_wide is the packer)
+     *   bias9       fp32 [9][C] */
+    int channels;
+    const void* weight_skip;
 } dc_upfuse_args_t;
 
 int dc_conv_upfused(const dc_upfuse_args_t* args, void* stream);
@@ -201,6 +209,11 @@ typedef struct dc_model_desc {
      * dc_upfuse_args.weight / .bias9; NULL = run the two layers separately from weight[19], weight[20]. */
     const void* fused_weight1;
     const float* fused_bias1;
+    /* Optional, levels 2..4 ([0] = upconv2 + dec2.0, ...): dc_upfuse_args.weight / .weight_skip / .bias9 for
+     * channels = 128, 256, 512; a NULL fused_wide_x[i] runs the two layers separately. */
+    const void* fused_wide_x[3];
+    const void* fused_wide_s[3];
+    const float* fused_wide_b[3];
     /* Optional: weights of enc1.3 ([0]) and dec1.3 ([1]) in the dc_conv_args.weight_par layout (used when
      * dilations[0] == 1); NULL = weight[1] / weight[21] through the generic kernels. */
     const void* par_weight[2];

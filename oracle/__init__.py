@@ -164,23 +164,24 @@ _BLOCKS = [("enc1", 1), ("enc2", 2), ("enc3", 4), ("enc4", 8), ("bottleneck", 16
 
 
 def composed_upconv_conv3x3(x, skip, comp, skipw, bias9, relu=True):
-    """CPU evaluation of the fused level-1 layer (include/unetdc_b200.h dc_conv_upfused) from the composed weights:
-    x f32 [B,128,H,W], skip f32 [B,64,2H,2W], comp [4 classes][2][2][64][128], skipw [3][3][64][64], bias9 [9,64]
-    -> f32 [B,64,2H,2W].  Equal (up to rounding) to conv_transpose2d -> cat -> conv2d(padding=1) of
+    """CPU evaluation of a fused upconv + conv layer (include/unetdc_b200.h dc_conv_upfused) from the composed weights:
+    x f32 [B,2C,H,W], skip f32 [B,C,2H,2W], comp [4 classes][2][2][C][2C], skipw [3][3][C][C], bias9 [9,C]
+    -> f32 [B,C,2H,2W].  Equal (up to rounding) to conv_transpose2d -> cat -> conv2d(padding=1) of
     models/model_2.py:76-77, restated per output parity class: class (py, px) is a 2x2 conv over x zero-padded by one
     pixel, read from (py, px), plus the 3x3 over skip, plus the bias of the pixel's border class."""
     import torch
     import torch.nn.functional as F
 
     B, _, H, W = x.shape
+    C = skip.shape[1]
     xp = F.pad(x, (1, 1, 1, 1))
-    out = torch.zeros((B, 64, 2 * H, 2 * W), dtype=torch.float32)
+    out = torch.zeros((B, C, 2 * H, 2 * W), dtype=torch.float32)
     for py in range(2):
         for px in range(2):
             k = comp[py * 2 + px].to(torch.float32).permute(2, 3, 0, 1).contiguous()       # [co][cx][a][b]
             out[:, :, py::2, px::2] = F.conv2d(xp[:, :, py:py + H + 1, px:px + W + 1], k)
     out += F.conv2d(skip, skipw.to(torch.float32).permute(2, 3, 0, 1).contiguous(), padding=1)
-    b9 = bias9.to(torch.float32).reshape(3, 3, 64)
+    b9 = bias9.to(torch.float32).reshape(3, 3, C)
     rows = torch.ones(2 * H, dtype=torch.long); rows[0] = 0; rows[-1] = 2
     cols = torch.ones(2 * W, dtype=torch.long); cols[0] = 0; cols[-1] = 2
     out += b9[rows][:, cols].permute(2, 0, 1).unsqueeze(0)
@@ -188,7 +189,7 @@ def composed_upconv_conv3x3(x, skip, comp, skipw, bias9, relu=True):
 
 
 def unetdc_forward(state_dict, x, dilations=(1, 2, 4, 8, 16), emulate_bf16=False, gray_input=False, round_last=False,
-                   fused_level1=None):
+                   fused_level1=None, fused_levels=None):
     """Plain PyTorch fp32 restatement of reference models/model_2.py:56-80 in eval mode.
 
     state_dict uses the reference's 136 keys; x: f32 [B,3,H,W]; returns f32 [B,1,H,W] probs.
@@ -202,7 +203,8 @@ def unetdc_forward(state_dict, x, dilations=(1, 2, 4, 8, 16), emulate_bf16=False
     to 3 channels; the CUDA stem then feeds the exact integers and folds 1/255 and the 3 channels into the weights.
     ``round_last``: models with out_channels != 1 store the last feature map in bf16 before the 1x1 head kernel.
     ``fused_level1`` (emulation only): (comp, skipw, bias9) of the composed upconv1 + dec1.0 layer the CUDA path runs by
-    default (model.compose_upconv; None = the two layers separately, `up` stored in bf16)."""
+    default (model.compose_upconv; None = the two layers separately, `up` stored in bf16); ``fused_levels``: the same
+    for any decoder level, {level: (comp, skipw, bias9)}."""
     import torch
     import torch.nn.functional as F
 
@@ -231,6 +233,9 @@ def unetdc_forward(state_dict, x, dilations=(1, 2, 4, 8, 16), emulate_bf16=False
         t = cbr(t, p, 3, d)
         return r(t) if round_out else t
 
+    fused_levels = dict(fused_levels or {})
+    if fused_level1 is not None:
+        fused_levels[1] = fused_level1
     with torch.no_grad():
         x = x.detach().to(torch.float32).cpu()
         skips = []
@@ -241,10 +246,11 @@ def unetdc_forward(state_dict, x, dilations=(1, 2, 4, 8, 16), emulate_bf16=False
             t = F.max_pool2d(t, 2)
         t = block(t, "bottleneck", dilations[4])            # model_2.py:64
         for lvl in (4, 3, 2, 1):                            # model_2.py:67-77
-            if lvl == 1 and emulate_bf16 and fused_level1 is not None:
-                t = r(composed_upconv_conv3x3(t, skips[0], *(b.cpu() for b in fused_level1)))
-                t = cbr(t, "dec1", 3, 1)
-                t = r(t) if round_last else t
+            fl = fused_levels.get(lvl) if emulate_bf16 else None
+            if fl is not None:
+                t = r(composed_upconv_conv3x3(t, skips[lvl - 1], *(b.cpu() for b in fl)))
+                t = cbr(t, f"dec{lvl}", 3, 1)
+                t = r(t) if (lvl > 1 or round_last) else t
                 continue
             t = r(F.conv_transpose2d(t, r(sd[f"upconv{lvl}.weight"]), sd[f"upconv{lvl}.bias"], stride=2))
             t = torch.cat([t, skips[lvl - 1]], dim=1)

@@ -203,6 +203,47 @@ def test_upconv_conv3x3_fused(cuda_device, B, H, W):
     assert float(err) < 0.05, f"fused layer vs unfused fp32 chain: max err {float(err):.4f}"
 
 
+WIDE_CASES = [
+    # C, B, H, W of the transposed conv's input
+    (128, 1, 16, 8), (128, 2, 24, 20), (128, 1, 40, 24),
+    (256, 1, 16, 8), (256, 2, 24, 12), (256, 1, 8, 8),
+    (512, 1, 16, 8), (512, 2, 16, 16), (512, 1, 24, 20),
+]
+
+
+@pytest.mark.parametrize("C,B,H,W", WIDE_CASES)
+def test_upconv_conv3x3_fused_wide(cuda_device, C, B, H, W):
+    """dc_conv_upfused for the deeper decoder levels (upconv{2,3,4} + dec{2,3,4}.0: conv_upfused_wide_kernel, the
+    parity classes walked in passes) against the CPU evaluation of the same composed weights and, loosely, the
+    unfused fp32 chain."""
+    import torch
+    import torch.nn.functional as F
+    import oracle
+    from unet_dc_segmentation_b200 import layers
+    from unet_dc_segmentation_b200.model import compose_upconv, pack_upfused_wide
+    g = torch.Generator().manual_seed(C + B * 1000 + H * 10 + W)
+    wu = torch.randn(2 * C, C, 2, 2, generator=g) / (2 * C) ** 0.5
+    bu = torch.randn(C, generator=g) * 0.3
+    wd = torch.randn(C, 2 * C, 3, 3, generator=g) / (3.0 * (2 * C) ** 0.5)
+    bd = torch.randn(C, generator=g) * 0.1
+    comp, skipw, bias9 = compose_upconv(wu, bu, wd, bd)
+    wx, ws = pack_upfused_wide(comp, skipw)
+    x = _rand_act(B, H, W, 2 * C, 5)
+    cat = _rand_act(B, 2 * H, 2 * W, 2 * C, 6)            # skip = channels [C, 2C) of a 2C-channel buffer
+    xs, ss = x.float().permute(0, 3, 1, 2), cat[..., C:].float().permute(0, 3, 1, 2)
+    for relu in (True, False):
+        want = oracle.composed_upconv_conv3x3(xs, ss, comp, skipw, bias9, relu=relu).permute(0, 2, 3, 1)
+        out = torch.full((B, 2 * H, 2 * W, C + 32), 7.0, dtype=torch.bfloat16).cuda()
+        layers.upconv_conv3x3(x.cuda(), cat.cuda(), wx.cuda(), bias9.cuda(), relu=relu, skip_offset=C, out=out,
+                              out_offset=16, weight_skip=ws.cuda())
+        torch.cuda.synchronize()
+        _close(out[..., 16:16 + C], want, f"fused upconv+conv C={C} {B}x{H}x{W} relu={relu}")
+        assert bool((out[..., :16] == 7).all()) and bool((out[..., 16 + C:] == 7).all())
+    chain = F.relu(F.conv2d(torch.cat([F.conv_transpose2d(xs, wu, bu, stride=2), ss], 1), wd, bd, padding=1)).permute(0, 2, 3, 1)
+    err = (out[..., 16:16 + C].float().cpu().clamp(min=0) - chain).abs().max()
+    assert float(err) < 0.06, f"fused layer vs unfused fp32 chain: max err {float(err):.4f}"
+
+
 PARITY_CASES = [(1, 32, 16), (2, 32, 16), (1, 80, 48), (3, 48, 40), (2, 128, 128), (1, 16, 16), (1, 2, 2)]
 
 

@@ -33,9 +33,11 @@ pytestmark = pytest.mark.gpu
 
 
 def _fused(sd):
-    """Blobs of the composed upconv1 + dec1.0 layer the CUDA forward runs by default (UNetDC.fuse_level1)."""
-    from unet_dc_segmentation_b200.model import fused_level1_blobs
-    return fused_level1_blobs({k: v.detach().float().cpu() for k, v in sd.items() if k.startswith(("dec1.", "upconv1."))})
+    """Composed weights of the decoder levels the CUDA forward runs as one launch each by default (UNetDC.fuse_level1,
+    UNetDC.fuse_levels), for the emulation."""
+    from unet_dc_segmentation_b200.model import fused_level_blobs
+    cpu = {k: v.detach().float().cpu() for k, v in sd.items() if k.startswith(("dec", "upconv"))}
+    return {lvl: fused_level_blobs(cpu, lvl) for lvl in (1, 2, 3, 4)}
 
 
 PROB_TOL = 0.08
@@ -78,7 +80,7 @@ def test_forward_vs_reference_golden(cuda_device, tag, cls):
     x = torch.from_numpy(np.repeat(g[f"{tag}/images"][:, None], 3, 1).astype(np.float32) / 255.0)
     y = m(x.to(cuda_device))
     assert y.shape == (2, 1, 64, 64) and y.dtype == torch.float32
-    emu = oracle.unetdc_forward(sd, x, dil, emulate_bf16=True, fused_level1=_fused(sd)).numpy()
+    emu = oracle.unetdc_forward(sd, x, dil, emulate_bf16=True, fused_levels=_fused(sd)).numpy()
     _check_probs(y.cpu().numpy(), g[f"{tag}/probs"], emu, tag)
 
 
@@ -91,8 +93,8 @@ def test_forward_vs_oracle_sizes(cuda_device, B, H, W):
     imgs = np.stack([synthetic_image(max(H, W), 300 + b)[:H, :W] for b in range(B)])
     x = torch.from_numpy(np.repeat(imgs[:, None], 3, 1).astype(np.float32) / 255.0)
     want = oracle.unetdc_forward(sd, x).numpy()
-    emu = oracle.unetdc_forward(sd, x, emulate_bf16=True, fused_level1=_fused(sd)).numpy()
-    emu_gray = oracle.unetdc_forward(sd, x, emulate_bf16=True, fused_level1=_fused(sd), gray_input=True).numpy()
+    emu = oracle.unetdc_forward(sd, x, emulate_bf16=True, fused_levels=_fused(sd)).numpy()
+    emu_gray = oracle.unetdc_forward(sd, x, emulate_bf16=True, fused_levels=_fused(sd), gray_input=True).numpy()
     _check_probs(m(x.to(cuda_device)).cpu().numpy(), want, emu, f"f32 NCHW {B}x{H}x{W}")
     # u8 entry points (the /255 happens in the first kernel)
     mask_g, prob_g = m.predict_u8(torch.from_numpy(imgs).to(cuda_device), 0.3, return_prob=True)
@@ -117,6 +119,7 @@ def test_forward_with_level1_unfused(cuda_device):
     m = _model("UNetDC", sd, cuda_device)
     y_fused = m(x.to(cuda_device)).cpu().numpy()
     m.fuse_level1 = m.parity_level1 = False          # the generic kernels for enc1.3 / dec1.3 as well
+    m.fuse_levels = ()
     m.invalidate()
     assert m.num_launches() == 22
     y = m(x.to(cuda_device)).cpu().numpy()
@@ -135,7 +138,7 @@ def test_module_contract(cuda_device):
         m.train()(torch.zeros(1, 3, 16, 16, device=cuda_device))   # eval-mode only
     with pytest.raises(ValueError):
         m.eval()(torch.zeros(1, 3, 24, 16, device=cuda_device))    # H, W multiples of 16
-    assert m.num_launches() == 21          # stem + 17 conv3x3 + 3 upconv (upconv1 rides in dec1.0)
+    assert m.num_launches() == 18          # stem + 17 conv3x3 (the four upconvs ride in dec{l}.0)
 
 
 def test_whole_path_vs_reference_golden(cuda_device):
@@ -259,7 +262,7 @@ def test_forward_other_dilation_sets(cuda_device, dil):
     imgs = np.stack([synthetic_image(128, 700 + b) for b in range(2)])
     x = torch.from_numpy(np.repeat(imgs[:, None], 3, 1).astype(np.float32) / 255.0)
     want = oracle.unetdc_forward(sd, x, dil).numpy()
-    emu = oracle.unetdc_forward(sd, x, dil, emulate_bf16=True, fused_level1=_fused(sd)).numpy()
+    emu = oracle.unetdc_forward(sd, x, dil, emulate_bf16=True, fused_levels=_fused(sd)).numpy()
     _check_probs(m(x.to(cuda_device)).cpu().numpy(), want, emu, f"dilations {dil}")
 
 
@@ -313,10 +316,10 @@ def test_other_channel_counts(cuda_device, cin, cout):
     y = m(x.to(cuda_device))
     assert tuple(y.shape) == (2, cout, 48, 64)
     want = oracle.unetdc_forward(sd, x).numpy()
-    emu = oracle.unetdc_forward(sd, x, emulate_bf16=True, fused_level1=_fused(sd), round_last=(cout != 1)).numpy()
+    emu = oracle.unetdc_forward(sd, x, emulate_bf16=True, fused_levels=_fused(sd), round_last=(cout != 1)).numpy()
     _check_probs(y.cpu().numpy(), want, emu if (cin, cout) != (3, 1) else None, f"UNetDC({cin},{cout})")
     assert float(want.std()) > 0.05, "degenerate test: the reference output is flat"
-    assert m.num_launches() == 21 + (cin != 3) + (cout != 1)
+    assert m.num_launches() == 18 + (cin != 3) + (cout != 1)
     if cin != 3:
         with pytest.raises(ValueError):
             m.predict_u8(torch.zeros(1, 48, 64, dtype=torch.uint8, device=cuda_device), 0.3)

@@ -11,9 +11,11 @@ pytestmark = pytest.mark.gpu
 
 
 def _fused(sd):
-    """Blobs of the composed upconv1 + dec1.0 layer the CUDA forward runs by default (UNetDC.fuse_level1)."""
-    from unet_dc_segmentation_b200.model import fused_level1_blobs
-    return fused_level1_blobs({k: v.detach().float().cpu() for k, v in sd.items() if k.startswith(("dec1.", "upconv1."))})
+    """Composed weights of the decoder levels the CUDA forward runs as one launch each by default (UNetDC.fuse_level1,
+    UNetDC.fuse_levels), for the emulation."""
+    from unet_dc_segmentation_b200.model import fused_level_blobs
+    cpu = {k: v.detach().float().cpu() for k, v in sd.items() if k.startswith(("dec", "upconv"))}
+    return {lvl: fused_level_blobs(cpu, lvl) for lvl in (1, 2, 3, 4)}
 
 
 @pytest.fixture(scope="module")
@@ -115,7 +117,7 @@ def test_forward_parity_at_full_size(run):
     pre = rolling_ball_device(run["dev_frames"][idx], 50).cpu().numpy()          # bit-exact vs cv2 (test above)
     x = torch.from_numpy(np.repeat(pre[:, None], 3, 1).astype(np.float32) / 255.0)
     ref = oracle.unetdc_forward(sd, x).numpy()[:, 0]
-    emu = oracle.unetdc_forward(sd, x, emulate_bf16=True, fused_level1=_fused(sd), gray_input=True).numpy()[:, 0]
+    emu = oracle.unetdc_forward(sd, x, emulate_bf16=True, fused_levels=_fused(sd), gray_input=True).numpy()[:, 0]
     got = run["probs"][idx, 0].cpu().numpy()
     masks = run["masks"][idx].cpu().numpy()
     e_ref, e_emu = np.abs(got - ref), np.abs(got - emu)

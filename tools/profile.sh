@@ -10,8 +10,8 @@ mkdir -p gpurun_out
 python bench.py $ARGS > gpurun_out/plain_$TAG.json 2> gpurun_out/plain_$TAG.err || { echo "plain run failed"; tail gpurun_out/plain_$TAG.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py $ARGS > /dev/null 2>&1; echo "launch list rc=$?"
-# one warm forward = 21 launches (stem + 20 conv, upconv1 rides in dec1.0); 3 warm-up steps precede it
-ncu --metrics $M --clock-control none -k regex:'conv_|stem_' -s 63 -c 21 --csv --log-file gpurun_out/fwd_metrics_$TAG.csv \
+# one warm forward = 18 launches (stem + 17 conv, the upconvs ride in dec{l}.0); 3 warm-up steps precede it
+ncu --metrics $M --clock-control none -k regex:'conv_|stem_' -s 54 -c 18 --csv --log-file gpurun_out/fwd_metrics_$TAG.csv \
     python bench.py $ARGS > /dev/null 2>&1; echo "forward metrics rc=$?"
 ncu --metrics $M --clock-control none -k regex:'morph_|stretch_|ccl_' -s 30 -c 10 --csv --log-file gpurun_out/aux_metrics_$TAG.csv \
     python bench.py $ARGS > /dev/null 2>&1; echo "aux metrics rc=$?"

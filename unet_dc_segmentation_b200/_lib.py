@@ -16,7 +16,7 @@ DC_KIND_CONV3X3, DC_KIND_UPCONV2 = 0, 1
 DC_EPI_STORE, DC_EPI_STORE_POOL, DC_EPI_HEAD, DC_EPI_UPSCATTER = 0, 1, 2, 3
 DC_NUM_LAYERS = 23
 DC_CONV_FAMILY_AUTO, DC_CONV_FAMILY_NO_PAIR, DC_CONV_FAMILY_GENERIC = 0, 1, 2
-ABI_VERSION = 203          # DC_ABI_VERSION of include/unetdc_b200.h these ctypes structures mirror
+ABI_VERSION = 204          # DC_ABI_VERSION of include/unetdc_b200.h these ctypes structures mirror
 
 EXPORTS = [
     "dc_last_error", "dc_version", "dc_device_check", "dc_conv_tc", "dc_conv_upfused", "dc_debug_upfuse_schedule", "dc_debug_set_upfuse_mode", "dc_debug_set_conv_family", "dc_stem", "dc_model_create",
@@ -61,7 +61,9 @@ class ModelDesc(Structure):
     _fields_ = [
         ("weight", c_void_p * DC_NUM_LAYERS), ("bias", c_void_p * DC_NUM_LAYERS),
         ("dilations", c_int * 5), ("base_channels", c_int), ("in_channels", c_int), ("out_channels", c_int),
-        ("fused_weight1", c_void_p), ("fused_bias1", c_void_p), ("par_weight", c_void_p * 2),
+        ("fused_weight1", c_void_p), ("fused_bias1", c_void_p),
+        ("fused_wide_x", c_void_p * 3), ("fused_wide_s", c_void_p * 3), ("fused_wide_b", c_void_p * 3),
+        ("par_weight", c_void_p * 2),
     ]
 
 
@@ -72,6 +74,7 @@ class UpfuseArgs(Structure):
         ("skip", c_void_p), ("skip_stride", c_int),
         ("weight", c_void_p), ("bias9", c_void_p), ("relu", c_int),
         ("out", c_void_p), ("out_stride", c_int), ("out_offset", c_int),
+        ("channels", c_int), ("weight_skip", c_void_p),
     ]
 
 

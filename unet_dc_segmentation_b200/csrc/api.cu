@@ -65,6 +65,7 @@ struct dc_model {
     float bias64[DC_NUM_LAYERS][64];
     bool has_bias64[DC_NUM_LAYERS];
     bool fused1;             // upconv1 + dec1.0 as one launch (desc.fused_weight1)
+    bool fused[4];           // [l]: upconv{l+1} + dec{l+1}.0 as one launch ([0] == fused1)
     float fused_bias9[9 * 64];
 };
 
@@ -87,9 +88,12 @@ struct ForwardBuffers {
 // forward_impl below); two buffers may share memory when their lifetimes do not intersect.  Largest first, each at
 // the lowest offset that is free for its whole lifetime.  At 32 x 1024^2 this is 15.6 GB (the skip halves of cat[0..3]
 // have to survive the whole bottom of the U) instead of the 30.5 GB of one private buffer per tensor.
-// fused1 (upconv1 + dec1.0 as one launch, number 20): cat[0] holds only the skip half (64 channels), and dec2.3's
-// output is read by the launch that writes ad[0], so it has to live one launch longer.
-ForwardBuffers carve(char* base, int B, int H, int W, bool generic_in = false, bool generic_out = false, bool fused1 = false) {
+// fused[l] (upconv{l+1} + dec{l+1}.0 as one launch, at the number of the dec launch): cat[l] holds only the skip half,
+// and the transposed conv's input is read by the launch that writes ad[l], so it has to live one launch longer.
+ForwardBuffers carve(char* base, int B, int H, int W, bool generic_in = false, bool generic_out = false,
+                     const bool* fused = nullptr) {
+    const bool none[4] = {false, false, false, false};
+    if (!fused) fused = none;
     ForwardBuffers f;
     memset(&f, 0, sizeof(f));
     struct Item { size_t bytes; int t0, t1; char** slot; size_t off; };
@@ -106,12 +110,12 @@ ForwardBuffers carve(char* base, int B, int H, int W, bool generic_in = false, b
         const size_t C = (size_t)64 << l;
         add(&f.a[l], px * C, 2 * l, 2 * l + 1);
         if (l < 4) {
-            add(&f.cat[l], px * (l == 0 && fused1 ? 1 : 2) * C, 2 * l + 1, 20 - 3 * l);
+            add(&f.cat[l], px * (fused[l] ? 1 : 2) * C, 2 * l + 1, 20 - 3 * l);
             add(&f.pool[l], px / 4 * C, 2 * l + 1, 2 * l + 2);
             add(&f.ad[l], px * C, 20 - 3 * l, 21 - 3 * l);
-            if (l > 0) add(&f.db[l], px * C, 21 - 3 * l, 22 - 3 * l + (l == 1 && fused1 ? 1 : 0));
+            if (l > 0) add(&f.db[l], px * C, 21 - 3 * l, 22 - 3 * l + (fused[l - 1] ? 1 : 0));
         } else {
-            add(&f.bott, px * C, 9, 10);
+            add(&f.bott, px * C, 9, 10 + (fused[3] ? 1 : 0));
         }
     }
     int order[24];
@@ -174,8 +178,9 @@ int dc_conv_upfused(const dc_upfuse_args_t* args, void* stream) {
     int rc = check_current_device(nullptr);
     if (rc != DC_OK) return rc;
     DC_REQUIRE(args && args->bias9, DC_EINVAL, "dc_conv_upfused: null argument");
-    float bias9[9 * 64];        // single-layer entry (tests): the interior row travels as kernel parameters
-    DC_CUDA(cudaMemcpy(bias9, args->bias9, sizeof(bias9), cudaMemcpyDeviceToHost));
+    float bias9[9 * 64];        // single-layer entry (tests): level 1's interior row travels as kernel parameters
+    if (args->channels == 0 || args->channels == 64)
+        DC_CUDA(cudaMemcpy(bias9, args->bias9, sizeof(bias9), cudaMemcpyDeviceToHost));
     return launch_conv_upfused(args, (cudaStream_t)stream, bias9);
 }
 
@@ -305,6 +310,15 @@ int dc_model_create(dc_model_t** out, int device, const dc_model_desc_t* desc) {
         m->has_bias64[layer] = true;
     }
     m->fused1 = desc->fused_weight1 != nullptr;
+    m->fused[0] = m->fused1;
+    for (int l = 1; l < 4; ++l) {
+        m->fused[l] = desc->fused_wide_x[l - 1] != nullptr;
+        if (m->fused[l] && !(desc->fused_wide_s[l - 1] && desc->fused_wide_b[l - 1])) {
+            delete m;
+            set_error("dc_model_create: fused_wide_x[%d] without fused_wide_s / fused_wide_b", l - 1);
+            return DC_EINVAL;
+        }
+    }
     if (m->fused1) {
         e = desc->fused_bias1 ? cudaMemcpy(m->fused_bias9, desc->fused_bias1, sizeof(m->fused_bias9), cudaMemcpyDeviceToHost)
                               : cudaErrorInvalidValue;
@@ -326,13 +340,15 @@ int dc_forward_workspace_bytes(const dc_model_t* m, int B, int H, int W, size_t*
     DC_REQUIRE(m && bytes, DC_EINVAL, "dc_forward_workspace_bytes: null argument");
     DC_REQUIRE(B > 0 && H > 0 && W > 0 && H % 16 == 0 && W % 16 == 0, DC_EINVAL,
                "dc_forward: H and W must be positive multiples of 16 (got %d x %d x %d)", B, H, W);
-    *bytes = carve(nullptr, B, H, W, m->cin != 3, m->cout != 1, m->fused1).total;
+    *bytes = carve(nullptr, B, H, W, m->cin != 3, m->cout != 1, m->fused).total;
     return DC_OK;
 }
 
 int dc_forward_num_launches(const dc_model_t* m) {
     // stem + 17 conv3x3 + 4 upconv (+ the input conversion / the 1x1 head kernel for other channel counts)
-    return 22 + (m && m->cin != 3 ? 1 : 0) + (m && m->cout != 1 ? 1 : 0) - (m && m->fused1 ? 1 : 0);
+    int n = 22 + (m && m->cin != 3 ? 1 : 0) + (m && m->cout != 1 ? 1 : 0);
+    for (int l = 0; m && l < 4; ++l) n -= m->fused[l] ? 1 : 0;
+    return n;
 }
 
 }  // extern "C"
@@ -351,7 +367,7 @@ static int forward_impl(dc_model_t* m, int in_kind, const void* in, int B, int H
     DC_REQUIRE(dev == m->device, DC_EINVAL, "dc_forward: model lives on device %d, current device is %d", m->device, dev);
     const bool gen_in = m->cin != 3, gen_out = m->cout != 1;
     DC_REQUIRE(!gen_in || in_kind == 0, DC_EINVAL, "dc_forward: u8 inputs need in_channels == 3 (model has %d)", m->cin);
-    ForwardBuffers f = carve((char*)workspace, B, H, W, gen_in, gen_out, m->fused1);
+    ForwardBuffers f = carve((char*)workspace, B, H, W, gen_in, gen_out, m->fused);
     DC_REQUIRE(workspace_bytes >= f.total, DC_EWORKSPACE, "dc_forward: workspace too small (%zu < %zu)", workspace_bytes,
                f.total);
     DC_REQUIRE(((uintptr_t)workspace & 255) == 0, DC_EINVAL, "dc_forward: workspace must be 256-byte aligned");
@@ -407,8 +423,8 @@ static int forward_impl(dc_model_t* m, int in_kind, const void* in, int B, int H
         const int h = H >> l, w = W >> l, c = 64 << l;
         DC_TRY(conv(2 * l, DC_KIND_CONV3X3, DC_EPI_STORE, 1, h, w, c / 2, c, d.dilations[l], f.pool[l - 1], c / 2, f.a[l], c,
                     0, nullptr));
-        DC_TRY(conv(2 * l + 1, DC_KIND_CONV3X3, DC_EPI_STORE_POOL, 1, h, w, c, c, d.dilations[l], f.a[l], c, f.cat[l], 2 * c,
-                    c, f.pool[l]));
+        DC_TRY(conv(2 * l + 1, DC_KIND_CONV3X3, DC_EPI_STORE_POOL, 1, h, w, c, c, d.dilations[l], f.a[l], c, f.cat[l],
+                    m->fused[l] ? c : 2 * c, m->fused[l] ? 0 : c, f.pool[l]));
     }
     // bottleneck (model_2.py:64)
     DC_TRY(conv(8, DC_KIND_CONV3X3, DC_EPI_STORE, 1, H >> 4, W >> 4, 512, 1024, d.dilations[4], f.pool[3], 512, f.a[4], 1024,
@@ -420,15 +436,18 @@ static int forward_impl(dc_model_t* m, int in_kind, const void* in, int B, int H
     for (int l = 3; l >= 0; --l) {
         const int h = H >> l, w = W >> l, c = 64 << l;
         const int base = 10 + 3 * (3 - l);
-        if (l == 0 && m->fused1) {
-            // upconv1 + dec1.0 in one launch: `up` (channels [0,64) of cat[0]) is never written
+        if (m->fused[l]) {
+            // upconv + dec.0 in one launch: `up` (channels [0,c) of cat[l]) is never written, cat[l] is the skip alone
             dc_upfuse_args_t u;
             memset(&u, 0, sizeof(u));
-            u.B = B; u.H = h / 2; u.W = w / 2;
+            u.B = B; u.H = h / 2; u.W = w / 2; u.channels = c;
             u.x = src; u.x_stride = 2 * c;
-            u.skip = f.cat[0]; u.skip_stride = c;
-            u.weight = d.fused_weight1; u.bias9 = d.fused_bias1; u.relu = 1;
-            u.out = f.ad[0]; u.out_stride = c; u.out_offset = 0;
+            u.skip = f.cat[l]; u.skip_stride = c;
+            u.weight = l == 0 ? d.fused_weight1 : d.fused_wide_x[l - 1];
+            u.weight_skip = l == 0 ? nullptr : d.fused_wide_s[l - 1];
+            u.bias9 = l == 0 ? d.fused_bias1 : d.fused_wide_b[l - 1];
+            u.relu = 1;
+            u.out = f.ad[l]; u.out_stride = c; u.out_offset = 0;
             DC_TRY(launch_conv_upfused(&u, stream, m->fused_bias9));
         } else {
         DC_TRY(conv(base, DC_KIND_UPCONV2, DC_EPI_UPSCATTER, 0, h / 2, w / 2, 2 * c, c, 1, src, 2 * c, f.cat[l], 2 * c, 0,

@@ -88,7 +88,8 @@ __device__ __forceinline__ int fast_div(int n, const FastDiv& f) {
 struct alignas(64) ConvParams {
     CUtensorMap tmA;
     CUtensorMap tmB;
-    CUtensorMap tmS;                // conv_upfused2_kernel only: the skip tensor as two column-parity planes
+    CUtensorMap tmS;                // parity-class kernels only: the skip tensor as two column-parity planes
+    CUtensorMap tmB2;               // conv_upfused_wide_kernel only: the skip half of the 3x3 weights
     int B, H, W, Cin, Cout;
     int dil, ntaps, kchunks;
     int tiles_w, tiles_h, n_tiles, total_tiles, m_tiles;      // m_tiles = pixel tiles = total_tiles / n_tiles
@@ -107,8 +108,9 @@ struct alignas(64) ConvParams {
     uint8_t* mask_out;
     // conv_halo_kernel only
     int region_w, region_h, region_stride, nstages, nbstages;
-    // parity-class kernels: 1 = p.bias is row 4 of a [9][64] border-class table (conv_upfused2_kernel)
+    // parity-class kernels: 1 = p.bias is row 4 of a [9][Cout] border-class table (upconv folded in)
     int border_bias;
+    int real_ntiles;                // conv_upfused_wide_kernel: n-tiles of Cout (p.n_tiles also counts the class groups)
 };
 
 struct TileCoord {
@@ -260,7 +262,15 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
             tile = blockIdx.x + it * gridDim.x;
             if (tile >= p.total_tiles) break;
         }
-        const TileCoord t = decode_tile<TH, UPF ? TW : TW * NHALF>(p, tile, BN);
+        TileCoord t = decode_tile<TH, UPF ? TW : TW * NHALF>(p, tile, BN);
+        // UPF with fewer than four classes per pass (conv_upfused_wide_kernel): the n-tile index also carries the class
+        // group; accumulator `half` is parity class cls_base + half
+        int cls_base = 0;
+        if (UPF) {
+            const int cg = t.n0 / p.Cout;
+            t.n0 -= cg * p.Cout;
+            cls_base = cg * NHALF;
+        }
         const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(&tfull_bar[as], aphase);
@@ -271,8 +281,8 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
 #pragma unroll 1
             for (int half = COOP ? group : 0; half < NHALF; half += COOP ? EPI_GROUPS : 1) {
                 // UPF: accumulator `half` = parity class (half / 2, half % 2) of half-resolution pixel (t.h0 + lh, t.w0 + lw)
-                const int h = UPF ? 2 * (t.h0 + lh) + (half >> 1) : t.h0 + lh;
-                const int w = UPF ? 2 * (t.w0 + lw) + (half & 1) : t.w0 + half * TW + lw;
+                const int h = UPF ? 2 * (t.h0 + lh) + ((cls_base + half) >> 1) : t.h0 + lh;
+                const int w = UPF ? 2 * (t.w0 + lw) + ((cls_base + half) & 1) : t.w0 + half * TW + lw;
                 const int H_out = UPF ? 2 * p.H : p.H, W_out = UPF ? 2 * p.W : p.W;
                 float head_acc = p.head_b;
                 const uint32_t taddr = tstage + (uint32_t)(half * BN);
@@ -313,7 +323,7 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
         uint32_t vbuf[2][32];
         tmem_ld32(tbase, vbuf[0]);
         // warp-uniform offsets of this tile
-        const long long tile_off = up_geo ? (((long long)t.img * (2 * p.H) + 2 * t.h0) * (2 * p.W) + 2 * t.w0) * p.out_stride
+        const long long tile_off = up_geo ? (((long long)t.img * (2 * p.H) + 2 * t.h0) * (2 * p.W) + 2 * t.w0) * p.out_stride + (UPF ? t.n0 : 0)
                                           : (((long long)t.img * p.H + t.h0) * p.W + t.w0) * p.out_stride + t.n0;
         const long long ptile_off = UPF ? (((long long)t.img * p.H + t.h0) * p.W + t.w0) * p.pool_stride + t.n0
                                         : (((long long)t.img * (p.H >> 1) + (t.h0 >> 1)) * (p.W >> 1) + (t.w0 >> 1)) * p.pool_stride + t.n0;
@@ -341,7 +351,7 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                     vmask |= (uint32_t)((row < hmax) && (col < wmax)) << r;
                 }
                 pval = (2 * prow < hmax) && (2 * pcol < wmax);
-                half_off = UPF ? ((long long)(half >> 1) * (2 * p.W) + (half & 1)) * p.out_stride : half * TW * cs;
+                half_off = UPF ? ((long long)((cls_base + half) >> 1) * (2 * p.W) + ((cls_base + half) & 1)) * p.out_stride : half * TW * cs;
                 phalf_off = (long long)(half * (TW / 2)) * p.pool_stride;
             }
             int bias_at = t.n0 + c0;
@@ -381,11 +391,12 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                 // taps of the 3x3 that fall outside the (upsampled) image carry no transposed-conv bias: only the
                 // pixels of the first / last output row and column differ from the interior constant
                 const int hh = t.h0 + lh, ww = t.w0 + lw;
-                const int rc = ((half >> 1) == 0 && hh == 0) ? 0 : (((half >> 1) == 1 && hh == p.H - 1) ? 2 : 1);
-                const int cc9 = ((half & 1) == 0 && ww == 0) ? 0 : (((half & 1) == 1 && ww == p.W - 1) ? 2 : 1);
-                if (rc * 3 + cc9 != 4) {               // p.bias = the interior row (4) of the fp32 [9][64] class table
-                    const float* b4 = p.bias + c0;
-                    const float* bc = b4 + (rc * 3 + cc9 - 4) * 64;
+                const int py = (cls_base + half) >> 1, px = (cls_base + half) & 1;
+                const int rc = (py == 0 && hh == 0) ? 0 : ((py == 1 && hh == p.H - 1) ? 2 : 1);
+                const int cc9 = (px == 0 && ww == 0) ? 0 : ((px == 1 && ww == p.W - 1) ? 2 : 1);
+                if (rc * 3 + cc9 != 4) {               // p.bias = the interior row (4) of the fp32 [9][Cout] class table
+                    const float* b4 = p.bias + t.n0 + c0;
+                    const float* bc = b4 + (rc * 3 + cc9 - 4) * p.Cout;
 #pragma unroll
                     for (int k = 0; k < 32; ++k) x[k] += __ldg(bc + k) - __ldg(b4 + k);
                 }
@@ -1192,6 +1203,239 @@ conv_upfused2_kernel(const __grid_constant__ ConvParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------- upconv{2,3,4} folded into dec{2,3,4}.0
+// The composition of conv_upfused2_kernel for Cout = 128 / 256 / 512, where the four parity classes of a tile no longer
+// fit TMEM at once (4 x BN x 2 stages): a tile is walked in PASSES of NCLS = 256 / BN classes (BN = 128: the two
+// classes of one output-row parity; BN = 256: one class), each pass a full K loop into NCLS accumulators, and the pass
+// index rides in the n-tile index (p.n_tiles = class groups x real n-tiles), so the tile / pair / epilogue machinery
+// is the ordinary one.  These layers are tensor-bound at N >= 128, so no window sharing: one MMA per (class, tap).
+// K order per pass: [x chunk, x chunk, skip chunk] x (C / 64) -- Cx = 2 C, so the two x chunks between consecutive
+// skip chunks (4096 tensor cycles) cover the load of the single 78 KB skip slot; x chunks rotate through three 23 KB
+// slots.  Weights stream through a ring of three 16 KB slots, each worth 512 tensor cycles: an x slot holds the
+// (chunk, tap) tiles of the pass's NCLS classes (NCLS x BN/2 rows per CTA), a skip slot one (chunk, tap) tile shared by
+// the classes (BN/2 rows).
+constexpr int UPW_XSLOTS = 2;
+constexpr int UPW_RING = 5;
+constexpr int UPW_BIAS_BYTES = 2048;
+constexpr size_t UPW_SMEM = UPW_RING * UPF_GROUP_BYTES + UPW_XSLOTS * UPF_U_BYTES + 2 * UPF_PLANE_BYTES + 1024 + HALO_BAR_BYTES +
+                            UPW_BIAS_BYTES + EPI_STAGE_TOTAL;
+static_assert(UPW_SMEM <= 227 * 1024, "conv_upfused_wide_kernel: shared memory");
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv_upfused_wide_kernel(const __grid_constant__ ConvParams p) {
+    constexpr int NCLS = 256 / BN;                       // classes per pass
+    constexpr int TMEM_COLS = 512;
+    constexpr int SKIP_TILE_BYTES = (BN / 2) * 128;      // one (chunk, tap) skip tile per CTA
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* w_ring = smem;
+    uint8_t* x_reg = w_ring + UPW_RING * UPF_GROUP_BYTES;
+    uint8_t* s_reg = x_reg + UPW_XSLOTS * UPF_U_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_reg + 2 * UPF_PLANE_BYTES);      // [0..2] x slots, [3] the skip slot
+    uint64_t* empty_bar = full_bar + HALO_MAX_STAGES;
+    uint64_t* bfull_bar = empty_bar + HALO_MAX_STAGES;
+    uint64_t* bempty_bar = bfull_bar + HALO_MAX_STAGES;
+    uint64_t* tfull_bar = bempty_bar + HALO_MAX_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + HALO_BAR_BYTES);
+    uint8_t* stg_s = reinterpret_cast<uint8_t*>(full_bar) + HALO_BAR_BYTES + UPW_BIAS_BYTES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int n_pairs = pair_count(p);
+    const int SC = p.kchunks;                            // skip chunks; x chunks = 2 * SC
+
+    stage_bias(p, bias_s);
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmB);
+        tma_prefetch_desc(&p.tmB2);
+        tma_prefetch_desc(&p.tmS);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < HALO_MAX_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1);
+            mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8 * EPI_GROUPS); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ region producer (one per CTA)
+        int xs = 0;
+        uint32_t xph = 0, sph = 0;
+        for (int pair = cluster_id; pair < n_pairs; pair += n_clusters) {
+            const TileCoord t = decode_tile<HT_H, HT_W>(p, pair_to_tile(p, pair, (int)rank), BN);
+            for (int g = 0; g < SC; ++g) {
+                for (int r = 0; r < 2; ++r) {
+                    mbar_wait(&empty_bar[xs], xph ^ 1u);
+                    if (elect_one()) {
+                        if (leader) mbar_expect_tx(&full_bar[xs], 2u * UPF_U_BYTES);
+                        tma_load_4d_2sm(x_reg + xs * UPF_U_BYTES, &p.tmA, &full_bar[xs], (2 * g + r) * KCHUNK, t.w0 - 1, t.h0 - 1, t.img);
+                    }
+                    __syncwarp();
+                    if (++xs == UPW_XSLOTS) { xs = 0; xph ^= 1u; }
+                }
+                mbar_wait(&empty_bar[3], sph ^ 1u);
+                if (elect_one()) {
+                    if (leader) mbar_expect_tx(&full_bar[3], 4u * UPF_PLANE_BYTES);
+                    tma_load_5d_2sm(s_reg, &p.tmS, &full_bar[3], g * KCHUNK, 1, t.w0 - 1, 2 * t.h0 - 1, t.img);
+                    tma_load_5d_2sm(s_reg + UPF_PLANE_BYTES, &p.tmS, &full_bar[3], g * KCHUNK, 0, t.w0, 2 * t.h0 - 1, t.img);
+                }
+                __syncwarp();
+                sph ^= 1u;
+            }
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------------ weight producer (one per CTA)
+        // x tiles: [class group][n-tile][CTA][x chunk][tap][NCLS x BN/2 rows]; skip tiles: [n-tile][CTA][chunk][tap][BN/2 rows]
+        int bg = 0;
+        uint32_t bphase = 0;
+        for (int pair = cluster_id; pair < n_pairs; pair += n_clusters) {
+            const int nt_eff = pair - fast_div(pair, p.fd_ntiles) * p.n_tiles;       // class group * real n-tiles + n-tile
+            const int nt = nt_eff % p.real_ntiles;
+            const int xrow0 = ((nt_eff * 2 + (int)rank) * 2 * SC) * 4 * UPF_GROUP_ROWS;
+            const int srow0 = ((nt * 2 + (int)rank) * SC) * 9 * (BN / 2);
+            for (int g = 0; g < SC; ++g) {
+                for (int j = 0; j < 8; ++j) {                     // x chunk 2 g + (j >> 2), tap j & 3
+                    mbar_wait(&bempty_bar[bg], bphase ^ 1u);
+                    if (elect_one()) {
+                        if (leader) mbar_expect_tx(&bfull_bar[bg], 2u * UPF_GROUP_BYTES);
+                        tma_load_2d_2sm(w_ring + bg * UPF_GROUP_BYTES, &p.tmB, &bfull_bar[bg], 0, xrow0 + (g * 8 + j) * UPF_GROUP_ROWS);
+                    }
+                    __syncwarp();
+                    if (++bg == UPW_RING) { bg = 0; bphase ^= 1u; }
+                }
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait(&bempty_bar[bg], bphase ^ 1u);
+                    if (elect_one()) {
+                        if (leader) mbar_expect_tx(&bfull_bar[bg], 2u * SKIP_TILE_BYTES);
+                        tma_load_2d_2sm(w_ring + bg * UPF_GROUP_BYTES, &p.tmB2, &bfull_bar[bg], 0, srow0 + (g * 9 + tap) * (BN / 2));
+                    }
+                    __syncwarp();
+                    if (++bg == UPW_RING) { bg = 0; bphase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (leader) {
+            const uint32_t idesc = umma_idesc_bf16(2 * TILE_M, BN);
+            const uint64_t adesc_x = umma_desc_sw128_strided(smem_u32(x_reg), UPF_U_W * 128u);
+            const uint64_t adesc_s = umma_desc_sw128_strided(smem_u32(s_reg), 2u * UPF_S_W * 128u);
+            const uint64_t bdesc_ring = umma_desc_sw128(smem_u32(w_ring));
+            int bg = 0, xs = 0;
+            uint32_t bphase = 0, xph = 0, sph = 0;
+            int it = 0;
+            for (int pair = cluster_id; pair < n_pairs; pair += n_clusters, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+                const int nt_eff = pair - fast_div(pair, p.fd_ntiles) * p.n_tiles;
+                const int cls_base = (nt_eff / p.real_ntiles) * NCLS;
+                // descriptor offsets (16-byte units) of class `half`'s windows relative to tap (0, 0)
+                uint32_t xoff[NCLS], soff_row[NCLS];
+                int spx[NCLS];
+#pragma unroll
+                for (int half = 0; half < NCLS; ++half) {
+                    const int py = (cls_base + half) >> 1, px = (cls_base + half) & 1;
+                    xoff[half] = (uint32_t)((py * UPF_U_W + px) * 8);
+                    soff_row[half] = (uint32_t)(py * UPF_S_W * 8);
+                    spx[half] = px;
+                }
+                mbar_wait(&tempty_bar[as], aphase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * NCLS * BN);
+                uint32_t accumulate = 0;
+#pragma unroll 1
+                for (int g = 0; g < SC; ++g) {
+#pragma unroll 1
+                    for (int r = 0; r < 2; ++r) {
+                        mbar_wait(&full_bar[xs], xph);
+                        tc_fence_after();
+                        const uint64_t areg = adesc_x + (uint64_t)(xs * (UPF_U_BYTES >> 4));
+#pragma unroll
+                        for (int tap = 0; tap < 4; ++tap) {
+                            mbar_wait(&bfull_bar[bg], bphase);
+                            tc_fence_after();
+                            const uint64_t wg = bdesc_ring + (uint64_t)(bg * (UPF_GROUP_BYTES >> 4));
+                            if (elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < KCHUNK / 16; ++k) {
+#pragma unroll
+                                    for (int half = 0; half < NCLS; ++half)
+                                        umma_bf16_2sm(d_tmem + (uint32_t)(half * BN),
+                                                      areg + (uint64_t)(xoff[half] + (uint32_t)(((tap >> 1) * UPF_U_W + (tap & 1)) * 8 + 2 * k)),
+                                                      wg + (uint64_t)(half * (BN / 2) * 8 + 2 * k), idesc, (k == 0) ? accumulate : 1u);
+                                }
+                                umma_commit_2sm(&bempty_bar[bg]);
+                            }
+                            __syncwarp();
+                            accumulate = 1;
+                            if (++bg == UPW_RING) { bg = 0; bphase ^= 1u; }
+                        }
+                        if (elect_one()) umma_commit_2sm(&empty_bar[xs]);
+                        __syncwarp();
+                        if (++xs == UPW_XSLOTS) { xs = 0; xph ^= 1u; }
+                    }
+                    mbar_wait(&full_bar[3], sph);
+                    tc_fence_after();
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&bfull_bar[bg], bphase);
+                        tc_fence_after();
+                        const uint64_t wg = bdesc_ring + (uint64_t)(bg * (UPF_GROUP_BYTES >> 4));
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < KCHUNK / 16; ++k) {
+#pragma unroll
+                                for (int half = 0; half < NCLS; ++half) {
+                                    const int cx = spx[half] + tap % 3;
+                                    const uint32_t off = (uint32_t)((cx & 1) * (UPF_PLANE_BYTES >> 4) + ((tap / 3) * UPF_S_W + (cx >> 1)) * 8) + soff_row[half];
+                                    umma_bf16_2sm(d_tmem + (uint32_t)(half * BN), adesc_s + (uint64_t)(off + (uint32_t)(2 * k)), wg + (uint64_t)(2 * k), idesc, 1u);
+                                }
+                            }
+                            umma_commit_2sm(&bempty_bar[bg]);
+                        }
+                        __syncwarp();
+                        if (++bg == UPW_RING) { bg = 0; bphase ^= 1u; }
+                    }
+                    if (elect_one()) umma_commit_2sm(&empty_bar[3]);
+                    __syncwarp();
+                    sph ^= 1u;
+                }
+                if (elect_one()) umma_commit_2sm(&tfull_bar[as]);
+                __syncwarp();
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        run_epilogue<BN, HT_H, HT_W, NCLS, true, true, true>(p, warp & 3, lane, (warp - EPI_WARP0) >> 2, tmem_base, tfull_bar, tempty_bar,
+                                                             bias_s, stg_s);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    }
+}
+
 // ---------------------------------------------------------------------------- 64 -> 64 channel 3x3 layers by parity class
 // The skip chunk of conv_upfused2_kernel on its own is a plain Conv2d(64, 64, 3, padding 1) computed per output parity
 // class: enc1.3 and dec1.3 (models/model_2.py:10, :30) run through it.  Same windows, same shared-window MMA schedule
@@ -1912,17 +2156,97 @@ int launch_conv_tc(const dc_conv_args_t* a, cudaStream_t stream, const float* bi
     }
 }
 
+// C = 128 / 256 / 512: conv_upfused_wide_kernel (arguments validated by launch_conv_upfused)
+static int launch_conv_upfused_wide(const dc_upfuse_args_t* a, cudaStream_t stream) {
+    const int C = a->channels;
+    const int BN = C == 128 ? 128 : 256;
+    const int ncls = 256 / BN, groups = 4 / ncls, real_ntiles = C / BN, SC = C / KCHUNK;
+    DC_REQUIRE(a->weight_skip && ((uintptr_t)a->weight_skip & 15) == 0, DC_EINVAL, "dc_conv_upfused: weight_skip");
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)2 * C, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B};
+        cuuint64_t str[3] = {(cuuint64_t)a->x_stride * 2, (cuuint64_t)a->W * a->x_stride * 2,
+                             (cuuint64_t)a->H * a->W * a->x_stride * 2};
+        cuuint32_t box[4] = {KCHUNK, UPF_U_W, UPF_U_H, 1};
+        int rc = encode_map(&p.tmA, a->x, 4, dims, str, box);
+        if (rc != DC_OK) return rc;
+    }
+    {
+        const cuuint64_t ps = (cuuint64_t)a->skip_stride * 2;
+        cuuint64_t dims[5] = {(cuuint64_t)C, 2, (cuuint64_t)a->W, (cuuint64_t)(2 * a->H), (cuuint64_t)a->B};
+        cuuint64_t str[4] = {ps, 2 * ps, 2 * (cuuint64_t)a->W * ps, 4 * (cuuint64_t)a->H * a->W * ps};
+        cuuint32_t box[5] = {KCHUNK, 1, UPF_S_W, UPF_S_H, 1};
+        int rc = encode_map(&p.tmS, a->skip, 5, dims, str, box);
+        if (rc != DC_OK) return rc;
+    }
+    {   // composed weights: [class group][n-tile][CTA][x chunk][tap][ncls x BN/2 rows][64]
+        cuuint64_t dims[2] = {KCHUNK, (cuuint64_t)groups * real_ntiles * 2 * (2 * SC) * 4 * UPF_GROUP_ROWS};
+        cuuint64_t str[1] = {KCHUNK * 2};
+        cuuint32_t box[2] = {KCHUNK, UPF_GROUP_ROWS};
+        int rc = encode_map(&p.tmB, a->weight, 2, dims, str, box);
+        if (rc != DC_OK) return rc;
+    }
+    {   // skip weights: [n-tile][CTA][chunk][tap][BN/2 rows][64]
+        cuuint64_t dims[2] = {KCHUNK, (cuuint64_t)real_ntiles * 2 * SC * 9 * (BN / 2)};
+        cuuint64_t str[1] = {KCHUNK * 2};
+        cuuint32_t box[2] = {KCHUNK, (cuuint32_t)(BN / 2)};
+        int rc = encode_map(&p.tmB2, a->weight_skip, 2, dims, str, box);
+        if (rc != DC_OK) return rc;
+    }
+    p.B = a->B; p.H = a->H; p.W = a->W; p.Cin = 3 * C; p.Cout = C;
+    p.dil = 1; p.ntaps = 9; p.kchunks = SC;
+    p.tiles_w = ceil_div(a->W, HT_W);
+    p.tiles_h = ceil_div(a->H, HT_H);
+    p.n_tiles = groups * real_ntiles;
+    p.real_ntiles = real_ntiles;
+    const long long total = (long long)a->B * p.tiles_w * p.tiles_h * p.n_tiles;
+    DC_REQUIRE(total < (1ll << 31), DC_EINVAL, "dc_conv_upfused: too many tiles");
+    p.total_tiles = (int)total;
+    p.m_tiles = p.total_tiles / p.n_tiles;
+    p.fd_ntiles = make_fastdiv(p.n_tiles); p.fd_per_img = make_fastdiv(p.tiles_h * p.tiles_w); p.fd_tiles_w = make_fastdiv(p.tiles_w);
+    p.epilogue = DC_EPI_STORE;
+    p.relu = a->relu != 0;
+    p.bias = a->bias9 + 4 * C;
+    p.border_bias = 1;
+    p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+    p.out_stride = a->out_stride; p.out_offset = a->out_offset;
+
+    const int n_pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int max_clusters = num_sms() / 2;
+    const int grid = 2 * (n_pairs < max_clusters ? n_pairs : max_clusters);
+#define DC_UPW_CASE(bn)                                                                                      \
+    if (BN == bn) {                                                                                          \
+        static unsigned long long attr_done = 0;                                                             \
+        int rc = set_max_smem_once(conv_upfused_wide_kernel<bn>, (int)UPW_SMEM, &attr_done);                 \
+        if (rc != DC_OK) return rc;                                                                          \
+        conv_upfused_wide_kernel<bn><<<grid, NUM_THREADS, UPW_SMEM, stream>>>(p);                            \
+    }
+    DC_UPW_CASE(128) DC_UPW_CASE(256)
+#undef DC_UPW_CASE
+    DC_CUDA(cudaGetLastError());
+    return DC_OK;
+}
+
 int launch_conv_upfused(const dc_upfuse_args_t* a, cudaStream_t stream, const float* bias9_host) {
-    DC_REQUIRE(a && a->x && a->skip && a->weight && a->bias9 && a->out && bias9_host, DC_EINVAL,
+    DC_REQUIRE(a && a->x && a->skip && a->weight && a->bias9 && a->out, DC_EINVAL,
                "dc_conv_upfused: null pointer argument");
+    const int C = a->channels ? a->channels : 64;
+    DC_REQUIRE(C == 64 || C == 128 || C == 256 || C == 512, DC_EINVAL, "dc_conv_upfused: channels %d (64, 128, 256 or 512)", C);
+    DC_REQUIRE(C != 64 || bias9_host, DC_EINVAL, "dc_conv_upfused: null pointer argument");
     DC_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0, DC_EINVAL, "dc_conv_upfused: bad shape %d x %d x %d", a->B, a->H, a->W);
-    DC_REQUIRE(a->x_stride >= 128 && a->x_stride % 8 == 0 && a->skip_stride >= 64 && a->skip_stride % 8 == 0, DC_EINVAL,
+    DC_REQUIRE(a->x_stride >= 2 * C && a->x_stride % 8 == 0 && a->skip_stride >= C && a->skip_stride % 8 == 0, DC_EINVAL,
                "dc_conv_upfused: x_stride %d / skip_stride %d", a->x_stride, a->skip_stride);
     DC_REQUIRE(((uintptr_t)a->x & 15) == 0 && ((uintptr_t)a->skip & 15) == 0 && ((uintptr_t)a->weight & 15) == 0 &&
                    ((uintptr_t)a->out & 15) == 0,
                DC_EINVAL, "dc_conv_upfused: x / skip / weight / out must be 16-byte aligned");
-    DC_REQUIRE(a->out_stride % 8 == 0 && a->out_offset % 8 == 0 && a->out_offset >= 0 && a->out_stride >= a->out_offset + 64,
+    DC_REQUIRE(a->out_stride % 8 == 0 && a->out_offset % 8 == 0 && a->out_offset >= 0 && a->out_stride >= a->out_offset + C,
                DC_EINVAL, "dc_conv_upfused: out_stride %d / out_offset %d", a->out_stride, a->out_offset);
+    if (C != 64) {
+        dc_upfuse_args_t b = *a;
+        b.channels = C;
+        return launch_conv_upfused_wide(&b, stream);
+    }
     ConvParams p;
     memset(&p, 0, sizeof(p));
     {   // x: [B, H, W, 128 of x_stride], one haloed region per 64-channel chunk

@@ -81,16 +81,22 @@ def upconv2x2(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, out: to
 
 
 def upconv_conv3x3(x: torch.Tensor, skip: torch.Tensor, weight: torch.Tensor, bias9: torch.Tensor, relu: bool = True,
-                   skip_offset: int = 0, out: torch.Tensor | None = None, out_offset: int = 0) -> torch.Tensor:
-    """ConvTranspose2d(128, 64, 2, 2) -> cat([up, skip]) -> 3x3 conv (+bias, +ReLU) as one launch (dc_conv_upfused).
-    x: bf16 [B,H,W,128]; skip: bf16 [B,2H,2W,S] read at channels [skip_offset, skip_offset + 64); weight / bias9 from
-    model.compose_upconv.  Returns bf16 [B,2H,2W,64] (or `out`, written at channel out_offset)."""
+                   skip_offset: int = 0, out: torch.Tensor | None = None, out_offset: int = 0,
+                   weight_skip: torch.Tensor | None = None) -> torch.Tensor:
+    """ConvTranspose2d(2C, C, 2, 2) -> cat([up, skip]) -> 3x3 conv (+bias, +ReLU) as one launch (dc_conv_upfused).
+    x: bf16 [B,H,W,2C]; skip: bf16 [B,2H,2W,S] read at channels [skip_offset, skip_offset + C); C = bias9.shape[1].
+    C = 64: weight from model.pack_upfused; C = 128 / 256 / 512: weight, weight_skip from model.pack_upfused_wide.
+    Returns bf16 [B,2H,2W,C] (or `out`, written at channel out_offset)."""
     _lib.require_cuda(x, "x")
     B, H, W, S = x.shape
+    c = int(bias9.shape[1])
     if out is None:
-        out = torch.empty((B, 2 * H, 2 * W, 64), dtype=torch.bfloat16, device=x.device)
+        out = torch.empty((B, 2 * H, 2 * W, c), dtype=torch.bfloat16, device=x.device)
     a = _lib.UpfuseArgs()
     a.B, a.H, a.W = B, H, W
+    a.channels = c
+    if weight_skip is not None:
+        a.weight_skip = weight_skip.data_ptr()
     a.x, a.x_stride = x.data_ptr(), S
     a.skip, a.skip_stride = skip.data_ptr() + 2 * int(skip_offset), skip.shape[3]
     a.weight, a.bias9, a.relu = weight.data_ptr(), bias9.data_ptr(), int(relu)

@@ -71,7 +71,7 @@ def compose_upconv(wu, bu, wd, bd):
                            (column): bd plus bu through the taps that lie inside the upsampled image."""
     cx, c = wu.shape[:2]
     co = wd.shape[0]
-    assert (cx, c, co) == (128, 64, 64) and wd.shape[1] == 2 * c, "level-1 shapes only"
+    assert cx == 2 * c and co == c and wd.shape[1] == 2 * c and c in (64, 128, 256, 512), "UNet decoder shapes only"
     wu64, wd64 = wu.double(), wd.double()
     wd_up, wd_skip = wd64[:, :c], wd64[:, c:]
     comp = torch.zeros((4, 2, 2, co, cx), dtype=torch.float64, device=wd.device)
@@ -131,11 +131,33 @@ def pack_par3x3(w):
     return pack_upfused(None, w.permute(2, 3, 0, 1).to(torch.bfloat16).contiguous())
 
 
+def pack_upfused_wide(comp, skipw):
+    """compose_upconv weights for C = 128 / 256 / 512 in the order conv_upfused_wide_kernel streams them
+    (include/unetdc_b200.h dc_upfuse_args): returns (weight, weight_skip),
+      weight      [class group][n-tile][CTA][x chunk][tap a*2+b][classes of the group x BN/2 rows][64]
+      weight_skip [n-tile][CTA][chunk][tap ky*3+kx][BN/2 rows][64]
+    with BN = min(C, 256), 256 / BN classes per group, row r of a tile = output channel n-tile*BN + CTA*BN/2 + r."""
+    c = comp.shape[3]
+    bn = min(c, 256)
+    ncls, nt, hb = 256 // bn, c // bn, bn // 2
+    xc, sc = 2 * c // 64, c // 64
+    # comp [cls][a][b][co][cx] -> [group][cls in group][tap][n-tile][cta][hb][x chunk][64]
+    w = comp.reshape(4 // ncls, ncls, 4, nt, 2, hb, xc, 64)
+    w = w.permute(0, 3, 4, 6, 2, 1, 5, 7).contiguous()                 # [group][nt][cta][xchunk][tap][cls][hb][64]
+    weight = w.reshape(-1, 64)
+    s = skipw.reshape(9, nt, 2, hb, sc, 64).permute(1, 2, 4, 0, 3, 5).contiguous()   # [nt][cta][chunk][tap][hb][64]
+    return weight, s.reshape(-1, 64)
+
+
+def fused_level_blobs(sd, lvl: int = 1, eps: float = 1e-5):
+    """(comp, skipw, bias9) of the composed upconv{lvl} + dec{lvl}.0 layer from a state_dict (on the tensors' device)."""
+    wd, bd = fold_conv_bn(sd[f"dec{lvl}.0.weight"], sd[f"dec{lvl}.0.bias"], sd[f"dec{lvl}.1.weight"], sd[f"dec{lvl}.1.bias"],
+                          sd[f"dec{lvl}.1.running_mean"], sd[f"dec{lvl}.1.running_var"], eps)
+    return compose_upconv(sd[f"upconv{lvl}.weight"].float(), sd[f"upconv{lvl}.bias"].float(), wd, bd)
+
+
 def fused_level1_blobs(sd, eps: float = 1e-5):
-    """(comp, skipw, bias9) of the composed upconv1 + dec1.0 layer from a state_dict (on the tensors' own device)."""
-    wd, bd = fold_conv_bn(sd["dec1.0.weight"], sd["dec1.0.bias"], sd["dec1.1.weight"], sd["dec1.1.bias"],
-                          sd["dec1.1.running_mean"], sd["dec1.1.running_var"], eps)
-    return compose_upconv(sd["upconv1.weight"].float(), sd["upconv1.bias"].float(), wd, bd)
+    return fused_level_blobs(sd, 1, eps)
 
 
 class _Packed:
@@ -188,6 +210,14 @@ class _Packed:
             self.blobs += [fw, fb]
             desc.fused_weight1 = fw.data_ptr()
             desc.fused_bias1 = fb.data_ptr()
+        for lvl in (2, 3, 4):
+            if lvl in module.fuse_levels:
+                comp, skipw, fb = fused_level_blobs(sd, lvl, module._bn_eps(f"dec{lvl}", 1))
+                wx, ws = pack_upfused_wide(comp, skipw)
+                self.blobs += [wx, ws, fb]
+                desc.fused_wide_x[lvl - 2] = wx.data_ptr()
+                desc.fused_wide_s[lvl - 2] = ws.data_ptr()
+                desc.fused_wide_b[lvl - 2] = fb.data_ptr()
         self.device = device
         self.handle = C.c_void_p()
         with torch.cuda.device(device):
@@ -218,6 +248,8 @@ class UNetDC(nn.Module):
     # upconv1 + dec1.0 as one launch with host-composed weights (csrc/conv_tc.cu conv_upfused2_kernel); False runs the
     # two layers separately (set it before the first forward, or call invalidate())
     fuse_level1 = True
+    # upconv{l} + dec{l}.0 as one launch for l in fuse_levels (2, 3, 4: conv_upfused_wide_kernel)
+    fuse_levels = (2, 3, 4)
     # enc1.3 and dec1.3 per output parity class with shared windows (conv_par2_kernel; taken when dilations[0] == 1)
     parity_level1 = True
 

@@ -46,18 +46,19 @@ def forward_flops(H: int, W: int, dilations=(1, 2, 4, 8, 16), in_bounds: bool = 
     return sum(layer_flops(l, in_bounds) for l in conv_layers(H, W, dilations))
 
 
-def launch_flops(H: int, W: int, dilations=(1, 2, 4, 8, 16), in_bounds: bool = True, fused_level1: bool = False):
-    """FLOPs per kernel launch of dc_forward (22 launches: out_conv is fused into the last one; 21 with
-    ``fused_level1``, where upconv1 and dec1.0 are one launch -- counted with the FLOPs of the two layers it replaces,
-    the composed form executes K = 1088 instead of 2 x 128 + 1152 per output pixel)."""
+def launch_flops(H: int, W: int, dilations=(1, 2, 4, 8, 16), in_bounds: bool = True, fused_level1: bool = False,
+                 fused_levels=()):
+    """FLOPs per kernel launch of dc_forward (22 launches: out_conv is fused into the last one; one fewer per decoder
+    level whose upconv rides in the following conv -- ``fused_level1`` / ``fused_levels`` -- counted with the FLOPs of
+    the two layers it replaces: the composed form executes K = 17 C instead of 20 C per output pixel and channel)."""
     ls = conv_layers(H, W, dilations)
     fl = [layer_flops(l, in_bounds) for l in ls]
     fl[-2] += fl[-1]
     names, fl = [l[0] for l in ls[:-1]], fl[:-1]
-    if fused_level1:
-        i = names.index("upconv1")
-        assert names[i + 1] == "dec1.0"
-        names[i:i + 2] = ["upconv1+dec1.0"]
+    for lvl in sorted(set(fused_levels) | ({1} if fused_level1 else set())):
+        i = names.index(f"upconv{lvl}")
+        assert names[i + 1] == f"dec{lvl}.0"
+        names[i:i + 2] = [f"upconv{lvl}+dec{lvl}.0"]
         fl[i:i + 2] = [fl[i] + fl[i + 1]]
     return names, fl
 
