@@ -91,6 +91,12 @@ def test_flop_model_matches_baseline_md():
     assert abs(sum(fl) - wl.forward_flops(1024, 1024)) < 1.0
     # plain UNet (models/model.py) = dilation 1 everywhere: same nominal FLOPs, more in-bounds taps
     assert wl.forward_flops(256, 256, (1, 1, 1, 1, 1)) > wl.forward_flops(256, 256)
+    # decoder levels run as one composed launch each: names merge, the algorithmic FLOPs stay, the issued ones drop
+    names_f, fl_f = wl.launch_flops(1024, 1024, fused_level1=True, fused_levels=(2, 3, 4))
+    assert len(names_f) == 18 and "upconv3+dec3.0" in names_f and abs(sum(fl_f) - sum(fl)) < 1.0
+    assert wl.forward_flops_issued(1024, 1024) == wl.forward_flops(1024, 1024)
+    r = wl.forward_flops_issued(1024, 1024, fused_levels=(1, 2, 3, 4)) / wl.forward_flops(1024, 1024)
+    assert 0.92 < r < 0.94              # 4 levels x 11 % of the FLOPs x (1 - 17/20)
 
 
 def test_synthetic_inputs_are_seeded():

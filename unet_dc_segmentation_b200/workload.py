@@ -46,6 +46,24 @@ def forward_flops(H: int, W: int, dilations=(1, 2, 4, 8, 16), in_bounds: bool = 
     return sum(layer_flops(l, in_bounds) for l in conv_layers(H, W, dilations))
 
 
+def forward_flops_issued(H: int, W: int, dilations=(1, 2, 4, 8, 16), fused_levels=(), in_bounds: bool = True) -> float:
+    """FLOPs the kernels actually issue for one forward: a decoder level whose upconv is composed into the following
+    conv (2x2 taps over the 2C-channel half-resolution input + 3x3 over the C-channel skip) runs K = 8 C + 9 C per
+    output pixel and channel instead of the 2 C + 18 C of the two layers it replaces."""
+    total = 0.0
+    for l in conv_layers(H, W, dilations):
+        name, kind, h, w, cin, cout, d = l
+        lvl = int(name[6]) if name.startswith("upconv") else (int(name[3]) if name.startswith("dec") and name.endswith(".0") else 0)
+        if lvl in fused_levels and kind == "upconv2x2":
+            continue                                         # rides in dec{lvl}.0
+        if lvl in fused_levels:
+            f = _inb(h, 1) * _inb(w, 1) if in_bounds else 1.0
+            total += 2.0 * cout * h * w * (4 * cin + 9 * cout * f)      # cin = 2 C here: x taps 4 x 2C, skip taps 9 x C
+        else:
+            total += layer_flops(l, in_bounds)
+    return total
+
+
 def launch_flops(H: int, W: int, dilations=(1, 2, 4, 8, 16), in_bounds: bool = True, fused_level1: bool = False,
                  fused_levels=()):
     """FLOPs per kernel launch of dc_forward (22 launches: out_conv is fused into the last one; one fewer per decoder
