@@ -2,7 +2,7 @@
 
     python tools/sweep.py [--sizes 512,1024,2048,4096] [--out profiles/r01_sweep.md]
 
-Forward only (dc_forward: stem + 17 conv3x3 + 4 upconv, threshold fused), u8 grayscale frames resident in HBM,
+Forward only (dc_forward: stem + 17 conv3x3, the four transposed convs composed into dec{l}.0, threshold fused), u8 grayscale frames resident in HBM,
 CUDA events, 3 warm-up + 5 timed calls per point.  Batch is chosen so the activation workspace stays under ~60 GB.
 TFLOP/s uses the conservative in-bounds FLOP count; peak = MEASURED_PEAKS.json sustained bf16.
 """
