@@ -345,7 +345,8 @@ int dc_forward_workspace_bytes(const dc_model_t* m, int B, int H, int W, size_t*
 }
 
 int dc_forward_num_launches(const dc_model_t* m) {
-    // stem + 17 conv3x3 + 4 upconv (+ the input conversion / the 1x1 head kernel for other channel counts)
+    // stem + 17 conv3x3 + 4 upconv (+ the input conversion / the 1x1 head kernel for other channel counts), minus one per
+    // decoder level whose upconv is composed into the following conv
     int n = 22 + (m && m->cin != 3 ? 1 : 0) + (m && m->cout != 1 ? 1 : 0);
     for (int l = 0; m && l < 4; ++l) n -= m->fused[l] ? 1 : 0;
     return n;

@@ -6,7 +6,7 @@ Same constructor, same 136 ``state_dict`` keys and shapes, same call contract
 parameters live in ordinary ``nn.Conv2d`` / ``nn.BatchNorm2d`` / ``nn.ConvTranspose2d`` holders (that is
 what fixes the state_dict), but ``forward`` never calls them: on the first call in eval mode the weights
 are BatchNorm-folded in fp32, repacked K-major to bf16 and handed to ``dc_model_create``; every call then
-runs ``dc_forward`` (22 kernel launches, see csrc/api.cu).  There is no PyTorch or CPU fallback.
+runs ``dc_forward`` (18 kernel launches with the decoder levels fused, 22 without; see csrc/api.cu).  There is no PyTorch or CPU fallback.
 
 ``UNet`` is the reference's plain ``models/model.py`` network: identical state_dict, dilation 1 everywhere.
 """
