@@ -208,3 +208,38 @@ def test_pack_upfused_follows_the_kernel_schedule():
     # first MMA: window (1, 1) of x chunk 0, all four classes -> classes 0, 1 in CTA 0, classes 2, 3 in CTA 1
     assert torch.equal(blob[0, :64], comp[0, 1, 1][:, :64]) and torch.equal(blob[0, 64:128], comp[1, 1, 0][:, :64])
     assert torch.equal(blob[1, :64], comp[2, 0, 1][:, :64]) and torch.equal(blob[1, 64:128], comp[3, 0, 0][:, :64])
+
+
+def test_upf_schedule_include_is_current(tmp_path):
+    """csrc/upf_schedule.inc is generated (tools/gen_upf_schedule.py); the committed copy must be what the generator writes."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    repo = Path(__file__).resolve().parent.parent
+    out = tmp_path / "upf_schedule.inc"
+    subprocess.run([sys.executable, str(repo / "tools" / "gen_upf_schedule.py"), str(out)], check=True, capture_output=True)
+    assert out.read_text() == (repo / "unet_dc_segmentation_b200" / "csrc" / "upf_schedule.inc").read_text()
+
+
+def test_pack_upfused_wide_layout():
+    """Weight blobs of the deeper fused decoder levels: every (class group, n-tile, CTA, chunk, tap, class, row) lands
+    where conv_upfused_wide_kernel's producers read it (include/unetdc_b200.h dc_upfuse_args)."""
+    import torch
+    from unet_dc_segmentation_b200 import model as M
+    g = torch.Generator().manual_seed(7)
+    for C in (128, 256, 512):
+        bn = min(C, 256)
+        ncls, nt, hb = 256 // bn, C // bn, bn // 2
+        xc, sc = 2 * C // 64, C // 64
+        comp = torch.randn(4, 2, 2, C, 2 * C, generator=g).bfloat16()
+        skipw = torch.randn(3, 3, C, C, generator=g).bfloat16()
+        wx, ws = M.pack_upfused_wide(comp, skipw)
+        assert tuple(wx.shape) == ((4 // ncls) * nt * 2 * xc * 4 * 128, 64) and tuple(ws.shape) == (nt * 2 * sc * 9 * hb, 64)
+        for _ in range(200):
+            grp, t, cta, ch, tap, ci, r = (int(torch.randint(0, n, (1,), generator=g)) for n in (4 // ncls, nt, 2, xc, 4, ncls, hb))
+            row = (((((grp * nt + t) * 2 + cta) * xc + ch) * 4 + tap) * ncls + ci) * hb + r
+            cls, co = grp * ncls + ci, t * bn + cta * hb + r
+            assert torch.equal(wx[row], comp[cls, tap >> 1, tap & 1, co, ch * 64:(ch + 1) * 64])
+            ch_s, tap_s = ch % sc, int(torch.randint(0, 9, (1,), generator=g))
+            row = (((t * 2 + cta) * sc + ch_s) * 9 + tap_s) * hb + r
+            assert torch.equal(ws[row], skipw[tap_s // 3, tap_s % 3, co, ch_s * 64:(ch_s + 1) * 64])
