@@ -243,3 +243,44 @@ def test_pack_upfused_wide_layout():
             ch_s, tap_s = ch % sc, int(torch.randint(0, 9, (1,), generator=g))
             row = (((t * 2 + cta) * sc + ch_s) * 9 + tap_s) * hb + r
             assert torch.equal(ws[row], skipw[tap_s // 3, tap_s % 3, co, ch_s * 64:(ch_s + 1) * 64])
+
+
+def test_upf_schedule_issue_code_matches_its_tables():
+    """The straight-line MMA issue code of csrc/upf_schedule.inc (literal descriptor offsets) against the definitions:
+    per (mode, chunk kind, group) every MMA reads the window of its table entry (x chunk: (r*10 + c)*8; skip chunk:
+    column-parity plane (c & 1), row r, column c >> 1 of a 9-wide plane), takes its weights from the next free 32-row
+    sub-tile of the group's ring slot, writes the accumulator of its first class with N = 64 * classes, and only the
+    first MMA to touch a class in a tile's first chunk may overwrite."""
+    import re
+    from pathlib import Path
+    txt = (Path(__file__).resolve().parent.parent / "unet_dc_segmentation_b200" / "csrc" / "upf_schedule.inc").read_text()
+    ops = {}
+    for m in re.finditer(r"upf_(u|s)_op<(\d)>\(int i\) \{\s*switch \(i\) \{(.*?)default", txt, re.S):
+        ops[(m.group(1), int(m.group(2)))] = [tuple(int(v) for v in t) for t in
+                                              re.findall(r"UpfOp\{(\d+), (\d+), (\d+), (\d+)\}", m.group(3))]
+    assert len(ops) == 8
+    plane = (9 * 34 * 128) >> 4
+    for m in re.finditer(r"upf_issue_group<(\d), (\d), (\d)>\(.*?\) \{(.*?)\n\}", txt, re.S):
+        mode, kind, g = int(m.group(1)), int(m.group(2)), int(m.group(3))
+        calls = re.findall(r"umma_bf16_2sm\(d \+ (\d+)u, a \+ (\d+)ull, b \+ (\d+)ull, 0x([0-9a-f]+)u, ([^)]*)\);", m.group(4))
+        table = ops[("u" if kind == 0 else "s", mode)]
+        # the group's entries: groups are consecutive runs of the table whose classes add up to 4
+        runs, cur, tot = [], [], 0
+        for o in table:
+            cur.append(o); tot += o[3]
+            if tot == 4:
+                runs.append(cur); cur, tot = [], 0
+        grp = runs[g]
+        assert len(calls) == 4 * len(grp)
+        for k in range(4):
+            sub = 0
+            for j, (r, c, cls0, ncls) in enumerate(grp):
+                d, a, b, idesc, acc = calls[k * len(grp) + j]
+                want_a = (r * 10 + c) * 8 if kind == 0 else (c & 1) * plane + (r * 9 + (c >> 1)) * 8
+                assert (int(d), int(a), int(b)) == (cls0 * 64, want_a + 2 * k, sub * 256 + 2 * k)
+                assert (int(idesc, 16) >> 17) & 0x3F == (64 * ncls) >> 3 and (int(idesc, 16) >> 24) & 0x1F == 256 >> 4
+                if "fresh" in acc:
+                    assert k == 0 and kind != 1
+                sub += ncls
+        if kind != 1 and g == 0:
+            assert any("fresh" in c[4] for c in calls)
