@@ -186,7 +186,7 @@ class _Packed:
                     w = pack_conv3x3(wp)
                 else:
                     w = pack_conv3x3(wf)
-                    if module.parity_level1 and (name, idx) in (("enc1", 3), ("dec1", 3)):
+                    if module.parity_level1 and idx == 3 and name in module.parity_layers:
                         wp = pack_par3x3(wf)
                         self.blobs.append(wp)
                         desc.par_weight[0 if name == "enc1" else 1] = wp.data_ptr()
@@ -252,6 +252,7 @@ class UNetDC(nn.Module):
     fuse_levels = (2, 3, 4)
     # enc1.3 and dec1.3 per output parity class with shared windows (conv_par2_kernel; taken when dilations[0] == 1)
     parity_level1 = True
+    parity_layers = ("enc1", "dec1")
 
     def __init__(self, in_channels: int = 3, out_channels: int = 1):
         super().__init__()
