@@ -12,15 +12,18 @@ from unet_dc_segmentation_b200.synth import calibrated_state_dict              #
 B, S = 32, 1024
 dev = torch.device("cuda:0")
 sd = calibrated_state_dict(seed=0, calib_size=64, n_calib=1)
-variants = {"enc1.3 + dec1.3 by parity class": ("enc1", "dec1"), "dec1.3 only": ("dec1",), "enc1.3 only": ("enc1",), "neither": ()}
+# name -> (parity_layers, fuse_level1, fuse_levels)
+variants = {"enc1.3 + dec1.3 by parity class": (("enc1", "dec1"), True, (2, 3, 4)), "dec1.3 only": (("dec1",), True, (2, 3, 4)),
+            "enc1.3 only": (("enc1",), True, (2, 3, 4)), "neither": ((), True, (2, 3, 4)),
+            "fused: level 1 only": (("enc1", "dec1"), True, ()), "fused: none (22 launches)": ((), False, ())}
 if len(sys.argv) > 1:
     variants = {k: v for k, v in variants.items() if any(k.startswith(a) for a in sys.argv[1].split(","))}
 ROUNDS = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 models = {}
-for name, layers in variants.items():
+for name, (layers, f1, fl) in variants.items():
     m = UNetDC(3, 1)
     m.load_state_dict(sd)
-    m.parity_layers = layers
+    m.parity_layers, m.fuse_level1, m.fuse_levels = layers, f1, fl
     models[name] = m.to(dev).eval()
 frames = torch.randint(0, 256, (B, S, S), dtype=torch.uint8, device=dev)
 times = {k: [] for k in variants}
