@@ -473,7 +473,10 @@ def run_b200(args):
                    "l2": f"{NVAR} distinct input batches rotated; per-step activation traffic (tens of GB) >> 126 MB L2",
                    "droplets_per_image": float(counts.mean())},
         "roofline": {"kernel": f"dc_forward = {n_launch} tcgen05 launches (stem, conv, fused upconv+conv kernels)", "bound": "tensor",
-                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "frac_note": "algorithmic FLOPs of the reference network / time / peak; the kernels issue fewer FLOPs "
+                                  "than that (see `issued`), so this can exceed 1",
+                     "traffic": traffic,
                      "traffic_note": f"DRAM bytes per dc_forward ({n_launch} launches) from the ncu capture {traffic_src}; "
                                      "activations written once + read once would be ~84 GB unfused (SURVEY 8d)",
                      "peak_source": f"{ptype} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
