@@ -337,3 +337,24 @@ def test_bad_arguments_raise(cuda_device):
     with pytest.raises(_lib.DcError) as ei:
         layers.conv3x3(x, w, torch.zeros(64).cuda())
     assert ei.value.code == _lib.DC_EINVAL and "multiple of 64" in str(ei.value)
+
+
+def test_upfused_bad_arguments_raise(cuda_device):
+    """dc_conv_upfused refuses what it cannot run: channel counts outside 64 / 128 / 256 / 512, a wide level without its
+    skip-weight blob, strides smaller than the channels read, misaligned output slices."""
+    import torch
+    from unet_dc_segmentation_b200 import _lib, layers
+    z = lambda *s: torch.zeros(s, dtype=torch.bfloat16).cuda()
+    with pytest.raises(_lib.DcError) as ei:                               # C = 96
+        layers.upconv_conv3x3(z(1, 8, 8, 192), z(1, 16, 16, 96), z(16, 64), torch.zeros(9, 96).cuda())
+    assert ei.value.code == _lib.DC_EINVAL and "channels" in str(ei.value)
+    with pytest.raises(_lib.DcError) as ei:                               # C = 128 without weight_skip
+        layers.upconv_conv3x3(z(1, 8, 8, 256), z(1, 16, 16, 128), z(8192, 64), torch.zeros(9, 128).cuda())
+    assert ei.value.code == _lib.DC_EINVAL and "weight_skip" in str(ei.value)
+    with pytest.raises(_lib.DcError) as ei:                               # x narrower than 2 C
+        layers.upconv_conv3x3(z(1, 8, 8, 64), z(1, 16, 16, 64), z(2, 2176, 64), torch.zeros(9, 64).cuda())
+    assert ei.value.code == _lib.DC_EINVAL and "x_stride" in str(ei.value)
+    with pytest.raises(_lib.DcError) as ei:                               # output slice not 16-byte aligned
+        layers.upconv_conv3x3(z(1, 8, 8, 128), z(1, 16, 16, 64), z(2, 2176, 64), torch.zeros(9, 64).cuda(),
+                              out=z(1, 16, 16, 80), out_offset=4)
+    assert ei.value.code == _lib.DC_EINVAL and "out_offset" in str(ei.value)

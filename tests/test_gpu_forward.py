@@ -127,6 +127,25 @@ def test_forward_with_level1_unfused(cuda_device):
     assert np.abs(y - y_fused).max() <= PROB_TOL
 
 
+@pytest.mark.parametrize("layers,levels", [(("enc1",), (2,)), (("dec1",), (3, 4)), ((), (2, 3, 4)), (("enc1", "dec1"), ())])
+def test_forward_schedule_switches(cuda_device, layers, levels):
+    """Every combination of the schedule switches (UNetDC.parity_layers, UNetDC.fuse_levels) is the same network: each
+    is held to the emulation of ITS schedule."""
+    import torch
+    from unet_dc_segmentation_b200.model import fused_level_blobs
+    from unet_dc_segmentation_b200.synth import calibrated_state_dict, synthetic_image
+    sd = calibrated_state_dict(seed=0, calib_size=64, n_calib=2)
+    imgs = np.stack([synthetic_image(96, 510 + b)[:64, :96] for b in range(2)])
+    x = torch.from_numpy(np.repeat(imgs[:, None], 3, 1).astype(np.float32) / 255.0)
+    m = _model("UNetDC", sd, cuda_device)
+    m.parity_layers, m.fuse_levels = layers, levels
+    m.invalidate()
+    assert m.num_launches() == 21 - len(levels)
+    cpu = {k: v.detach().float().cpu() for k, v in sd.items() if k.startswith(("dec", "upconv"))}
+    emu = oracle.unetdc_forward(sd, x, emulate_bf16=True, fused_levels={l: fused_level_blobs(cpu, l) for l in (1,) + tuple(levels)})
+    _check_probs(m(x.to(cuda_device)).cpu().numpy(), oracle.unetdc_forward(sd, x).numpy(), emu.numpy(), f"{layers} {levels}")
+
+
 def test_module_contract(cuda_device):
     import torch
     import unet_dc_segmentation_b200 as pkg
