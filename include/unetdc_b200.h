@@ -49,7 +49,7 @@ extern "C" {
 
 /* Bumped whenever a struct or signature in this header changes; dc_version() returns the value the library was
  * built with and the Python binding refuses to load a library that disagrees. */
-#define DC_ABI_VERSION 204
+#define DC_ABI_VERSION 205
 
 const char* dc_last_error(void);
 int dc_version(void);
@@ -143,10 +143,11 @@ typedef struct dc_upfuse_args {
 
 int dc_conv_upfused(const dc_upfuse_args_t* args, void* stream);
 /* Host only (no GPU needed): the MMA schedule of dc_conv_upfused, 5 ints per MMA in issue order = {chunk (0, 1: x
- * channels [64 chunk, 64 chunk + 64); 2: skip), window row, window column, first class, classes (1, 2 or 4)}.
+ * channels [64 chunk, 64 chunk + 64); 2: skip), window row, window column, first accumulator slot, slots (1, 2 or 4)};
+ * accumulator slot s holds output parity class s ^ (s >> 1).
  * Class cls of an MMA on window (r, c) uses tap (r - py, c - px) of its 2x2 (x chunks) or 3x3 (skip) weights; its B
  * operand is the classes' [64 co][64 ci] tiles stacked, rows [0, N/2) in the first CTA's half of the blob and
- * [N/2, N) in the second's.  Returns the number of MMAs (42) or a negative DC_E* code. */
+ * [N/2, N) in the second's.  Returns the number of MMAs (38) or a negative DC_E* code. */
 int dc_debug_upfuse_schedule(int* out, int cap);
 /* TEST / MEASUREMENT AID, never called on the product path: which windows dc_conv_upfused shares between classes
  * (0, the default: N = 256 / 128 / 64 MMAs as the windows allow; 1: no sharing, one N = 64 MMA per class and tap;

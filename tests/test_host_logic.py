@@ -189,25 +189,26 @@ def test_pack_upfused_follows_the_kernel_schedule():
     import torch
     from unet_dc_segmentation_b200 import model as M
     sched = M.upfuse_schedule()
-    assert len(sched) == 42
+    assert len(sched) == 2 * 10 + 18
     seen = set()
     rows = 0
-    for chunk, r, c, cls0, ncls in sched:
-        assert ncls in (1, 2, 4) and cls0 % ncls == 0
-        for cls in range(cls0, cls0 + ncls):
+    for chunk, r, c, slot0, nslots in sched:
+        assert nslots in (1, 2, 4) and slot0 + nslots <= 4
+        for slot in range(slot0, slot0 + nslots):
+            cls = slot ^ (slot >> 1)                        # accumulators in Gray order: 0, 1, 3, 2
             ky, kx = r - (cls >> 1), c - (cls & 1)
             assert 0 <= ky < (3 if chunk == 2 else 2) and 0 <= kx < (3 if chunk == 2 else 2)
             assert (chunk, cls, ky, kx) not in seen
             seen.add((chunk, cls, ky, kx))
-        rows += 32 * ncls
+        rows += 32 * nslots
     assert len(seen) == 2 * 4 * 4 + 4 * 9 and rows == 2176
     comp = torch.arange(4 * 2 * 2 * 64 * 128, dtype=torch.float32).reshape(4, 2, 2, 64, 128).bfloat16()
     skipw = -torch.arange(9 * 64 * 64, dtype=torch.float32).reshape(3, 3, 64, 64).bfloat16()
     blob = M.pack_upfused(comp, skipw)
     assert tuple(blob.shape) == (2, 2176, 64)
-    # first MMA: window (1, 1) of x chunk 0, all four classes -> classes 0, 1 in CTA 0, classes 2, 3 in CTA 1
+    # first MMA: window (1, 1) of x chunk 0, all four slots -> classes 0, 1 in CTA 0, classes 3, 2 in CTA 1
     assert torch.equal(blob[0, :64], comp[0, 1, 1][:, :64]) and torch.equal(blob[0, 64:128], comp[1, 1, 0][:, :64])
-    assert torch.equal(blob[1, :64], comp[2, 0, 1][:, :64]) and torch.equal(blob[1, 64:128], comp[3, 0, 0][:, :64])
+    assert torch.equal(blob[1, :64], comp[3, 0, 0][:, :64]) and torch.equal(blob[1, 64:128], comp[2, 0, 1][:, :64])
 
 
 def test_upf_schedule_include_is_current(tmp_path):

@@ -264,7 +264,9 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
         }
         TileCoord t = decode_tile<TH, UPF ? TW : TW * NHALF>(p, tile, BN);
         // UPF with fewer than four classes per pass (conv_upfused_wide_kernel): the n-tile index also carries the class
-        // group; accumulator `half` is parity class cls_base + half
+        // group; accumulator `half` is parity class cls_base + half.  With all four classes in one pass (NHALF == 4) the
+        // accumulators sit in Gray order 0, 1, 3, 2 (class = half ^ (half >> 1)): three of the four class pairings are
+        // then adjacent TMEM ranges and run as one N = 128 MMA (tools/gen_upf_schedule.py)
         int cls_base = 0;
         if (UPF) {
             const int cg = t.n0 / p.Cout;
@@ -281,8 +283,9 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
 #pragma unroll 1
             for (int half = COOP ? group : 0; half < NHALF; half += COOP ? EPI_GROUPS : 1) {
                 // UPF: accumulator `half` = parity class (half / 2, half % 2) of half-resolution pixel (t.h0 + lh, t.w0 + lw)
-                const int h = UPF ? 2 * (t.h0 + lh) + ((cls_base + half) >> 1) : t.h0 + lh;
-                const int w = UPF ? 2 * (t.w0 + lw) + ((cls_base + half) & 1) : t.w0 + half * TW + lw;
+                const int cls = NHALF == 4 ? (half ^ (half >> 1)) : cls_base + half;
+                const int h = UPF ? 2 * (t.h0 + lh) + (cls >> 1) : t.h0 + lh;
+                const int w = UPF ? 2 * (t.w0 + lw) + (cls & 1) : t.w0 + half * TW + lw;
                 const int H_out = UPF ? 2 * p.H : p.H, W_out = UPF ? 2 * p.W : p.W;
                 float head_acc = p.head_b;
                 const uint32_t taddr = tstage + (uint32_t)(half * BN);
@@ -351,7 +354,8 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                     vmask |= (uint32_t)((row < hmax) && (col < wmax)) << r;
                 }
                 pval = (2 * prow < hmax) && (2 * pcol < wmax);
-                half_off = UPF ? ((long long)((cls_base + half) >> 1) * (2 * p.W) + ((cls_base + half) & 1)) * p.out_stride : half * TW * cs;
+                const int cls = NHALF == 4 ? (half ^ (half >> 1)) : cls_base + half;
+                half_off = UPF ? ((long long)(cls >> 1) * (2 * p.W) + (cls & 1)) * p.out_stride : half * TW * cs;
                 phalf_off = (long long)(half * (TW / 2)) * p.pool_stride;
             }
             int bias_at = t.n0 + c0;
@@ -391,7 +395,8 @@ __device__ __forceinline__ void run_epilogue(const ConvParams& p, const int e, c
                 // taps of the 3x3 that fall outside the (upsampled) image carry no transposed-conv bias: only the
                 // pixels of the first / last output row and column differ from the interior constant
                 const int hh = t.h0 + lh, ww = t.w0 + lw;
-                const int py = (cls_base + half) >> 1, px = (cls_base + half) & 1;
+                const int cls = NHALF == 4 ? (half ^ (half >> 1)) : cls_base + half;
+                const int py = cls >> 1, px = cls & 1;
                 const int rc = (py == 0 && hh == 0) ? 0 : ((py == 1 && hh == p.H - 1) ? 2 : 1);
                 const int cc9 = (px == 0 && ww == 0) ? 0 : ((px == 1 && ww == p.W - 1) ? 2 : 1);
                 if (rc * 3 + cc9 != 4) {               // p.bias = the interior row (4) of the fp32 [9][Cout] class table
@@ -1014,8 +1019,9 @@ conv_halo2_kernel(const __grid_constant__ ConvParams p) {
 // 128 the MMA unit gets): that bounds the ordinary N = 64 layers at 74 % tensor.  Here the window only depends on
 // (py + a, px + b) resp. (py + ky, px + kx), so several classes read the SAME window -- with different weights into
 // ADJACENT accumulators -- and run as one MMA of N = 128 (classes 0,1 or 2,3) or N = 256 (all four) whose B operand is
-// the classes' weight tiles stacked: 11 MMAs instead of 16 per K = 16 step of an x chunk, 20 instead of 36 for the
-// skip chunk, same tensor cycles, A reads 44 / 80 KB instead of 64 / 144 KB.  The schedule is the table below; the
+// the classes' weight tiles stacked; the accumulators sit in Gray order (slot s = class s ^ (s >> 1)) so that three of
+// the four class pairings are adjacent: 10 MMAs instead of 16 per K = 16 step of an x chunk, 18 instead of 36 for the
+// skip chunk, same tensor cycles, A reads 40 / 72 KB instead of 64 / 144 KB.  The schedule is the table below; the
 // host packs the weights in exactly this order (dc_debug_upfuse_schedule), per CTA of the pair (a pair MMA takes rows
 // [0, N/2) of B from the leader and [N/2, N) from the peer), and they stream through a ring of 16 KB groups (= 512
 // tensor cycles each; within a group the MMAs go to different accumulators, so no chain waits for itself).

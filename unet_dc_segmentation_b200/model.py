@@ -94,7 +94,8 @@ def compose_upconv(wu, bu, wd, bd):
 
 
 def upfuse_schedule():
-    """The MMA schedule of dc_conv_upfused (host-only library call): rows (chunk, r, c, cls0, ncls)."""
+    """The MMA schedule of dc_conv_upfused (host-only library call): rows (chunk, r, c, slot0, nslots).  Accumulator
+    slot s holds parity class s ^ (s >> 1) (Gray order 0, 1, 3, 2)."""
     buf = (C.c_int * (5 * 128))()
     n = _lib.load().dc_debug_upfuse_schedule(buf, len(buf))
     _lib.check(min(n, 0))
@@ -103,9 +104,10 @@ def upfuse_schedule():
 
 def pack_upfused(comp, skipw):
     """Weights of compose_upconv in the order the kernel's MMAs consume them: bf16 [2 CTAs][2176 rows][64 ci].
-    An MMA on window (r, c) covering classes cls0 .. cls0+ncls-1 takes, for class (py, px), tap (r - py, c - px) of
-    chunk 0 / 1 (x channels [0,64) / [64,128)) or of the skip weights (chunk 2); its B operand is those [64 co][64 ci]
-    tiles stacked, the first half of the rows in CTA 0's blob and the second half in CTA 1's.
+    An MMA on window (r, c) covering accumulator slots slot0 .. slot0+n-1 (slot s = class s ^ (s >> 1)) takes, for class
+    (py, px), tap (r - py, c - px) of chunk 0 / 1 (x channels [0,64) / [64,128)) or of the skip weights (chunk 2); its
+    B operand is those [64 co][64 ci] tiles stacked in slot order, the first half of the rows in CTA 0's blob and the
+    second half in CTA 1's.
     comp = None: the skip part alone = a plain 64 -> 64 channel 3x3 layer by parity class, [2][1152][64]
     (dc_conv_args.weight_par)."""
     halves = ([], [])
@@ -113,7 +115,8 @@ def pack_upfused(comp, skipw):
         if comp is None and chunk != 2:
             continue
         tiles = []
-        for cls in range(cls0, cls0 + ncls):
+        for slot in range(cls0, cls0 + ncls):
+            cls = slot ^ (slot >> 1)
             py, px = cls >> 1, cls & 1
             tiles.append(skipw[r - py, c - px] if chunk == 2 else comp[cls, r - py, c - px][:, chunk * 64:(chunk + 1) * 64])
         rows = torch.cat(tiles, 0)                                   # [64 * ncls][64]
